@@ -1,0 +1,151 @@
+/*
+ * nerfqa_b200 — C-ABI of the B200-native DISTS / A-DISTS frame-pair scorer.
+ *
+ * This is the drop-in boundary for the full-reference perceptual-distance hot path of
+ * kobejean/nerf-qa.  Every entry point cites the reference interface it replaces (paths relative to
+ * the reference checkout).  The reference is pure Python over torch, so what a maintainer binds here
+ * is exactly what nerf_qa/DISTS_pytorch/DISTS_pt.py and nerf_qa/ADISTS/ADISTS.py do with ATen today;
+ * INTEGRATION.md shows the ctypes / torch glue.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / CUDA types in signatures (`stream` is a
+ *     cudaStream_t passed as void*; NULL = the legacy default stream);
+ *   - every call returns 0 (NQA_OK) or a negative nqa_status; nqa_last_error() gives the message
+ *     of the calling thread's last failure; no exception crosses the boundary;
+ *   - image tensors are NCHW fp32, values nominally in [0,1], x and y of identical shape
+ *     (ADISTS.py:138 asserts it; DISTS_pt.py relies on it);
+ *   - "device" pointers must live on the context's GPU; "any" pointers may be host or device (UVA);
+ *   - the caller owns all input/output buffers and the stream; the context owns packed weights and
+ *     a workspace arena that grows on demand (no allocation after warm-up at a fixed shape);
+ *   - calls on one context are not thread-safe (same contract as a torch nn.Module); use one
+ *     context per GPU, one process (or thread) per GPU;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with NQA_ERR_CUDA.
+ */
+#ifndef NERFQA_B200_H
+#define NERFQA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define NQA_API __attribute__((visibility("default")))
+#else
+#define NQA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NQA_NUM_CONVS 13      /* torchvision vgg16.features idx 0..28 convs (DISTS_pt.py:36-49)      */
+#define NQA_NUM_LEVELS 6      /* [x, relu1_2, relu2_2, relu3_3, relu4_3, relu5_3] (DISTS_pt.py:103)  */
+#define NQA_NUM_CHANNELS 1475 /* sum(chns) = 3+64+128+256+512+512 (DISTS_pt.py:57)                   */
+
+typedef struct nqa_ctx nqa_ctx;
+
+typedef enum nqa_status {
+  NQA_OK = 0,
+  NQA_ERR_INVALID = -1, /* null pointer / bad enum / bad argument            */
+  NQA_ERR_CUDA = -2,    /* CUDA runtime or driver failure, or no device      */
+  NQA_ERR_SHAPE = -3,   /* B,H,W out of range (a pyramid level would vanish) */
+  NQA_ERR_STATE = -4,   /* weights / alpha-beta not set yet                  */
+  NQA_ERR_NOMEM = -5    /* workspace allocation failed                       */
+} nqa_status;
+
+/* Arithmetic of the VGG trunk (SURVEY.md §7 "parity tolerance"):
+ *   FP32  — fp32 activations, fp32 CUDA-core FMA convolutions; per-frame scores within 1e-4
+ *           relative of the reference's fp32 CPU result;
+ *   BF16  — bf16 activations, tcgen05 (kind::f16, bf16 operands) with fp32 accumulation in TMEM;
+ *           per-frame scores within 2e-3 absolute;
+ *   BF16X3 — fp32 activations carried as bf16 hi+lo pairs, three tcgen05 MMAs per k-block
+ *           (hi*hi + hi*lo + lo*hi), fp32 accumulation; fp32-class accuracy (1e-4 relative) on the
+ *           tensor pipe.
+ * Statistics, pooling and A-DISTS window math always accumulate in fp32 (final moments in fp64). */
+typedef enum nqa_precision { NQA_PREC_FP32 = 0, NQA_PREC_BF16 = 1, NQA_PREC_BF16X3 = 2 } nqa_precision;
+
+/* Message of the calling thread's most recent failing call ("" if none). */
+NQA_API const char* nqa_last_error(void);
+/* Library version, major*10000 + minor*100 + patch. */
+NQA_API int nqa_version(void);
+
+/* One context per GPU.  Replaces module construction + `.to(device)` (DISTS_pt.py:28-80,
+ * ADISTS.py:36-69). */
+NQA_API int nqa_ctx_create(int device, nqa_ctx** out);
+NQA_API int nqa_ctx_destroy(nqa_ctx* ctx);
+
+/* VGG16 conv parameters, OIHW fp32 weights and fp32 biases in torchvision features order
+ * (state_dict keys stage{k}.{idx}.weight/bias; DISTS_pt.py:30-49).  `w[i]`/`b[i]` are "any"
+ * pointers; the library repacks into its own layouts and keeps the copies. */
+NQA_API int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const float* const b[NQA_NUM_CONVS]);
+
+/* DISTS channel weights alpha/beta, 1475 floats each ("any" pointers), RAW as stored in the module
+ * (DISTS_pt.py:58-80); the division by w_sum = sum(alpha)+sum(beta) (DISTS_pt.py:127-129) happens
+ * inside the scoring calls. */
+NQA_API int nqa_set_alpha_beta(nqa_ctx* ctx, const float* alpha, const float* beta);
+
+/* DISTS.forward(x, y) (DISTS_pt.py:105-148): per-frame scores.
+ *   x, y       device, [B,3,H,W] fp32
+ *   score_out  device, [B] fp32
+ *   s1s2_out   device or NULL, [B,2,1475] fp32: per-channel S1 then S2 (DISTS_pt.py:134,141), what
+ *              the backward of the alpha/beta combination needs
+ * Asynchronous on `stream`. */
+NQA_API int nqa_dists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int precision,
+                      float* score_out, float* s1s2_out, void* stream);
+
+/* Same computation from HOST buffers: x_host/y_host/score_host are host pointers (pinned memory
+ * gives full PCIe rate).  Frames are streamed host->device in micro-batches on a copy stream that
+ * overlaps the compute stream; returns after the scores are in score_host.  This is the call
+ * prep.py:186-190 makes implicitly with `.to(device)` ... `.cpu()`. */
+NQA_API int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W,
+                           int precision, float* score_host);
+
+/* DISTS.forward_once(x) (DISTS_pt.py:91-103): levels 1..5 as NCHW fp32 device tensors
+ * (level 0 is x itself).  feats_out[k-1] must hold B*C_k*H_k*W_k floats,
+ * C = {64,128,256,512,512}, H_k = (H_{k-1}-1)/2+1 from level 2 on. */
+NQA_API int nqa_dists_features(nqa_ctx* ctx, const float* x, int B, int H, int W, int precision,
+                       float* const feats_out[NQA_NUM_LEVELS - 1], void* stream);
+
+/* DISTS.forward_from_feats(feats0, feats1) (DISTS_pt.py:181-208): six NCHW fp32 device tensors per
+ * image; level k has C_k channels and the pyramid sizes implied by H, W (level 0 = [B,3,H,W]). */
+NQA_API int nqa_dists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],
+                         const float* const feats_y[NQA_NUM_LEVELS], int B, int H, int W, float* score_out,
+                         float* s1s2_out, void* stream);
+
+/* ADISTS.forward(x, y, as_loss=False) (ADISTS.py:137-197): per-frame scores [B] (device).
+ * `window` is the gaussian window size (21 in the reference, ADISTS.py:34); a level smaller than
+ * the window uses whole-map statistics (the reference's bare `except`, ADISTS.py:91-97,175-180).
+ * Asymmetric: structure-probability maps and entropy weights come from x (ADISTS.py:147,153).
+ * precision: NQA_PREC_FP32 or NQA_PREC_BF16 trunk; the A-DISTS statistics themselves are always fp32. */
+NQA_API int nqa_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window,
+                       int precision, float* score_out, void* stream);
+
+/* The statistics half of ADISTS.forward (ADISTS.py:147-197) from six NCHW fp32 device tensors per
+ * image (the reference's forward_once format, level 0 = the raw frames). */
+NQA_API int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],
+                          const float* const feats_y[NQA_NUM_LEVELS], int B, int H, int W, int window,
+                          float* score_out, void* stream);
+
+/* Standalone L2pooling / Downsample on an NCHW fp32 device tensor (DISTS_pt.py:11-25,
+ * ADISTS.py:16-31): out[B,C,(H-1)/2+1,(W-1)/2+1] = sqrt(hanning3x3(x^2, stride 2, pad 1) + 1e-12). */
+NQA_API int nqa_l2pool(nqa_ctx* ctx, const float* x, int B, int C, int H, int W, float* out, void* stream);
+
+/* Op-level 3x3 convolution + bias + ReLU (stride 1, zero pad 1) through the selected implementation,
+ * for kernel parity tests: x [B,Cin,H,W], w [Cout,Cin,3,3], bias [Cout], out [B,Cout,H,W], all NCHW /
+ * OIHW fp32 device tensors; Cin and Cout multiples of 64, Cout <= 512.  Equivalent of one
+ * `Conv2d(3x3, padding=1)` + `ReLU` pair of torchvision's vgg16.features (DISTS_pt.py:36-49). */
+NQA_API int nqa_conv3x3_relu(nqa_ctx* ctx, const float* x, const float* w, const float* bias, int B, int Cin, int Cout,
+                             int H, int W, int precision, float* out, void* stream);
+
+/* Bytes of device workspace the context currently holds (after warm-up this stops growing). */
+NQA_API int nqa_workspace_bytes(nqa_ctx* ctx, size_t* bytes);
+
+/* Number of kernels this library has launched on the context since creation (bench accounting). */
+NQA_API int nqa_launch_count(nqa_ctx* ctx, uint64_t* launches);
+
+/* Micro-batch (frame pairs per trunk pass) the scheduler would use for this shape. */
+NQA_API int nqa_micro_batch(nqa_ctx* ctx, int B, int H, int W, int precision, int* pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFQA_B200_H */

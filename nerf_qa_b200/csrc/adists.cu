@@ -1,0 +1,739 @@
+// A-DISTS statistics stage (nerf_qa/ADISTS/ADISTS.py:71-100, 127-135, 147-197) on planar fp32 levels.
+//
+// Restructuring that preserves the reference's results:
+//   * the 21x21 gaussian window is rank-1 -> two 21-tap passes through shared memory;
+//   * windowed statistics are taken of the RAW features and scaled by the per-channel 1/||f||
+//     afterwards (filtering is linear), which yields compute_prob's un-normalised mean / variance
+//     from the same five filtered maps -> 5 filters per channel instead of 7;
+//   * sum_c w_c((1-ps) T_c + ps S_c) = (1-ps) sum_c w_c T_c + ps sum_c w_c S_c, so the window kernel
+//     reduces over channels on the fly and emits three 1-channel maps per level (sum w T, sum w S,
+//     sum gamma_c); the [B,C,h,w] statistic maps never reach HBM;
+//   * entropy weights depend only on the first image and are computed before the window pass;
+//   * the coarse-to-fine ps chain runs on the small 1-channel maps with multi-block reductions whose
+//     last block combines the partials in a fixed order (deterministic).
+//
+// Pass structure per micro-batch: (1) per-channel sums, (2) entropy, (3) channel weights,
+// (4) window / global statistics per level, (5) ps chain + D per level (k = 5..0), (6) score.
+#include <math.h>
+
+#include "adists.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nqa {
+
+namespace {
+
+constexpr int WT = 32;           // window kernel: 32x32 output pixels per block
+constexpr int kRedBlocks = 128;  // blocks per frame pair in the map reductions
+
+struct Taps {
+  float g[kAdistsMaxWindow];
+};
+
+struct LvlScal {   // per (pair, level) scalars of the ps chain
+  float mean, stdv, gmin, gmax;   // of gamma over the map
+  float pmin, pmax;               // of ps_n * interp(prev)
+  float d;                        // mean_hw((1-ps) A + ps B)
+  float pad;
+};
+
+struct LevelPlan {
+  int c, h, w, hw, choff;
+  bool windowed;
+  int oh, ow, on;          // window map (1x1 in the global-statistics fallback)
+  int chunks;              // planar-sum chunks
+  int tiles_x, tiles_y, csplit;
+  size_t off_sum, off_ent, off_a, off_b, off_g, off_ps;  // byte offsets into the workspace
+};
+
+struct Plan {
+  LevelPlan lv[kNumLevels];
+  size_t off_chan, off_e, off_wt, off_scal, off_red, off_cnt;
+  size_t total;
+};
+
+size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+Plan make_plan(int pairs, int H, int W, int window) {
+  Plan p;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off = a256(off + bytes); return o; };
+  int h = H, w = W;
+  for (int k = 0; k < kNumLevels; ++k) {
+    if (k >= 2) { h = pooled(h); w = pooled(w); }
+    LevelPlan& L = p.lv[k];
+    L.c = level_channels(k); L.h = h; L.w = w; L.hw = h * w; L.choff = level_offset(k);
+    L.windowed = h >= window && w >= window;
+    L.oh = L.windowed ? h - window + 1 : 1;
+    L.ow = L.windowed ? w - window + 1 : 1;
+    L.on = L.oh * L.ow;
+    L.chunks = stats_chunks_planar(L.hw, L.c, pairs);
+    L.tiles_x = ceil_div(L.ow, WT);
+    L.tiles_y = ceil_div(L.oh, WT);
+    L.csplit = 1;
+    if (L.windowed) {
+      // split the channel loop across blocks until the level fills ~2 waves (deep levels have few tiles)
+      const int blocks = L.tiles_x * L.tiles_y * pairs;
+      int cs = ceil_div(2 * kNumSMs, blocks);
+      if (cs > L.c / 8) cs = L.c / 8;
+      if (cs < 1) cs = 1;
+      L.csplit = cs;
+    }
+    L.off_sum = take((size_t)pairs * L.chunks * 7 * L.c * sizeof(float));
+    L.off_ent = take((size_t)pairs * L.chunks * L.c * sizeof(float));
+    L.off_a = take((size_t)pairs * L.csplit * L.on * sizeof(float));
+    L.off_b = take((size_t)pairs * L.csplit * L.on * sizeof(float));
+    L.off_g = take((size_t)pairs * L.csplit * L.on * sizeof(float));
+    L.off_ps = take((size_t)pairs * L.on * sizeof(float));
+  }
+  p.off_chan = take((size_t)pairs * kTotalChannels * 8 * sizeof(double));
+  p.off_e = take((size_t)pairs * kTotalChannels * sizeof(double));
+  p.off_wt = take((size_t)pairs * kTotalChannels * sizeof(float));
+  p.off_scal = take((size_t)pairs * kNumLevels * sizeof(LvlScal));
+  p.off_red = take((size_t)pairs * kRedBlocks * 4 * sizeof(double));
+  p.off_cnt = take((size_t)pairs * sizeof(unsigned int));
+  p.total = off + 256;
+  return p;
+}
+
+// ================================================================================================
+// (1) per-(pair, channel) sums over the map: x, y, x^2, y^2, xy, relu(x), relu(x)^2
+// grid = (chunks, C, pairs); partial[((b*chunks + chunk)*7 + s)*C + ch]
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+sums7_kernel(const float* __restrict__ x, const float* __restrict__ y, int c, int hw, int chunks,
+             float* __restrict__ partials) {
+  const int chunk = blockIdx.x, ch = blockIdx.y, b = blockIdx.z;
+  const int per = ceil_div(ceil_div(hw, chunks), 4) * 4;
+  const int p0 = chunk * per, p1 = min(hw, p0 + per);
+  const float* px = x + ((size_t)b * c + ch) * hw;
+  const float* py = y + ((size_t)b * c + ch) * hw;
+  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto acc = [&](float a, float d) {
+    const float r = fmaxf(a, 0.f);
+    s[0] += a; s[1] += d;
+    s[2] = fmaf(a, a, s[2]); s[3] = fmaf(d, d, s[3]); s[4] = fmaf(a, d, s[4]);
+    s[5] += r; s[6] = fmaf(r, r, s[6]);
+  };
+  const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(py) & 15) == 0);
+  if (vec_ok && p1 > p0) {
+    const int n4 = (p1 - p0) / 4;
+    const float4* qx = reinterpret_cast<const float4*>(px + p0);
+    const float4* qy = reinterpret_cast<const float4*>(py + p0);
+#pragma unroll 2
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const float4 a = __ldg(qx + i), d = __ldg(qy + i);
+      acc(a.x, d.x); acc(a.y, d.y); acc(a.z, d.z); acc(a.w, d.w);
+    }
+    for (int p = p0 + n4 * 4 + threadIdx.x; p < p1; p += 256) acc(px[p], py[p]);
+  } else {
+    for (int p = p0 + threadIdx.x; p < p1; p += 256) acc(px[p], py[p]);
+  }
+  __shared__ float sm[7][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const float v = warp_sum(s[i]);
+    if (lane == 0) sm[i][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += sm[threadIdx.x][q];
+    partials[(((size_t)b * chunks + chunk) * 7 + threadIdx.x) * c + ch] = v;
+  }
+}
+
+// chan[b][1475][8] (double): 1/max(||x||,eps), 1/max(||y||,eps), entropy scale, mean x, mean y, E[x^2], E[y^2], E[xy]
+struct SumLevels {
+  const float* partials[kNumLevels];
+  int chunks[kNumLevels];
+  int hw[kNumLevels];
+};
+
+__global__ void __launch_bounds__(256)
+chan_kernel(SumLevels sl, double* __restrict__ chan) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) {
+    const int k = c < 3 ? 0 : c < 67 ? 1 : c < 195 ? 2 : c < 451 ? 3 : c < 963 ? 4 : 5;
+    const int C = level_channels(k), cc = c - level_offset(k), chunks = sl.chunks[k];
+    const float* base = sl.partials[k] + (size_t)b * chunks * 7 * C + cc;
+    double s[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int ch = 0; ch < chunks; ++ch)
+#pragma unroll
+      for (int i = 0; i < 7; ++i) s[i] += (double)base[((size_t)ch * 7 + i) * C];
+    const double n = (double)sl.hw[k];
+    const double eps = 1e-12;
+    const double nx = fmax(sqrt(s[2]), eps), ny = fmax(sqrt(s[3]), eps), nr = fmax(sqrt(s[6]), eps);
+    const double a = 1.0 / nr;
+    double* o = chan + ((size_t)b * kTotalChannels + c) * 8;
+    o[0] = 1.0 / nx;
+    o[1] = 1.0 / ny;
+    o[2] = a / (a * s[5] + eps);   // p = relu(x) * o[2]  (ADISTS.py:130-132)
+    o[3] = s[0] / n;
+    o[4] = s[1] / n;
+    o[5] = s[2] / n;
+    o[6] = s[3] / n;
+    o[7] = s[4] / n;
+  }
+}
+
+// ================================================================================================
+// (2) entropy of the first image's channels: E_c = -sum_hw p log2(p + 1e-12)   (ADISTS.py:133)
+// grid = (chunks, C, pairs); partial[(b*chunks + chunk)*C + ch]
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+entropy_kernel(const float* __restrict__ x, int c, int hw, int chunks, int choff, const double* __restrict__ chan,
+               float* __restrict__ partials) {
+  const int chunk = blockIdx.x, ch = blockIdx.y, b = blockIdx.z;
+  const int per = ceil_div(ceil_div(hw, chunks), 4) * 4;
+  const int p0 = chunk * per, p1 = min(hw, p0 + per);
+  const float* px = x + ((size_t)b * c + ch) * hw;
+  const float scale = (float)chan[((size_t)b * kTotalChannels + choff + ch) * 8 + 2];
+  float s = 0.f;
+  auto acc = [&](float a) {
+    const float p = fmaxf(a, 0.f) * scale;
+    s -= p * log2f(p + 1e-12f);
+  };
+  const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & 15) == 0);
+  if (vec_ok && p1 > p0) {
+    const int n4 = (p1 - p0) / 4;
+    const float4* qx = reinterpret_cast<const float4*>(px + p0);
+#pragma unroll 2
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const float4 a = __ldg(qx + i);
+      acc(a.x); acc(a.y); acc(a.z); acc(a.w);
+    }
+    for (int p = p0 + n4 * 4 + threadIdx.x; p < p1; p += 256) acc(px[p]);
+  } else {
+    for (int p = p0 + threadIdx.x; p < p1; p += 256) acc(px[p]);
+  }
+  __shared__ float sm[33];
+  const float tot = block_sum<float>(s, sm);
+  if (threadIdx.x == 0) partials[((size_t)b * chunks + chunk) * c + ch] = tot;
+}
+
+// ================================================================================================
+// (3) channel weights: per-level normalise * C_k, concat, normalise, clamp(mean +- 0.5 std),
+// renormalise (ADISTS.py:134-135, 155-160).  grid = pairs.
+// ================================================================================================
+struct EntLevels {
+  const float* partials[kNumLevels];
+  int chunks[kNumLevels];
+};
+
+__global__ void __launch_bounds__(256)
+weights_kernel(EntLevels el, float* __restrict__ wt) {
+  __shared__ double e[kTotalChannels];
+  __shared__ double red[33];
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) {
+    const int k = c < 3 ? 0 : c < 67 ? 1 : c < 195 ? 2 : c < 451 ? 3 : c < 963 ? 4 : 5;
+    const int C = level_channels(k), cc = c - level_offset(k), chunks = el.chunks[k];
+    const float* base = el.partials[k] + (size_t)b * chunks * C + cc;
+    double s = 0;
+    for (int ch = 0; ch < chunks; ++ch) s += (double)base[(size_t)ch * C];
+    e[c] = s;
+  }
+  __syncthreads();
+  for (int k = 0; k < kNumLevels; ++k) {
+    const int C = level_channels(k), off = level_offset(k);
+    double part = 0;
+    for (int c = threadIdx.x; c < C; c += 256) part += e[off + c];
+    const double tot = block_sum<double>(part, red);
+    for (int c = threadIdx.x; c < C; c += 256) e[off + c] = e[off + c] / (tot + 1e-12) * (double)C;
+    __syncthreads();
+  }
+  double part = 0;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) part += e[c];
+  const double tot = block_sum<double>(part, red);
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) e[c] /= tot;
+  __syncthreads();
+  part = 0;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) part += e[c];
+  const double mean = block_sum<double>(part, red) / kTotalChannels;
+  part = 0;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) part += (e[c] - mean) * (e[c] - mean);
+  const double sd = sqrt(block_sum<double>(part, red) / kTotalChannels);
+  const double lo = mean - 0.5 * sd, hi = mean + 0.5 * sd;
+  part = 0;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) {
+    e[c] = fmin(fmax(e[c], lo), hi);
+    part += e[c];
+  }
+  const double tot2 = block_sum<double>(part, red);
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) wt[(size_t)b * kTotalChannels + c] = (float)(e[c] / tot2);
+}
+
+// ================================================================================================
+// (4a) window statistics.  Block = 32x32 output pixels of one frame pair, loops over a channel range:
+// loads the (32+WIN-1)^2 raw tiles of x and y, horizontal 5-quantity pass into shared memory, vertical
+// pass in registers, then per-pixel T, S, gamma accumulated over channels.
+// grid = (tiles_x*tiles_y, csplit, pairs); out maps [pairs][csplit][oh*ow].
+// ================================================================================================
+template <int WIN>
+__global__ void __launch_bounds__(256, 2)
+window_kernel(const float* __restrict__ fx, const float* __restrict__ fy, int c, int h, int w, int oh, int ow,
+              int tiles_x, int csplit, int choff, const double* __restrict__ chan, const float* __restrict__ wt,
+              Taps taps, float* __restrict__ amap, float* __restrict__ bmap, float* __restrict__ gmap) {
+  constexpr int IN = WT + WIN - 1;
+  constexpr int LDI = IN | 1;     // odd row stride: conflict-free when lanes walk down rows
+  constexpr int LDH = WT + 1;
+  constexpr int RX = 8;           // output columns per thread in the horizontal pass
+  constexpr int RY = 4;           // output rows per thread in the vertical pass
+  static_assert(IN <= 64, "horizontal pass maps rows onto two warps per column group");
+  extern __shared__ float smem[];
+  float* sx = smem;
+  float* sy = sx + IN * LDI;
+  float* hb = sy + IN * LDI;      // [5][IN][LDH]
+
+  const int tile = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
+  const int oy0 = (tile / tiles_x) * WT, ox0 = (tile % tiles_x) * WT;
+  const int c_per = ceil_div(c, csplit);
+  const int c_begin = split * c_per, c_end = min(c, c_begin + c_per);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  float g[WIN];
+#pragma unroll
+  for (int t = 0; t < WIN; ++t) g[t] = taps.g[t];
+
+  // horizontal role: column group jg (8 output columns), input row hr
+  const int jg = warp & 3, hr = (warp >> 2) * 32 + lane;
+  // vertical role: output column vj, output rows vi0..vi0+3
+  const int vj = lane, vi0 = warp * RY;
+
+  float acc_a[RY], acc_b[RY], acc_g[RY];
+#pragma unroll
+  for (int i = 0; i < RY; ++i) acc_a[i] = acc_b[i] = acc_g[i] = 0.f;
+
+  for (int ch = c_begin; ch < c_end; ++ch) {
+    const float* px = fx + ((size_t)b * c + ch) * h * w;
+    const float* py = fy + ((size_t)b * c + ch) * h * w;
+    __syncthreads();  // previous channel's vertical pass has finished reading hb; sx/sy are free
+    for (int idx = threadIdx.x; idx < IN * IN; idx += 256) {
+      const int r = idx / IN, col = idx - r * IN;
+      const int gy = oy0 + r, gx = ox0 + col;
+      float vx = 0.f, vy = 0.f;
+      if (gy < h && gx < w) {
+        vx = __ldg(px + (size_t)gy * w + gx);
+        vy = __ldg(py + (size_t)gy * w + gx);
+      }
+      sx[r * LDI + col] = vx;
+      sy[r * LDI + col] = vy;
+    }
+    __syncthreads();
+    if (hr < IN) {
+      float o0[RX], o1[RX], o2[RX], o3[RX], o4[RX];
+#pragma unroll
+      for (int j = 0; j < RX; ++j) o0[j] = o1[j] = o2[j] = o3[j] = o4[j] = 0.f;
+      const float* rx = sx + hr * LDI + jg * RX;
+      const float* ry = sy + hr * LDI + jg * RX;
+#pragma unroll
+      for (int t = 0; t < RX + WIN - 1; ++t) {
+        const float a = rx[t], d = ry[t];
+        const float aa = a * a, dd = d * d, ad = a * d;
+#pragma unroll
+        for (int j = 0; j < RX; ++j) {
+          if (t - j >= 0 && t - j < WIN) {
+            const float gw = g[t - j];
+            o0[j] = fmaf(gw, a, o0[j]);
+            o1[j] = fmaf(gw, d, o1[j]);
+            o2[j] = fmaf(gw, aa, o2[j]);
+            o3[j] = fmaf(gw, dd, o3[j]);
+            o4[j] = fmaf(gw, ad, o4[j]);
+          }
+        }
+      }
+      float* hrow = hb + hr * LDH + jg * RX;
+#pragma unroll
+      for (int j = 0; j < RX; ++j) {
+        hrow[0 * IN * LDH + j] = o0[j];
+        hrow[1 * IN * LDH + j] = o1[j];
+        hrow[2 * IN * LDH + j] = o2[j];
+        hrow[3 * IN * LDH + j] = o3[j];
+        hrow[4 * IN * LDH + j] = o4[j];
+      }
+    }
+    __syncthreads();
+    float v[5][RY];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int i = 0; i < RY; ++i) v[k][i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < RY + WIN - 1; ++t) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float hv = hb[(k * IN + vi0 + t) * LDH + vj];
+#pragma unroll
+        for (int i = 0; i < RY; ++i)
+          if (t - i >= 0 && t - i < WIN) v[k][i] = fmaf(g[t - i], hv, v[k][i]);
+      }
+    }
+    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * 8;
+    const float ax = (float)cs[0], ay = (float)cs[1];
+    const float wc = wt[(size_t)b * kTotalChannels + choff + ch];
+#pragma unroll
+    for (int i = 0; i < RY; ++i) {
+      const float mxr = v[0][i], myr = v[1][i];
+      const float mx = ax * mxr, my = ay * myr;
+      const float vx = ax * ax * v[2][i] - mx * mx;
+      const float vy = ay * ay * v[3][i] - my * my;
+      const float cov = ax * ay * v[4][i] - mx * my;
+      const float t_ = (2.f * mx * my + 1e-6f) / (mx * mx + my * my + 1e-6f);
+      const float s_ = (2.f * cov + 1e-6f) / (vx + vy + 1e-6f);
+      acc_a[i] = fmaf(wc, t_, acc_a[i]);
+      acc_b[i] = fmaf(wc, s_, acc_b[i]);
+      acc_g[i] += (v[2][i] - mxr * mxr) / (mxr + 1e-12f);   // compute_prob, raw features (ADISTS.py:81-84)
+    }
+  }
+  const size_t mbase = ((size_t)b * csplit + split) * oh * ow;
+#pragma unroll
+  for (int i = 0; i < RY; ++i) {
+    const int oy = oy0 + vi0 + i, ox = ox0 + vj;
+    if (oy < oh && ox < ow) {
+      const size_t o = mbase + (size_t)oy * ow + ox;
+      amap[o] = acc_a[i];
+      bmap[o] = acc_b[i];
+      gmap[o] = acc_g[i];
+    }
+  }
+}
+
+// (4b) global-statistics fallback for a level smaller than the window (ADISTS.py:91-97, 175-180).
+// grid = pairs; writes the 1x1 "maps".
+__global__ void __launch_bounds__(256)
+global_level_kernel(int c, int choff, const double* __restrict__ chan, const float* __restrict__ wt,
+                    float* __restrict__ amap, float* __restrict__ bmap, float* __restrict__ gmap) {
+  __shared__ double red[33];
+  const int b = blockIdx.x;
+  double pa = 0, pb = 0, pg = 0;
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * 8;
+    const double ax = cs[0], ay = cs[1];
+    const double mxr = cs[3], myr = cs[4];
+    const double mx = ax * mxr, my = ay * myr;
+    const double vx = ax * ax * cs[5] - mx * mx, vy = ay * ay * cs[6] - my * my;
+    const double cov = ax * ay * cs[7] - mx * my;
+    const double t_ = (2.0 * mx * my + 1e-6) / (mx * mx + my * my + 1e-6);
+    const double s_ = (2.0 * cov + 1e-6) / (vx + vy + 1e-6);
+    const double wc = (double)wt[(size_t)b * kTotalChannels + choff + ch];
+    pa += wc * t_;
+    pb += wc * s_;
+    pg += (cs[5] - mxr * mxr) / (mxr + 1e-12);
+  }
+  const double ta = block_sum<double>(pa, red);
+  const double tb = block_sum<double>(pb, red);
+  const double tg = block_sum<double>(pg, red);
+  if (threadIdx.x == 0) {
+    amap[b] = (float)ta;
+    bmap[b] = (float)tb;
+    gmap[b] = (float)tg;
+  }
+}
+
+// ================================================================================================
+// (5) ps chain on the 1-channel maps (ADISTS.py:85-99).  Three multi-block reductions per windowed
+// level; the last block of each frame pair combines the block partials in index order.
+// ================================================================================================
+struct MapArgs {
+  const float* amap; const float* bmap; const float* gmap;   // [pairs][csplit][on]
+  int csplit, on, oh, ow, c;
+  const float* prev;     // coarser ps_prod [pairs][ph*pw], or nullptr = ones
+  int ph, pw;
+  float* ps_out;         // [pairs][on]
+  LvlScal* scal;         // [pairs][6]
+  int level;
+  double* red;           // [pairs][kRedBlocks][4]
+  unsigned int* cnt;     // [pairs]
+};
+
+__device__ inline float map_sum(const float* m, int csplit, int on, int b, int i) {
+  float s = 0.f;
+  for (int q = 0; q < csplit; ++q) s += m[((size_t)b * csplit + q) * on + i];
+  return s;
+}
+
+// bilinear, align_corners=True (torch upsample_bilinear2d semantics)
+__device__ inline float interp_prev(const float* prev, int ph, int pw, int b, int oy, int ox, int oh, int ow) {
+  if (!prev) return 1.f;
+  const float* p = prev + (size_t)b * ph * pw;
+  const float sy = oh > 1 ? (float)(ph - 1) / (float)(oh - 1) : 0.f;
+  const float sx = ow > 1 ? (float)(pw - 1) / (float)(ow - 1) : 0.f;
+  const float fy = sy * oy, fxx = sx * ox;
+  const int y0 = (int)fy, x0 = (int)fxx;
+  const int y1 = y0 + (y0 < ph - 1 ? 1 : 0), x1 = x0 + (x0 < pw - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fxx - x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * p[y0 * pw + x0] + lx * p[y0 * pw + x1]) + ly * (hx * p[y1 * pw + x0] + lx * p[y1 * pw + x1]);
+}
+
+__device__ inline float sigmoidf_ref(float z) { return 1.f / (1.f + expf(-z)); }
+
+// returns true in the last block of this pair to finish (after all partials are visible)
+__device__ inline bool publish_partials(double* red, unsigned int* cnt, int b, const double (&vals)[4]) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    double* r = red + ((size_t)b * kRedBlocks + blockIdx.x) * 4;
+    r[0] = vals[0]; r[1] = vals[1]; r[2] = vals[2]; r[3] = vals[3];
+    __threadfence();
+    const unsigned int done = atomicAdd(cnt + b, 1u);
+    is_last = done == gridDim.x - 1;
+    if (is_last) cnt[b] = 0;  // re-arm for the next reduction (stream-ordered)
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// R1: mean / unbiased std / min / max of gamma
+__global__ void __launch_bounds__(256)
+gamma_stats_kernel(MapArgs a) {
+  __shared__ double redd[33];
+  __shared__ float redf[33];
+  const int b = blockIdx.y;
+  double s = 0, ss = 0;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < a.on; i += gridDim.x * 256) {
+    const float gmm = map_sum(a.gmap, a.csplit, a.on, b, i) / (float)a.c;
+    s += gmm; ss += (double)gmm * gmm;
+    mn = fminf(mn, gmm); mx = fmaxf(mx, gmm);
+  }
+  const double ts = block_sum<double>(s, redd), tss = block_sum<double>(ss, redd);
+  // block min / max
+  mn = warp_min(mn); mx = warp_max(mx);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { redf[threadIdx.x >> 5] = mn; }
+  __syncthreads();
+  float bmn = INFINITY;
+  for (int q = 0; q < 8; ++q) bmn = fminf(bmn, redf[q]);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { redf[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  float bmx = -INFINITY;
+  for (int q = 0; q < 8; ++q) bmx = fmaxf(bmx, redf[q]);
+  const double vals[4] = {ts, tss, (double)bmn, (double)bmx};
+  if (publish_partials(a.red, a.cnt, b, vals) && threadIdx.x == 0) {
+    double S = 0, SS = 0, MN = INFINITY, MX = -INFINITY;
+    for (unsigned int q = 0; q < gridDim.x; ++q) {
+      const double* r = a.red + ((size_t)b * kRedBlocks + q) * 4;
+      S += r[0]; SS += r[1]; MN = fmin(MN, r[2]); MX = fmax(MX, r[3]);
+    }
+    const double n = (double)a.on, mean = S / n;
+    const double var = (SS - n * mean * mean) / (n - 1.0);   // unbiased (torch.std default); n == 1 -> NaN like torch
+    LvlScal* sc = a.scal + (size_t)b * kNumLevels + a.level;
+    sc->mean = (float)mean;
+    sc->stdv = var != var ? NAN : (float)sqrt(fmax(var, 0.0));
+    sc->gmin = (float)MN;
+    sc->gmax = (float)MX;
+  }
+}
+
+__device__ inline float ps_norm(const MapArgs& a, const LvlScal& sc, int b, int i) {
+  const float gmm = map_sum(a.gmap, a.csplit, a.on, b, i) / (float)a.c;
+  const float den = sc.stdv + 1e-12f;
+  const float ps = sigmoidf_ref((gmm - sc.mean) / den);
+  const float smin = sigmoidf_ref((sc.gmin - sc.mean) / den), smax = sigmoidf_ref((sc.gmax - sc.mean) / den);
+  return (ps - smin) / (smax - smin + 1e-12f);
+}
+
+// R2: min / max of ps_n * interp(prev)
+__global__ void __launch_bounds__(256)
+prod_minmax_kernel(MapArgs a) {
+  __shared__ float redf[33];
+  const int b = blockIdx.y;
+  const LvlScal sc = a.scal[(size_t)b * kNumLevels + a.level];
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < a.on; i += gridDim.x * 256) {
+    const int oy = i / a.ow, ox = i - oy * a.ow;
+    const float pr = ps_norm(a, sc, b, i) * interp_prev(a.prev, a.ph, a.pw, b, oy, ox, a.oh, a.ow);
+    mn = fminf(mn, pr); mx = fmaxf(mx, pr);
+  }
+  mn = warp_min(mn); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  float bmn = INFINITY;
+  for (int q = 0; q < 8; ++q) bmn = fminf(bmn, redf[q]);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  float bmx = -INFINITY;
+  for (int q = 0; q < 8; ++q) bmx = fmaxf(bmx, redf[q]);
+  const double vals[4] = {(double)bmn, (double)bmx, 0.0, 0.0};
+  if (publish_partials(a.red, a.cnt, b, vals) && threadIdx.x == 0) {
+    double MN = INFINITY, MX = -INFINITY;
+    for (unsigned int q = 0; q < gridDim.x; ++q) {
+      const double* r = a.red + ((size_t)b * kRedBlocks + q) * 4;
+      MN = fmin(MN, r[0]); MX = fmax(MX, r[1]);
+    }
+    LvlScal* sc2 = a.scal + (size_t)b * kNumLevels + a.level;
+    sc2->pmin = (float)MN;
+    sc2->pmax = (float)MX;
+  }
+}
+
+// R3: store the normalised ps_prod map and reduce D_k = mean((1-ps) A + ps B)
+__global__ void __launch_bounds__(256)
+prod_store_kernel(MapArgs a) {
+  __shared__ double redd[33];
+  const int b = blockIdx.y;
+  const LvlScal sc = a.scal[(size_t)b * kNumLevels + a.level];
+  double s = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < a.on; i += gridDim.x * 256) {
+    const int oy = i / a.ow, ox = i - oy * a.ow;
+    const float pr = ps_norm(a, sc, b, i) * interp_prev(a.prev, a.ph, a.pw, b, oy, ox, a.oh, a.ow);
+    const float p = (pr - sc.pmin) / (sc.pmax - sc.pmin + 1e-12f);
+    a.ps_out[(size_t)b * a.on + i] = p;
+    const float av = map_sum(a.amap, a.csplit, a.on, b, i), bv = map_sum(a.bmap, a.csplit, a.on, b, i);
+    s += (double)((1.f - p) * av + p * bv);
+  }
+  const double ts = block_sum<double>(s, redd);
+  const double vals[4] = {ts, 0.0, 0.0, 0.0};
+  if (publish_partials(a.red, a.cnt, b, vals) && threadIdx.x == 0) {
+    double S = 0;
+    for (unsigned int q = 0; q < gridDim.x; ++q) S += a.red[((size_t)b * kRedBlocks + q) * 4];
+    a.scal[(size_t)b * kNumLevels + a.level].d = (float)(S / (double)a.on);
+  }
+}
+
+// fallback level: ps = sigmoid(gamma), ps_prod = ps * interp(prev -> 1x1), no min-max (ADISTS.py:92-97)
+__global__ void fallback_ps_kernel(MapArgs a, int pairs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= pairs) return;
+  const float gmm = a.gmap[b] / (float)a.c;
+  const float ps = sigmoidf_ref(gmm);
+  const float pr = ps * interp_prev(a.prev, a.ph, a.pw, b, 0, 0, 1, 1);
+  a.ps_out[b] = pr;
+  a.scal[(size_t)b * kNumLevels + a.level].d = (1.f - pr) * a.amap[b] + pr * a.bmap[b];
+}
+
+// (6) score = 1 - sum_k D_k, accumulated k = 5..0 like the reference loop (ADISTS.py:165-197)
+__global__ void final_kernel(const LvlScal* __restrict__ scal, int pairs, float* __restrict__ score) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= pairs) return;
+  float d = 0.f;
+  for (int k = kNumLevels - 1; k >= 0; --k) d += scal[(size_t)b * kNumLevels + k].d;
+  score[b] = 1.f - d;
+}
+
+Taps make_taps(int window) {
+  // ADISTS.gaussian (ADISTS.py:102-104): exp in double, stored as fp32, normalised in fp32
+  Taps t;
+  const double sigma = window / 3.0;
+  float sum = 0.f;
+  for (int i = 0; i < kAdistsMaxWindow; ++i) t.g[i] = 0.f;
+  for (int i = 0; i < window; ++i) {
+    const double d = (double)(i - window / 2);
+    t.g[i] = (float)exp(-(d * d) / (2.0 * sigma * sigma));
+    sum += t.g[i];
+  }
+  for (int i = 0; i < window; ++i) t.g[i] = t.g[i] / sum;
+  return t;
+}
+
+template <int WIN>
+int launch_window(const LevelPlan& L, const float* fx, const float* fy, int pairs, const double* chan, const float* wt,
+                  const Taps& taps, float* amap, float* bmap, float* gmap, cudaStream_t st) {
+  constexpr int IN = WT + WIN - 1;
+  constexpr int LDI = IN | 1;
+  constexpr size_t smem = (size_t)(2 * IN * LDI + 5 * IN * (WT + 1)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(window_kernel<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  dim3 grid(L.tiles_x * L.tiles_y, L.csplit, pairs);
+  window_kernel<WIN><<<grid, 256, smem, st>>>(fx, fy, L.c, L.h, L.w, L.oh, L.ow, L.tiles_x, L.csplit, L.choff, chan, wt,
+                                             taps, amap, bmap, gmap);
+  return 1;
+}
+
+}  // namespace
+
+bool adists_window_supported(int window) { return window == 21 || window == 11 || window == 7; }
+
+size_t adists_workspace_bytes(int pairs, int H, int W, int window) { return make_plan(pairs, H, W, window).total; }
+
+int adists_stage(const float* const fx[6], const float* const fy[6], int pairs, int H, int W, int window, void* ws,
+                 float* score, cudaStream_t st) {
+  const Plan p = make_plan(pairs, H, W, window);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  double* chan = reinterpret_cast<double*>(base + p.off_chan);
+  float* wt = F(p.off_wt);
+  LvlScal* scal = reinterpret_cast<LvlScal*>(base + p.off_scal);
+  double* red = reinterpret_cast<double*>(base + p.off_red);
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(base + p.off_cnt);
+  const Taps taps = make_taps(window);
+  int launches = 0;
+
+  cudaMemsetAsync(cnt, 0, (size_t)pairs * sizeof(unsigned int), st);
+
+  SumLevels sl;
+  EntLevels el;
+  for (int k = 0; k < kNumLevels; ++k) {
+    const LevelPlan& L = p.lv[k];
+    dim3 grid(L.chunks, L.c, pairs);
+    sums7_kernel<<<grid, 256, 0, st>>>(fx[k], fy[k], L.c, L.hw, L.chunks, F(L.off_sum));
+    ++launches;
+    sl.partials[k] = F(L.off_sum); sl.chunks[k] = L.chunks; sl.hw[k] = L.hw;
+    el.partials[k] = F(L.off_ent); el.chunks[k] = L.chunks;
+  }
+  chan_kernel<<<pairs, 256, 0, st>>>(sl, chan);
+  ++launches;
+  for (int k = 0; k < kNumLevels; ++k) {
+    const LevelPlan& L = p.lv[k];
+    dim3 grid(L.chunks, L.c, pairs);
+    entropy_kernel<<<grid, 256, 0, st>>>(fx[k], L.c, L.hw, L.chunks, L.choff, chan, F(L.off_ent));
+    ++launches;
+  }
+  weights_kernel<<<pairs, 256, 0, st>>>(el, wt);
+  ++launches;
+
+  for (int k = 0; k < kNumLevels; ++k) {
+    const LevelPlan& L = p.lv[k];
+    if (L.windowed) {
+      switch (window) {
+        case 21: launches += launch_window<21>(L, fx[k], fy[k], pairs, chan, wt, taps, F(L.off_a), F(L.off_b), F(L.off_g), st); break;
+        case 11: launches += launch_window<11>(L, fx[k], fy[k], pairs, chan, wt, taps, F(L.off_a), F(L.off_b), F(L.off_g), st); break;
+        default: launches += launch_window<7>(L, fx[k], fy[k], pairs, chan, wt, taps, F(L.off_a), F(L.off_b), F(L.off_g), st); break;
+      }
+    } else {
+      global_level_kernel<<<pairs, 256, 0, st>>>(L.c, L.choff, chan, wt, F(L.off_a), F(L.off_b), F(L.off_g));
+      ++launches;
+    }
+  }
+
+  const float* prev = nullptr;
+  int ph = 1, pw = 1;
+  for (int k = kNumLevels - 1; k >= 0; --k) {
+    const LevelPlan& L = p.lv[k];
+    MapArgs a;
+    a.amap = F(L.off_a); a.bmap = F(L.off_b); a.gmap = F(L.off_g);
+    a.csplit = L.csplit; a.on = L.on; a.oh = L.oh; a.ow = L.ow; a.c = L.c;
+    a.prev = prev; a.ph = ph; a.pw = pw;
+    a.ps_out = F(L.off_ps); a.scal = scal; a.level = k; a.red = red; a.cnt = cnt;
+    if (L.windowed) {
+      int nblk = ceil_div(L.on, 256 * 4);
+      if (nblk > kRedBlocks) nblk = kRedBlocks;
+      if (nblk < 1) nblk = 1;
+      dim3 grid(nblk, pairs);
+      gamma_stats_kernel<<<grid, 256, 0, st>>>(a);
+      prod_minmax_kernel<<<grid, 256, 0, st>>>(a);
+      prod_store_kernel<<<grid, 256, 0, st>>>(a);
+      launches += 3;
+    } else {
+      fallback_ps_kernel<<<ceil_div(pairs, 128), 128, 0, st>>>(a, pairs);
+      ++launches;
+    }
+    prev = a.ps_out; ph = L.oh; pw = L.ow;
+  }
+  final_kernel<<<ceil_div(pairs, 128), 128, 0, st>>>(scal, pairs, score);
+  ++launches;
+  return launches;
+}
+
+}  // namespace nqa

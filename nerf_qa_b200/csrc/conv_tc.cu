@@ -1,0 +1,474 @@
+// 3x3 convolution + bias + ReLU as an implicit GEMM on the Blackwell tensor pipe (sm_100a).
+//
+//   D[pixels, cout] = sum_{tap, cin} A[pixel shifted by tap, cin] * W[cout, tap, cin]
+//
+//   * activations NHWC bf16; one CTA tile = 128 output pixels arranged as a TH x TW rectangle
+//     (TH*TW = 128) x BLOCK_N output channels;
+//   * per k-block (one filter tap x 64 input channels) ONE 4-D TMA box load {64 ch, TW, TH, 1} at the
+//     tap-shifted coordinate brings the A tile into shared memory in the canonical K-major
+//     SWIZZLE_128B layout (out-of-image rows/columns are zero-filled by TMA = the conv's zero
+//     padding); one 2-D TMA box {64 k, BLOCK_N} brings the weight tile;
+//   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by one thread, accumulators in TMEM,
+//     double-buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * epilogue warps: tcgen05.ld -> +bias -> ReLU -> bf16 -> 16-byte global stores (NHWC);
+//   * persistent: grid = #SMs, static round-robin over (pixel tile, channel tile) with the channel
+//     tile fastest so CTAs that share an A tile run back to back and hit L2;
+//   * bf16x3 ("split") mode: activations and weights are carried as bf16 hi+lo pairs and each k-step
+//     issues hi*hi + hi*lo + lo*hi into the same fp32 accumulator (fp32-class accuracy).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+//
+// Reference semantics: torchvision vgg16.features convs as used by
+// nerf_qa/DISTS_pytorch/DISTS_pt.py:36-49 and nerf_qa/ADISTS/ADISTS.py:44-57.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nqa {
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                            // bf16 elements = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;              // watchdog: trap instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) {
+      printf("nerfqa_b200 conv_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, ignored for swizzled K-major) | SBO>>4 [32,46) (= 1024 B between
+// 8-row groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=bf16 (bits 7, 10), both
+// K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Params {
+  int n, h, w, cin, cout;
+  int tw_log2, tiles_w, tiles_h;
+  int num_n_tiles, num_tiles;
+  const float* bias;
+  bf16* out;
+  bf16* out_lo;
+};
+
+template <int BLOCK_N, bool SPLIT>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * (SPLIT ? 2 : 1);
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/;
+};
+
+template <int BLOCK_N, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
+                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
+                  const Params p) {
+  using C = Cfg<BLOCK_N, SPLIT>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;    // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* bias_s = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256);  // [cout <= 512]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tw = 1 << p.tw_log2, th = BLOCK_M >> p.tw_log2;
+  const int kb_per_tile = 9 * (p.cin / BLOCK_K);
+
+  for (int i = threadIdx.x; i < p.cout; i += NUM_THREADS) bias_s[i] = p.bias[i];
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    if (SPLIT) {
+      prefetch_tmap(&tmap_a_lo);
+      prefetch_tmap(&tmap_b_lo);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        int m_tile = tile / p.num_n_tiles;
+        const int twi = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+        const int thi = m_tile % p.tiles_h;
+        const int img = m_tile / p.tiles_h;
+        const int h0 = thi * th, w0 = twi * tw, n0 = n_tile * BLOCK_N;
+        for (int cb = 0; cb < p.cin / BLOCK_K; ++cb) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            uint8_t* sb = sa + A_TILE_BYTES;
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            const int r = tap / 3, s = tap % 3;
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, w0 + s - 1, h0 + r - 1, img);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + cb * BLOCK_K, n0);
+            if (SPLIT) {
+              uint8_t* sa_lo = sb + C::B_TILE_BYTES;
+              uint8_t* sb_lo = sa_lo + A_TILE_BYTES;
+              tma_load_4d(sa_lo, &tmap_a_lo, &full_bar[stage], cb * BLOCK_K, w0 + s - 1, h0 + r - 1, img);
+              tma_load_2d(sb_lo, &tmap_b_lo, &full_bar[stage], tap * p.cin + cb * BLOCK_K, n0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < kb_per_tile; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * UMMA_K * 2);
+            const uint64_t db = make_smem_desc(sb + k * UMMA_K * 2);
+            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (SPLIT) {
+              const uint32_t sa_lo = sb + C::B_TILE_BYTES, sb_lo = sa_lo + A_TILE_BYTES;
+              const uint64_t da_lo = make_smem_desc(sa_lo + k * UMMA_K * 2);
+              const uint64_t db_lo = make_smem_desc(sb_lo + k * UMMA_K * 2);
+              umma_bf16(d_tmem, da, db_lo, idesc, 1u);
+              umma_bf16(d_tmem, da_lo, db, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
+          if (kb == kb_per_tile - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    const int m = quarter * 32 + lane;
+    const int lh = m >> p.tw_log2, lw = m & (tw - 1);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int n_tile = tile % p.num_n_tiles;
+      int m_tile = tile / p.num_n_tiles;
+      const int twi = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int thi = m_tile % p.tiles_h;
+      const int img = m_tile / p.tiles_h;
+      const int oy = thi * th + lh, ox = twi * tw + lw, n0 = n_tile * BLOCK_N;
+      const bool valid = oy < p.h && ox < p.w;
+      const size_t obase = (((size_t)img * p.h + oy) * p.w + ox) * p.cout + n0;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bias_s[n0 + ch * 32 + j], 0.f);
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + obase + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 t;
+            t.x = Vec<bf16>::pack2(v[q * 8 + 0], v[q * 8 + 1]);
+            t.y = Vec<bf16>::pack2(v[q * 8 + 2], v[q * 8 + 3]);
+            t.z = Vec<bf16>::pack2(v[q * 8 + 4], v[q * 8 + 5]);
+            t.w = Vec<bf16>::pack2(v[q * 8 + 6], v[q * 8 + 7]);
+            dst[q] = t;
+          }
+          if (SPLIT) {
+            uint4* dlo = reinterpret_cast<uint4*>(p.out_lo + obase + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float l[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) l[j] = v[q * 8 + j] - __bfloat162float(__float2bfloat16_rn(v[q * 8 + j]));
+              uint4 t;
+              t.x = Vec<bf16>::pack2(l[0], l[1]);
+              t.y = Vec<bf16>::pack2(l[2], l[3]);
+              t.z = Vec<bf16>::pack2(l[4], l[5]);
+              t.w = Vec<bf16>::pack2(l[6], l[7]);
+              dlo[q] = t;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int g_sm_count = kNumSMs;
+
+static int choose_tw_log2(int h, int w) {
+  // pick the TH x TW = 128 rectangle that wastes the fewest MMA rows on this image size
+  int best = 3;
+  long best_cost = -1;
+  for (int l = 3; l <= 7; ++l) {
+    const int tw = 1 << l, th = 128 >> l;
+    const long cost = (long)ceil_div(w, tw) * tw * (long)ceil_div(h, th) * th;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = l; }
+  }
+  return best;
+}
+
+static bool encode_act_map(CUtensorMap* map, const bf16* ptr, int n, int h, int w, int c, int tw, int th) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool encode_w_map(CUtensorMap* map, const bf16* ptr, int cout, int k, int block_n) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)cout};
+  const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N, bool SPLIT>
+static int launch_impl(const ConvTcPlan& plan, cudaStream_t st) {
+  using C = Cfg<BLOCK_N, SPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    attr_set = true;
+  }
+  Params p;
+  p.n = plan.n; p.h = plan.h; p.w = plan.w; p.cin = plan.cin; p.cout = plan.cout;
+  p.tw_log2 = plan.tw_log2; p.tiles_w = plan.tiles_w; p.tiles_h = plan.tiles_h;
+  p.num_n_tiles = plan.cout / BLOCK_N;
+  p.num_tiles = plan.n * plan.tiles_h * plan.tiles_w * p.num_n_tiles;
+  p.bias = plan.bias; p.out = plan.out; p.out_lo = plan.out_lo;
+  const int grid = p.num_tiles < g_sm_count ? p.num_tiles : g_sm_count;
+  conv3x3_tc_kernel<BLOCK_N, SPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(plan.tmap_a, plan.tmap_a_lo, plan.tmap_b,
+                                                                             plan.tmap_b_lo, p);
+  return 1;
+}
+
+}  // namespace tc
+
+void conv_tc_set_sm_count(int sms) { tc::g_sm_count = sms > 0 ? sms : kNumSMs; }
+
+int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
+                      const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout, bool split,
+                      const char** err) {
+  if (cin % tc::BLOCK_K != 0 || cout % 64 != 0 || cout > 512) { *err = "conv_tc: cin must be a multiple of 64, cout a multiple of 64 and <= 512"; return 1; }
+  plan->n = n; plan->h = h; plan->w = w; plan->cin = cin; plan->cout = cout;
+  plan->split = split; plan->bias = bias; plan->out = out; plan->out_lo = out_lo;
+  plan->tw_log2 = tc::choose_tw_log2(h, w);
+  const int tw = 1 << plan->tw_log2, th = 128 >> plan->tw_log2;
+  plan->tiles_w = ceil_div(w, tw);
+  plan->tiles_h = ceil_div(h, th);
+  // bf16x3 stages are twice as large, so cap its channel tile at 128 to keep >= 3 pipeline stages
+  plan->block_n = cout >= 256 ? (split ? 128 : 256) : cout >= 128 ? 128 : 64;
+  if (!tc::get_encode_fn()) { *err = "conv_tc: cuTensorMapEncodeTiled entry point not available"; return 1; }
+  bool ok = tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, tw, th) &&
+            tc::encode_w_map(&plan->tmap_b, wk, cout, 9 * cin, plan->block_n);
+  if (split)
+    ok = ok && tc::encode_act_map(&plan->tmap_a_lo, in_lo, n, h, w, cin, tw, th) &&
+         tc::encode_w_map(&plan->tmap_b_lo, wk_lo, cout, 9 * cin, plan->block_n);
+  else {
+    plan->tmap_a_lo = plan->tmap_a;
+    plan->tmap_b_lo = plan->tmap_b;
+  }
+  if (!ok) { *err = "conv_tc: cuTensorMapEncodeTiled failed"; return 1; }
+  return 0;
+}
+
+int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st) {
+  if (plan.split) {
+    switch (plan.block_n) {
+      case 64: return tc::launch_impl<64, true>(plan, st);
+      default: return tc::launch_impl<128, true>(plan, st);
+    }
+  }
+  switch (plan.block_n) {
+    case 64: return tc::launch_impl<64, false>(plan, st);
+    case 128: return tc::launch_impl<128, false>(plan, st);
+    default: return tc::launch_impl<256, false>(plan, st);
+  }
+}
+
+}  // namespace nqa

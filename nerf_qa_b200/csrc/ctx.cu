@@ -1,0 +1,793 @@
+// C-ABI of nerfqa_b200 (include/nerfqa_b200.h): context, weight packing, workspace arena, micro-batch
+// scheduling and the per-call kernel sequences for DISTS / A-DISTS.
+//
+// Reference call structure being replaced: DISTS.forward -> forward_once x2 -> statistics loop
+// (nerf_qa/DISTS_pytorch/DISTS_pt.py:91-148), ADISTS.forward (nerf_qa/ADISTS/ADISTS.py:137-197).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nerfqa_b200.h"
+#include "adists.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace nqa;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(NQA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static const int kConvCin[kNumConvs] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};
+static const int kConvCout[kNumConvs] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
+static const int kStageConvs[5] = {2, 2, 3, 3, 3};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  void reset() { used = 0; }
+  void* take(size_t bytes) {
+    const size_t a = (used + 255) & ~(size_t)255;
+    used = a + bytes;
+    return base + a;
+  }
+};
+
+struct nqa_ctx {
+  int device = 0;
+  int sm_count = kNumSMs;
+  bool have_weights = false, have_alpha_beta = false;
+  float* w11 = nullptr;                  // conv1_1 [27][64]
+  float* bias[kNumConvs] = {};           // fp32
+  float* w_f32[kNumConvs] = {};          // [9][cin][cout]
+  bf16* w_hi[kNumConvs] = {};            // [cout][9][cin]
+  bf16* w_lo[kNumConvs] = {};            // residual of the bf16 rounding (bf16x3)
+  float* alpha = nullptr;
+  float* beta = nullptr;
+  Arena arena;
+  uint64_t launches = 0;
+  cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+  float* stage_in[2] = {};               // device staging for the host path
+  size_t stage_cap = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int ensure_arena(nqa_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->arena.cap) return NQA_OK;
+  if (ctx->arena.base) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(ctx->arena.base));
+    ctx->arena.base = nullptr;
+    ctx->arena.cap = 0;
+  }
+  const size_t want = bytes + (bytes >> 4) + (1 << 20);
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(NQA_ERR_NOMEM, "workspace allocation of %zu bytes failed", want);
+  }
+  ctx->arena.base = static_cast<char*>(p);
+  ctx->arena.cap = want;
+  return NQA_OK;
+}
+
+size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+void level_dims(int H, int W, int (&h)[kNumLevels], int (&w)[kNumLevels]) {
+  h[0] = h[1] = H;
+  w[0] = w[1] = W;
+  for (int k = 2; k < kNumLevels; ++k) {
+    h[k] = pooled(h[k - 1]);
+    w[k] = pooled(w[k - 1]);
+  }
+}
+
+int check_shape(int B, int H, int W) {
+  if (B < 1) return fail(NQA_ERR_SHAPE, "batch size %d < 1", B);
+  if (H < 1 || W < 1) return fail(NQA_ERR_SHAPE, "image size %dx%d is empty", H, W);
+  if ((long long)H * W > (1ll << 28)) return fail(NQA_ERR_SHAPE, "image size %dx%d too large", H, W);
+  return NQA_OK;
+}
+
+int elem_bytes(int prec) { return prec == NQA_PREC_FP32 ? 4 : 2; }
+int carriers(int prec) { return prec == NQA_PREC_BF16X3 ? 2 : 1; }
+
+// images per trunk pass: ~8 full-HD frames keep every layer's grid at several waves while the
+// ping-pong activations stay in the low GBs.
+int pick_micro_pairs(int B, int H, int W) {
+  const long long target = 8ll * 1080 * 1920;
+  long long pairs = target / (2ll * H * W);
+  if (pairs < 1) pairs = 1;
+  if (pairs > 256) pairs = 256;
+  if (pairs > B) pairs = B;
+  return (int)pairs;
+}
+
+// ---- weight packing kernels ---------------------------------------------------------------------
+__global__ void pack_w11_kernel(const float* __restrict__ w, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 27*64
+  if (i < 27 * 64) {
+    const int k = i / 64, co = i % 64;
+    out[i] = w[co * 27 + k];
+  }
+}
+__global__ void pack_w_kernel(const float* __restrict__ w, int cin, int cout, float* __restrict__ w_f32,
+                              bf16* __restrict__ w_hi, bf16* __restrict__ w_lo) {
+  const size_t total = (size_t)cout * cin * 9;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 9);
+    const int ci = (int)((i / 9) % cin);
+    const int co = (int)(i / (9 * (size_t)cin));
+    const float v = w[i];  // OIHW
+    w_f32[((size_t)tap * cin + ci) * cout + co] = v;
+    const bf16 hi = __float2bfloat16_rn(v);
+    const size_t kidx = (size_t)co * 9 * cin + (size_t)tap * cin + ci;
+    w_hi[kidx] = hi;
+    w_lo[kidx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+// ---- trunk --------------------------------------------------------------------------------------
+template <typename T>
+struct TrunkBufs {
+  T* ping[2] = {nullptr, nullptr};
+  T* ping_lo[2] = {nullptr, nullptr};   // bf16x3 residual carrier
+};
+
+template <typename T>
+size_t trunk_bytes(int n, int H, int W, int prec) {
+  const size_t big = align256((size_t)n * H * W * 64 * sizeof(T));
+  return 2 * big * carriers(prec) + 4096;
+}
+
+template <typename T>
+void trunk_alloc(nqa_ctx* ctx, TrunkBufs<T>* b, int n, int H, int W, int prec) {
+  const size_t big = (size_t)n * H * W * 64 * sizeof(T);
+  for (int i = 0; i < 2; ++i) {
+    b->ping[i] = static_cast<T*>(ctx->arena.take(big));
+    if (prec == NQA_PREC_BF16X3) b->ping_lo[i] = static_cast<T*>(ctx->arena.take(big));
+  }
+}
+
+template <typename T>
+int conv_layer(nqa_ctx* ctx, int li, const T* in, const T* in_lo, T* out, T* out_lo, int n, int h, int w, int prec,
+               cudaStream_t st);
+
+template <>
+int conv_layer<float>(nqa_ctx* ctx, int li, const float* in, const float*, float* out, float*, int n, int h, int w, int,
+                      cudaStream_t st) {
+  ctx->launches += launch_conv3x3_f32(in, out, ctx->w_f32[li], ctx->bias[li], n, h, w, kConvCin[li], kConvCout[li], st);
+  return NQA_OK;
+}
+template <>
+int conv_layer<bf16>(nqa_ctx* ctx, int li, const bf16* in, const bf16* in_lo, bf16* out, bf16* out_lo, int n, int h,
+                     int w, int prec, cudaStream_t st) {
+  ConvTcPlan plan;
+  const char* err = "";
+  const bool split = prec == NQA_PREC_BF16X3;
+  if (conv_tc_make_plan(&plan, in, in_lo, ctx->w_hi[li], ctx->w_lo[li], ctx->bias[li], out, out_lo, n, h, w,
+                        kConvCin[li], kConvCout[li], split, &err))
+    return fail(NQA_ERR_CUDA, "%s (layer %d, %dx%dx%d)", err, li, n, h, w);
+  ctx->launches += launch_conv3x3_tc(plan, st);
+  return NQA_OK;
+}
+
+// Runs normalise + VGG16 on images [x(0..nx), y(0..n-nx)], ping-ponging between two NHWC buffers sized
+// for the largest activation (64 x H x W).  After the last conv of stage k (1..5) calls
+// on_level(k, feat, feat_lo, h, w) with the stage's NHWC output enqueued; the buffer stays valid until
+// the next stage's second layer is enqueued, i.e. consumers enqueued inside on_level are safe.
+template <typename T, typename F>
+int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H, int W, int prec, TrunkBufs<T>& bufs,
+              cudaStream_t st, F&& on_level) {
+  const bool split = prec == NQA_PREC_BF16X3;
+  int h = H, w = W;
+  int cur = 0;  // ping-pong slot holding the live activation
+  int li = 0;
+  for (int stage = 0; stage < 5; ++stage) {
+    if (stage > 0) {
+      const int c = kConvCout[li - 1];
+      ctx->launches += launch_l2pool_nhwc<T>(bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, bufs.ping[cur ^ 1],
+                                             split ? bufs.ping_lo[cur ^ 1] : nullptr, n, h, w, c, st);
+      h = pooled(h);
+      w = pooled(w);
+      cur ^= 1;
+    }
+    for (int j = 0; j < kStageConvs[stage]; ++j, ++li) {
+      if (li == 0) {
+        ctx->launches += launch_conv1_1<T>(x, y, nx, n, h, w, ctx->w11, ctx->bias[0], bufs.ping[0],
+                                           split ? bufs.ping_lo[0] : nullptr, st);
+        cur = 0;
+      } else {
+        const int rc = conv_layer<T>(ctx, li, bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, bufs.ping[cur ^ 1],
+                                     split ? bufs.ping_lo[cur ^ 1] : nullptr, n, h, w, prec, st);
+        if (rc != NQA_OK) return rc;
+        cur ^= 1;
+      }
+    }
+    on_level(stage + 1, bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, h, w);
+  }
+  return NQA_OK;
+}
+
+template <typename T>
+void level_to_nchw(nqa_ctx* ctx, const T* f, const T* f_lo, float* dst, int n, int c, int h, int w, cudaStream_t st);
+template <>
+void level_to_nchw<float>(nqa_ctx* ctx, const float* f, const float*, float* dst, int n, int c, int h, int w,
+                          cudaStream_t st) {
+  ctx->launches += launch_nhwc_to_nchw<float>(f, dst, n, c, h, w, st);
+}
+template <>
+void level_to_nchw<bf16>(nqa_ctx* ctx, const bf16* f, const bf16* f_lo, float* dst, int n, int c, int h, int w,
+                         cudaStream_t st) {
+  if (f_lo)
+    ctx->launches += launch_nhwc_split_to_nchw(f, f_lo, dst, n, c, h, w, st);
+  else
+    ctx->launches += launch_nhwc_to_nchw<bf16>(f, dst, n, c, h, w, st);
+}
+
+// ---- DISTS: one micro-batch --------------------------------------------------------------------
+struct PartialBufs {
+  float* p[kNumLevels];
+  int chunks[kNumLevels];
+};
+
+size_t partial_bytes(int pairs, int H, int W, int prec, PartialBufs* pb /* may be null */, bool planar_all) {
+  int h[kNumLevels], w[kNumLevels];
+  level_dims(H, W, h, w);
+  size_t total = 0;
+  for (int k = 0; k < kNumLevels; ++k) {
+    const int c = level_channels(k);
+    const int chunks = (k == 0 || planar_all) ? stats_chunks_planar(h[k] * w[k], c, pairs)
+                                              : stats_chunks_nhwc(h[k] * w[k], c, elem_bytes(prec), pairs);
+    if (pb) pb->chunks[k] = chunks;
+    total += align256((size_t)pairs * chunks * 5 * c * sizeof(float));
+  }
+  return total + 4096;
+}
+
+void partial_alloc(nqa_ctx* ctx, int pairs, PartialBufs* pb) {
+  for (int k = 0; k < kNumLevels; ++k)
+    pb->p[k] = static_cast<float*>(ctx->arena.take((size_t)pairs * pb->chunks[k] * 5 * level_channels(k) * sizeof(float)));
+}
+
+int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float* score, float* s1s2, cudaStream_t st) {
+  int h[kNumLevels], w[kNumLevels];
+  level_dims(H, W, h, w);
+  FinalizeParams fp;
+  for (int k = 0; k < kNumLevels; ++k) {
+    fp.lv[k].partials = pb.p[k];
+    fp.lv[k].chunks = pb.chunks[k];
+    fp.lv[k].C = level_channels(k);
+    fp.lv[k].choff = level_offset(k);
+    fp.lv[k].inv_n = 1.0 / ((double)h[k] * w[k]);
+  }
+  ctx->launches += launch_dists_finalize(fp, ctx->alpha, ctx->beta, pairs, score, s1s2, nullptr, st);
+  return NQA_OK;
+}
+
+template <typename T>
+size_t dists_mb_bytes(int pairs, int H, int W, int prec) {
+  return trunk_bytes<T>(2 * pairs, H, W, prec) + partial_bytes(pairs, H, W, prec, nullptr, false);
+}
+
+template <typename T>
+int dists_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, int H, int W, int prec, float* score,
+                      float* s1s2, cudaStream_t st) {
+  ctx->arena.reset();
+  TrunkBufs<T> bufs;
+  trunk_alloc<T>(ctx, &bufs, 2 * pairs, H, W, prec);
+  PartialBufs pb;
+  partial_bytes(pairs, H, W, prec, &pb, false);
+  partial_alloc(ctx, pairs, &pb);
+
+  // level 0: the RAW frames (DISTS_pt.py:103 returns x itself, not the normalised tensor)
+  ctx->launches += launch_stats_planar(x, y, pairs, 3, H * W, pb.chunks[0], pb.p[0], st);
+  const int rc = run_trunk<T>(ctx, x, y, pairs, 2 * pairs, H, W, prec, bufs, st,
+                              [&](int k, const T* f, const T* f_lo, int h, int w) {
+                                const size_t half = (size_t)pairs * h * w * level_channels(k);
+                                ctx->launches += launch_stats_nhwc<T>(f, f + half, f_lo, f_lo ? f_lo + half : nullptr, pairs,
+                                                                     h * w, level_channels(k), pb.chunks[k], pb.p[k], st);
+                              });
+  if (rc != NQA_OK) return rc;
+  return finalize(ctx, pb, pairs, H, W, score, s1s2, st);
+}
+
+int dists_forward_device(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int prec, float* score,
+                         float* s1s2, cudaStream_t st) {
+  const int mb = pick_micro_pairs(B, H, W);
+  const size_t need = prec == NQA_PREC_FP32 ? dists_mb_bytes<float>(mb, H, W, prec) : dists_mb_bytes<bf16>(mb, H, W, prec);
+  int rc = ensure_arena(ctx, need);
+  if (rc != NQA_OK) return rc;
+  const size_t frame = (size_t)3 * H * W;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int pairs = B - b0 < mb ? B - b0 : mb;
+    float* s12 = s1s2 ? s1s2 + (size_t)b0 * 2 * kTotalChannels : nullptr;
+    rc = prec == NQA_PREC_FP32
+             ? dists_micro_batch<float>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, prec, score + b0, s12, st)
+             : dists_micro_batch<bf16>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, prec, score + b0, s12, st);
+    if (rc != NQA_OK) return rc;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int check_ready(nqa_ctx* ctx, bool need_ab) {
+  if (!ctx) return fail(NQA_ERR_INVALID, "null context");
+  if (!ctx->have_weights) return fail(NQA_ERR_STATE, "VGG weights not set (nqa_set_vgg_weights)");
+  if (need_ab && !ctx->have_alpha_beta) return fail(NQA_ERR_STATE, "alpha/beta not set (nqa_set_alpha_beta)");
+  return NQA_OK;
+}
+
+int check_prec(int prec) {
+  if (prec != NQA_PREC_FP32 && prec != NQA_PREC_BF16 && prec != NQA_PREC_BF16X3)
+    return fail(NQA_ERR_INVALID, "unknown precision %d", prec);
+  return NQA_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+const char* nqa_last_error(void) { return g_last_error.c_str(); }
+int nqa_version(void) { return 100; }
+
+int nqa_ctx_create(int device, nqa_ctx** out) {
+  if (!out) return fail(NQA_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
+    cudaGetLastError();
+    return fail(NQA_ERR_CUDA, "no CUDA device available (nerfqa_b200 has no CPU fallback)");
+  }
+  if (device < 0 || device >= count) return fail(NQA_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(NQA_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(NQA_ERR_CUDA, "device %d is sm_%d%d; nerfqa_b200 is built for sm_100a (B200) only", device, prop.major,
+                prop.minor);
+  nqa_ctx* ctx = new nqa_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  conv_tc_set_sm_count(ctx->sm_count);
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaMalloc(&ctx->alpha, kTotalChannels * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&ctx->beta, kTotalChannels * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&ctx->w11, 27 * 64 * sizeof(float)));
+  for (int i = 0; i < kNumConvs; ++i) {
+    const size_t nw = (size_t)kConvCout[i] * kConvCin[i] * 9;
+    CUDA_TRY(cudaMalloc(&ctx->bias[i], kConvCout[i] * sizeof(float)));
+    if (i > 0) {
+      CUDA_TRY(cudaMalloc(&ctx->w_f32[i], nw * sizeof(float)));
+      CUDA_TRY(cudaMalloc(&ctx->w_hi[i], nw * sizeof(bf16)));
+      CUDA_TRY(cudaMalloc(&ctx->w_lo[i], nw * sizeof(bf16)));
+    }
+  }
+  *out = ctx;
+  return NQA_OK;
+}
+
+int nqa_ctx_destroy(nqa_ctx* ctx) {
+  if (!ctx) return NQA_OK;
+  DeviceGuard guard(ctx->device);
+  cudaDeviceSynchronize();
+  cudaFree(ctx->alpha);
+  cudaFree(ctx->beta);
+  cudaFree(ctx->w11);
+  for (int i = 0; i < kNumConvs; ++i) {
+    cudaFree(ctx->bias[i]);
+    cudaFree(ctx->w_f32[i]);
+    cudaFree(ctx->w_hi[i]);
+    cudaFree(ctx->w_lo[i]);
+  }
+  cudaFree(ctx->arena.base);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ctx->stage_in[i]);
+    if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
+  cudaGetLastError();
+  delete ctx;
+  return NQA_OK;
+}
+
+int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const float* const b[NQA_NUM_CONVS]) {
+  if (!ctx || !w || !b) return fail(NQA_ERR_INVALID, "null argument");
+  for (int i = 0; i < kNumConvs; ++i)
+    if (!w[i] || !b[i]) return fail(NQA_ERR_INVALID, "null weight/bias pointer for conv %d", i);
+  DeviceGuard guard(ctx->device);
+  float* tmp = nullptr;
+  const size_t max_w = (size_t)512 * 512 * 9;
+  CUDA_TRY(cudaMalloc(&tmp, max_w * sizeof(float)));
+  for (int i = 0; i < kNumConvs; ++i) {
+    const size_t nw = (size_t)kConvCout[i] * kConvCin[i] * 9;
+    cudaError_t e = cudaMemcpy(tmp, w[i], nw * sizeof(float), cudaMemcpyDefault);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->bias[i], b[i], kConvCout[i] * sizeof(float), cudaMemcpyDefault);
+    if (e != cudaSuccess) {
+      cudaFree(tmp);
+      return fail(NQA_ERR_CUDA, "copying conv %d parameters failed: %s", i, cudaGetErrorString(e));
+    }
+    if (i == 0) {
+      pack_w11_kernel<<<(27 * 64 + 255) / 256, 256>>>(tmp, ctx->w11);
+    } else {
+      pack_w_kernel<<<1024, 256>>>(tmp, kConvCin[i], kConvCout[i], ctx->w_f32[i], ctx->w_hi[i], ctx->w_lo[i]);
+    }
+    ctx->launches += 1;
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      cudaFree(tmp);
+      return fail(NQA_ERR_CUDA, "packing conv %d failed: %s", i, cudaGetErrorString(e));
+    }
+  }
+  cudaFree(tmp);
+  ctx->have_weights = true;
+  return NQA_OK;
+}
+
+int nqa_set_alpha_beta(nqa_ctx* ctx, const float* alpha, const float* beta) {
+  if (!ctx || !alpha || !beta) return fail(NQA_ERR_INVALID, "null argument");
+  DeviceGuard guard(ctx->device);
+  CUDA_TRY(cudaMemcpy(ctx->alpha, alpha, kTotalChannels * sizeof(float), cudaMemcpyDefault));
+  CUDA_TRY(cudaMemcpy(ctx->beta, beta, kTotalChannels * sizeof(float), cudaMemcpyDefault));
+  ctx->have_alpha_beta = true;
+  return NQA_OK;
+}
+
+int nqa_dists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int precision, float* score_out,
+                      float* s1s2_out, void* stream) {
+  int rc = check_ready(ctx, true);
+  if (rc != NQA_OK) return rc;
+  if (!x || !y || !score_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  if ((rc = check_prec(precision)) != NQA_OK) return rc;
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  return dists_forward_device(ctx, x, y, B, H, W, precision, score_out, s1s2_out, static_cast<cudaStream_t>(stream));
+}
+
+int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W, int precision,
+                           float* score_host) {
+  int rc = check_ready(ctx, true);
+  if (rc != NQA_OK) return rc;
+  if (!x_host || !y_host || !score_host) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  if ((rc = check_prec(precision)) != NQA_OK) return rc;
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+
+  const int mb = pick_micro_pairs(B, H, W);
+  const size_t frame = (size_t)3 * H * W;
+  const size_t slot_floats = 2 * (size_t)mb * frame + (size_t)B;  // x frames, y frames (+ scores in slot 0)
+  if (slot_floats > ctx->stage_cap) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->stage_in[i]) CUDA_TRY(cudaFree(ctx->stage_in[i]));
+      ctx->stage_in[i] = nullptr;
+    }
+    ctx->stage_cap = 0;
+    for (int i = 0; i < 2; ++i)
+      if (cudaMalloc(&ctx->stage_in[i], slot_floats * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(NQA_ERR_NOMEM, "staging allocation of %zu bytes failed", slot_floats * sizeof(float));
+      }
+    ctx->stage_cap = slot_floats;
+  }
+  const size_t need = precision == NQA_PREC_FP32 ? dists_mb_bytes<float>(mb, H, W, precision)
+                                                 : dists_mb_bytes<bf16>(mb, H, W, precision);
+  if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
+  float* d_scores = ctx->stage_in[0] + 2 * (size_t)mb * frame;
+
+  int it = 0;
+  for (int b0 = 0; b0 < B; b0 += mb, ++it) {
+    const int slot = it & 1;
+    const int pairs = B - b0 < mb ? B - b0 : mb;
+    float* dx = ctx->stage_in[slot];
+    float* dy = dx + (size_t)mb * frame;
+    if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(dx, x_host + b0 * frame, pairs * frame * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(dy, y_host + b0 * frame, pairs * frame * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->compute_stream, ctx->ev_copied[slot], 0));
+    rc = precision == NQA_PREC_FP32
+             ? dists_micro_batch<float>(ctx, dx, dy, pairs, H, W, precision, d_scores + b0, nullptr, ctx->compute_stream)
+             : dists_micro_batch<bf16>(ctx, dx, dy, pairs, H, W, precision, d_scores + b0, nullptr, ctx->compute_stream);
+    if (rc != NQA_OK) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev_consumed[slot], ctx->compute_stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(score_host, d_scores, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, ctx->compute_stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->compute_stream));
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int features_impl(nqa_ctx* ctx, const float* x, int B, int H, int W, int prec, float* const* feats_out,
+                         cudaStream_t st) {
+  int mb = 2 * pick_micro_pairs((B + 1) / 2, H, W);
+  if (mb > B) mb = B;
+  int rc = ensure_arena(ctx, trunk_bytes<T>(mb, H, W, prec));
+  if (rc != NQA_OK) return rc;
+  const size_t frame = (size_t)3 * H * W;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int n = B - b0 < mb ? B - b0 : mb;
+    ctx->arena.reset();
+    TrunkBufs<T> bufs;
+    trunk_alloc<T>(ctx, &bufs, n, H, W, prec);
+    rc = run_trunk<T>(ctx, x + b0 * frame, x, n, n, H, W, prec, bufs, st,
+                      [&](int k, const T* f, const T* f_lo, int h, int w) {
+                        float* dst = feats_out[k - 1] + (size_t)b0 * level_channels(k) * h * w;
+                        level_to_nchw<T>(ctx, f, f_lo, dst, n, level_channels(k), h, w, st);
+                      });
+    if (rc != NQA_OK) return rc;
+  }
+  return NQA_OK;
+}
+
+extern "C" {
+
+int nqa_dists_features(nqa_ctx* ctx, const float* x, int B, int H, int W, int precision,
+                       float* const feats_out[NQA_NUM_LEVELS - 1], void* stream) {
+  int rc = check_ready(ctx, false);
+  if (rc != NQA_OK) return rc;
+  if (!x || !feats_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  for (int k = 0; k < kNumLevels - 1; ++k)
+    if (!feats_out[k]) return fail(NQA_ERR_INVALID, "null feature pointer for level %d", k + 1);
+  if ((rc = check_prec(precision)) != NQA_OK) return rc;
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = precision == NQA_PREC_FP32 ? features_impl<float>(ctx, x, B, H, W, precision, feats_out, st)
+                                  : features_impl<bf16>(ctx, x, B, H, W, precision, feats_out, st);
+  if (rc != NQA_OK) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_dists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],
+                         const float* const feats_y[NQA_NUM_LEVELS], int B, int H, int W, float* score_out,
+                         float* s1s2_out, void* stream) {
+  if (!ctx) return fail(NQA_ERR_INVALID, "null context");
+  if (!ctx->have_alpha_beta) return fail(NQA_ERR_STATE, "alpha/beta not set (nqa_set_alpha_beta)");
+  if (!feats_x || !feats_y || !score_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  for (int k = 0; k < kNumLevels; ++k)
+    if (!feats_x[k] || !feats_y[k]) return fail(NQA_ERR_INVALID, "null feature pointer for level %d", k);
+  int rc = check_shape(B, H, W);
+  if (rc != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PartialBufs pb;
+  const size_t need = partial_bytes(B, H, W, NQA_PREC_FP32, &pb, true);
+  if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
+  ctx->arena.reset();
+  partial_alloc(ctx, B, &pb);
+  int lh[kNumLevels], lw[kNumLevels];
+  level_dims(H, W, lh, lw);
+  for (int k = 0; k < kNumLevels; ++k)
+    ctx->launches += launch_stats_planar(feats_x[k], feats_y[k], B, level_channels(k), lh[k] * lw[k], pb.chunks[k],
+                                         pb.p[k], st);
+  rc = finalize(ctx, pb, B, H, W, score_out, s1s2_out, st);
+  if (rc != NQA_OK) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+}  // extern "C"
+
+// A-DISTS keeps all six levels of both images alive (the entropy weights are global over the 1475
+// channels), as planar fp32 -- the layout its window kernels want and the reference's own
+// forward_once format -- so its micro-batch is smaller than the DISTS one.
+static size_t adists_feat_bytes(int pairs, int H, int W) {
+  int h[kNumLevels], w[kNumLevels];
+  level_dims(H, W, h, w);
+  size_t total = 0;
+  for (int k = 1; k < kNumLevels; ++k) total += align256((size_t)2 * pairs * level_channels(k) * h[k] * w[k] * sizeof(float));
+  return total + 4096;
+}
+
+template <typename T>
+static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int prec,
+                       float* score_out, cudaStream_t st) {
+  int mb = pick_micro_pairs(B, H, W) / 2;
+  if (mb < 1) mb = 1;
+  int rc = ensure_arena(ctx, trunk_bytes<T>(2 * mb, H, W, prec) + adists_feat_bytes(mb, H, W) +
+                                 adists_workspace_bytes(mb, H, W, window));
+  if (rc != NQA_OK) return rc;
+  int lh[kNumLevels], lw[kNumLevels];
+  level_dims(H, W, lh, lw);
+  const size_t frame = (size_t)3 * H * W;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int pairs = B - b0 < mb ? B - b0 : mb;
+    ctx->arena.reset();
+    TrunkBufs<T> bufs;
+    trunk_alloc<T>(ctx, &bufs, 2 * pairs, H, W, prec);
+    float* planar[kNumLevels] = {};
+    for (int k = 1; k < kNumLevels; ++k)
+      planar[k] = static_cast<float*>(ctx->arena.take((size_t)2 * pairs * level_channels(k) * lh[k] * lw[k] * sizeof(float)));
+    void* ws = ctx->arena.take(adists_workspace_bytes(pairs, H, W, window));
+    const float* xb = x + b0 * frame;
+    const float* yb = y + b0 * frame;
+    rc = run_trunk<T>(ctx, xb, yb, pairs, 2 * pairs, H, W, prec, bufs, st,
+                      [&](int k, const T* f, const T* f_lo, int h, int w) {
+                        level_to_nchw<T>(ctx, f, f_lo, planar[k], 2 * pairs, level_channels(k), h, w, st);
+                      });
+    if (rc != NQA_OK) return rc;
+    const float* fx[kNumLevels];
+    const float* fy[kNumLevels];
+    fx[0] = xb;
+    fy[0] = yb;
+    for (int k = 1; k < kNumLevels; ++k) {
+      fx[k] = planar[k];
+      fy[k] = planar[k] + (size_t)pairs * level_channels(k) * lh[k] * lw[k];
+    }
+    ctx->launches += adists_stage(fx, fy, pairs, H, W, window, ws, score_out + b0, st);
+  }
+  return NQA_OK;
+}
+
+static int check_window(int window) {
+  if (window < 1 || window > kAdistsMaxWindow || (window & 1) == 0)
+    return fail(NQA_ERR_INVALID, "window %d must be odd and in [1,%d]", window, kAdistsMaxWindow);
+  if (!adists_window_supported(window))
+    return fail(NQA_ERR_INVALID, "this build has window kernels for 7, 11 and 21 (the reference default); got %d", window);
+  return NQA_OK;
+}
+
+extern "C" {
+
+int nqa_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int precision,
+                       float* score_out, void* stream) {
+  int rc = check_ready(ctx, false);
+  if (rc != NQA_OK) return rc;
+  if (!x || !y || !score_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  if ((rc = check_prec(precision)) != NQA_OK) return rc;
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  if ((rc = check_window(window)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, score_out, st)
+                                  : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, score_out, st);
+  if (rc != NQA_OK) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],
+                          const float* const feats_y[NQA_NUM_LEVELS], int B, int H, int W, int window, float* score_out,
+                          void* stream) {
+  if (!ctx) return fail(NQA_ERR_INVALID, "null context");
+  if (!feats_x || !feats_y || !score_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  for (int k = 0; k < kNumLevels; ++k)
+    if (!feats_x[k] || !feats_y[k]) return fail(NQA_ERR_INVALID, "null feature pointer for level %d", k);
+  int rc = check_shape(B, H, W);
+  if (rc != NQA_OK) return rc;
+  if ((rc = check_window(window)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = ensure_arena(ctx, adists_workspace_bytes(B, H, W, window) + 4096)) != NQA_OK) return rc;
+  ctx->arena.reset();
+  void* ws = ctx->arena.take(adists_workspace_bytes(B, H, W, window));
+  ctx->launches += adists_stage(feats_x, feats_y, B, H, W, window, ws, score_out, st);
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_l2pool(nqa_ctx* ctx, const float* x, int B, int C, int H, int W, float* out, void* stream) {
+  if (!ctx || !x || !out) return fail(NQA_ERR_INVALID, "null argument");
+  if (B < 1 || C < 1 || H < 1 || W < 1) return fail(NQA_ERR_SHAPE, "empty tensor %dx%dx%dx%d", B, C, H, W);
+  DeviceGuard guard(ctx->device);
+  ctx->launches += launch_l2pool_nchw(x, out, B, C, H, W, static_cast<cudaStream_t>(stream));
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_conv3x3_relu(nqa_ctx* ctx, const float* x, const float* w, const float* bias, int B, int Cin, int Cout, int H,
+                     int W, int precision, float* out, void* stream) {
+  if (!ctx || !x || !w || !bias || !out) return fail(NQA_ERR_INVALID, "null argument");
+  int rc = check_prec(precision);
+  if (rc != NQA_OK) return rc;
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  if (Cin % 64 != 0 || Cout % 64 != 0 || Cin < 64 || Cout < 64 || Cout > 512 || Cin > 512)
+    return fail(NQA_ERR_SHAPE, "Cin/Cout must be multiples of 64 in [64,512], got %d/%d", Cin, Cout);
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nin = (size_t)B * H * W * Cin, nout = (size_t)B * H * W * Cout, nw = (size_t)Cout * Cin * 9;
+  const size_t need = 2 * align256(nin * 4) + 2 * align256(nout * 4) + align256(nw * 4) + 2 * align256(nw * 2) + 8192;
+  if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
+  ctx->arena.reset();
+  float* w_f32 = static_cast<float*>(ctx->arena.take(nw * 4));
+  bf16* w_hi = static_cast<bf16*>(ctx->arena.take(nw * 2));
+  bf16* w_lo = static_cast<bf16*>(ctx->arena.take(nw * 2));
+  pack_w_kernel<<<1024, 256, 0, st>>>(w, Cin, Cout, w_f32, w_hi, w_lo);
+  ctx->launches += 1;
+  if (precision == NQA_PREC_FP32) {
+    float* in_t = static_cast<float*>(ctx->arena.take(nin * 4));
+    float* out_t = static_cast<float*>(ctx->arena.take(nout * 4));
+    ctx->launches += launch_nchw_to_nhwc<float>(x, in_t, nullptr, B, Cin, H, W, st);
+    ctx->launches += launch_conv3x3_f32(in_t, out_t, w_f32, bias, B, H, W, Cin, Cout, st);
+    ctx->launches += launch_nhwc_to_nchw<float>(out_t, out, B, Cout, H, W, st);
+  } else {
+    const bool split = precision == NQA_PREC_BF16X3;
+    bf16* in_hi = static_cast<bf16*>(ctx->arena.take(nin * 2));
+    bf16* in_lo = static_cast<bf16*>(ctx->arena.take(nin * 2));
+    bf16* out_hi = static_cast<bf16*>(ctx->arena.take(nout * 2));
+    bf16* out_lo = static_cast<bf16*>(ctx->arena.take(nout * 2));
+    ctx->launches += launch_nchw_to_nhwc<bf16>(x, in_hi, split ? in_lo : nullptr, B, Cin, H, W, st);
+    ConvTcPlan plan;
+    const char* err = "";
+    if (conv_tc_make_plan(&plan, in_hi, in_lo, w_hi, w_lo, bias, out_hi, out_lo, B, H, W, Cin, Cout, split, &err))
+      return fail(NQA_ERR_CUDA, "%s", err);
+    ctx->launches += launch_conv3x3_tc(plan, st);
+    if (split)
+      ctx->launches += launch_nhwc_split_to_nchw(out_hi, out_lo, out, B, Cout, H, W, st);
+    else
+      ctx->launches += launch_nhwc_to_nchw<bf16>(out_hi, out, B, Cout, H, W, st);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_workspace_bytes(nqa_ctx* ctx, size_t* bytes) {
+  if (!ctx || !bytes) return fail(NQA_ERR_INVALID, "null argument");
+  *bytes = ctx->arena.cap + 2 * ctx->stage_cap * sizeof(float);
+  return NQA_OK;
+}
+
+int nqa_launch_count(nqa_ctx* ctx, uint64_t* launches) {
+  if (!ctx || !launches) return fail(NQA_ERR_INVALID, "null argument");
+  *launches = ctx->launches;
+  return NQA_OK;
+}
+
+int nqa_micro_batch(nqa_ctx* ctx, int B, int H, int W, int precision, int* pairs) {
+  if (!ctx || !pairs) return fail(NQA_ERR_INVALID, "null argument");
+  int rc = check_shape(B, H, W);
+  if (rc != NQA_OK) return rc;
+  (void)precision;
+  *pairs = pick_micro_pairs(B, H, W);
+  return NQA_OK;
+}
+
+}  // extern "C"

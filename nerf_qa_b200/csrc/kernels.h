@@ -1,0 +1,95 @@
+// Host-side launchers of the nerfqa_b200 kernels.  Every launcher enqueues on `st`, returns the number
+// of kernels it launched, and never synchronises.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace nqa {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- statistics -----------------------------------------------------------------------------------
+// Partial sums of one pyramid level: partials[((b*chunks + chunk)*5 + s)*C + c], s in
+// {sum x, sum y, sum x^2, sum y^2, sum x*y}; fp32 per chunk, combined in fp64 by the finalize kernel.
+struct LevelPartials {
+  const float* partials;
+  int chunks;
+  int C;
+  int choff;     // first channel of this level inside the 1475-vector
+  double inv_n;  // 1 / (H_k * W_k)
+};
+struct FinalizeParams {
+  LevelPartials lv[6];
+};
+
+int stats_chunks_nhwc(int hw, int c, int elem_bytes, int pairs);
+int stats_chunks_planar(int hw, int c, int pairs);
+
+// fx_lo/fy_lo != nullptr: bf16x3 carrier, value = hi + lo
+template <typename T>
+int launch_stats_nhwc(const T* fx, const T* fy, const T* fx_lo, const T* fy_lo, int pairs, int hw, int c, int chunks,
+                      float* partials, cudaStream_t st);
+// NCHW fp32 planes (level 0 and the from_feats API): x[b][c][hw]
+int launch_stats_planar(const float* x, const float* y, int pairs, int c, int hw, int chunks, float* partials,
+                        cudaStream_t st);
+// score[b] = 1 - sum_c (alpha_c/w S1 + beta_c/w S2); optional s1s2[b][2][1475]; optional moments[b][1475][5]
+// (mean x, mean y, var x, var y, cov) for the backward pass.
+int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const float* beta, int pairs, float* score,
+                          float* s1s2, float* moments, cudaStream_t st);
+
+// ---- pooling / layout -----------------------------------------------------------------------------
+template <typename T>
+int launch_l2pool_nhwc(const T* in, const T* in_lo, T* out, T* out_lo, int n, int h, int w, int c, cudaStream_t st);
+int launch_l2pool_nchw(const float* in, float* out, int n, int c, int h, int w, cudaStream_t st);
+template <typename T>
+int launch_nhwc_to_nchw(const T* in, float* out, int n, int c, int h, int w, cudaStream_t st);
+template <typename T>
+int launch_nchw_to_nhwc(const float* in, T* out, T* out_lo, int n, int c, int h, int w, cudaStream_t st);
+// bf16x3 carrier: hi = bf16(v), lo = bf16(v - hi)
+int launch_nhwc_split_to_nchw(const bf16* hi, const bf16* lo, float* out, int n, int c, int h, int w, cudaStream_t st);
+
+// ---- convolutions ---------------------------------------------------------------------------------
+// conv1_1 fused with the input normalisation: images [0,nx) come from x, [nx,n) from y (NCHW fp32);
+// weights packed [27][64] (k = (ci*3 + r)*3 + s), output NHWC [n,h,w,64].  If out_lo != nullptr the output is
+// written as a bf16 hi/lo pair (T must be bf16).
+template <typename T>
+int launch_conv1_1(const float* x, const float* y, int nx, int n, int h, int w, const float* wpack, const float* bias,
+                   T* out, T* out_lo, cudaStream_t st);
+// strict fp32 CUDA-core conv: NHWC fp32, weights [9][cin][cout]
+int launch_conv3x3_f32(const float* in, float* out, const float* wpack, const float* bias, int n, int h, int w, int cin,
+                       int cout, cudaStream_t st);
+
+// tcgen05 implicit-GEMM conv: NHWC bf16 activations, weights [cout][9][cin] bf16 (K-major), fp32 bias.
+// split = bf16x3 mode (hi/lo pairs for activations and weights, three MMAs per k-step).
+struct ConvTcPlan {
+  CUtensorMap tmap_a, tmap_a_lo, tmap_b, tmap_b_lo;
+  int n, h, w, cin, cout;
+  int tw_log2;
+  int tiles_w, tiles_h;
+  int block_n;
+  bool split;
+  const float* bias;
+  bf16* out;
+  bf16* out_lo;
+};
+// Fills the tensor maps; returns 0 on success, nonzero + message on failure.
+int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
+                      const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout, bool split,
+                      const char** err);
+int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st);
+void conv_tc_set_sm_count(int sms);
+
+// ---- A-DISTS --------------------------------------------------------------------------------------
+// See adists.cu.
+struct AdistsLevel {
+  int c, h, w;       // level shape
+  int oh, ow;        // window-map shape (h-win+1, w-win+1) or 1x1 in the global-statistics fallback
+  bool windowed;
+  int choff;
+};
+
+}  // namespace nqa

@@ -1,0 +1,419 @@
+// L2pooling, DISTS statistics + finalize, layout transforms.  All HBM-bound: 16-byte vector accesses,
+// coalesced along the NHWC channel axis, fp32 accumulation, fp64 only in the tiny finalize step.
+//
+// Reference semantics: nerf_qa/DISTS_pytorch/DISTS_pt.py:11-25 (L2pooling), :113-148 (statistics).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nqa {
+
+// ================================================================================================
+// DISTS statistics, NHWC.  grid = (chunks, pairs); each block owns a contiguous pixel range of one
+// frame pair and all C channels; thread = (pixel lane, channel vector).  Per thread at most a few
+// hundred sequential fp32 adds per accumulator (SURVEY.md §7 "variance numerics").
+// ================================================================================================
+constexpr int kStatsThreads = 256;
+
+template <typename T, bool SPLIT>
+__global__ void __launch_bounds__(kStatsThreads)
+stats_nhwc_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* __restrict__ fx_lo,
+                  const T* __restrict__ fy_lo, int hw, int c, int chunks, float* __restrict__ partials) {
+  constexpr int V = Vec<T>::N;
+  const int groups = c / V;                 // channel vectors per pixel (<= 256)
+  const int ppi = kStatsThreads / groups;   // pixels per block iteration
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int per = ceil_div(hw, chunks);
+  const int p0 = chunk * per, p1 = min(hw, p0 + per);
+
+  float sx[V], sy[V], sxx[V], syy[V], sxy[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) sx[i] = sy[i] = sxx[i] = syy[i] = sxy[i] = 0.f;
+
+  if (pl < ppi) {
+    const size_t off = (size_t)b * hw * c + (size_t)g * V;
+    const T* px = fx + off;
+    const T* py = fy + off;
+#pragma unroll 4
+    for (int p = p0 + pl; p < p1; p += ppi) {
+      float vx[V], vy[V];
+      Vec<T>::load_stream(px + (size_t)p * c, vx);
+      Vec<T>::load_stream(py + (size_t)p * c, vy);
+      if (SPLIT) {  // bf16x3 carrier: value = hi + lo
+        float lx[V], ly[V];
+        Vec<T>::load_stream(fx_lo + off + (size_t)p * c, lx);
+        Vec<T>::load_stream(fy_lo + off + (size_t)p * c, ly);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { vx[i] += lx[i]; vy[i] += ly[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        sx[i] += vx[i];
+        sy[i] += vy[i];
+        sxx[i] = fmaf(vx[i], vx[i], sxx[i]);
+        syy[i] = fmaf(vy[i], vy[i], syy[i]);
+        sxy[i] = fmaf(vx[i], vy[i], sxy[i]);
+      }
+    }
+  }
+
+  __shared__ float red[kStatsThreads * V];
+  float* outp = partials + ((size_t)b * chunks + chunk) * 5 * c;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const float* src = s == 0 ? sx : s == 1 ? sy : s == 2 ? sxx : s == 3 ? syy : sxy;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = src[i];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += kStatsThreads) {
+      const int gg = ch / V, ii = ch % V;
+      float acc = 0.f;
+      for (int q = 0; q < ppi; ++q) acc += red[(q * groups + gg) * V + ii];
+      outp[s * c + ch] = acc;
+    }
+  }
+}
+
+int stats_chunks_nhwc(int hw, int c, int elem_bytes, int pairs) {
+  const int v = 16 / elem_bytes;
+  const int groups = c / v;
+  const int ppi = kStatsThreads / groups;
+  // <= 256 sequential adds per accumulator, but at least ~2 waves of blocks when the level allows it
+  int chunks = ceil_div(hw, ppi * 256);
+  const int want = ceil_div(2 * kNumSMs, pairs);
+  const int cap = ceil_div(hw, ppi * 8);
+  if (chunks < want) chunks = want < cap ? want : cap;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+template <typename T>
+int launch_stats_nhwc(const T* fx, const T* fy, const T* fx_lo, const T* fy_lo, int pairs, int hw, int c, int chunks,
+                      float* partials, cudaStream_t st) {
+  dim3 grid(chunks, pairs);
+  if (fx_lo)
+    stats_nhwc_kernel<T, true><<<grid, kStatsThreads, 0, st>>>(fx, fy, fx_lo, fy_lo, hw, c, chunks, partials);
+  else
+    stats_nhwc_kernel<T, false><<<grid, kStatsThreads, 0, st>>>(fx, fy, nullptr, nullptr, hw, c, chunks, partials);
+  return 1;
+}
+template int launch_stats_nhwc<float>(const float*, const float*, const float*, const float*, int, int, int, int,
+                                      float*, cudaStream_t);
+template int launch_stats_nhwc<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, int, int, int, int, float*,
+                                     cudaStream_t);
+
+// ================================================================================================
+// DISTS statistics on NCHW fp32 planes (level 0 = raw frames; every level of forward_from_feats).
+// grid = (chunks, C, pairs).
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+stats_planar_kernel(const float* __restrict__ x, const float* __restrict__ y, int c, int hw, int chunks,
+                    float* __restrict__ partials) {
+  const int chunk = blockIdx.x, ch = blockIdx.y, b = blockIdx.z;
+  const int per = ceil_div(ceil_div(hw, chunks), 4) * 4;  // keep 16-byte alignment of chunk starts when hw % 4 == 0
+  const int p0 = chunk * per, p1 = min(hw, p0 + per);
+  const float* px = x + ((size_t)b * c + ch) * hw;
+  const float* py = y + ((size_t)b * c + ch) * hw;
+  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(py) & 15) == 0);
+  if (vec_ok) {
+    const int n4 = (p1 - p0) / 4;
+    const float4* qx = reinterpret_cast<const float4*>(px + p0);
+    const float4* qy = reinterpret_cast<const float4*>(py + p0);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const float4 a = __ldcs(qx + i), d = __ldcs(qy + i);
+      s[0] += (a.x + a.y) + (a.z + a.w);
+      s[1] += (d.x + d.y) + (d.z + d.w);
+      s[2] += fmaf(a.x, a.x, a.y * a.y) + fmaf(a.z, a.z, a.w * a.w);
+      s[3] += fmaf(d.x, d.x, d.y * d.y) + fmaf(d.z, d.z, d.w * d.w);
+      s[4] += fmaf(a.x, d.x, a.y * d.y) + fmaf(a.z, d.z, a.w * d.w);
+    }
+    for (int p = p0 + n4 * 4 + threadIdx.x; p < p1; p += 256) {
+      const float a = px[p], d = py[p];
+      s[0] += a; s[1] += d; s[2] = fmaf(a, a, s[2]); s[3] = fmaf(d, d, s[3]); s[4] = fmaf(a, d, s[4]);
+    }
+  } else {
+    for (int p = p0 + threadIdx.x; p < p1; p += 256) {
+      const float a = px[p], d = py[p];
+      s[0] += a; s[1] += d; s[2] = fmaf(a, a, s[2]); s[3] = fmaf(d, d, s[3]); s[4] = fmaf(a, d, s[4]);
+    }
+  }
+  __shared__ float sm[5][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const float v = warp_sum(s[i]);
+    if (lane == 0) sm[i][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += sm[threadIdx.x][q];
+    partials[(((size_t)b * chunks + chunk) * 5 + threadIdx.x) * c + ch] = v;
+  }
+}
+
+int stats_chunks_planar(int hw, int c, int pairs) {
+  // 256 threads x float4 x <=64 iterations per accumulator
+  int chunks = ceil_div(hw, 256 * 4 * 64);
+  const int want = ceil_div(2 * kNumSMs, pairs * c);
+  const int cap = ceil_div(hw, 256 * 4);
+  if (chunks < want) chunks = want < cap ? want : cap;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+int launch_stats_planar(const float* x, const float* y, int pairs, int c, int hw, int chunks, float* partials,
+                        cudaStream_t st) {
+  dim3 grid(chunks, c, pairs);
+  stats_planar_kernel<<<grid, 256, 0, st>>>(x, y, c, hw, chunks, partials);
+  return 1;
+}
+
+// ================================================================================================
+// Finalize: moments -> S1,S2 -> alpha/beta-weighted sum -> score (DISTS_pt.py:127-148).
+// grid = pairs, 256 threads.  Chunk partials are combined in a fixed order in fp64 (deterministic,
+// batch-independent).
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+dists_finalize_kernel(FinalizeParams p, const float* __restrict__ alpha, const float* __restrict__ beta,
+                      float* __restrict__ score, float* __restrict__ s1s2, float* __restrict__ moments) {
+  __shared__ double smd[33];
+  const int b = blockIdx.x;
+  double wsum_part = 0.0;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) wsum_part += (double)alpha[c] + (double)beta[c];
+  const double wsum = block_sum<double>(wsum_part, smd);
+
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) {
+    const int k = c < 3 ? 0 : c < 67 ? 1 : c < 195 ? 2 : c < 451 ? 3 : c < 963 ? 4 : 5;
+    const LevelPartials lv = p.lv[k];
+    const int cc = c - lv.choff;
+    double s[5] = {0, 0, 0, 0, 0};
+    const float* base = lv.partials + (size_t)b * lv.chunks * 5 * lv.C + cc;
+    for (int ch = 0; ch < lv.chunks; ++ch) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) s[i] += (double)base[((size_t)ch * 5 + i) * lv.C];
+    }
+    const double mx = s[0] * lv.inv_n, my = s[1] * lv.inv_n;
+    const double vx = s[2] * lv.inv_n - mx * mx, vy = s[3] * lv.inv_n - my * my;
+    const double cov = s[4] * lv.inv_n - mx * my;
+    const double c1 = 1e-6, c2 = 1e-6;
+    const double s1 = (2.0 * mx * my + c1) / (mx * mx + my * my + c1);
+    const double s2 = (2.0 * cov + c2) / (vx + vy + c2);
+    if (s1s2) {
+      s1s2[((size_t)b * 2 + 0) * kTotalChannels + c] = (float)s1;
+      s1s2[((size_t)b * 2 + 1) * kTotalChannels + c] = (float)s2;
+    }
+    if (moments) {
+      float* m = moments + ((size_t)b * kTotalChannels + c) * 5;
+      m[0] = (float)mx; m[1] = (float)my; m[2] = (float)vx; m[3] = (float)vy; m[4] = (float)cov;
+    }
+    acc += ((double)alpha[c] * s1 + (double)beta[c] * s2) / wsum;
+  }
+  const double total = block_sum<double>(acc, smd);
+  if (threadIdx.x == 0) score[b] = (float)(1.0 - total);
+}
+
+int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const float* beta, int pairs, float* score,
+                          float* s1s2, float* moments, cudaStream_t st) {
+  dists_finalize_kernel<<<pairs, 256, 0, st>>>(p, alpha, beta, score, s1s2, moments);
+  return 1;
+}
+
+// ================================================================================================
+// L2pooling (DISTS_pt.py:22-25): out = sqrt(sum_{3x3} g * x^2 + 1e-12), g = [1 2 1]^T[1 2 1]/16,
+// stride 2, zero pad 1.  NHWC: thread = (output pixel, 16-byte channel vector).
+// ================================================================================================
+template <typename T, bool SPLIT>
+__global__ void __launch_bounds__(256)
+l2pool_nhwc_kernel(const T* __restrict__ in, const T* __restrict__ in_lo, T* __restrict__ out, T* __restrict__ out_lo,
+                   int n, int h, int w, int c, int ho, int wo) {
+  constexpr int V = Vec<T>::N;
+  const int groups = c / V;
+  const size_t total = (size_t)n * ho * wo * groups;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    size_t t = idx / groups;
+    const int ox = (int)(t % wo); t /= wo;
+    const int oy = (int)(t % ho);
+    const int img = (int)(t / ho);
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    const size_t boff = (size_t)img * h * w * c + (size_t)g * V;
+    const T* base = in + boff;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = 2 * oy - 1 + r;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = 2 * ox - 1 + s;
+        if (ix < 0 || ix >= w) continue;
+        const float wt = ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * (1.f / 16.f);
+        float v[V];
+        Vec<T>::load(base + ((size_t)iy * w + ix) * c, v);
+        if (SPLIT) {
+          float l[V];
+          Vec<T>::load(in_lo + boff + ((size_t)iy * w + ix) * c, l);
+#pragma unroll
+          for (int i = 0; i < V; ++i) v[i] += l[i];
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = fmaf(wt, v[i] * v[i], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = sqrtf(acc[i] + 1e-12f);
+    const size_t ooff = (((size_t)img * ho + oy) * wo + ox) * c + (size_t)g * V;
+    Vec<T>::store(out + ooff, acc);
+    if (SPLIT) {
+      float l[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) l[i] = acc[i] - to_float(from_float<T>(acc[i]));
+      Vec<T>::store(out_lo + ooff, l);
+    }
+  }
+}
+
+template <typename T>
+int launch_l2pool_nhwc(const T* in, const T* in_lo, T* out, T* out_lo, int n, int h, int w, int c, cudaStream_t st) {
+  const int ho = pooled(h), wo = pooled(w);
+  const size_t total = (size_t)n * ho * wo * (c / Vec<T>::N);
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  if (in_lo)
+    l2pool_nhwc_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(in, in_lo, out, out_lo, n, h, w, c, ho, wo);
+  else
+    l2pool_nhwc_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(in, nullptr, out, nullptr, n, h, w, c, ho, wo);
+  return 1;
+}
+template int launch_l2pool_nhwc<float>(const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
+template int launch_l2pool_nhwc<bf16>(const bf16*, const bf16*, bf16*, bf16*, int, int, int, int, cudaStream_t);
+
+// Standalone NCHW fp32 L2pooling (the nn.Module surface): thread = one output element.
+__global__ void __launch_bounds__(256)
+l2pool_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int h, int w, int ho, int wo) {
+  const size_t total = (size_t)planes * ho * wo;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % wo);
+    size_t t = idx / wo;
+    const int oy = (int)(t % ho);
+    const size_t pl = t / ho;
+    const float* base = in + pl * h * w;
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = 2 * oy - 1 + r;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = 2 * ox - 1 + s;
+        if (ix < 0 || ix >= w) continue;
+        const float wt = ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * (1.f / 16.f);
+        const float v = __ldg(base + (size_t)iy * w + ix);
+        acc = fmaf(wt, v * v, acc);
+      }
+    }
+    out[idx] = sqrtf(acc + 1e-12f);
+  }
+}
+
+int launch_l2pool_nchw(const float* in, float* out, int n, int c, int h, int w, cudaStream_t st) {
+  const int ho = pooled(h), wo = pooled(w);
+  const size_t total = (size_t)n * c * ho * wo;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  l2pool_nchw_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, n * c, h, w, ho, wo);
+  return 1;
+}
+
+// ================================================================================================
+// NHWC (internal) -> NCHW fp32 (API surface of forward_once), tiled transpose through smem.
+// grid = (ceil(hw/32), ceil(c/32), n), block = (32, 8).
+// ================================================================================================
+template <typename T, bool SPLIT>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const T* __restrict__ in, const T* __restrict__ in_lo, float* __restrict__ out, int c, int hw) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const T* src = in + (size_t)img * hw * c;
+  const T* src_lo = SPLIT ? in_lo + (size_t)img * hw * c : nullptr;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, ch = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < hw && ch < c) {
+      v = to_float(src[(size_t)p * c + ch]);
+      if (SPLIT) v += to_float(src_lo[(size_t)p * c + ch]);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  float* dst = out + (size_t)img * c * hw;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ch = c0 + i, p = p0 + threadIdx.x;
+    if (p < hw && ch < c) dst[(size_t)ch * hw + p] = tile[threadIdx.x][i];
+  }
+}
+
+// NCHW fp32 -> NHWC T (optionally hi/lo split); op-level tests only, not on the scoring path.
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, T* __restrict__ out_lo, int c, int hw) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + (size_t)img * c * hw;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ch = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < hw && ch < c) ? src[(size_t)ch * hw + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, ch = c0 + threadIdx.x;
+    if (p < hw && ch < c) {
+      const float v = tile[threadIdx.x][i];
+      const T hi = from_float<T>(v);
+      out[((size_t)img * hw + p) * c + ch] = hi;
+      if (out_lo) out_lo[((size_t)img * hw + p) * c + ch] = from_float<T>(v - to_float(hi));
+    }
+  }
+}
+
+template <typename T>
+int launch_nchw_to_nhwc(const float* in, T* out, T* out_lo, int n, int c, int h, int w, cudaStream_t st) {
+  const int hw = h * w;
+  dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
+  nchw_to_nhwc_kernel<T><<<grid, block, 0, st>>>(in, out, out_lo, c, hw);
+  return 1;
+}
+template int launch_nchw_to_nhwc<float>(const float*, float*, float*, int, int, int, int, cudaStream_t);
+template int launch_nchw_to_nhwc<bf16>(const float*, bf16*, bf16*, int, int, int, int, cudaStream_t);
+
+template <typename T>
+int launch_nhwc_to_nchw(const T* in, float* out, int n, int c, int h, int w, cudaStream_t st) {
+  const int hw = h * w;
+  dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
+  nhwc_to_nchw_kernel<T, false><<<grid, block, 0, st>>>(in, nullptr, out, c, hw);
+  return 1;
+}
+template int launch_nhwc_to_nchw<float>(const float*, float*, int, int, int, int, cudaStream_t);
+template int launch_nhwc_to_nchw<bf16>(const bf16*, float*, int, int, int, int, cudaStream_t);
+
+int launch_nhwc_split_to_nchw(const bf16* hi, const bf16* lo, float* out, int n, int c, int h, int w, cudaStream_t st) {
+  const int hw = h * w;
+  dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
+  nhwc_to_nchw_kernel<bf16, true><<<grid, block, 0, st>>>(hi, lo, out, c, hw);
+  return 1;
+}
+
+}  // namespace nqa

@@ -1,0 +1,240 @@
+"""Drop-in ``DISTS`` scorer: same constructor, methods, attributes and state_dict layout as
+``nerf_qa/DISTS_pytorch/DISTS_pt.py`` (reference paths relative to /root/reference), with every forward
+routed through the C-ABI library (hand-written sm_100a kernels).  No eager-PyTorch fallback exists: CPU
+tensors raise.
+
+Differences a caller can observe are listed in DESIGN.md ("API deviations"): ``precision=`` selects the
+trunk arithmetic; ``require_grad=True`` (gradients w.r.t. the input frames) is not implemented yet.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .synth import CHNS, CONV_STAGE, VGG_CONVS, VGG_FEATURE_IDX
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+class L2pooling(nn.Module):
+    """``sqrt(hanning3x3(x^2, stride 2, pad 1) + 1e-12)`` (DISTS_pt.py:11-25).  ``filter_size=5`` yields a
+    3x3 kernel because the reference trims ``np.hanning(5)`` to its interior."""
+
+    def __init__(self, filter_size: int = 5, stride: int = 2, channels: Optional[int] = None, pad_off: int = 0):
+        super().__init__()
+        if filter_size != 5 or stride != 2:
+            raise NotImplementedError("nerf_qa_b200 implements the reference's L2pooling(filter_size=5, stride=2)")
+        self.padding = (filter_size - 2) // 2
+        self.stride = stride
+        self.channels = channels
+        a = np.hanning(filter_size)[1:-1]
+        g = torch.Tensor(a[:, None] * a[None, :])
+        g = g / torch.sum(g)
+        self.register_buffer("filter", g[None, None, :, :].repeat((self.channels, 1, 1, 1)))
+        self._ctx: Dict[int, _lib.Context] = {}
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        if not input.is_cuda:
+            raise _lib.NerfQAError("L2pooling: CUDA tensor required (no CPU fallback)")
+        idx = input.device.index
+        if idx not in self._ctx:
+            self._ctx[idx] = _lib.Context(input.device)
+        return self._ctx[idx].l2pool(input)
+
+
+def build_vgg_stages(module: nn.Module, pool_cls) -> None:
+    """stage1..stage5 with the reference's child names (DISTS_pt.py:31-49) so state_dict keys such as
+    ``stage3.10.weight`` / ``stage2.4.filter`` line up with reference checkpoints and torchvision's VGG16."""
+    stages = [nn.Sequential() for _ in range(5)]
+    pool_idx = {2: 4, 3: 9, 4: 16, 5: 23}
+    for st in range(2, 6):
+        stages[st - 1].add_module(str(pool_idx[st]), pool_cls(channels=CHNS[st - 1]))
+    for i, idx in enumerate(VGG_FEATURE_IDX):
+        cin, cout = VGG_CONVS[i]
+        st = CONV_STAGE[i]
+        stages[st - 1].add_module(str(idx), nn.Conv2d(cin, cout, kernel_size=3, padding=1))
+        stages[st - 1].add_module(str(idx + 1), nn.ReLU(inplace=True))
+    for k, s in enumerate(stages):
+        setattr(module, f"stage{k + 1}", s)
+
+
+def try_load_pretrained_vgg(module: nn.Module) -> bool:
+    """The reference downloads torchvision's ImageNet VGG16 (DISTS_pt.py:30).  Offline we only look in the
+    local torch hub cache; otherwise the (random) init stays and the caller is expected to load weights."""
+    path = os.path.join(torch.hub.get_dir(), "checkpoints", "vgg16-397923af.pth")
+    if not os.path.exists(path):
+        return False
+    sd = torch.load(path, map_location="cpu")
+    own = module.state_dict()
+    for i, idx in enumerate(VGG_FEATURE_IDX):
+        st = CONV_STAGE[i]
+        own[f"stage{st}.{idx}.weight"] = sd[f"features.{idx}.weight"]
+        own[f"stage{st}.{idx}.bias"] = sd[f"features.{idx}.bias"]
+    module.load_state_dict(own)
+    return True
+
+
+def conv_parameters(module: nn.Module):
+    ws, bs = [], []
+    for i, idx in enumerate(VGG_FEATURE_IDX):
+        conv = getattr(module, f"stage{CONV_STAGE[i]}")._modules[str(idx)]
+        ws.append(conv.weight)
+        bs.append(conv.bias)
+    return ws, bs
+
+
+class _TrunkModule(nn.Module):
+    """Shared plumbing of DISTS and ADISTS: per-device library contexts and weight upload tracking."""
+
+    precision: str
+
+    def _init_runtime(self, precision: str) -> None:
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+        self.precision = precision
+        self._contexts: Dict[int, _lib.Context] = {}
+
+    def _prec(self) -> int:
+        return _lib.PRECISIONS[self.precision]
+
+    def _context(self, device: torch.device) -> _lib.Context:
+        if device.type != "cuda":
+            raise _lib.NerfQAError("nerf_qa_b200 runs on CUDA (B200) tensors only; there is no CPU fallback")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        ctx = self._contexts.get(idx)
+        if ctx is None:
+            ctx = _lib.Context(torch.device("cuda", idx))
+            self._contexts[idx] = ctx
+        ws, bs = conv_parameters(self)
+        key = tuple((p.data_ptr(), p._version) for p in ws + bs)
+        if ctx.weights_key != key:
+            ctx.set_vgg_weights(ws, bs)
+            ctx.weights_key = key
+        return ctx
+
+    def forward_once(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """[x, relu1_2, relu2_2, relu3_3, relu4_3, relu5_3] as NCHW fp32 (DISTS_pt.py:91-103, ADISTS.py:112-125).
+        Level 0 is the RAW input, not the normalised tensor."""
+        ctx = self._context(x.device)
+        return [x] + ctx.features(x, self._prec())
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_contexts"] = {}
+        return state
+
+
+class _AlphaBetaCombine(torch.autograd.Function):
+    """score_b = 1 - sum_c (alpha_c S1_bc + beta_c S2_bc) / (sum alpha + sum beta)   (DISTS_pt.py:127-144).
+
+    Forward returns the kernel's score; backward gives the alpha/beta gradients from the saved per-channel
+    S1/S2 (no feature re-read): d score_b / d alpha_c = (-S1_bc + (1 - score_b)) / w."""
+
+    @staticmethod
+    def forward(ctx, score, s1s2, alpha, beta):
+        ctx.save_for_backward(score, s1s2, alpha, beta)
+        return score.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        score, s1s2, alpha, beta = ctx.saved_tensors
+        w = alpha.sum() + beta.sum()
+        d = (1.0 - score).unsqueeze(1)                                   # [B,1] = (dist1 + dist2)
+        ga = (grad_out.unsqueeze(1) * (d - s1s2[:, 0]) / w).sum(0)
+        gb = (grad_out.unsqueeze(1) * (d - s1s2[:, 1]) / w).sum(0)
+        return None, None, ga.reshape(alpha.shape), gb.reshape(beta.shape)
+
+
+class DISTS(_TrunkModule):
+    def __init__(self, load_weights: bool = True, from_feats: bool = False, precision: str = "bf16"):
+        super().__init__()
+        build_vgg_stages(self, L2pooling)
+        if not try_load_pretrained_vgg(self):
+            warnings.warn("torchvision VGG16 ImageNet weights not found in the local torch hub cache; the trunk keeps "
+                          "its random init until a state_dict is loaded (the reference downloads them).")
+        for param in self.parameters():
+            param.requires_grad = False
+
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, -1, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, -1, 1, 1))
+
+        self.chns = [3, 64, 128, 256, 512, 512]
+        self.register_parameter("alpha", nn.Parameter(torch.randn(1, sum(self.chns), 1, 1)))
+        self.register_parameter("beta", nn.Parameter(torch.randn(1, sum(self.chns), 1, 1)))
+        self.alpha.data.normal_(0.1, 0.01)
+        self.beta.data.normal_(0.1, 0.01)
+        if load_weights:
+            # the reference reads sys.prefix/weights.pt (DISTS_pt.py:63); the same learned alpha/beta ship here
+            ab = np.load(os.path.join(_DATA, "dists_alpha_beta.npy"))
+            self.alpha.data = torch.from_numpy(ab[0].copy()).view(1, -1, 1, 1)
+            self.beta.data = torch.from_numpy(ab[1].copy()).view(1, -1, 1, 1)
+        self._init_runtime(precision)
+
+    # -- weights ---------------------------------------------------------------------------------
+    def project_weights(self) -> None:
+        """DISTS_pt.py:82-89."""
+        lower_bound = torch.zeros_like(self.alpha.data)
+        lower_bound[:, :3, :, :] = 0.02
+        alpha = torch.max(self.alpha.data, lower_bound)
+        beta = torch.max(self.beta.data, lower_bound)
+        weight_sum = torch.cat([alpha, beta], dim=1).sum()
+        self.alpha.data = alpha / weight_sum
+        self.beta.data = beta / weight_sum
+
+    def _sync_alpha_beta(self, ctx: _lib.Context) -> None:
+        key = (self.alpha.data_ptr(), self.alpha._version, self.beta.data_ptr(), self.beta._version)
+        if ctx.ab_key != key:
+            ctx.set_alpha_beta(self.alpha, self.beta)
+            ctx.ab_key = key
+
+    def _finish(self, score, s1s2, batch_average: bool):
+        if torch.is_grad_enabled() and (self.alpha.requires_grad or self.beta.requires_grad):
+            score = _AlphaBetaCombine.apply(score, s1s2, self.alpha, self.beta)
+        return score.mean() if batch_average else score
+
+    # -- scoring ---------------------------------------------------------------------------------
+    def forward(self, x, y, require_grad: bool = False, batch_average: bool = False, warp=None, certainty=None):
+        """Per-frame DISTS scores ``[B]`` (or their mean).  ``warp`` / ``certainty`` are accepted and ignored
+        exactly like the reference (DISTS_pt.py:105)."""
+        if require_grad:
+            raise NotImplementedError("require_grad=True (gradients w.r.t. the frames through the VGG trunk) is not "
+                                      "implemented in nerf_qa_b200 yet; alpha/beta gradients are available")
+        ctx = self._context(x.device)
+        self._sync_alpha_beta(ctx)
+        score, s1s2 = ctx.dists_forward(x, y, self._prec(), want_s1s2=True)
+        return self._finish(score, s1s2, batch_average)
+
+    def forward_from_feats(self, feats0: Sequence[torch.Tensor], feats1: Sequence[torch.Tensor],
+                           batch_average: bool = False):
+        """DISTS_pt.py:181-208."""
+        ctx = self._context(feats0[0].device)
+        self._sync_alpha_beta(ctx)
+        score, s1s2 = ctx.dists_from_feats(feats0, feats1)
+        return self._finish(score, s1s2, batch_average)
+
+    def score_host(self, x: torch.Tensor, y: torch.Tensor, device: Optional[torch.device] = None) -> torch.Tensor:
+        """End-to-end call from HOST tensors (pinned recommended): streams frames to the GPU in micro-batches
+        overlapped with compute and returns CPU scores — what ``model(ref.to(device), dist.to(device)).cpu()``
+        does in prep.py:186-190, without staging the whole batch on the device first."""
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        ctx = self._context(dev)
+        self._sync_alpha_beta(ctx)
+        return ctx.dists_forward_host(x, y, self._prec())
+
+
+def prepare_image(image, resize: bool = True, keep_aspect_ratio: bool = False) -> torch.Tensor:
+    """PIL image -> [1,3,H,W] fp32 in [0,1], short side limited to 256 (DISTS_pt.py:210-217)."""
+    from torchvision import transforms
+    if resize and min(image.size) > 256:
+        if keep_aspect_ratio:
+            image = transforms.functional.resize(image, 256)
+        else:
+            image = transforms.functional.resize(image, (256, 256))
+    image = transforms.ToTensor()(image)
+    return image.unsqueeze(0)

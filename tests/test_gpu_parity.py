@@ -1,0 +1,170 @@
+"""End-to-end parity on the GPU against the golden vectors of the reference (tests/golden) and the CPU
+oracle: per-level features, per-frame scores, API behaviour.  Tolerances (BASELINE.json north_star):
+fp32-class paths 1e-4 relative, bf16 path 2e-3 absolute."""
+import numpy as np
+import pytest
+import torch
+
+from nerf_qa_b200 import _lib, synth
+from oracle import reference_oracle as O
+from tests._util import golden_inputs, make_adists, make_dists, rel_err, report
+
+pytestmark = pytest.mark.gpu
+
+DISTS_CASES = ["dists_64", "dists_odd_45x77", "dists_135x240", "dists_256"]
+ADISTS_CASES = ["adists_96x128", "adists_176", "adists_256", "adists_352x368"]
+
+
+@pytest.fixture(scope="module")
+def models():
+    return {p: make_dists(p) for p in ("fp32", "bf16", "bf16x3")}
+
+
+@pytest.fixture(scope="module")
+def amodels():
+    return {p: make_adists(p) for p in ("fp32", "bf16")}
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-4), ("bf16x3", 5e-4), ("bf16", 6e-2)])
+def test_features_per_level(models, vgg_weights, prec, tol):
+    x, _ = synth.make_frame_pairs(2, 45, 77, seed=3)
+    ws, bs = vgg_weights
+    want = O.trunk(x, ws, bs)
+    got = models[prec].forward_once(x.cuda())
+    assert got[0].data_ptr() == x.cuda().data_ptr() or torch.equal(got[0].cpu(), x)   # level 0 is the raw input
+    for k in range(1, 6):
+        g, w = got[k].cpu(), want[k]
+        assert g.shape == w.shape
+        err = float((g - w).abs().max() / w.abs().max())
+        print(f"[parity] features {prec} level {k}: max err / max|f| = {err:.3e}")
+        assert err < tol, f"level {k}"
+
+
+@pytest.mark.parametrize("name", DISTS_CASES)
+def test_dists_fp32_matches_reference(models, golden, name):
+    g = golden(name)
+    x, y = golden_inputs(g)
+    got = models["fp32"](x.cuda(), y.cuda()).cpu().numpy()
+    report(f"DISTS fp32 {name}", got, g["score_f32"])
+    assert rel_err(got, g["score_f32"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", DISTS_CASES)
+def test_dists_bf16x3_matches_reference(models, golden, name):
+    g = golden(name)
+    x, y = golden_inputs(g)
+    got = models["bf16x3"](x.cuda(), y.cuda()).cpu().numpy()
+    report(f"DISTS bf16x3 {name}", got, g["score_f32"])
+    assert rel_err(got, g["score_f32"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", DISTS_CASES)
+def test_dists_bf16_matches_reference(models, golden, name):
+    g = golden(name)
+    x, y = golden_inputs(g)
+    got = models["bf16"](x.cuda(), y.cuda()).cpu().numpy()
+    report(f"DISTS bf16 {name}", got, g["score_f32"])
+    assert np.max(np.abs(got - g["score_f32"])) < 2e-3
+
+
+@pytest.mark.parametrize("name", ADISTS_CASES)
+def test_adists_fp32_matches_reference(amodels, golden, name):
+    g = golden(name)
+    x, y = golden_inputs(g)
+    got = amodels["fp32"](x.cuda(), y.cuda(), as_loss=False).cpu().numpy()
+    report(f"A-DISTS fp32 {name}", got, g["score_f32"])
+    assert rel_err(got, g["score_f32"]) < 1e-4
+    swapped = amodels["fp32"](y.cuda(), x.cuda(), as_loss=False).cpu().numpy()
+    assert rel_err(swapped, g["score_swapped"]) < 1e-4          # asymmetric in its arguments
+    loss = float(amodels["fp32"](x.cuda(), y.cuda()))            # default as_loss=True -> scalar
+    assert abs(loss - float(g["score_as_loss"])) < 1e-4 * abs(float(g["score_as_loss"]))
+
+
+@pytest.mark.parametrize("name", ADISTS_CASES)
+def test_adists_bf16_matches_reference(amodels, golden, name):
+    g = golden(name)
+    x, y = golden_inputs(g)
+    got = amodels["bf16"](x.cuda(), y.cuda(), as_loss=False).cpu().numpy()
+    report(f"A-DISTS bf16 {name}", got, g["score_f32"])
+    assert np.max(np.abs(got - g["score_f32"])) < 2e-3
+
+
+def test_dists_api_behaviour(models, golden):
+    g = golden("dists_64")
+    x, y = golden_inputs(g)
+    m = models["fp32"]
+    xs, ys = x.cuda(), y.cuda()
+    s = m(xs, ys)
+    assert s.shape == (5,) and s.dtype == torch.float32 and s.is_cuda
+    avg = m(xs, ys, batch_average=True)
+    assert avg.dim() == 0 and abs(float(avg) - float(g["score_batch_avg"])) < 1e-4 * float(g["score_batch_avg"])
+    assert torch.equal(m(xs, ys, warp=1, certainty=2), s)             # ignored kwargs, deterministic
+    one = m(xs[:1], ys[:1])
+    assert one.shape == (1,)                                           # DISTS_pt keeps [1], not 0-d
+    assert torch.equal(one, s[:1])                                     # batch-independent reduction order
+    f0, f1 = m.forward_once(xs), m.forward_once(ys)
+    assert torch.allclose(m.forward_from_feats(f0, f1), s, rtol=1e-5, atol=1e-7)
+    with pytest.raises(_lib.NerfQAError):
+        m(x, y)                                                        # CPU tensors: no fallback
+    with pytest.raises(_lib.NerfQAError):
+        m(xs, ys[:, :, :32])
+    sym = m(ys, xs)
+    assert torch.allclose(sym, s, rtol=1e-5, atol=1e-7)                # DISTS is symmetric
+    ident = m(xs, xs)
+    assert float(ident.abs().max()) < 1e-6                             # identical frames -> 0
+
+
+def test_alpha_beta_gradients_match_oracle(models, vgg_weights):
+    x, y = synth.make_frame_pairs(3, 64, 64, seed=11)
+    m = models["fp32"]
+    m.alpha.requires_grad_(True); m.beta.requires_grad_(True)
+    m.alpha.grad = None; m.beta.grad = None
+    s = m(x.cuda(), y.cuda())
+    (s * torch.tensor([1.0, 2.0, -0.5], device="cuda")).sum().backward()
+    ws, bs = vgg_weights
+    a = m.alpha.detach().cpu().clone().requires_grad_(True)
+    b = m.beta.detach().cpu().clone().requires_grad_(True)
+    with torch.no_grad():
+        fx, fy = O.trunk(x, ws, bs), O.trunk(y, ws, bs)
+    so = O.dists_from_feats(fx, fy, a, b)
+    (so * torch.tensor([1.0, 2.0, -0.5])).sum().backward()
+    report("grad alpha", m.alpha.grad.cpu().flatten(), a.grad.flatten())
+    report("grad beta", m.beta.grad.cpu().flatten(), b.grad.flatten())
+    torch.testing.assert_close(m.alpha.grad.cpu().flatten(), a.grad.flatten(), rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(m.beta.grad.cpu().flatten(), b.grad.flatten(), rtol=1e-3, atol=1e-5)
+    m.alpha.requires_grad_(False); m.beta.requires_grad_(False)
+
+
+def test_host_path_equals_device_path(models):
+    x, y = synth.make_frame_pairs(6, 135, 240, seed=5)
+    m = models["bf16"]
+    dev = m(x.cuda(), y.cuda()).cpu()
+    host = m.score_host(x.pin_memory(), y.pin_memory())
+    assert torch.equal(dev, host)
+
+
+def test_micro_batching_is_batch_independent(models):
+    # 1080p: the scheduler streams 4 pairs per trunk pass; scores must not depend on the batch composition
+    x, y = synth.make_frame_pairs(5, 1080, 1920, seed=21)
+    m = models["bf16"]
+    xs, ys = x.cuda(), y.cuda()
+    full = m(xs, ys)
+    for i in (0, 4):
+        assert torch.equal(m(xs[i:i + 1], ys[i:i + 1]), full[i:i + 1])
+    assert float(m(xs[:2], xs[:2]).abs().max()) < 1e-6
+
+
+def test_dists_1080p_against_oracle(models, vgg_weights, alpha_beta):
+    """BASELINE config 2 shape, one pair (the oracle needs ~10 s of CPU per pair)."""
+    x, y = synth.make_frame_pairs(1, 1080, 1920, seed=31)
+    ws, bs = vgg_weights
+    a, b = alpha_beta
+    with torch.no_grad():
+        want = O.dists_score(x, y, ws, bs, a, b).numpy()
+    for prec, check in (("fp32", "rel"), ("bf16x3", "rel"), ("bf16", "abs")):
+        got = models[prec](x.cuda(), y.cuda()).cpu().numpy()
+        report(f"DISTS 1080p {prec}", got, want)
+        if check == "rel":
+            assert rel_err(got, want) < 1e-4
+        else:
+            assert np.max(np.abs(got - want)) < 2e-3
