@@ -142,6 +142,23 @@ NQA_API int nqa_workspace_bytes(nqa_ctx* ctx, size_t* bytes);
 /* Number of kernels this library has launched on the context since creation (bench accounting). */
 NQA_API int nqa_launch_count(nqa_ctx* ctx, uint64_t* launches);
 
+/* Per-kernel-family device timing with CUDA events recorded on the launching stream around every
+ * launch (bench.py's live roofline numbers).  nqa_profile_read synchronises the device, returns the
+ * milliseconds and launch counts accumulated since the previous read, and resets them. */
+#define NQA_NUM_KERNEL_FAMILIES 8
+enum nqa_kernel_family {
+  NQA_K_CONV_TC = 0,  /* tcgen05 implicit-GEMM 3x3 conv + bias + ReLU          */
+  NQA_K_CONV1_1 = 1,  /* normalise + conv1_1 (CUDA cores)                      */
+  NQA_K_CONV_F32 = 2, /* strict fp32 conv (CUDA cores)                         */
+  NQA_K_L2POOL = 3,   /* L2pooling                                             */
+  NQA_K_STATS = 4,    /* DISTS per-level statistics (NHWC + planar level 0)    */
+  NQA_K_FINALIZE = 5, /* S1/S2 + alpha/beta combination                        */
+  NQA_K_LAYOUT = 6,   /* NHWC <-> NCHW conversions                             */
+  NQA_K_ADISTS = 7    /* the whole A-DISTS statistics stage                    */
+};
+NQA_API int nqa_profile_enable(nqa_ctx* ctx, int on);
+NQA_API int nqa_profile_read(nqa_ctx* ctx, double ms[NQA_NUM_KERNEL_FAMILIES], uint64_t launches[NQA_NUM_KERNEL_FAMILIES]);
+
 /* Micro-batch (frame pairs per trunk pass) the scheduler would use for this shape. */
 NQA_API int nqa_micro_batch(nqa_ctx* ctx, int B, int H, int W, int precision, int* pairs);
 

@@ -24,7 +24,9 @@ EXPORTS = (
     "nqa_set_alpha_beta", "nqa_dists_forward", "nqa_dists_forward_host", "nqa_dists_features",
     "nqa_dists_from_feats", "nqa_adists_forward", "nqa_adists_from_feats", "nqa_l2pool",
     "nqa_workspace_bytes", "nqa_launch_count", "nqa_micro_batch", "nqa_conv3x3_relu",
+    "nqa_profile_enable", "nqa_profile_read",
 )
+KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists")
 
 
 class NerfQAError(RuntimeError):
@@ -62,6 +64,8 @@ def load_library() -> ctypes.CDLL:
     lib.nqa_conv3x3_relu.argtypes = [vp, fp, fp, fp, ci, ci, ci, ci, ci, ci, fp, vp]
     lib.nqa_workspace_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.nqa_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+    lib.nqa_profile_enable.argtypes = [vp, ci]
+    lib.nqa_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     lib.nqa_micro_batch.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(ci)]
     for name in EXPORTS:
         if name not in ("nqa_last_error",):
@@ -234,6 +238,16 @@ class Context:
         n = ctypes.c_uint64()
         _check(self.lib.nqa_launch_count(self.handle, ctypes.byref(n)))
         return int(n.value)
+
+    def profile_enable(self, on: bool) -> None:
+        _check(self.lib.nqa_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self):
+        """{family: (milliseconds, launches)} accumulated since the previous read (synchronises the device)."""
+        ms = (ctypes.c_double * len(KERNEL_FAMILIES))()
+        n = (ctypes.c_uint64 * len(KERNEL_FAMILIES))()
+        _check(self.lib.nqa_profile_read(self.handle, ms, n))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_FAMILIES)}
 
     def workspace_bytes(self) -> int:
         n = ctypes.c_size_t()

@@ -74,7 +74,8 @@ Plan make_plan(int pairs, int H, int W, int window) {
     L.csplit = 1;
     if (L.windowed) {
       // split the channel loop across blocks until the level fills ~2 waves (deep levels have few tiles)
-      const int blocks = L.tiles_x * L.tiles_y * pairs;
+      // (batch-independent on purpose: the channel split fixes the summation order of a frame's maps)
+      const int blocks = L.tiles_x * L.tiles_y;
       int cs = ceil_div(2 * kNumSMs, blocks);
       if (cs > L.c / 8) cs = L.c / 8;
       if (cs < 1) cs = 1;

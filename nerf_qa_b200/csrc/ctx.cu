@@ -68,6 +68,36 @@ struct nqa_ctx {
   cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
   float* stage_in[2] = {};               // device staging for the host path
   size_t stage_cap = 0;
+  // optional per-family profiling (CUDA events on the launching stream)
+  bool profiling = false;
+  struct ProfRec { int family; cudaEvent_t a, b; uint64_t launches; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+};
+
+// Brackets the launches made inside its scope with two events when profiling is on.
+struct ProfScope {
+  nqa_ctx* ctx;
+  cudaStream_t st;
+  int family;
+  uint64_t before;
+  cudaEvent_t a = nullptr;
+  static cudaEvent_t get(nqa_ctx* c) {
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ProfScope(nqa_ctx* c, int fam, cudaStream_t s) : ctx(c), st(s), family(fam), before(c->launches) {
+    if (ctx->profiling) { a = get(ctx); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (a) {
+      cudaEvent_t b = get(ctx);
+      cudaEventRecord(b, st);
+      ctx->prof_recs.push_back({family, a, b, ctx->launches - before});
+    }
+  }
 };
 
 namespace {
@@ -188,6 +218,7 @@ int conv_layer(nqa_ctx* ctx, int li, const T* in, const T* in_lo, T* out, T* out
 template <>
 int conv_layer<float>(nqa_ctx* ctx, int li, const float* in, const float*, float* out, float*, int n, int h, int w, int,
                       cudaStream_t st) {
+  ProfScope ps(ctx, NQA_K_CONV_F32, st);
   ctx->launches += launch_conv3x3_f32(in, out, ctx->w_f32[li], ctx->bias[li], n, h, w, kConvCin[li], kConvCout[li], st);
   return NQA_OK;
 }
@@ -200,6 +231,7 @@ int conv_layer<bf16>(nqa_ctx* ctx, int li, const bf16* in, const bf16* in_lo, bf
   if (conv_tc_make_plan(&plan, in, in_lo, ctx->w_hi[li], ctx->w_lo[li], ctx->bias[li], out, out_lo, n, h, w,
                         kConvCin[li], kConvCout[li], split, &err))
     return fail(NQA_ERR_CUDA, "%s (layer %d, %dx%dx%d)", err, li, n, h, w);
+  ProfScope ps(ctx, NQA_K_CONV_TC, st);
   ctx->launches += launch_conv3x3_tc(plan, st);
   return NQA_OK;
 }
@@ -218,6 +250,7 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
   for (int stage = 0; stage < 5; ++stage) {
     if (stage > 0) {
       const int c = kConvCout[li - 1];
+      ProfScope ps(ctx, NQA_K_L2POOL, st);
       ctx->launches += launch_l2pool_nhwc<T>(bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, bufs.ping[cur ^ 1],
                                              split ? bufs.ping_lo[cur ^ 1] : nullptr, n, h, w, c, st);
       h = pooled(h);
@@ -226,6 +259,7 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
     }
     for (int j = 0; j < kStageConvs[stage]; ++j, ++li) {
       if (li == 0) {
+        ProfScope ps(ctx, NQA_K_CONV1_1, st);
         ctx->launches += launch_conv1_1<T>(x, y, nx, n, h, w, ctx->w11, ctx->bias[0], bufs.ping[0],
                                            split ? bufs.ping_lo[0] : nullptr, st);
         cur = 0;
@@ -246,11 +280,13 @@ void level_to_nchw(nqa_ctx* ctx, const T* f, const T* f_lo, float* dst, int n, i
 template <>
 void level_to_nchw<float>(nqa_ctx* ctx, const float* f, const float*, float* dst, int n, int c, int h, int w,
                           cudaStream_t st) {
+  ProfScope ps(ctx, NQA_K_LAYOUT, st);
   ctx->launches += launch_nhwc_to_nchw<float>(f, dst, n, c, h, w, st);
 }
 template <>
 void level_to_nchw<bf16>(nqa_ctx* ctx, const bf16* f, const bf16* f_lo, float* dst, int n, int c, int h, int w,
                          cudaStream_t st) {
+  ProfScope ps(ctx, NQA_K_LAYOUT, st);
   if (f_lo)
     ctx->launches += launch_nhwc_split_to_nchw(f, f_lo, dst, n, c, h, w, st);
   else
@@ -293,6 +329,7 @@ int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float
     fp.lv[k].choff = level_offset(k);
     fp.lv[k].inv_n = 1.0 / ((double)h[k] * w[k]);
   }
+  ProfScope ps(ctx, NQA_K_FINALIZE, st);
   ctx->launches += launch_dists_finalize(fp, ctx->alpha, ctx->beta, pairs, score, s1s2, nullptr, st);
   return NQA_OK;
 }
@@ -313,10 +350,14 @@ int dists_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, i
   partial_alloc(ctx, pairs, &pb);
 
   // level 0: the RAW frames (DISTS_pt.py:103 returns x itself, not the normalised tensor)
-  ctx->launches += launch_stats_planar(x, y, pairs, 3, H * W, pb.chunks[0], pb.p[0], st);
+  {
+    ProfScope ps(ctx, NQA_K_STATS, st);
+    ctx->launches += launch_stats_planar(x, y, pairs, 3, H * W, pb.chunks[0], pb.p[0], st);
+  }
   const int rc = run_trunk<T>(ctx, x, y, pairs, 2 * pairs, H, W, prec, bufs, st,
                               [&](int k, const T* f, const T* f_lo, int h, int w) {
                                 const size_t half = (size_t)pairs * h * w * level_channels(k);
+                                ProfScope ps(ctx, NQA_K_STATS, st);
                                 ctx->launches += launch_stats_nhwc<T>(f, f + half, f_lo, f_lo ? f_lo + half : nullptr, pairs,
                                                                      h * w, level_channels(k), pb.chunks[k], pb.p[k], st);
                               });
@@ -427,6 +468,8 @@ int nqa_ctx_destroy(nqa_ctx* ctx) {
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
   }
+  for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
   cudaGetLastError();
@@ -605,9 +648,11 @@ int nqa_dists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS
   partial_alloc(ctx, B, &pb);
   int lh[kNumLevels], lw[kNumLevels];
   level_dims(H, W, lh, lw);
-  for (int k = 0; k < kNumLevels; ++k)
+  for (int k = 0; k < kNumLevels; ++k) {
+    ProfScope ps(ctx, NQA_K_STATS, st);
     ctx->launches += launch_stats_planar(feats_x[k], feats_y[k], B, level_channels(k), lh[k] * lw[k], pb.chunks[k],
                                          pb.p[k], st);
+  }
   rc = finalize(ctx, pb, B, H, W, score_out, s1s2_out, st);
   if (rc != NQA_OK) return rc;
   CUDA_TRY(cudaGetLastError());
@@ -662,6 +707,7 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
       fx[k] = planar[k];
       fy[k] = planar[k] + (size_t)pairs * level_channels(k) * lh[k] * lw[k];
     }
+    ProfScope ps(ctx, NQA_K_ADISTS, st);
     ctx->launches += adists_stage(fx, fy, pairs, H, W, window, ws, score_out + b0, st);
   }
   return NQA_OK;
@@ -709,7 +755,10 @@ int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVEL
   if ((rc = ensure_arena(ctx, adists_workspace_bytes(B, H, W, window) + 4096)) != NQA_OK) return rc;
   ctx->arena.reset();
   void* ws = ctx->arena.take(adists_workspace_bytes(B, H, W, window));
-  ctx->launches += adists_stage(feats_x, feats_y, B, H, W, window, ws, score_out, st);
+  {
+    ProfScope ps(ctx, NQA_K_ADISTS, st);
+    ctx->launches += adists_stage(feats_x, feats_y, B, H, W, window, ws, score_out, st);
+  }
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;
 }
@@ -778,6 +827,31 @@ int nqa_workspace_bytes(nqa_ctx* ctx, size_t* bytes) {
 int nqa_launch_count(nqa_ctx* ctx, uint64_t* launches) {
   if (!ctx || !launches) return fail(NQA_ERR_INVALID, "null argument");
   *launches = ctx->launches;
+  return NQA_OK;
+}
+
+int nqa_profile_enable(nqa_ctx* ctx, int on) {
+  if (!ctx) return fail(NQA_ERR_INVALID, "null context");
+  ctx->profiling = on != 0;
+  return NQA_OK;
+}
+
+int nqa_profile_read(nqa_ctx* ctx, double ms[NQA_NUM_KERNEL_FAMILIES], uint64_t launches[NQA_NUM_KERNEL_FAMILIES]) {
+  if (!ctx || !ms || !launches) return fail(NQA_ERR_INVALID, "null argument");
+  DeviceGuard guard(ctx->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i < NQA_NUM_KERNEL_FAMILIES; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  for (auto& r : ctx->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.family >= 0 && r.family < NQA_NUM_KERNEL_FAMILIES) {
+      ms[r.family] += (double)t;
+      launches[r.family] += r.launches;
+    }
+    ctx->prof_pool.push_back(r.a);
+    ctx->prof_pool.push_back(r.b);
+  }
+  ctx->prof_recs.clear();
+  cudaGetLastError();
   return NQA_OK;
 }
 

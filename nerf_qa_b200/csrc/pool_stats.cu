@@ -75,7 +75,10 @@ stats_nhwc_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* _
   }
 }
 
-int stats_chunks_nhwc(int hw, int c, int elem_bytes, int pairs) {
+// NOTE: the partition depends on the level shape only, never on the batch, so that a frame's score is
+// bit-identical whatever micro-batch it travels in.
+int stats_chunks_nhwc(int hw, int c, int elem_bytes, int /*pairs*/) {
+  const int pairs = 1;
   const int v = 16 / elem_bytes;
   const int groups = c / v;
   const int ppi = kStatsThreads / groups;
@@ -157,7 +160,8 @@ stats_planar_kernel(const float* __restrict__ x, const float* __restrict__ y, in
   }
 }
 
-int stats_chunks_planar(int hw, int c, int pairs) {
+int stats_chunks_planar(int hw, int c, int /*pairs*/) {
+  const int pairs = 1;
   // 256 threads x float4 x <=64 iterations per accumulator
   int chunks = ceil_div(hw, 256 * 4 * 64);
   const int want = ceil_div(2 * kNumSMs, pairs * c);

@@ -11,6 +11,14 @@ from tests._util import golden_inputs, make_adists, make_dists, rel_err, report
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    # alpha/beta are trainable exactly like in the reference (created after its freeze loop), so scores carry
+    # grad; the parity tests read plain values
+    with torch.no_grad():
+        yield
+
 DISTS_CASES = ["dists_64", "dists_odd_45x77", "dists_135x240", "dists_256"]
 ADISTS_CASES = ["adists_96x128", "adists_176", "adists_256", "adists_352x368"]
 
@@ -119,15 +127,17 @@ def test_alpha_beta_gradients_match_oracle(models, vgg_weights):
     m = models["fp32"]
     m.alpha.requires_grad_(True); m.beta.requires_grad_(True)
     m.alpha.grad = None; m.beta.grad = None
-    s = m(x.cuda(), y.cuda())
-    (s * torch.tensor([1.0, 2.0, -0.5], device="cuda")).sum().backward()
+    with torch.enable_grad():
+        s = m(x.cuda(), y.cuda())
+        (s * torch.tensor([1.0, 2.0, -0.5], device="cuda")).sum().backward()
     ws, bs = vgg_weights
     a = m.alpha.detach().cpu().clone().requires_grad_(True)
     b = m.beta.detach().cpu().clone().requires_grad_(True)
     with torch.no_grad():
         fx, fy = O.trunk(x, ws, bs), O.trunk(y, ws, bs)
-    so = O.dists_from_feats(fx, fy, a, b)
-    (so * torch.tensor([1.0, 2.0, -0.5])).sum().backward()
+    with torch.enable_grad():
+        so = O.dists_from_feats(fx, fy, a, b)
+        (so * torch.tensor([1.0, 2.0, -0.5])).sum().backward()
     report("grad alpha", m.alpha.grad.cpu().flatten(), a.grad.flatten())
     report("grad beta", m.beta.grad.cpu().flatten(), b.grad.flatten())
     torch.testing.assert_close(m.alpha.grad.cpu().flatten(), a.grad.flatten(), rtol=1e-3, atol=1e-5)
