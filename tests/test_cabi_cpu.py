@@ -1,0 +1,113 @@
+"""CPU-only checks of the drop-in boundary: the library loads, exports every symbol the header declares,
+fails loudly without a GPU, and the Python modules keep the reference's surface."""
+import ctypes
+import os
+import re
+import warnings
+
+import pytest
+import torch
+
+import nerf_qa_b200
+from nerf_qa_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "nerfqa_b200.h")).read()
+    return sorted(set(re.findall(r"NQA_API\s+[\w\s\*]+?\b(nqa_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = nerf_qa_b200.load_library()
+    declared = _header_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/nerfqa_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert lib.nqa_version() >= 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    lib = nerf_qa_b200.load_library()
+    h = ctypes.c_void_p()
+    rc = lib.nqa_ctx_create(0, ctypes.byref(h))
+    assert rc == -2 and b"no CUDA device" in lib.nqa_last_error()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = nerf_qa_b200.DISTS()
+        a = nerf_qa_b200.ADISTS()
+    x = torch.rand(1, 3, 32, 32)
+    with pytest.raises(_lib.NerfQAError):
+        m(x, x)
+    with pytest.raises(_lib.NerfQAError):
+        a(x, x)
+    with pytest.raises(_lib.NerfQAError):
+        m.forward_once(x)
+    with pytest.raises(_lib.NerfQAError):
+        nerf_qa_b200.L2pooling(channels=3)(x)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "nerf_qa_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read(), f"{f} mentions the oracle"
+
+
+def test_state_dict_layout_matches_reference():
+    """34 keys with the reference's names, shapes of torchvision's VGG16."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = nerf_qa_b200.DISTS()
+    sd = m.state_dict()
+    assert len(sd) == 34
+    assert sd["alpha"].shape == (1, 1475, 1, 1) and sd["beta"].shape == (1, 1475, 1, 1)
+    assert abs(float(sd["alpha"].sum() + sd["beta"].sum()) - 1.0) < 1e-5      # shipped weights are normalised
+    assert sd["mean"].flatten().tolist() == pytest.approx([0.485, 0.456, 0.406])
+    for key, shape in {"stage1.0.weight": (64, 3, 3, 3), "stage1.2.bias": (64,), "stage2.4.filter": (64, 1, 3, 3),
+                       "stage3.9.filter": (128, 1, 3, 3), "stage3.14.weight": (256, 256, 3, 3),
+                       "stage4.16.filter": (256, 1, 3, 3), "stage5.23.filter": (512, 1, 3, 3),
+                       "stage5.28.weight": (512, 512, 3, 3)}.items():
+        assert tuple(sd[key].shape) == shape, key
+    assert all(not p.requires_grad for n, p in m.named_parameters() if n.startswith("stage"))
+    assert m.alpha.requires_grad and m.beta.requires_grad                     # created after the freeze loop
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = nerf_qa_b200.ADISTS()
+    asd = a.state_dict()
+    assert "windows.0" in asd and asd["windows.5"].shape == (512, 1, 21, 21) and "stage2.4.filter" in asd
+    assert abs(float(asd["windows.1"][0].sum()) - 1.0) < 1e-5
+
+
+def test_project_weights_matches_oracle():
+    from oracle import reference_oracle as O
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = nerf_qa_b200.DISTS()
+    m.alpha.data = m.alpha.data - 0.001
+    a0, b0 = m.alpha.data.clone(), m.beta.data.clone()
+    m.project_weights()
+    pa, pb = O.project_weights(a0, b0)
+    torch.testing.assert_close(m.alpha.data, pa)
+    torch.testing.assert_close(m.beta.data, pb)
+
+
+def test_alpha_beta_backward_formula():
+    """The autograd glue around the kernel's (score, S1, S2) equals autograd through the plain expression."""
+    from nerf_qa_b200.dists import _AlphaBetaCombine
+    g = torch.Generator().manual_seed(0)
+    s1s2 = torch.rand(3, 2, 1475, generator=g, dtype=torch.float64)
+    alpha = torch.rand(1, 1475, 1, 1, generator=g, dtype=torch.float64, requires_grad=True)
+    beta = torch.rand(1, 1475, 1, 1, generator=g, dtype=torch.float64, requires_grad=True)
+    w = alpha.sum() + beta.sum()
+    plain = 1 - ((s1s2[:, 0] * alpha.flatten()).sum(1) + (s1s2[:, 1] * beta.flatten()).sum(1)) / w
+    coef = torch.tensor([1.0, -2.0, 0.5], dtype=torch.float64)
+    ga, gb = torch.autograd.grad((plain * coef).sum(), [alpha, beta])
+    out = _AlphaBetaCombine.apply(plain.detach(), s1s2, alpha, beta)
+    ga2, gb2 = torch.autograd.grad((out * coef).sum(), [alpha, beta])
+    torch.testing.assert_close(ga2, ga)
+    torch.testing.assert_close(gb2, gb)
