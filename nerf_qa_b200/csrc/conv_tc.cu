@@ -22,9 +22,15 @@
 // Reference semantics: torchvision vgg16.features convs as used by
 // nerf_qa/DISTS_pytorch/DISTS_pt.py:36-49 and nerf_qa/ADISTS/ADISTS.py:44-57.
 #include <stdio.h>
+#include <stdlib.h>
+
+#ifndef NQA_CONV_HALO_DEFAULT
+#define NQA_CONV_HALO_DEFAULT 1
+#endif
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace nqa {
 
@@ -35,109 +41,6 @@ constexpr int BLOCK_K = 64;                            // bf16 elements = 128 by
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
 constexpr int NUM_THREADS = 192;
-constexpr uint32_t SPIN_LIMIT = 1u << 28;              // watchdog: trap instead of hanging the GPU
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > SPIN_LIMIT) {
-      printf("nerfqa_b200 conv_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (=1, ignored for swizzled K-major) | SBO>>4 [32,46) (= 1024 B between
-// 8-row groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=bf16 (bits 7, 10), both
-// K-major, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 struct Params {
   int n, h, w, cin, cout;
   int tw_log2, tiles_w, tiles_h;
@@ -371,6 +274,18 @@ static EncodeTiledFn get_encode_fn() {
 
 static int g_sm_count = kNumSMs;
 
+// NQA_CONV_HALO: 0 = plain kernel everywhere; 1..4 = halo-reuse kernel for Cin <= 128 with
+// (halo width, base-offset mode) = (10,0) (10,1) (16,0) (16,1).
+static int halo_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("NQA_CONV_HALO");
+    mode = e ? atoi(e) : NQA_CONV_HALO_DEFAULT;
+    if (mode < 0 || mode > 4) mode = 0;
+  }
+  return mode;
+}
+
 static int choose_tw_log2(int h, int w) {
   // pick the TH x TW = 128 rectangle that wastes the fewest MMA rows on this image size
   int best = 3;
@@ -438,13 +353,27 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
   plan->n = n; plan->h = h; plan->w = w; plan->cin = cin; plan->cout = cout;
   plan->split = split; plan->bias = bias; plan->out = out; plan->out_lo = out_lo;
   plan->tw_log2 = tc::choose_tw_log2(h, w);
-  const int tw = 1 << plan->tw_log2, th = 128 >> plan->tw_log2;
-  plan->tiles_w = ceil_div(w, tw);
-  plan->tiles_h = ceil_div(h, th);
+  int tw = 1 << plan->tw_log2, th = 128 >> plan->tw_log2;
   // bf16x3 stages are twice as large, so cap its channel tile at 128 to keep >= 3 pipeline stages
   plan->block_n = cout >= 256 ? (split ? 128 : 256) : cout >= 128 ? 128 : 64;
+  // thin layers: halo-reuse kernel (A tile fetched once instead of nine times)
+  plan->halo = false;
+  plan->halo_hbw = 10;
+  plan->halo_desc_mode = 0;
+  const int halo_mode = tc::halo_mode();
+  if (halo_mode > 0 && !split && cin <= 128) {
+    plan->halo = true;
+    plan->halo_desc_mode = (halo_mode - 1) & 1;
+    plan->halo_hbw = ((halo_mode - 1) & 2) ? 16 : 10;
+    plan->tw_log2 = 3;
+    tw = 8;
+    th = 16;
+  }
+  plan->tiles_w = ceil_div(w, tw);
+  plan->tiles_h = ceil_div(h, th);
   if (!tc::get_encode_fn()) { *err = "conv_tc: cuTensorMapEncodeTiled entry point not available"; return 1; }
-  bool ok = tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, tw, th) &&
+  bool ok = (plan->halo ? tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, plan->halo_hbw, th + 2)
+                        : tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, tw, th)) &&
             tc::encode_w_map(&plan->tmap_b, wk, cout, 9 * cin, plan->block_n);
   if (split)
     ok = ok && tc::encode_act_map(&plan->tmap_a_lo, in_lo, n, h, w, cin, tw, th) &&
@@ -458,6 +387,12 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
 }
 
 int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st) {
+  if (plan.halo) {
+    const int rc = launch_conv3x3_tc_halo(plan, tc::g_sm_count, st);
+    if (rc > 0) return rc;
+    fprintf(stderr, "nerfqa_b200: halo conv configuration does not fit (cin %d cout %d)\n", plan.cin, plan.cout);
+    return 0;
+  }
   if (plan.split) {
     switch (plan.block_n) {
       case 64: return tc::launch_impl<64, true>(plan, st);

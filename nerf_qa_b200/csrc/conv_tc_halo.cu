@@ -1,0 +1,282 @@
+// Halo-reuse variant of the tcgen05 3x3 convolution for the thin layers (Cin <= 128), where the plain
+// kernel (conv_tc.cu) is bound by re-fetching the A tile nine times from L2.
+//
+//   * output tile = 16 rows x 8 columns of pixels (M = 128, m = 8*row + col);
+//   * per 64-channel chunk ONE 4-D TMA box {64 ch, HBW, 18, 1} brings the (16+2) x HBW halo (HBW >= 10) into
+//     shared memory, one 128-byte SWIZZLE_128B row per pixel, zero-filled outside the image;
+//   * the A operand of tap (r, s) is the SAME buffer viewed through a shifted UMMA descriptor: start address
+//     + (r*HBW + s)*128 bytes, 8-row groups (= one tile row) HBW*128 bytes apart (SBO);
+//   * weights either stay resident in shared memory for the whole kernel (9*Cin*BLOCK_N*2 bytes; conv1_2 and
+//     conv2_1) or stream through their own mbarrier ring (conv2_2, conv3_1);
+//   * everything else (persistent tile loop, TMEM double buffering, epilogue) as in conv_tc.cu.
+//
+// The 128-byte swizzle is a function of shared-memory address bits; TMA writes and UMMA reads agree as
+// long as the descriptor's base-offset field describes the phase of the (non 1024-byte-aligned) start
+// address.  `desc_mode` selects how that field is filled (validated on hardware by tests/test_gpu_ops.py).
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace nqa {
+namespace tch {
+
+using namespace tc;
+
+constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
+constexpr int TH = 16, TW = 8, HALO_H = TH + 2;
+constexpr int NUM_THREADS = 192;
+
+struct Params {
+  int n, h, w, cin, cout;
+  int tiles_w, tiles_h, num_n_tiles, num_tiles;
+  int hbw;          // halo box width in pixels (10 or 16)
+  int desc_mode;    // 0: base_offset = 0, 1: base_offset = (start >> 7) & 7
+  int a_stage_bytes;
+  const float* bias;
+  bf16* out;
+};
+
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr, uint32_t sbo_bytes, int desc_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (desc_mode & 1) d |= (uint64_t)((addr >> 7) & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BLOCK_N, bool RESIDENT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const Params p, int a_stages, int b_stages) {
+  constexpr int B_TILE = BLOCK_N * BLOCK_K * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int chunks = p.cin / BLOCK_K;
+  uint8_t* a_smem = smem;                                        // [a_stages][a_stage_bytes]
+  uint8_t* b_smem = smem + a_stages * p.a_stage_bytes;           // resident: [chunks*9][B_TILE]; ring: [b_stages][B_TILE]
+  const int b_slots = RESIDENT ? chunks * 9 : b_stages;
+  uint8_t* tail = b_smem + (size_t)b_slots * B_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* a_full = bars;                 // [4]
+  uint64_t* a_empty = bars + 4;            // [4]
+  uint64_t* b_full = bars + 8;             // [8] (ring) / [0] = weights loaded (resident)
+  uint64_t* b_empty = bars + 16;           // [8]
+  uint64_t* tmem_full = bars + 24;         // [2]
+  uint64_t* tmem_empty = bars + 26;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  float* bias_s = reinterpret_cast<float*>(tail + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < p.cout; i += NUM_THREADS) bias_s[i] = p.bias[i];
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(2 * BLOCK_N))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t a_bytes = (uint32_t)(HALO_H * p.hbw * 128);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      if (RESIDENT) {
+        // all weights of this CTA's channel tile, once (num_n_tiles == 1 in resident mode)
+        mbar_expect_tx(&b_full[0], (uint32_t)(chunks * 9 * B_TILE));
+        for (int cb = 0; cb < chunks; ++cb)
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_2d(b_smem + (size_t)(cb * 9 + tap) * B_TILE, &tmap_b, &b_full[0], tap * p.cin + cb * BLOCK_K, 0);
+      }
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        int m_tile = tile / p.num_n_tiles;
+        const int twi = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+        const int thi = m_tile % p.tiles_h;
+        const int img = m_tile / p.tiles_h;
+        const int h0 = thi * TH, w0 = twi * TW, n0 = n_tile * BLOCK_N;
+        for (int cb = 0; cb < chunks; ++cb) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          mbar_expect_tx(&a_full[as], a_bytes);
+          tma_load_4d(a_smem + (size_t)as * p.a_stage_bytes, &tmap_a, &a_full[as], cb * BLOCK_K, w0 - 1, h0 - 1, img);
+          if (++as == a_stages) { as = 0; aph ^= 1; }
+          if (!RESIDENT) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_expect_tx(&b_full[bs], B_TILE);
+              tma_load_2d(b_smem + (size_t)bs * B_TILE, &tmap_b, &b_full[bs], tap * p.cin + cb * BLOCK_K, n0);
+              if (++bs == b_stages) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      const uint32_t a_sbo = (uint32_t)(p.hbw * 128);
+      if (RESIDENT) {
+        mbar_wait(&b_full[0], 0);
+        tc_fence_after();
+      }
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int cb = 0; cb < chunks; ++cb) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(a_smem + (size_t)as * p.a_stage_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t b_base;
+            if (RESIDENT) {
+              b_base = smem_u32(b_smem + (size_t)(cb * 9 + tap) * B_TILE);
+            } else {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              b_base = smem_u32(b_smem + (size_t)bs * B_TILE);
+            }
+            const int r = tap / 3, s = tap - r * 3;
+            const uint32_t a_tap = a_base + (uint32_t)((r * p.hbw + s) * 128);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t da = make_desc_sw128(a_tap + k * UMMA_K * 2, a_sbo, p.desc_mode);
+              const uint64_t db = make_desc_sw128(b_base + k * UMMA_K * 2, 1024, 0);
+              umma_bf16(d_tmem, da, db, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+            if (!RESIDENT) {
+              umma_commit(&b_empty[bs]);
+              if (++bs == b_stages) { bs = 0; bph ^= 1; }
+            }
+          }
+          umma_commit(&a_empty[as]);
+          if (++as == a_stages) { as = 0; aph ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const int lh = m >> 3, lw = m & 7;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int n_tile = tile % p.num_n_tiles;
+      int m_tile = tile / p.num_n_tiles;
+      const int twi = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int thi = m_tile % p.tiles_h;
+      const int img = m_tile / p.tiles_h;
+      const int oy = thi * TH + lh, ox = twi * TW + lw, n0 = n_tile * BLOCK_N;
+      const bool valid = oy < p.h && ox < p.w;
+      const size_t obase = (((size_t)img * p.h + oy) * p.w + ox) * p.cout + n0;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + obase + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[q * 8 + j]) + bias_s[n0 + ch * 32 + q * 8 + j], 0.f);
+            uint4 t;
+            t.x = Vec<bf16>::pack2(v[0], v[1]);
+            t.y = Vec<bf16>::pack2(v[2], v[3]);
+            t.z = Vec<bf16>::pack2(v[4], v[5]);
+            t.w = Vec<bf16>::pack2(v[6], v[7]);
+            dst[q] = t;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N))
+                 : "memory");
+  }
+}
+
+template <int BLOCK_N, bool RESIDENT>
+static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
+  constexpr int B_TILE = BLOCK_N * BLOCK_K * 2;
+  Params p;
+  p.n = plan.n; p.h = plan.h; p.w = plan.w; p.cin = plan.cin; p.cout = plan.cout;
+  p.tiles_w = plan.tiles_w; p.tiles_h = plan.tiles_h;
+  p.num_n_tiles = plan.cout / BLOCK_N;
+  p.num_tiles = plan.n * plan.tiles_h * plan.tiles_w * p.num_n_tiles;
+  p.hbw = plan.halo_hbw; p.desc_mode = plan.halo_desc_mode;
+  p.a_stage_bytes = (HALO_H * plan.halo_hbw * 128 + 1023) & ~1023;
+  p.bias = plan.bias; p.out = plan.out;
+  const int chunks = plan.cin / BLOCK_K;
+  const int budget = 226 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*bias*/;
+  int a_stages, b_stages = 0;
+  if (RESIDENT) {
+    const int wbytes = chunks * 9 * B_TILE;
+    a_stages = (budget - wbytes) / p.a_stage_bytes;
+    if (a_stages > 4) a_stages = 4;
+    if (a_stages < 2) return -1;
+  } else {
+    a_stages = 2;
+    b_stages = (budget - a_stages * p.a_stage_bytes) / B_TILE;
+    if (b_stages > 8) b_stages = 8;
+    if (b_stages < 3) return -1;
+  }
+  const int smem = a_stages * p.a_stage_bytes + (RESIDENT ? chunks * 9 : b_stages) * B_TILE + 1024 + 256 + 2048;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(conv3x3_tc_halo_kernel<BLOCK_N, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_smem = smem;
+  }
+  const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+  conv3x3_tc_halo_kernel<BLOCK_N, RESIDENT><<<grid, NUM_THREADS, smem, st>>>(plan.tmap_a, plan.tmap_b, p, a_stages, b_stages);
+  return 1;
+}
+
+}  // namespace tch
+
+// Returns launches (1) or -1 if the configuration does not fit.
+int launch_conv3x3_tc_halo(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
+  const bool resident = (size_t)9 * plan.cin * plan.block_n * 2 <= 150 * 1024 && plan.block_n == plan.cout;
+  if (plan.block_n == 64) return resident ? tch::launch_impl<64, true>(plan, sm_count, st) : tch::launch_impl<64, false>(plan, sm_count, st);
+  if (plan.block_n == 128) return resident ? tch::launch_impl<128, true>(plan, sm_count, st) : tch::launch_impl<128, false>(plan, sm_count, st);
+  return tch::launch_impl<256, false>(plan, sm_count, st);
+}
+
+}  // namespace nqa

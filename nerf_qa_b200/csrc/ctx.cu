@@ -55,7 +55,8 @@ struct nqa_ctx {
   int device = 0;
   int sm_count = kNumSMs;
   bool have_weights = false, have_alpha_beta = false;
-  float* w11 = nullptr;                  // conv1_1 [27][64]
+  float* w11 = nullptr;                  // conv1_1 [27][64] (CUDA-core path)
+  bf16* w11_img = nullptr;               // conv1_1 [2][64*32] UMMA operand image (tensor path)
   float* bias[kNumConvs] = {};           // fp32
   float* w_f32[kNumConvs] = {};          // [9][cin][cout]
   bf16* w_hi[kNumConvs] = {};            // [cout][9][cin]
@@ -215,6 +216,22 @@ template <typename T>
 int conv_layer(nqa_ctx* ctx, int li, const T* in, const T* in_lo, T* out, T* out_lo, int n, int h, int w, int prec,
                cudaStream_t st);
 
+template <typename T>
+void conv1_1_layer(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int h, int w, T* out, T* out_lo,
+                   cudaStream_t st);
+template <>
+void conv1_1_layer<float>(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int h, int w, float* out,
+                          float* out_lo, cudaStream_t st) {
+  ProfScope ps(ctx, NQA_K_CONV1_1, st);
+  ctx->launches += launch_conv1_1<float>(x, y, nx, n, h, w, ctx->w11, ctx->bias[0], out, out_lo, st);
+}
+template <>
+void conv1_1_layer<bf16>(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int h, int w, bf16* out,
+                         bf16* out_lo, cudaStream_t st) {
+  ProfScope ps(ctx, NQA_K_CONV1_1, st);
+  ctx->launches += launch_conv1_1_tc(x, y, nx, n, h, w, ctx->w11_img, ctx->bias[0], out, out_lo, ctx->sm_count, st);
+}
+
 template <>
 int conv_layer<float>(nqa_ctx* ctx, int li, const float* in, const float*, float* out, float*, int n, int h, int w, int,
                       cudaStream_t st) {
@@ -259,9 +276,7 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
     }
     for (int j = 0; j < kStageConvs[stage]; ++j, ++li) {
       if (li == 0) {
-        ProfScope ps(ctx, NQA_K_CONV1_1, st);
-        ctx->launches += launch_conv1_1<T>(x, y, nx, n, h, w, ctx->w11, ctx->bias[0], bufs.ping[0],
-                                           split ? bufs.ping_lo[0] : nullptr, st);
+        conv1_1_layer<T>(ctx, x, y, nx, n, h, w, bufs.ping[0], split ? bufs.ping_lo[0] : nullptr, st);
         cur = 0;
       } else {
         const int rc = conv_layer<T>(ctx, li, bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, bufs.ping[cur ^ 1],
@@ -297,6 +312,7 @@ void level_to_nchw<bf16>(nqa_ctx* ctx, const bf16* f, const bf16* f_lo, float* d
 struct PartialBufs {
   float* p[kNumLevels];
   int chunks[kNumLevels];
+  double* terms;
 };
 
 size_t partial_bytes(int pairs, int H, int W, int prec, PartialBufs* pb /* may be null */, bool planar_all) {
@@ -310,12 +326,14 @@ size_t partial_bytes(int pairs, int H, int W, int prec, PartialBufs* pb /* may b
     if (pb) pb->chunks[k] = chunks;
     total += align256((size_t)pairs * chunks * 5 * c * sizeof(float));
   }
+  total += align256((size_t)pairs * kTotalChannels * sizeof(double));
   return total + 4096;
 }
 
 void partial_alloc(nqa_ctx* ctx, int pairs, PartialBufs* pb) {
   for (int k = 0; k < kNumLevels; ++k)
     pb->p[k] = static_cast<float*>(ctx->arena.take((size_t)pairs * pb->chunks[k] * 5 * level_channels(k) * sizeof(float)));
+  pb->terms = static_cast<double*>(ctx->arena.take((size_t)pairs * kTotalChannels * sizeof(double)));
 }
 
 int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float* score, float* s1s2, cudaStream_t st) {
@@ -330,7 +348,7 @@ int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float
     fp.lv[k].inv_n = 1.0 / ((double)h[k] * w[k]);
   }
   ProfScope ps(ctx, NQA_K_FINALIZE, st);
-  ctx->launches += launch_dists_finalize(fp, ctx->alpha, ctx->beta, pairs, score, s1s2, nullptr, st);
+  ctx->launches += launch_dists_finalize(fp, ctx->alpha, ctx->beta, pairs, score, s1s2, nullptr, pb.terms, st);
   return NQA_OK;
 }
 
@@ -436,6 +454,7 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   CUDA_TRY(cudaMalloc(&ctx->alpha, kTotalChannels * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ctx->beta, kTotalChannels * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ctx->w11, 27 * 64 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&ctx->w11_img, 2 * 64 * 32 * sizeof(bf16)));
   for (int i = 0; i < kNumConvs; ++i) {
     const size_t nw = (size_t)kConvCout[i] * kConvCin[i] * 9;
     CUDA_TRY(cudaMalloc(&ctx->bias[i], kConvCout[i] * sizeof(float)));
@@ -456,6 +475,7 @@ int nqa_ctx_destroy(nqa_ctx* ctx) {
   cudaFree(ctx->alpha);
   cudaFree(ctx->beta);
   cudaFree(ctx->w11);
+  cudaFree(ctx->w11_img);
   for (int i = 0; i < kNumConvs; ++i) {
     cudaFree(ctx->bias[i]);
     cudaFree(ctx->w_f32[i]);
@@ -495,6 +515,7 @@ int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const
     }
     if (i == 0) {
       pack_w11_kernel<<<(27 * 64 + 255) / 256, 256>>>(tmp, ctx->w11);
+      ctx->launches += launch_pack_w11_tc(tmp, ctx->w11_img, 0);
     } else {
       pack_w_kernel<<<1024, 256>>>(tmp, kConvCin[i], kConvCout[i], ctx->w_f32[i], ctx->w_hi[i], ctx->w_lo[i]);
     }

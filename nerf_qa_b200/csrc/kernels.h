@@ -38,8 +38,9 @@ int launch_stats_planar(const float* x, const float* y, int pairs, int c, int hw
                         cudaStream_t st);
 // score[b] = 1 - sum_c (alpha_c/w S1 + beta_c/w S2); optional s1s2[b][2][1475]; optional moments[b][1475][5]
 // (mean x, mean y, var x, var y, cov) for the backward pass.
+// terms: [pairs][1475] fp64 scratch
 int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const float* beta, int pairs, float* score,
-                          float* s1s2, float* moments, cudaStream_t st);
+                          float* s1s2, float* moments, double* terms, cudaStream_t st);
 
 // ---- pooling / layout -----------------------------------------------------------------------------
 template <typename T>
@@ -59,6 +60,11 @@ int launch_nhwc_split_to_nchw(const bf16* hi, const bf16* lo, float* out, int n,
 template <typename T>
 int launch_conv1_1(const float* x, const float* y, int nx, int n, int h, int w, const float* wpack, const float* bias,
                    T* out, T* out_lo, cudaStream_t st);
+// tensor-pipe version (bf16 / bf16x3): im2col rows built by producer warps, K = 27 padded to 32.
+// wimg: [2][64*32] bf16 shared-memory image of the weights (hi, lo) from launch_pack_w11_tc.
+int launch_pack_w11_tc(const float* w_oihw, bf16* img, cudaStream_t st);
+int launch_conv1_1_tc(const float* x, const float* y, int nx, int n, int h, int w, const bf16* wimg, const float* bias,
+                      bf16* out, bf16* out_lo, int sm_count, cudaStream_t st);
 // strict fp32 CUDA-core conv: NHWC fp32, weights [9][cin][cout]
 int launch_conv3x3_f32(const float* in, float* out, const float* wpack, const float* bias, int n, int h, int w, int cin,
                        int cout, cudaStream_t st);
@@ -72,6 +78,9 @@ struct ConvTcPlan {
   int tiles_w, tiles_h;
   int block_n;
   bool split;
+  bool halo;           // halo-reuse kernel (conv_tc_halo.cu): tile 16x8, A halo loaded once per 64-channel chunk
+  int halo_hbw;        // halo box width in pixels
+  int halo_desc_mode;  // how the UMMA descriptor's base-offset field is filled
   const float* bias;
   bf16* out;
   bf16* out_lo;
@@ -81,6 +90,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
                       const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout, bool split,
                       const char** err);
 int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st);
+int launch_conv3x3_tc_halo(const ConvTcPlan& plan, int sm_count, cudaStream_t st);
 void conv_tc_set_sm_count(int sms);
 
 // ---- A-DISTS --------------------------------------------------------------------------------------

@@ -84,7 +84,7 @@ int stats_chunks_nhwc(int hw, int c, int elem_bytes, int /*pairs*/) {
   const int ppi = kStatsThreads / groups;
   // <= 256 sequential adds per accumulator, but at least ~2 waves of blocks when the level allows it
   int chunks = ceil_div(hw, ppi * 256);
-  const int want = ceil_div(2 * kNumSMs, pairs);
+  const int want = 64 / pairs;  // enough blocks per frame pair to spread a small level over the SMs
   const int cap = ceil_div(hw, ppi * 8);
   if (chunks < want) chunks = want < cap ? want : cap;
   if (chunks < 1) chunks = 1;
@@ -164,7 +164,7 @@ int stats_chunks_planar(int hw, int c, int /*pairs*/) {
   const int pairs = 1;
   // 256 threads x float4 x <=64 iterations per accumulator
   int chunks = ceil_div(hw, 256 * 4 * 64);
-  const int want = ceil_div(2 * kNumSMs, pairs * c);
+  const int want = ceil_div(64, pairs * c);
   const int cap = ceil_div(hw, 256 * 4);
   if (chunks < want) chunks = want < cap ? want : cap;
   if (chunks < 1) chunks = 1;
@@ -180,29 +180,38 @@ int launch_stats_planar(const float* x, const float* y, int pairs, int c, int hw
 
 // ================================================================================================
 // Finalize: moments -> S1,S2 -> alpha/beta-weighted sum -> score (DISTS_pt.py:127-148).
-// grid = pairs, 256 threads.  Chunk partials are combined in a fixed order in fp64 (deterministic,
-// batch-independent).
+// Stage 1, grid = (ceil(1475/64), pairs), 256 threads = 64 channels x 4 chunk lanes: chunk partials are
+// combined in fp64 in a fixed order (lane q takes chunks q, q+4, ...; lanes combined 0..3), so the
+// result is deterministic and batch-independent.  Stage 2, grid = pairs: ordered sum of the 1475
+// per-channel terms.
 // ================================================================================================
-__global__ void __launch_bounds__(256)
-dists_finalize_kernel(FinalizeParams p, const float* __restrict__ alpha, const float* __restrict__ beta,
-                      float* __restrict__ score, float* __restrict__ s1s2, float* __restrict__ moments) {
-  __shared__ double smd[33];
-  const int b = blockIdx.x;
-  double wsum_part = 0.0;
-  for (int c = threadIdx.x; c < kTotalChannels; c += 256) wsum_part += (double)alpha[c] + (double)beta[c];
-  const double wsum = block_sum<double>(wsum_part, smd);
+constexpr int kFinCh = 64;
 
-  double acc = 0.0;
-  for (int c = threadIdx.x; c < kTotalChannels; c += 256) {
+__global__ void __launch_bounds__(256)
+dists_terms_kernel(FinalizeParams p, const float* __restrict__ alpha, const float* __restrict__ beta,
+                   double* __restrict__ terms, float* __restrict__ s1s2, float* __restrict__ moments) {
+  __shared__ double sm[4][kFinCh][5];
+  const int b = blockIdx.y;
+  const int cl = threadIdx.x % kFinCh, q = threadIdx.x / kFinCh;
+  const int c = blockIdx.x * kFinCh + cl;
+  double s[5] = {0, 0, 0, 0, 0};
+  LevelPartials lv = p.lv[0];
+  if (c < kTotalChannels) {
     const int k = c < 3 ? 0 : c < 67 ? 1 : c < 195 ? 2 : c < 451 ? 3 : c < 963 ? 4 : 5;
-    const LevelPartials lv = p.lv[k];
+    lv = p.lv[k];
     const int cc = c - lv.choff;
-    double s[5] = {0, 0, 0, 0, 0};
     const float* base = lv.partials + (size_t)b * lv.chunks * 5 * lv.C + cc;
-    for (int ch = 0; ch < lv.chunks; ++ch) {
+    for (int ch = q; ch < lv.chunks; ch += 4) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) s[i] += (double)base[((size_t)ch * 5 + i) * lv.C];
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) sm[q][cl][i] = s[i];
+  __syncthreads();
+  if (q == 0 && c < kTotalChannels) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) s[i] = ((sm[0][cl][i] + sm[1][cl][i]) + sm[2][cl][i]) + sm[3][cl][i];
     const double mx = s[0] * lv.inv_n, my = s[1] * lv.inv_n;
     const double vx = s[2] * lv.inv_n - mx * mx, vy = s[3] * lv.inv_n - my * my;
     const double cov = s[4] * lv.inv_n - mx * my;
@@ -217,16 +226,31 @@ dists_finalize_kernel(FinalizeParams p, const float* __restrict__ alpha, const f
       float* m = moments + ((size_t)b * kTotalChannels + c) * 5;
       m[0] = (float)mx; m[1] = (float)my; m[2] = (float)vx; m[3] = (float)vy; m[4] = (float)cov;
     }
-    acc += ((double)alpha[c] * s1 + (double)beta[c] * s2) / wsum;
+    terms[(size_t)b * kTotalChannels + c] = (double)alpha[c] * s1 + (double)beta[c] * s2;
   }
-  const double total = block_sum<double>(acc, smd);
-  if (threadIdx.x == 0) score[b] = (float)(1.0 - total);
+}
+
+__global__ void __launch_bounds__(256)
+dists_score_kernel(const double* __restrict__ terms, const float* __restrict__ alpha, const float* __restrict__ beta,
+                   float* __restrict__ score) {
+  __shared__ double smd[33];
+  const int b = blockIdx.x;
+  double wpart = 0.0, tpart = 0.0;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) {
+    wpart += (double)alpha[c] + (double)beta[c];
+    tpart += terms[(size_t)b * kTotalChannels + c];
+  }
+  const double wsum = block_sum<double>(wpart, smd);
+  const double total = block_sum<double>(tpart, smd);
+  if (threadIdx.x == 0) score[b] = (float)(1.0 - total / wsum);
 }
 
 int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const float* beta, int pairs, float* score,
-                          float* s1s2, float* moments, cudaStream_t st) {
-  dists_finalize_kernel<<<pairs, 256, 0, st>>>(p, alpha, beta, score, s1s2, moments);
-  return 1;
+                          float* s1s2, float* moments, double* terms, cudaStream_t st) {
+  dim3 grid(ceil_div(kTotalChannels, kFinCh), pairs);
+  dists_terms_kernel<<<grid, 256, 0, st>>>(p, alpha, beta, terms, s1s2, moments);
+  dists_score_kernel<<<pairs, 256, 0, st>>>(terms, alpha, beta, score);
+  return 2;
 }
 
 // ================================================================================================
