@@ -145,7 +145,7 @@ NQA_API int nqa_launch_count(nqa_ctx* ctx, uint64_t* launches);
 /* Per-kernel-family device timing with CUDA events recorded on the launching stream around every
  * launch (bench.py's live roofline numbers).  nqa_profile_read synchronises the device, returns the
  * milliseconds and launch counts accumulated since the previous read, and resets them. */
-#define NQA_NUM_KERNEL_FAMILIES 8
+#define NQA_NUM_KERNEL_FAMILIES 10
 enum nqa_kernel_family {
   NQA_K_CONV_TC = 0,  /* tcgen05 implicit-GEMM 3x3 conv + bias + ReLU          */
   NQA_K_CONV1_1 = 1,  /* normalise + conv1_1 (CUDA cores)                      */
@@ -154,7 +154,9 @@ enum nqa_kernel_family {
   NQA_K_STATS = 4,    /* DISTS per-level statistics (NHWC + planar level 0)    */
   NQA_K_FINALIZE = 5, /* S1/S2 + alpha/beta combination                        */
   NQA_K_LAYOUT = 6,   /* NHWC <-> NCHW conversions                             */
-  NQA_K_ADISTS = 7    /* the whole A-DISTS statistics stage                    */
+  NQA_K_ADISTS = 7,   /* the whole A-DISTS statistics stage                    */
+  NQA_K_POOL_STATS = 8, /* fused L2pooling + DISTS statistics (levels 1..4)    */
+  NQA_K_STAGE1 = 9    /* fused normalise + conv1_1 + conv1_2 (tcgen05)         */
 };
 NQA_API int nqa_profile_enable(nqa_ctx* ctx, int on);
 NQA_API int nqa_profile_read(nqa_ctx* ctx, double ms[NQA_NUM_KERNEL_FAMILIES], uint64_t launches[NQA_NUM_KERNEL_FAMILIES]);

@@ -26,7 +26,8 @@ EXPORTS = (
     "nqa_workspace_bytes", "nqa_launch_count", "nqa_micro_batch", "nqa_conv3x3_relu",
     "nqa_profile_enable", "nqa_profile_read",
 )
-KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists")
+KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists", "pool_stats",
+                   "stage1")
 
 
 class NerfQAError(RuntimeError):

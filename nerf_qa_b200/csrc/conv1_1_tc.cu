@@ -27,19 +27,7 @@ constexpr int W_BYTES = NOUT * KPAD * 2;     // 4 KB
 constexpr int NUM_PRODUCER_SETS = 2;         // 2 x 128 producer threads, alternating tiles
 constexpr int NUM_THREADS = (NUM_PRODUCER_SETS * 4 + 1 + 4) * 32;  // 8 producer warps, 1 MMA warp, 4 epilogue warps
 
-// canonical K-major, no swizzle: 8x8 core matrices (8 rows x 16 bytes) stored as 128 contiguous bytes;
-// K-adjacent core matrices 128 B apart (LBO), 8-row groups 512 B apart (SBO).
-__host__ __device__ inline int a_offset_bytes(int row, int kchunk /* 8 elements */) {
-  return (row >> 3) * 512 + kchunk * 128 + (row & 7) * 16;
-}
-__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
-  d |= (uint64_t)(128 >> 4) << 16;   // LBO
-  d |= (uint64_t)(512 >> 4) << 32;   // SBO
-  d |= (uint64_t)1 << 46;            // descriptor version
-  return d;                          // layout_type 0 = no swizzle
-}
+__host__ __device__ inline int a_offset_bytes(int row, int kchunk) { return noswz_offset_bytes(row, kchunk); }
 
 struct Params {
   const float* x;
@@ -160,20 +148,20 @@ conv1_1_tc_kernel(const Params p) {
       mbar_arrive(&full_bar[stage]);
     }
   } else if (warp == 8) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, NOUT);
-      const uint32_t w_hi = smem_u32(w_smem), w_lo = w_hi + W_BYTES;
-      for (int local = 0;; ++local) {
-        const int tile = blockIdx.x + local * gridDim.x;
-        if (tile >= p.num_tiles) break;
-        const int stage = local % STAGES;
-        const uint32_t phase = (local / STAGES) & 1;
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
+    // =============================== MMA issuer (whole warp, one elected lane issues) ===============================
+    constexpr uint32_t idesc = make_idesc(TILE_M, NOUT);
+    const uint32_t w_hi = smem_u32(w_smem), w_lo = w_hi + W_BYTES;
+    for (int local = 0;; ++local) {
+      const int tile = blockIdx.x + local * gridDim.x;
+      if (tile >= p.num_tiles) break;
+      const int stage = local % STAGES;
+      const uint32_t phase = (local / STAGES) & 1;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_hi = smem_u32(a_smem + stage * A_STAGE), a_lo = a_hi + A_BYTES;
         const uint32_t d_tmem = tmem_base + acc * NOUT;
 #pragma unroll
@@ -188,6 +176,7 @@ conv1_1_tc_kernel(const Params p) {
         umma_commit(&empty_bar[stage]);
         umma_commit(&tmem_full[acc]);
       }
+      __syncwarp();
     }
   } else {
     // =============================== epilogue ===============================

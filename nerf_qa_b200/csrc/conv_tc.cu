@@ -112,20 +112,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        int m_tile = tile / p.num_n_tiles;
-        const int twi = m_tile % p.tiles_w; m_tile /= p.tiles_w;
-        const int thi = m_tile % p.tiles_h;
-        const int img = m_tile / p.tiles_h;
-        const int h0 = thi * th, w0 = twi * tw, n0 = n_tile * BLOCK_N;
-        for (int cb = 0; cb < p.cin / BLOCK_K; ++cb) {
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+    // =============================== TMA producer (whole warp, one elected lane issues) ===============================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      int m_tile = tile / p.num_n_tiles;
+      const int twi = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int thi = m_tile % p.tiles_h;
+      const int img = m_tile / p.tiles_h;
+      const int h0 = thi * th, w0 = twi * tw, n0 = n_tile * BLOCK_N;
+      for (int cb = 0; cb < p.cin / BLOCK_K; ++cb) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
             uint8_t* sb = sa + A_TILE_BYTES;
             mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
@@ -138,46 +138,48 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               tma_load_4d(sa_lo, &tmap_a_lo, &full_bar[stage], cb * BLOCK_K, w0 + s - 1, h0 + r - 1, img);
               tma_load_2d(sb_lo, &tmap_b_lo, &full_bar[stage], tap * p.cin + cb * BLOCK_K, n0);
             }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // =============================== MMA issuer (whole warp, one elected lane issues) ===============================
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < kb_per_tile; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < kb_per_tile; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + A_TILE_BYTES;
+          const uint64_t da0 = make_smem_desc(sa), db0 = make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * UMMA_K * 2);
-            const uint64_t db = make_smem_desc(sb + k * UMMA_K * 2);
+            // advancing K by 16 elements = 32 bytes = 2 units of the descriptor's 16-byte address field
+            const uint64_t da = da0 + (uint64_t)(k * 2), db = db0 + (uint64_t)(k * 2);
             umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             if (SPLIT) {
-              const uint32_t sa_lo = sb + C::B_TILE_BYTES, sb_lo = sa_lo + A_TILE_BYTES;
-              const uint64_t da_lo = make_smem_desc(sa_lo + k * UMMA_K * 2);
-              const uint64_t db_lo = make_smem_desc(sb_lo + k * UMMA_K * 2);
+              const uint64_t da_lo = make_smem_desc(sb + C::B_TILE_BYTES) + (uint64_t)(k * 2);
+              const uint64_t db_lo = make_smem_desc(sb + C::B_TILE_BYTES + A_TILE_BYTES) + (uint64_t)(k * 2);
               umma_bf16(d_tmem, da, db_lo, idesc, 1u);
               umma_bf16(d_tmem, da_lo, db, idesc, 1u);
             }
           }
           umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
           if (kb == kb_per_tile - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -344,6 +346,14 @@ static int launch_impl(const ConvTcPlan& plan, cudaStream_t st) {
 
 }  // namespace tc
 
+int conv_tc_make_act_map(CUtensorMap* map, const bf16* ptr, int n, int h, int w, int c, int box_w, int box_h) {
+  return tc::encode_act_map(map, ptr, n, h, w, c, box_w, box_h) ? 0 : 1;
+}
+
+int conv_tc_make_weight_map(CUtensorMap* map, const bf16* wk, int cout, int k, int block_n) {
+  return tc::encode_w_map(map, wk, cout, k, block_n) ? 0 : 1;
+}
+
 void conv_tc_set_sm_count(int sms) { tc::g_sm_count = sms > 0 ? sms : kNumSMs; }
 
 int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
@@ -361,13 +371,18 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
   plan->halo_hbw = 10;
   plan->halo_desc_mode = 0;
   const int halo_mode = tc::halo_mode();
-  if (halo_mode > 0 && !split && cin <= 128) {
+  static const int halo_max_cin = getenv("NQA_CONV_HALO_MAXCIN") ? atoi(getenv("NQA_CONV_HALO_MAXCIN")) : 256;
+  if (halo_mode > 0 && !split && cin <= halo_max_cin) {
     plan->halo = true;
-    plan->halo_desc_mode = (halo_mode - 1) & 1;
+    plan->halo_desc_mode = 0;   // base-offset field 0: validated on hardware (swizzle follows absolute address bits)
     plan->halo_hbw = ((halo_mode - 1) & 2) ? 16 : 10;
     plan->tw_log2 = 3;
     tw = 8;
     th = 16;
+    // 128 -> 128 channels: two 64-channel tiles whose weights (147 KB) stay resident in shared memory beat one
+    // 128-channel tile whose weights stream from L2 for every pixel tile (NQA_CONV_N64=0 restores the latter)
+    static const bool n64 = getenv("NQA_CONV_N64") ? atoi(getenv("NQA_CONV_N64")) != 0 : true;
+    if (n64 && cin == 128 && cout == 128) plan->block_n = 64;
   }
   plan->tiles_w = ceil_div(w, tw);
   plan->tiles_h = ceil_div(h, th);
@@ -375,6 +390,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
   bool ok = (plan->halo ? tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, plan->halo_hbw, th + 2)
                         : tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, tw, th)) &&
             tc::encode_w_map(&plan->tmap_b, wk, cout, 9 * cin, plan->block_n);
+  if (plan->halo) ok = ok && tc::encode_act_map(&plan->tmap_out, out, n, h, w, cout, tw, th);
   if (split)
     ok = ok && tc::encode_act_map(&plan->tmap_a_lo, in_lo, n, h, w, cin, tw, th) &&
          tc::encode_w_map(&plan->tmap_b_lo, wk_lo, cout, 9 * cin, plan->block_n);

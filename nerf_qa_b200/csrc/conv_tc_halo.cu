@@ -25,6 +25,7 @@ using namespace tc;
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int TH = 16, TW = 8, HALO_H = TH + 2;
 constexpr int NUM_THREADS = 192;
+constexpr int STG_BYTES = 2 * 128 * 128;   // two 64-channel sub-tiles of 128 pixels
 
 struct Params {
   int n, h, w, cin, cout;
@@ -36,27 +37,17 @@ struct Params {
   bf16* out;
 };
 
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr, uint32_t sbo_bytes, int desc_mode) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3ffff) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  if (desc_mode & 1) d |= (uint64_t)((addr >> 7) & 7) << 49;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 template <int BLOCK_N, bool RESIDENT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       const Params p, int a_stages, int b_stages) {
+                       const __grid_constant__ CUtensorMap tmap_out, const Params p, int a_stages, int b_stages) {
   constexpr int B_TILE = BLOCK_N * BLOCK_K * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int chunks = p.cin / BLOCK_K;
-  uint8_t* a_smem = smem;                                        // [a_stages][a_stage_bytes]
-  uint8_t* b_smem = smem + a_stages * p.a_stage_bytes;           // resident: [chunks*9][B_TILE]; ring: [b_stages][B_TILE]
+  uint8_t* stg_smem = smem;                                      // [2][128 x 128 B] output staging for the TMA store
+  uint8_t* a_smem = smem + STG_BYTES;                            // [a_stages][a_stage_bytes]
+  uint8_t* b_smem = a_smem + a_stages * p.a_stage_bytes;         // resident: [chunks*9][B_TILE]; ring: [b_stages][B_TILE]
   const int b_slots = RESIDENT ? chunks * 9 : b_stages;
   uint8_t* tail = b_smem + (size_t)b_slots * B_TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
@@ -75,6 +66,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_out);
     for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
@@ -94,96 +86,121 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const uint32_t a_bytes = (uint32_t)(HALO_H * p.hbw * 128);
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      if (RESIDENT) {
-        // all weights of this CTA's channel tile, once (num_n_tiles == 1 in resident mode)
+    // =============================== TMA producer (whole warp, one elected lane issues) ===============================
+    if (RESIDENT) {
+      // all weights of this CTA's channel tile, once: the grid is a multiple of num_n_tiles, so with the
+      // channel tile fastest in the tile order a CTA sees the same channel tile for its whole life
+      if (elect_one()) {
+        const int wn0 = (blockIdx.x % p.num_n_tiles) * BLOCK_N;
         mbar_expect_tx(&b_full[0], (uint32_t)(chunks * 9 * B_TILE));
         for (int cb = 0; cb < chunks; ++cb)
           for (int tap = 0; tap < 9; ++tap)
-            tma_load_2d(b_smem + (size_t)(cb * 9 + tap) * B_TILE, &tmap_b, &b_full[0], tap * p.cin + cb * BLOCK_K, 0);
+            tma_load_2d(b_smem + (size_t)(cb * 9 + tap) * B_TILE, &tmap_b, &b_full[0], tap * p.cin + cb * BLOCK_K, wn0);
       }
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        int m_tile = tile / p.num_n_tiles;
-        const int twi = m_tile % p.tiles_w; m_tile /= p.tiles_w;
-        const int thi = m_tile % p.tiles_h;
-        const int img = m_tile / p.tiles_h;
-        const int h0 = thi * TH, w0 = twi * TW, n0 = n_tile * BLOCK_N;
-        for (int cb = 0; cb < chunks; ++cb) {
-          mbar_wait(&a_empty[as], aph ^ 1);
+      __syncwarp();
+    }
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      int m_tile = tile / p.num_n_tiles;
+      const int twi = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int thi = m_tile % p.tiles_h;
+      const int img = m_tile / p.tiles_h;
+      const int h0 = thi * TH, w0 = twi * TW, n0 = n_tile * BLOCK_N;
+      for (int cb = 0; cb < chunks; ++cb) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&a_full[as], a_bytes);
           tma_load_4d(a_smem + (size_t)as * p.a_stage_bytes, &tmap_a, &a_full[as], cb * BLOCK_K, w0 - 1, h0 - 1, img);
-          if (++as == a_stages) { as = 0; aph ^= 1; }
-          if (!RESIDENT) {
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&b_empty[bs], bph ^ 1);
+        }
+        __syncwarp();
+        if (++as == a_stages) { as = 0; aph ^= 1; }
+        if (!RESIDENT) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (elect_one()) {
               mbar_expect_tx(&b_full[bs], B_TILE);
               tma_load_2d(b_smem + (size_t)bs * B_TILE, &tmap_b, &b_full[bs], tap * p.cin + cb * BLOCK_K, n0);
-              if (++bs == b_stages) { bs = 0; bph ^= 1; }
             }
+            __syncwarp();
+            if (++bs == b_stages) { bs = 0; bph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
-      const uint32_t a_sbo = (uint32_t)(p.hbw * 128);
-      if (RESIDENT) {
-        mbar_wait(&b_full[0], 0);
+    // =============================== MMA issuer (whole warp, one elected lane issues) ===============================
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+    const uint32_t a_sbo = (uint32_t)(p.hbw * 128);
+    if (RESIDENT) {
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+    }
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int cb = 0; cb < chunks; ++cb) {
+        mbar_wait(&a_full[as], aph);
         tc_fence_after();
-      }
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int cb = 0; cb < chunks; ++cb) {
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(a_smem + (size_t)as * p.a_stage_bytes);
-          for (int tap = 0; tap < 9; ++tap) {
-            uint32_t b_base;
-            if (RESIDENT) {
-              b_base = smem_u32(b_smem + (size_t)(cb * 9 + tap) * B_TILE);
-            } else {
-              mbar_wait(&b_full[bs], bph);
-              tc_fence_after();
-              b_base = smem_u32(b_smem + (size_t)bs * B_TILE);
-            }
-            const int r = tap / 3, s = tap - r * 3;
-            const uint32_t a_tap = a_base + (uint32_t)((r * p.hbw + s) * 128);
+        const uint32_t a_base = smem_u32(a_smem + (size_t)as * p.a_stage_bytes);
+        // descriptor of tap (0,0), k = 0; taps and k-steps only move the 16-byte-granular start-address field
+        const uint64_t da0 = make_desc_sw128(a_base, a_sbo, 0);
+        if (RESIDENT) {
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t da = make_desc_sw128(a_tap + k * UMMA_K * 2, a_sbo, p.desc_mode);
-              const uint64_t db = make_desc_sw128(b_base + k * UMMA_K * 2, 1024, 0);
-              umma_bf16(d_tmem, da, db, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int r = tap / 3, s = tap - r * 3;
+              const uint64_t da_tap = da0 + (uint64_t)((r * p.hbw + s) * 8);
+              const uint64_t db_tap = make_desc_sw128(smem_u32(b_smem + (size_t)(cb * 9 + tap) * B_TILE), 1024, 0);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16(d_tmem, da_tap + (uint64_t)(k * 2), db_tap + (uint64_t)(k * 2), idesc,
+                          (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
             }
-            if (!RESIDENT) {
-              umma_commit(&b_empty[bs]);
-              if (++bs == b_stages) { bs = 0; bph ^= 1; }
-            }
+            umma_commit(&a_empty[as]);
+            if (cb == chunks - 1) umma_commit(&tmem_full[acc]);
           }
-          umma_commit(&a_empty[as]);
-          if (++as == a_stages) { as = 0; aph ^= 1; }
+          __syncwarp();
+        } else {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            if (elect_one()) {
+              const int r = tap / 3, s = tap - r * 3;
+              const uint64_t da_tap = da0 + (uint64_t)((r * p.hbw + s) * 8);
+              const uint64_t db_tap = make_desc_sw128(smem_u32(b_smem + (size_t)bs * B_TILE), 1024, 0);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16(d_tmem, da_tap + (uint64_t)(k * 2), db_tap + (uint64_t)(k * 2), idesc,
+                          (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_commit(&b_empty[bs]);
+              if (tap == 8) {
+                umma_commit(&a_empty[as]);
+                if (cb == chunks - 1) umma_commit(&tmem_full[acc]);
+              }
+            }
+            __syncwarp();
+            if (++bs == b_stages) { bs = 0; bph ^= 1; }
+          }
         }
-        umma_commit(&tmem_full[acc]);
+        if (++as == a_stages) { as = 0; aph ^= 1; }
       }
     }
   } else {
     // =============================== epilogue ===============================
+    // thread = pixel (TMEM lane); per 64-channel sub-tile its 128-byte row is staged in the swizzled layout of the
+    // output tensor map and ONE TMA store writes the 16 x 8 x 64 box (full lines, edges clipped by the TMA unit).
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
-    const int lh = m >> 3, lw = m & 7;
-    int local = 0;
+    const bool elected = warp == 2 && lane == 0;
+    int local = 0, sub = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -192,36 +209,47 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const int twi = m_tile % p.tiles_w; m_tile /= p.tiles_w;
       const int thi = m_tile % p.tiles_h;
       const int img = m_tile / p.tiles_h;
-      const int oy = thi * TH + lh, ox = twi * TW + lw, n0 = n_tile * BLOCK_N;
-      const bool valid = oy < p.h && ox < p.w;
-      const size_t obase = (((size_t)img * p.h + oy) * p.w + ox) * p.cout + n0;
+      const int n0 = n_tile * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + ch * 32, r);
-        tmem_ld_wait();
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + obase + ch * 32);
+      for (int c64 = 0; c64 < BLOCK_N / 64; ++c64, ++sub) {
+        uint8_t* stg = stg_smem + (sub & 1) * (128 * 128);
+        if (elected) tma_store_wait_read<1>();        // the store issued two sub-tiles ago has read this buffer
+        named_bar_sync(2, 128);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c64 * 64 + half * 32, r);
+          tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[q * 8 + j]) + bias_s[n0 + ch * 32 + q * 8 + j], 0.f);
+            for (int j = 0; j < 8; ++j)
+              v[j] = fmaxf(__uint_as_float(r[q * 8 + j]) + bias_s[n0 + c64 * 64 + half * 32 + q * 8 + j], 0.f);
             uint4 t;
             t.x = Vec<bf16>::pack2(v[0], v[1]);
             t.y = Vec<bf16>::pack2(v[2], v[3]);
             t.z = Vec<bf16>::pack2(v[4], v[5]);
             t.w = Vec<bf16>::pack2(v[6], v[7]);
-            dst[q] = t;
+            *reinterpret_cast<uint4*>(stg + m * 128 + (((half * 4 + q) ^ (m & 7)) << 4)) = t;
           }
         }
+        if (c64 == BLOCK_N / 64 - 1) {                // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (elected) {
+          tma_store_4d(&tmap_out, stg, n0 + c64 * 64, twi * TW, thi * TH, img);
+          tma_store_commit();
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (elected) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -245,7 +273,7 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
   p.a_stage_bytes = (HALO_H * plan.halo_hbw * 128 + 1023) & ~1023;
   p.bias = plan.bias; p.out = plan.out;
   const int chunks = plan.cin / BLOCK_K;
-  const int budget = 226 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*bias*/;
+  const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*bias*/ - STG_BYTES;
   int a_stages, b_stages = 0;
   if (RESIDENT) {
     const int wbytes = chunks * 9 * B_TILE;
@@ -258,14 +286,16 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
     if (b_stages > 8) b_stages = 8;
     if (b_stages < 3) return -1;
   }
-  const int smem = a_stages * p.a_stage_bytes + (RESIDENT ? chunks * 9 : b_stages) * B_TILE + 1024 + 256 + 2048;
+  const int smem = STG_BYTES + a_stages * p.a_stage_bytes + (RESIDENT ? chunks * 9 : b_stages) * B_TILE + 1024 + 256 + 2048;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     cudaFuncSetAttribute(conv3x3_tc_halo_kernel<BLOCK_N, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_smem = smem;
   }
-  const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-  conv3x3_tc_halo_kernel<BLOCK_N, RESIDENT><<<grid, NUM_THREADS, smem, st>>>(plan.tmap_a, plan.tmap_b, p, a_stages, b_stages);
+  int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+  if (RESIDENT) grid -= grid % p.num_n_tiles;
+  conv3x3_tc_halo_kernel<BLOCK_N, RESIDENT><<<grid, NUM_THREADS, smem, st>>>(plan.tmap_a, plan.tmap_b, plan.tmap_out, p, a_stages,
+                                                                             b_stages);
   return 1;
 }
 
@@ -273,7 +303,7 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
 
 // Returns launches (1) or -1 if the configuration does not fit.
 int launch_conv3x3_tc_halo(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
-  const bool resident = (size_t)9 * plan.cin * plan.block_n * 2 <= 150 * 1024 && plan.block_n == plan.cout;
+  const bool resident = (size_t)9 * plan.cin * plan.block_n * 2 <= 150 * 1024;
   if (plan.block_n == 64) return resident ? tch::launch_impl<64, true>(plan, sm_count, st) : tch::launch_impl<64, false>(plan, sm_count, st);
   if (plan.block_n == 128) return resident ? tch::launch_impl<128, true>(plan, sm_count, st) : tch::launch_impl<128, false>(plan, sm_count, st);
   return tch::launch_impl<256, false>(plan, sm_count, st);

@@ -7,7 +7,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/nerfqa_b200.h"
@@ -63,6 +66,9 @@ struct nqa_ctx {
   bf16* w_lo[kNumConvs] = {};            // residual of the bf16 rounding (bf16x3)
   float* alpha = nullptr;
   float* beta = nullptr;
+  CUtensorMap w12_map;                   // conv1_2 weights for the fused stage-1 kernel
+  bool fuse_stage1 = true;               // NQA_STAGE1_FUSED=0 falls back to conv1_1 + conv1_2 kernels
+  bool fuse_pool_stats = true;           // NQA_POOL_STATS_FUSED=0 falls back to separate pooling / statistics kernels
   Arena arena;
   uint64_t launches = 0;
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
@@ -255,8 +261,10 @@ int conv_layer<bf16>(nqa_ctx* ctx, int li, const bf16* in, const bf16* in_lo, bf
 
 // Runs normalise + VGG16 on images [x(0..nx), y(0..n-nx)], ping-ponging between two NHWC buffers sized
 // for the largest activation (64 x H x W).  After the last conv of stage k (1..5) calls
-// on_level(k, feat, feat_lo, h, w) with the stage's NHWC output enqueued; the buffer stays valid until
-// the next stage's second layer is enqueued, i.e. consumers enqueued inside on_level are safe.
+// on_level(k, feat, feat_lo, h, w, pooled_dst) with the stage's NHWC output enqueued; pooled_dst is the buffer the
+// next stage reads (nullptr after stage 5).  A consumer that already wrote the L2-pooled features there (the fused
+// pool + statistics kernel) returns true; otherwise the trunk enqueues the pooling kernel itself.  The level buffer
+// stays valid until the next stage's first conv is enqueued, i.e. consumers enqueued inside on_level are safe.
 template <typename T, typename F>
 int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H, int W, int prec, TrunkBufs<T>& bufs,
               cudaStream_t st, F&& on_level) {
@@ -265,17 +273,18 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
   int cur = 0;  // ping-pong slot holding the live activation
   int li = 0;
   for (int stage = 0; stage < 5; ++stage) {
-    if (stage > 0) {
-      const int c = kConvCout[li - 1];
-      ProfScope ps(ctx, NQA_K_L2POOL, st);
-      ctx->launches += launch_l2pool_nhwc<T>(bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, bufs.ping[cur ^ 1],
-                                             split ? bufs.ping_lo[cur ^ 1] : nullptr, n, h, w, c, st);
-      h = pooled(h);
-      w = pooled(w);
-      cur ^= 1;
-    }
     for (int j = 0; j < kStageConvs[stage]; ++j, ++li) {
-      if (li == 0) {
+      if (li == 0 && std::is_same<T, bf16>::value && !split && ctx->fuse_stage1) {
+        // normalise + conv1_1 + conv1_2 in one kernel; relu1_1 never reaches HBM
+        ProfScope ps(ctx, NQA_K_STAGE1, st);
+        const int nl = launch_stage1_fused(x, y, nx, n, h, w, ctx->w11_img, ctx->bias[0], ctx->w12_map, ctx->bias[1],
+                                           reinterpret_cast<bf16*>(bufs.ping[1]), ctx->sm_count, st);
+        if (nl <= 0) return fail(NQA_ERR_CUDA, "stage-1 kernel: cuTensorMapEncodeTiled failed (%dx%dx%d)", n, h, w);
+        ctx->launches += nl;
+        cur = 1;
+        ++li;
+        ++j;
+      } else if (li == 0) {
         conv1_1_layer<T>(ctx, x, y, nx, n, h, w, bufs.ping[0], split ? bufs.ping_lo[0] : nullptr, st);
         cur = 0;
       } else {
@@ -285,7 +294,18 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
         cur ^= 1;
       }
     }
-    on_level(stage + 1, bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, h, w);
+    T* pooled_dst = stage < 4 ? bufs.ping[cur ^ 1] : nullptr;
+    const bool pooled_done = on_level(stage + 1, bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, h, w, pooled_dst);
+    if (stage < 4) {
+      if (!pooled_done) {
+        ProfScope ps(ctx, NQA_K_L2POOL, st);
+        ctx->launches += launch_l2pool_nhwc<T>(bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, bufs.ping[cur ^ 1],
+                                               split ? bufs.ping_lo[cur ^ 1] : nullptr, n, h, w, kConvCout[li - 1], st);
+      }
+      h = pooled(h);
+      w = pooled(w);
+      cur ^= 1;
+    }
   }
   return NQA_OK;
 }
@@ -315,14 +335,16 @@ struct PartialBufs {
   double* terms;
 };
 
-size_t partial_bytes(int pairs, int H, int W, int prec, PartialBufs* pb /* may be null */, bool planar_all) {
+size_t partial_bytes(int pairs, int H, int W, int prec, PartialBufs* pb /* may be null */, bool planar_all,
+                     bool fused_pool = false) {
   int h[kNumLevels], w[kNumLevels];
   level_dims(H, W, h, w);
   size_t total = 0;
   for (int k = 0; k < kNumLevels; ++k) {
     const int c = level_channels(k);
     const int chunks = (k == 0 || planar_all) ? stats_chunks_planar(h[k] * w[k], c, pairs)
-                                              : stats_chunks_nhwc(h[k] * w[k], c, elem_bytes(prec), pairs);
+                       : (fused_pool && k < kNumLevels - 1) ? pool_stats_chunks(h[k], w[k], c, elem_bytes(prec))
+                                                            : stats_chunks_nhwc(h[k] * w[k], c, elem_bytes(prec), pairs);
     if (pb) pb->chunks[k] = chunks;
     total += align256((size_t)pairs * chunks * 5 * c * sizeof(float));
   }
@@ -352,9 +374,12 @@ int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float
   return NQA_OK;
 }
 
+// levels 1..4 of the non-split trunks: L2pooling and the level's statistics in one pass (pool_stats_kernel)
+bool use_fused_pool(const nqa_ctx* ctx, int prec) { return ctx->fuse_pool_stats && prec != NQA_PREC_BF16X3; }
+
 template <typename T>
-size_t dists_mb_bytes(int pairs, int H, int W, int prec) {
-  return trunk_bytes<T>(2 * pairs, H, W, prec) + partial_bytes(pairs, H, W, prec, nullptr, false);
+size_t dists_mb_bytes(const nqa_ctx* ctx, int pairs, int H, int W, int prec) {
+  return trunk_bytes<T>(2 * pairs, H, W, prec) + partial_bytes(pairs, H, W, prec, nullptr, false, use_fused_pool(ctx, prec));
 }
 
 template <typename T>
@@ -363,8 +388,9 @@ int dists_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, i
   ctx->arena.reset();
   TrunkBufs<T> bufs;
   trunk_alloc<T>(ctx, &bufs, 2 * pairs, H, W, prec);
+  const bool fused_pool = use_fused_pool(ctx, prec);
   PartialBufs pb;
-  partial_bytes(pairs, H, W, prec, &pb, false);
+  partial_bytes(pairs, H, W, prec, &pb, false, fused_pool);
   partial_alloc(ctx, pairs, &pb);
 
   // level 0: the RAW frames (DISTS_pt.py:103 returns x itself, not the normalised tensor)
@@ -373,11 +399,20 @@ int dists_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, i
     ctx->launches += launch_stats_planar(x, y, pairs, 3, H * W, pb.chunks[0], pb.p[0], st);
   }
   const int rc = run_trunk<T>(ctx, x, y, pairs, 2 * pairs, H, W, prec, bufs, st,
-                              [&](int k, const T* f, const T* f_lo, int h, int w) {
-                                const size_t half = (size_t)pairs * h * w * level_channels(k);
+                              [&](int k, const T* f, const T* f_lo, int h, int w, T* pooled_dst) {
+                                const int c = level_channels(k);
+                                const size_t half = (size_t)pairs * h * w * c;
+                                if (fused_pool && pooled_dst) {
+                                  const size_t half_out = (size_t)pairs * pooled(h) * pooled(w) * c;
+                                  ProfScope ps(ctx, NQA_K_POOL_STATS, st);
+                                  ctx->launches += launch_pool_stats<T>(f, f + half, pooled_dst, pooled_dst + half_out, pairs,
+                                                                        h, w, c, pb.chunks[k], pb.p[k], st);
+                                  return true;
+                                }
                                 ProfScope ps(ctx, NQA_K_STATS, st);
                                 ctx->launches += launch_stats_nhwc<T>(f, f + half, f_lo, f_lo ? f_lo + half : nullptr, pairs,
-                                                                     h * w, level_channels(k), pb.chunks[k], pb.p[k], st);
+                                                                     h * w, c, pb.chunks[k], pb.p[k], st);
+                                return false;
                               });
   if (rc != NQA_OK) return rc;
   return finalize(ctx, pb, pairs, H, W, score, s1s2, st);
@@ -386,7 +421,7 @@ int dists_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, i
 int dists_forward_device(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int prec, float* score,
                          float* s1s2, cudaStream_t st) {
   const int mb = pick_micro_pairs(B, H, W);
-  const size_t need = prec == NQA_PREC_FP32 ? dists_mb_bytes<float>(mb, H, W, prec) : dists_mb_bytes<bf16>(mb, H, W, prec);
+  const size_t need = prec == NQA_PREC_FP32 ? dists_mb_bytes<float>(ctx, mb, H, W, prec) : dists_mb_bytes<bf16>(ctx, mb, H, W, prec);
   int rc = ensure_arena(ctx, need);
   if (rc != NQA_OK) return rc;
   const size_t frame = (size_t)3 * H * W;
@@ -445,6 +480,8 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   conv_tc_set_sm_count(ctx->sm_count);
+  if (const char* e = getenv("NQA_STAGE1_FUSED")) ctx->fuse_stage1 = atoi(e) != 0;
+  if (const char* e = getenv("NQA_POOL_STATS_FUSED")) ctx->fuse_pool_stats = atoi(e) != 0;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
@@ -527,6 +564,8 @@ int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const
     }
   }
   cudaFree(tmp);
+  if (conv_tc_make_weight_map(&ctx->w12_map, ctx->w_hi[1], 64, 9 * 64, 64) != 0)
+    return fail(NQA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the conv1_2 weights");
   ctx->have_weights = true;
   return NQA_OK;
 }
@@ -577,8 +616,8 @@ int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_hos
       }
     ctx->stage_cap = slot_floats;
   }
-  const size_t need = precision == NQA_PREC_FP32 ? dists_mb_bytes<float>(mb, H, W, precision)
-                                                 : dists_mb_bytes<bf16>(mb, H, W, precision);
+  const size_t need = precision == NQA_PREC_FP32 ? dists_mb_bytes<float>(ctx, mb, H, W, precision)
+                                                 : dists_mb_bytes<bf16>(ctx, mb, H, W, precision);
   if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
   float* d_scores = ctx->stage_in[0] + 2 * (size_t)mb * frame;
 
@@ -621,9 +660,10 @@ static int features_impl(nqa_ctx* ctx, const float* x, int B, int H, int W, int 
     TrunkBufs<T> bufs;
     trunk_alloc<T>(ctx, &bufs, n, H, W, prec);
     rc = run_trunk<T>(ctx, x + b0 * frame, x, n, n, H, W, prec, bufs, st,
-                      [&](int k, const T* f, const T* f_lo, int h, int w) {
+                      [&](int k, const T* f, const T* f_lo, int h, int w, T*) {
                         float* dst = feats_out[k - 1] + (size_t)b0 * level_channels(k) * h * w;
                         level_to_nchw<T>(ctx, f, f_lo, dst, n, level_channels(k), h, w, st);
+                        return false;
                       });
     if (rc != NQA_OK) return rc;
   }
@@ -716,8 +756,9 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     const float* xb = x + b0 * frame;
     const float* yb = y + b0 * frame;
     rc = run_trunk<T>(ctx, xb, yb, pairs, 2 * pairs, H, W, prec, bufs, st,
-                      [&](int k, const T* f, const T* f_lo, int h, int w) {
+                      [&](int k, const T* f, const T* f_lo, int h, int w, T*) {
                         level_to_nchw<T>(ctx, f, f_lo, planar[k], 2 * pairs, level_channels(k), h, w, st);
+                        return false;
                       });
     if (rc != NQA_OK) return rc;
     const float* fx[kNumLevels];

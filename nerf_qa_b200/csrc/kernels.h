@@ -45,6 +45,12 @@ int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const flo
 // ---- pooling / layout -----------------------------------------------------------------------------
 template <typename T>
 int launch_l2pool_nhwc(const T* in, const T* in_lo, T* out, T* out_lo, int n, int h, int w, int c, cudaStream_t st);
+// L2pooling of x and y features fused with the level's DISTS moment sums (one read of the level).
+// chunks = pool_stats_chunks(h, w, c, sizeof(T)) partial-sum slots per pair.
+int pool_stats_chunks(int h, int w, int c, int elem_bytes);
+template <typename T>
+int launch_pool_stats(const T* fx, const T* fy, T* px_out, T* py_out, int pairs, int h, int w, int c, int chunks,
+                      float* partials, cudaStream_t st);
 int launch_l2pool_nchw(const float* in, float* out, int n, int c, int h, int w, cudaStream_t st);
 template <typename T>
 int launch_nhwc_to_nchw(const T* in, float* out, int n, int c, int h, int w, cudaStream_t st);
@@ -73,6 +79,7 @@ int launch_conv3x3_f32(const float* in, float* out, const float* wpack, const fl
 // split = bf16x3 mode (hi/lo pairs for activations and weights, three MMAs per k-step).
 struct ConvTcPlan {
   CUtensorMap tmap_a, tmap_a_lo, tmap_b, tmap_b_lo;
+  CUtensorMap tmap_out;   // halo kernel: output [n,h,w,cout] with box {64, 8, 16, 1} for the TMA-store epilogue
   int n, h, w, cin, cout;
   int tw_log2;
   int tiles_w, tiles_h;
@@ -92,6 +99,16 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
 int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st);
 int launch_conv3x3_tc_halo(const ConvTcPlan& plan, int sm_count, cudaStream_t st);
 void conv_tc_set_sm_count(int sms);
+// 4-D SWIZZLE_128B tensor map over NHWC bf16 activations with box {64 channels, box_w, box_h, 1}; 0 on success.
+int conv_tc_make_act_map(CUtensorMap* map, const bf16* ptr, int n, int h, int w, int c, int box_w, int box_h);
+// 2-D SWIZZLE_128B tensor map over K-major weights [cout][k] bf16 with box {64, block_n}; 0 on success.
+int conv_tc_make_weight_map(CUtensorMap* map, const bf16* wk, int cout, int k, int block_n);
+
+// Fused VGG stage 1 (bf16 trunk): normalise + conv1_1 + ReLU + conv1_2 + ReLU, relu1_1 stays on chip
+// (stage1_fused.cu).  w1img from launch_pack_w11_tc, w2map from conv_tc_make_weight_map(.., 64, 576, 64).
+int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, int w, const bf16* w1img,
+                        const float* bias1, const CUtensorMap& w2map, const float* bias2, bf16* out, int sm_count,
+                        cudaStream_t st);
 
 // ---- A-DISTS --------------------------------------------------------------------------------------
 // See adists.cu.

@@ -325,6 +325,164 @@ int launch_l2pool_nhwc(const T* in, const T* in_lo, T* out, T* out_lo, int n, in
 template int launch_l2pool_nhwc<float>(const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
 template int launch_l2pool_nhwc<bf16>(const bf16*, const bf16*, bf16*, bf16*, int, int, int, int, cudaStream_t);
 
+// ================================================================================================
+// Fused L2pooling + DISTS statistics of one pyramid level (levels 1..4 of the scoring path): the level's
+// features of x and y are read ONCE; the kernel emits the pooled input of the next stage for both images
+// and the five moment sums per channel.  grid = (col blocks, row strips, pairs), 256 threads =
+// (pooled column lane, 16-byte channel vector).  A thread walks down R pooled rows of its pooled column:
+// per input row it loads the three columns 2ox-1..2ox+1 of x and y, forms the horizontal [1 2 1] sum of
+// squares, and combines rows with a rolling vertical [1 2 1] (the odd row is shared by two pooled rows).
+// Statistics are accumulated on the 2x2 pixels a pooled pixel owns ((2oy, 2oy+1) x (2ox, 2ox+1)), so every
+// input pixel is counted exactly once; <= 4R sequential fp32 adds per accumulator.
+// ================================================================================================
+// 4 channels per thread (8-byte bf16 / 16-byte fp32 vectors): keeps the kernel at ~64 registers so that four
+// blocks are resident per SM and enough loads are in flight to cover HBM latency.
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  __device__ static inline void load(const float* p, float (&v)[4]) { Vec<float>::load(p, v); }
+  __device__ static inline void store(float* p, const float (&v)[4]) { Vec<float>::store(p, v); }
+};
+template <> struct Vec4<bf16> {
+  __device__ static inline void load(const bf16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+  __device__ static inline void store(bf16* p, const float (&v)[4]) {
+    uint2 t;
+    t.x = Vec<bf16>::pack2(v[0], v[1]);
+    t.y = Vec<bf16>::pack2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+pool_stats_kernel(const T* __restrict__ fx, const T* __restrict__ fy, T* __restrict__ px_out, T* __restrict__ py_out,
+                  int h, int w, int c, int ho, int wo, int R, int chunks, float* __restrict__ partials) {
+  constexpr int V = 4;
+  const int G = c / V, PL = 256 / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int b = blockIdx.z;
+  const int ox = blockIdx.x * PL + pl;
+  const int oy0 = blockIdx.y * R, oy1 = min(ho, oy0 + R);
+  const bool active = ox < wo;
+
+  float s[5][V];
+#pragma unroll
+  for (int q = 0; q < 5; ++q)
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[q][i] = 0.f;
+
+  if (active) {
+    const size_t ioff = (size_t)b * h * w * c + (size_t)g * V;
+    const size_t ooff = (size_t)b * ho * wo * c + (size_t)g * V;
+    const T* bx = fx + ioff;
+    const T* by = fy + ioff;
+    const bool c0 = 2 * ox - 1 >= 0, c2 = 2 * ox + 1 < w;   // column 2ox always exists
+
+    // horizontal [1 2 1] of squares of input row iy for both images (+ statistics on the owned columns)
+    auto row = [&](int iy, bool own, float (&hx)[V], float (&hy)[V]) {
+      if (iy < 0 || iy >= h) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) hx[i] = hy[i] = 0.f;
+        return;
+      }
+      const T* rx = bx + ((size_t)iy * w + 2 * ox) * c;   // column 2ox
+      const T* ry = by + ((size_t)iy * w + 2 * ox) * c;
+      float x0[V], x1[V], x2[V], y0[V], y1[V], y2[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) x0[i] = y0[i] = x2[i] = y2[i] = 0.f;
+      Vec4<T>::load(rx, x1);
+      Vec4<T>::load(ry, y1);
+      if (c0) { Vec4<T>::load(rx - c, x0); Vec4<T>::load(ry - c, y0); }
+      if (c2) { Vec4<T>::load(rx + c, x2); Vec4<T>::load(ry + c, y2); }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xx1 = x1[i] * x1[i], yy1 = y1[i] * y1[i];
+        const float xx2 = x2[i] * x2[i], yy2 = y2[i] * y2[i];
+        hx[i] = fmaf(x0[i], x0[i], fmaf(2.f, xx1, xx2));
+        hy[i] = fmaf(y0[i], y0[i], fmaf(2.f, yy1, yy2));
+        if (own) {
+          s[0][i] += x1[i] + x2[i];
+          s[1][i] += y1[i] + y2[i];
+          s[2][i] += xx1 + xx2;
+          s[3][i] += yy1 + yy2;
+          s[4][i] += fmaf(x1[i], y1[i], x2[i] * y2[i]);
+        }
+      }
+    };
+
+    float px[V], py[V];   // horizontal sums of the odd row above (2oy - 1)
+    row(2 * oy0 - 1, false, px, py);
+#pragma unroll 1
+    for (int oy = oy0; oy < oy1; ++oy) {
+      float ax[V], ay[V], bx2[V], by2[V];
+      row(2 * oy, true, ax, ay);
+      row(2 * oy + 1, true, bx2, by2);
+      float ovx[V], ovy[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        ovx[i] = sqrtf((px[i] + 2.f * ax[i] + bx2[i]) * (1.f / 16.f) + 1e-12f);
+        ovy[i] = sqrtf((py[i] + 2.f * ay[i] + by2[i]) * (1.f / 16.f) + 1e-12f);
+        px[i] = bx2[i];
+        py[i] = by2[i];
+      }
+      const size_t o = ooff + ((size_t)oy * wo + ox) * c;
+      Vec4<T>::store(px_out + o, ovx);
+      Vec4<T>::store(py_out + o, ovy);
+    }
+  }
+
+  __shared__ float red[256 * V];
+  const int chunk = blockIdx.y * gridDim.x + blockIdx.x;
+  float* outp = partials + ((size_t)b * chunks + chunk) * 5 * c;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = s[q][i];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += 256) {
+      const int gg = ch / V, ii = ch % V;
+      float acc = 0.f;
+      for (int t = 0; t < PL; ++t) acc += red[(t * G + gg) * V + ii];
+      outp[q * c + ch] = acc;
+    }
+  }
+}
+
+// Partition of one level for pool_stats_kernel; depends on the level shape only (batch independence).
+void pool_stats_plan(int h, int w, int c, int elem_bytes, int* rows_per_block, int* col_blocks, int* strips) {
+  (void)elem_bytes;
+  const int groups = c / 4, pl = 256 / groups;   // 4 channels per thread
+  const int ho = pooled(h), wo = pooled(w);
+  const int cb = ceil_div(wo, pl);
+  int r = 16;
+  while (r > 2 && cb * ceil_div(ho, r) < 256) r >>= 1;
+  *rows_per_block = r;
+  *col_blocks = cb;
+  *strips = ceil_div(ho, r);
+}
+
+int pool_stats_chunks(int h, int w, int c, int elem_bytes) {
+  int r, cb, st;
+  pool_stats_plan(h, w, c, elem_bytes, &r, &cb, &st);
+  return cb * st;
+}
+
+template <typename T>
+int launch_pool_stats(const T* fx, const T* fy, T* px_out, T* py_out, int pairs, int h, int w, int c, int chunks,
+                      float* partials, cudaStream_t st) {
+  int r, cb, strips;
+  pool_stats_plan(h, w, c, (int)sizeof(T), &r, &cb, &strips);
+  dim3 grid(cb, strips, pairs);
+  pool_stats_kernel<T><<<grid, 256, 0, st>>>(fx, fy, px_out, py_out, h, w, c, pooled(h), pooled(w), r, chunks, partials);
+  return 1;
+}
+template int launch_pool_stats<float>(const float*, const float*, float*, float*, int, int, int, int, int, float*, cudaStream_t);
+template int launch_pool_stats<bf16>(const bf16*, const bf16*, bf16*, bf16*, int, int, int, int, int, float*, cudaStream_t);
+
 // Standalone NCHW fp32 L2pooling (the nn.Module surface): thread = one output element.
 __global__ void __launch_bounds__(256)
 l2pool_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int h, int w, int ho, int wo) {

@@ -42,6 +42,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp (elect.sync).  The tcgen05 / TMA issue loops are executed by the WHOLE warp with
+// warp-uniform operands and only the instruction itself is predicated on the elected lane: inside an
+// `if (lane == 0)` region the compiler cannot prove uniformity and wraps every UTCHMMA / UBLKCP in an
+// R2UR + ELECT + BRA.U.ANY serialisation loop (~100 cycles of issue latency per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -55,6 +71,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA store of a 4-D box from shared memory (bulk async group); out-of-bounds parts of the box are clipped.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -73,6 +108,34 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups (SBO) and a start address that
+// need not be 1024-byte aligned (halo-reuse kernels: the tap shift moves the start by whole 128-byte rows;
+// the swizzle is a function of the absolute shared-memory address, so TMA/generic writes and UMMA reads agree).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr, uint32_t sbo_bytes, int desc_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (desc_mode & 1) d |= (uint64_t)((addr >> 7) & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Canonical K-major layout without swizzle: 8x8 core matrices (8 rows x 16 bytes) stored as 128 contiguous
+// bytes; K-adjacent core matrices 128 B apart (LBO), 8-row groups 512 B apart (SBO) for a 32-element K extent.
+__host__ __device__ inline int noswz_offset_bytes(int row, int kchunk /* 8 elements */) {
+  return (row >> 3) * 512 + kchunk * 128 + (row & 7) * 16;
+}
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;   // LBO
+  d |= (uint64_t)(512 >> 4) << 32;   // SBO
+  d |= (uint64_t)1 << 46;            // descriptor version
+  return d;                          // layout_type 0 = no swizzle
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=bf16 (bits 7, 10), both

@@ -29,6 +29,7 @@ CONV_SHAPES = [
     (1, 64, 64, 16, 8),      # exactly one 128-pixel tile, BLOCK_N = 64
     (2, 64, 128, 37, 53),    # ragged edges, BLOCK_N = 128
     (1, 128, 256, 24, 40),   # BLOCK_N = 256, two k chunks
+    (2, 128, 128, 40, 21),   # two 64-channel tiles with resident weights (halo kernel, conv2_2 shape class)
     (2, 256, 512, 17, 30),   # two channel tiles per pixel tile
     (1, 512, 512, 9, 15),    # deep layer, 72 k-blocks, image smaller than a tile
     (3, 64, 64, 135, 240),   # many tiles per CTA (persistent loop, TMEM double buffering)

@@ -178,3 +178,48 @@ def test_dists_1080p_against_oracle(models, vgg_weights, alpha_beta):
             assert rel_err(got, want) < 1e-4
         else:
             assert np.max(np.abs(got - want)) < 2e-3
+
+
+def _fresh_bf16(env):
+    """A bf16 DISTS module whose library context was created under the given environment switches."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        m = make_dists("bf16")
+        m._context(torch.device("cuda:0"))           # the switches are read when the context is created
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return m
+
+
+@pytest.mark.parametrize("shape", [(2, 45, 77), (1, 135, 240), (1, 16, 8), (2, 64, 64)])
+def test_fused_stage1_is_bit_identical_to_two_kernels(shape):
+    """The fused normalise+conv1_1+conv1_2 kernel rounds relu1_1 to bf16 in shared memory exactly like the
+    two-kernel path rounds it on its way to HBM, and accumulates in the same order: features must be equal."""
+    b, h, w = shape
+    x, _ = synth.make_frame_pairs(b, h, w, seed=7)
+    fused = _fresh_bf16({"NQA_STAGE1_FUSED": "1"}).forward_once(x.cuda())
+    plain = _fresh_bf16({"NQA_STAGE1_FUSED": "0"}).forward_once(x.cuda())
+    for k in range(1, 6):
+        assert torch.equal(fused[k], plain[k]), f"level {k}"
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_fused_pool_stats_matches_separate_kernels(prec):
+    import os
+    x, y = synth.make_frame_pairs(3, 135, 240, seed=9)
+    outs = []
+    for flag in ("1", "0"):
+        os.environ["NQA_POOL_STATS_FUSED"] = flag
+        try:
+            m = make_dists(prec)
+            outs.append(m(x.cuda(), y.cuda()).cpu().numpy())
+        finally:
+            os.environ.pop("NQA_POOL_STATS_FUSED", None)
+    report(f"fused pool+stats vs separate ({prec})", outs[0], outs[1])
+    assert rel_err(outs[0], outs[1]) < (2e-3 if prec == "bf16" else 2e-5)
