@@ -368,6 +368,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
   plan->block_n = cout >= 256 ? (split ? 128 : 256) : cout >= 128 ? 128 : 64;
   // thin layers: halo-reuse kernel (A tile fetched once instead of nine times)
   plan->halo = false;
+  plan->pair = false;
   plan->halo_hbw = 10;
   plan->halo_desc_mode = 0;
   const int halo_mode = tc::halo_mode();
@@ -383,13 +384,19 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
     // 128-channel tile whose weights stream from L2 for every pixel tile (NQA_CONV_N64=0 restores the latter)
     static const bool n64 = getenv("NQA_CONV_N64") ? atoi(getenv("NQA_CONV_N64")) != 0 : true;
     if (n64 && cin == 128 && cout == 128) plan->block_n = 64;
+    // CTA pairs (tcgen05 cta_group::2): 256 pixels x block_n channels per instruction, each CTA holds half the weights
+    static const bool pair = getenv("NQA_CONV_PAIR") ? atoi(getenv("NQA_CONV_PAIR")) != 0 : true;
+    if (pair && cout >= 128 && (tc::g_sm_count & 1) == 0) {
+      plan->pair = true;
+      plan->block_n = cout >= 256 ? 256 : 128;
+    }
   }
   plan->tiles_w = ceil_div(w, tw);
   plan->tiles_h = ceil_div(h, th);
   if (!tc::get_encode_fn()) { *err = "conv_tc: cuTensorMapEncodeTiled entry point not available"; return 1; }
   bool ok = (plan->halo ? tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, plan->halo_hbw, th + 2)
                         : tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, tw, th)) &&
-            tc::encode_w_map(&plan->tmap_b, wk, cout, 9 * cin, plan->block_n);
+            tc::encode_w_map(&plan->tmap_b, wk, cout, 9 * cin, plan->pair ? plan->block_n / 2 : plan->block_n);
   if (plan->halo) ok = ok && tc::encode_act_map(&plan->tmap_out, out, n, h, w, cout, tw, th);
   if (split)
     ok = ok && tc::encode_act_map(&plan->tmap_a_lo, in_lo, n, h, w, cin, tw, th) &&
@@ -403,6 +410,12 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
 }
 
 int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st) {
+  if (plan.pair) {
+    const int rc = launch_conv3x3_tc_pair(plan, tc::g_sm_count, st);
+    if (rc > 0) return rc;
+    fprintf(stderr, "nerfqa_b200: CTA-pair conv configuration does not fit (cin %d cout %d)\n", plan.cin, plan.cout);
+    return 0;
+  }
   if (plan.halo) {
     const int rc = launch_conv3x3_tc_halo(plan, tc::g_sm_count, st);
     if (rc > 0) return rc;

@@ -85,6 +85,7 @@ struct ConvTcPlan {
   int tiles_w, tiles_h;
   int block_n;
   bool split;
+  bool pair;           // CTA-pair kernel (conv_tc_pair.cu): halo reuse + tcgen05 cta_group::2, weights box = block_n/2 rows
   bool halo;           // halo-reuse kernel (conv_tc_halo.cu): tile 16x8, A halo loaded once per 64-channel chunk
   int halo_hbw;        // halo box width in pixels
   int halo_desc_mode;  // how the UMMA descriptor's base-offset field is filled
@@ -98,6 +99,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
                       const char** err);
 int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st);
 int launch_conv3x3_tc_halo(const ConvTcPlan& plan, int sm_count, cudaStream_t st);
+int launch_conv3x3_tc_pair(const ConvTcPlan& plan, int sm_count, cudaStream_t st);
 void conv_tc_set_sm_count(int sms);
 // 4-D SWIZZLE_128B tensor map over NHWC bf16 activations with box {64 channels, box_w, box_h, 1}; 0 on success.
 int conv_tc_make_act_map(CUtensorMap* map, const bf16* ptr, int n, int h, int w, int c, int box_w, int box_h);

@@ -180,17 +180,18 @@ int launch_stats_planar(const float* x, const float* y, int pairs, int c, int hw
 
 // ================================================================================================
 // Finalize: moments -> S1,S2 -> alpha/beta-weighted sum -> score (DISTS_pt.py:127-148).
-// Stage 1, grid = (ceil(1475/64), pairs), 256 threads = 64 channels x 4 chunk lanes: chunk partials are
-// combined in fp64 in a fixed order (lane q takes chunks q, q+4, ...; lanes combined 0..3), so the
-// result is deterministic and batch-independent.  Stage 2, grid = pairs: ordered sum of the 1475
+// Stage 1, grid = (ceil(1475/64), pairs), 1024 threads = 64 channels x 16 chunk lanes: chunk partials are
+// combined in fp64 in a fixed order (lane q takes chunks q, q+16, ...; lanes combined 0..15 in sequence), so
+// the result is deterministic and batch-independent.  Stage 2, grid = pairs: ordered sum of the 1475
 // per-channel terms.
 // ================================================================================================
 constexpr int kFinCh = 64;
+constexpr int kFinLanes = 16;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinCh * kFinLanes)
 dists_terms_kernel(FinalizeParams p, const float* __restrict__ alpha, const float* __restrict__ beta,
                    double* __restrict__ terms, float* __restrict__ s1s2, float* __restrict__ moments) {
-  __shared__ double sm[4][kFinCh][5];
+  __shared__ double sm[kFinLanes][kFinCh][5];
   const int b = blockIdx.y;
   const int cl = threadIdx.x % kFinCh, q = threadIdx.x / kFinCh;
   const int c = blockIdx.x * kFinCh + cl;
@@ -201,7 +202,7 @@ dists_terms_kernel(FinalizeParams p, const float* __restrict__ alpha, const floa
     lv = p.lv[k];
     const int cc = c - lv.choff;
     const float* base = lv.partials + (size_t)b * lv.chunks * 5 * lv.C + cc;
-    for (int ch = q; ch < lv.chunks; ch += 4) {
+    for (int ch = q; ch < lv.chunks; ch += kFinLanes) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) s[i] += (double)base[((size_t)ch * 5 + i) * lv.C];
     }
@@ -211,7 +212,12 @@ dists_terms_kernel(FinalizeParams p, const float* __restrict__ alpha, const floa
   __syncthreads();
   if (q == 0 && c < kTotalChannels) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) s[i] = ((sm[0][cl][i] + sm[1][cl][i]) + sm[2][cl][i]) + sm[3][cl][i];
+    for (int i = 0; i < 5; ++i) {
+      double t = sm[0][cl][i];
+#pragma unroll
+      for (int l = 1; l < kFinLanes; ++l) t += sm[l][cl][i];
+      s[i] = t;
+    }
     const double mx = s[0] * lv.inv_n, my = s[1] * lv.inv_n;
     const double vx = s[2] * lv.inv_n - mx * mx, vy = s[3] * lv.inv_n - my * my;
     const double cov = s[4] * lv.inv_n - mx * my;
@@ -248,7 +254,7 @@ dists_score_kernel(const double* __restrict__ terms, const float* __restrict__ a
 int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const float* beta, int pairs, float* score,
                           float* s1s2, float* moments, double* terms, cudaStream_t st) {
   dim3 grid(ceil_div(kTotalChannels, kFinCh), pairs);
-  dists_terms_kernel<<<grid, 256, 0, st>>>(p, alpha, beta, terms, s1s2, moments);
+  dists_terms_kernel<<<grid, kFinCh * kFinLanes, 0, st>>>(p, alpha, beta, terms, s1s2, moments);
   dists_score_kernel<<<pairs, 256, 0, st>>>(terms, alpha, beta, score);
   return 2;
 }
@@ -335,24 +341,37 @@ template int launch_l2pool_nhwc<bf16>(const bf16*, const bf16*, bf16*, bf16*, in
 // Statistics are accumulated on the 2x2 pixels a pooled pixel owns ((2oy, 2oy+1) x (2ox, 2ox+1)), so every
 // input pixel is counted exactly once; <= 4R sequential fp32 adds per accumulator.
 // ================================================================================================
-// 4 channels per thread (8-byte bf16 / 16-byte fp32 vectors): keeps the kernel at ~64 registers so that four
-// blocks are resident per SM and enough loads are in flight to cover HBM latency.
+// 4 channels per thread (8-byte bf16 / 16-byte fp32 vectors) keep the kernel at ~80 registers (three resident
+// blocks per SM).  The kernel is as much issue-bound as HBM-bound (~25 instructions per x/y element pair), so the
+// fp32 math uses the sm_100 packed f32x2 instructions (two channels per FFMA2/FADD2/FMUL2).
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
-  __device__ static inline void load(const float* p, float (&v)[4]) { Vec<float>::load(p, v); }
-  __device__ static inline void store(float* p, const float (&v)[4]) { Vec<float>::store(p, v); }
+  __device__ static inline void load(const float* p, float2 (&v)[2]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = make_float2(t.x, t.y); v[1] = make_float2(t.z, t.w);
+  }
+  __device__ static inline void store(float* p, const float2 (&v)[2]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+  }
+  __device__ static inline float root(float v) { return sqrtf(v); }
 };
 template <> struct Vec4<bf16> {
-  __device__ static inline void load(const bf16* p, float (&v)[4]) {
+  __device__ static inline void load(const bf16* p, float2 (&v)[2]) {
     const uint2 t = *reinterpret_cast<const uint2*>(p);
-    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
-    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    v[0] = make_float2(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u));
+    v[1] = make_float2(__uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u));
   }
-  __device__ static inline void store(bf16* p, const float (&v)[4]) {
+  __device__ static inline void store(bf16* p, const float2 (&v)[2]) {
     uint2 t;
-    t.x = Vec<bf16>::pack2(v[0], v[1]);
-    t.y = Vec<bf16>::pack2(v[2], v[3]);
+    t.x = Vec<bf16>::pack2(v[0].x, v[0].y);
+    t.y = Vec<bf16>::pack2(v[1].x, v[1].y);
     *reinterpret_cast<uint2*>(p) = t;
+  }
+  // the result is rounded to bf16 (8 bits of mantissa): the 1-ulp-fp32 MUFU square root is exact enough
+  __device__ static inline float root(float v) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
   }
 };
 
@@ -367,12 +386,11 @@ pool_stats_kernel(const T* __restrict__ fx, const T* __restrict__ fy, T* __restr
   const int ox = blockIdx.x * PL + pl;
   const int oy0 = blockIdx.y * R, oy1 = min(ho, oy0 + R);
   const bool active = ox < wo;
+  const float2 zero2 = make_float2(0.f, 0.f), two2 = make_float2(2.f, 2.f);
 
-  float s[5][V];
+  float2 s[5][2];
 #pragma unroll
-  for (int q = 0; q < 5; ++q)
-#pragma unroll
-    for (int i = 0; i < V; ++i) s[q][i] = 0.f;
+  for (int q = 0; q < 5; ++q) s[q][0] = s[q][1] = zero2;
 
   if (active) {
     const size_t ioff = (size_t)b * h * w * c + (size_t)g * V;
@@ -382,55 +400,65 @@ pool_stats_kernel(const T* __restrict__ fx, const T* __restrict__ fy, T* __restr
     const bool c0 = 2 * ox - 1 >= 0, c2 = 2 * ox + 1 < w;   // column 2ox always exists
 
     // horizontal [1 2 1] of squares of input row iy for both images (+ statistics on the owned columns)
-    auto row = [&](int iy, bool own, float (&hx)[V], float (&hy)[V]) {
-      if (iy < 0 || iy >= h) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) hx[i] = hy[i] = 0.f;
+    // rx / ry point at column 2ox of the input row; rows outside the image contribute zeros
+    auto row = [&](const T* rx, const T* ry, bool in_image, bool own, float2 (&hx)[2], float2 (&hy)[2]) {
+      if (!in_image) {
+        hx[0] = hx[1] = hy[0] = hy[1] = zero2;
         return;
       }
-      const T* rx = bx + ((size_t)iy * w + 2 * ox) * c;   // column 2ox
-      const T* ry = by + ((size_t)iy * w + 2 * ox) * c;
-      float x0[V], x1[V], x2[V], y0[V], y1[V], y2[V];
-#pragma unroll
-      for (int i = 0; i < V; ++i) x0[i] = y0[i] = x2[i] = y2[i] = 0.f;
+      float2 x0[2] = {zero2, zero2}, x1[2], x2[2] = {zero2, zero2};
+      float2 y0[2] = {zero2, zero2}, y1[2], y2[2] = {zero2, zero2};
       Vec4<T>::load(rx, x1);
       Vec4<T>::load(ry, y1);
       if (c0) { Vec4<T>::load(rx - c, x0); Vec4<T>::load(ry - c, y0); }
       if (c2) { Vec4<T>::load(rx + c, x2); Vec4<T>::load(ry + c, y2); }
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float xx1 = x1[i] * x1[i], yy1 = y1[i] * y1[i];
-        const float xx2 = x2[i] * x2[i], yy2 = y2[i] * y2[i];
-        hx[i] = fmaf(x0[i], x0[i], fmaf(2.f, xx1, xx2));
-        hy[i] = fmaf(y0[i], y0[i], fmaf(2.f, yy1, yy2));
+      for (int i = 0; i < 2; ++i) {
+        const float2 xx1 = __fmul2_rn(x1[i], x1[i]), yy1 = __fmul2_rn(y1[i], y1[i]);
+        const float2 xx2 = __fmul2_rn(x2[i], x2[i]), yy2 = __fmul2_rn(y2[i], y2[i]);
+        hx[i] = __ffma2_rn(x0[i], x0[i], __ffma2_rn(two2, xx1, xx2));
+        hy[i] = __ffma2_rn(y0[i], y0[i], __ffma2_rn(two2, yy1, yy2));
         if (own) {
-          s[0][i] += x1[i] + x2[i];
-          s[1][i] += y1[i] + y2[i];
-          s[2][i] += xx1 + xx2;
-          s[3][i] += yy1 + yy2;
-          s[4][i] += fmaf(x1[i], y1[i], x2[i] * y2[i]);
+          s[0][i] = __fadd2_rn(s[0][i], __fadd2_rn(x1[i], x2[i]));
+          s[1][i] = __fadd2_rn(s[1][i], __fadd2_rn(y1[i], y2[i]));
+          s[2][i] = __fadd2_rn(s[2][i], __fadd2_rn(xx1, xx2));
+          s[3][i] = __fadd2_rn(s[3][i], __fadd2_rn(yy1, yy2));
+          s[4][i] = __fadd2_rn(s[4][i], __ffma2_rn(x1[i], y1[i], __fmul2_rn(x2[i], y2[i])));
         }
       }
     };
 
-    float px[V], py[V];   // horizontal sums of the odd row above (2oy - 1)
-    row(2 * oy0 - 1, false, px, py);
+    // running row pointers (column 2ox of row 2oy - 1); one 64-bit add per input row instead of a multiply
+    const ptrdiff_t rstride = (ptrdiff_t)w * c;
+    const T* rx = bx + ((ptrdiff_t)(2 * oy0 - 1) * w + 2 * ox) * c;
+    const T* ry = by + ((ptrdiff_t)(2 * oy0 - 1) * w + 2 * ox) * c;
+    T* ox_ptr = px_out + ooff + ((size_t)oy0 * wo + ox) * c;
+    T* oy_ptr = py_out + ooff + ((size_t)oy0 * wo + ox) * c;
+    const ptrdiff_t ostride = (ptrdiff_t)wo * c;
+    float2 px[2], py[2];   // horizontal sums of the odd row above (2oy - 1)
+    row(rx, ry, oy0 > 0, false, px, py);
+    const float2 sixteenth = make_float2(1.f / 16.f, 1.f / 16.f), eps = make_float2(1e-12f, 1e-12f);
 #pragma unroll 1
     for (int oy = oy0; oy < oy1; ++oy) {
-      float ax[V], ay[V], bx2[V], by2[V];
-      row(2 * oy, true, ax, ay);
-      row(2 * oy + 1, true, bx2, by2);
-      float ovx[V], ovy[V];
+      float2 ax[2], ay[2], bx2[2], by2[2];
+      row(rx + rstride, ry + rstride, true, true, ax, ay);               // row 2oy always exists
+      rx += 2 * rstride;
+      ry += 2 * rstride;
+      row(rx, ry, 2 * oy + 1 < h, true, bx2, by2);
+      float2 ovx[2], ovy[2];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        ovx[i] = sqrtf((px[i] + 2.f * ax[i] + bx2[i]) * (1.f / 16.f) + 1e-12f);
-        ovy[i] = sqrtf((py[i] + 2.f * ay[i] + by2[i]) * (1.f / 16.f) + 1e-12f);
+      for (int i = 0; i < 2; ++i) {
+        const float2 tx = __ffma2_rn(__fadd2_rn(__ffma2_rn(two2, ax[i], px[i]), bx2[i]), sixteenth, eps);
+        const float2 ty = __ffma2_rn(__fadd2_rn(__ffma2_rn(two2, ay[i], py[i]), by2[i]), sixteenth, eps);
+        ovx[i] = make_float2(Vec4<T>::root(tx.x), Vec4<T>::root(tx.y));
+        ovy[i] = make_float2(Vec4<T>::root(ty.x), Vec4<T>::root(ty.y));
         px[i] = bx2[i];
         py[i] = by2[i];
       }
-      const size_t o = ooff + ((size_t)oy * wo + ox) * c;
-      Vec4<T>::store(px_out + o, ovx);
-      Vec4<T>::store(py_out + o, ovy);
+      Vec4<T>::store(ox_ptr, ovx);
+      Vec4<T>::store(oy_ptr, ovy);
+      ox_ptr += ostride;
+      oy_ptr += ostride;
     }
   }
 
@@ -440,8 +468,7 @@ pool_stats_kernel(const T* __restrict__ fx, const T* __restrict__ fy, T* __restr
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = s[q][i];
+    *reinterpret_cast<float4*>(&red[threadIdx.x * V]) = make_float4(s[q][0].x, s[q][0].y, s[q][1].x, s[q][1].y);
     __syncthreads();
     for (int ch = threadIdx.x; ch < c; ch += 256) {
       const int gg = ch / V, ii = ch % V;

@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+set -x
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_gpu_all6.log 2>&1; echo "all rc=$?"
+tail -5 gpurun_out/t_gpu_all6.log
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1h.json 2> gpurun_out/bench_r1h.err; echo "bench rc=$?"
+cat gpurun_out/bench_r1h.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1h.csv python bench.py --steps 1 --warmup 3 --pairs 8 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list_r1h.log 2>&1; echo "ncu rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"stage1_fused|pool_stats" -c 2 -o gpurun_out/prof_r1h python bench.py --steps 1 --warmup 3 --pairs 4 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_r1h.log 2>&1; echo "ncu full rc=$?"
