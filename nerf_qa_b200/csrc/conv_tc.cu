@@ -372,7 +372,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
   plan->halo_hbw = 10;
   plan->halo_desc_mode = 0;
   const int halo_mode = tc::halo_mode();
-  static const int halo_max_cin = getenv("NQA_CONV_HALO_MAXCIN") ? atoi(getenv("NQA_CONV_HALO_MAXCIN")) : 256;
+  static const int halo_max_cin = getenv("NQA_CONV_HALO_MAXCIN") ? atoi(getenv("NQA_CONV_HALO_MAXCIN")) : 512;
   if (halo_mode > 0 && !split && cin <= halo_max_cin) {
     plan->halo = true;
     plan->halo_desc_mode = 0;   // base-offset field 0: validated on hardware (swizzle follows absolute address bits)
@@ -386,7 +386,8 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
     if (n64 && cin == 128 && cout == 128) plan->block_n = 64;
     // CTA pairs (tcgen05 cta_group::2): 256 pixels x block_n channels per instruction, each CTA holds half the weights
     static const bool pair = getenv("NQA_CONV_PAIR") ? atoi(getenv("NQA_CONV_PAIR")) != 0 : true;
-    if (pair && cout >= 128 && (tc::g_sm_count & 1) == 0) {
+    static const int pair_min_cin = getenv("NQA_PAIR_MINCIN") ? atoi(getenv("NQA_PAIR_MINCIN")) : 128;
+    if (pair && cout >= 128 && cin >= pair_min_cin && (tc::g_sm_count & 1) == 0) {
       plan->pair = true;
       plan->block_n = cout >= 256 ? 256 : 128;
     }

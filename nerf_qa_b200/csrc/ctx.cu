@@ -68,6 +68,7 @@ struct nqa_ctx {
   float* beta = nullptr;
   CUtensorMap w12_map;                   // conv1_2 weights for the fused stage-1 kernel
   bool fuse_stage1 = true;               // NQA_STAGE1_FUSED=0 falls back to conv1_1 + conv1_2 kernels
+  int micro_images = 16;                 // full-HD-equivalent images per trunk pass (NQA_MICRO_IMAGES)
   bool fuse_pool_stats = true;           // NQA_POOL_STATS_FUSED=0 falls back to separate pooling / statistics kernels
   Arena arena;
   uint64_t launches = 0;
@@ -161,10 +162,10 @@ int check_shape(int B, int H, int W) {
 int elem_bytes(int prec) { return prec == NQA_PREC_FP32 ? 4 : 2; }
 int carriers(int prec) { return prec == NQA_PREC_BF16X3 ? 2 : 1; }
 
-// images per trunk pass: ~8 full-HD frames keep every layer's grid at several waves while the
-// ping-pong activations stay in the low GBs.
-int pick_micro_pairs(int B, int H, int W) {
-  const long long target = 8ll * 1080 * 1920;
+// images per trunk pass: ~16 full-HD frames keep every layer's persistent grid at many tiles per CTA (small tail
+// effects on the 68 x 120 level) while the ping-pong activations stay below 10 GB (NQA_MICRO_IMAGES overrides).
+int pick_micro_pairs(const nqa_ctx* ctx, int B, int H, int W) {
+  const long long target = (long long)ctx->micro_images * 1080 * 1920;
   long long pairs = target / (2ll * H * W);
   if (pairs < 1) pairs = 1;
   if (pairs > 256) pairs = 256;
@@ -420,7 +421,7 @@ int dists_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, i
 
 int dists_forward_device(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int prec, float* score,
                          float* s1s2, cudaStream_t st) {
-  const int mb = pick_micro_pairs(B, H, W);
+  const int mb = pick_micro_pairs(ctx, B, H, W);
   const size_t need = prec == NQA_PREC_FP32 ? dists_mb_bytes<float>(ctx, mb, H, W, prec) : dists_mb_bytes<bf16>(ctx, mb, H, W, prec);
   int rc = ensure_arena(ctx, need);
   if (rc != NQA_OK) return rc;
@@ -482,6 +483,7 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   conv_tc_set_sm_count(ctx->sm_count);
   if (const char* e = getenv("NQA_STAGE1_FUSED")) ctx->fuse_stage1 = atoi(e) != 0;
   if (const char* e = getenv("NQA_POOL_STATS_FUSED")) ctx->fuse_pool_stats = atoi(e) != 0;
+  if (const char* e = getenv("NQA_MICRO_IMAGES")) ctx->micro_images = atoi(e) > 0 ? atoi(e) : 16;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
@@ -599,7 +601,7 @@ int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_hos
   if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
 
-  const int mb = pick_micro_pairs(B, H, W);
+  const int mb = pick_micro_pairs(ctx, B, H, W);
   const size_t frame = (size_t)3 * H * W;
   const size_t slot_floats = 2 * (size_t)mb * frame + (size_t)B;  // x frames, y frames (+ scores in slot 0)
   if (slot_floats > ctx->stage_cap) {
@@ -649,7 +651,7 @@ int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_hos
 template <typename T>
 static int features_impl(nqa_ctx* ctx, const float* x, int B, int H, int W, int prec, float* const* feats_out,
                          cudaStream_t st) {
-  int mb = 2 * pick_micro_pairs((B + 1) / 2, H, W);
+  int mb = 2 * pick_micro_pairs(ctx, (B + 1) / 2, H, W);
   if (mb > B) mb = B;
   int rc = ensure_arena(ctx, trunk_bytes<T>(mb, H, W, prec));
   if (rc != NQA_OK) return rc;
@@ -736,7 +738,7 @@ static size_t adists_feat_bytes(int pairs, int H, int W) {
 template <typename T>
 static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int prec,
                        float* score_out, cudaStream_t st) {
-  int mb = pick_micro_pairs(B, H, W) / 2;
+  int mb = pick_micro_pairs(ctx, B, H, W) / 2;
   if (mb < 1) mb = 1;
   int rc = ensure_arena(ctx, trunk_bytes<T>(2 * mb, H, W, prec) + adists_feat_bytes(mb, H, W) +
                                  adists_workspace_bytes(mb, H, W, window));
@@ -922,7 +924,7 @@ int nqa_micro_batch(nqa_ctx* ctx, int B, int H, int W, int precision, int* pairs
   int rc = check_shape(B, H, W);
   if (rc != NQA_OK) return rc;
   (void)precision;
-  *pairs = pick_micro_pairs(B, H, W);
+  *pairs = pick_micro_pairs(ctx, B, H, W);
   return NQA_OK;
 }
 

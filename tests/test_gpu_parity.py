@@ -19,6 +19,23 @@ def _no_grad():
     with torch.no_grad():
         yield
 
+def _fresh_bf16(env):
+    """A bf16 DISTS module whose library context was created under the given environment switches."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        m = make_dists("bf16")
+        m._context(torch.device("cuda:0"))           # the switches are read when the context is created
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return m
+
+
 DISTS_CASES = ["dists_64", "dists_odd_45x77", "dists_135x240", "dists_256"]
 ADISTS_CASES = ["adists_96x128", "adists_176", "adists_256", "adists_352x368"]
 
@@ -154,14 +171,17 @@ def test_host_path_equals_device_path(models):
 
 
 def test_micro_batching_is_batch_independent(models):
-    # 1080p: the scheduler streams 4 pairs per trunk pass; scores must not depend on the batch composition
+    # 1080p with 2 pairs per trunk pass (NQA_MICRO_IMAGES=4): 5 pairs stream as 2 + 2 + 1; a frame's score must not
+    # depend on the micro-batch it travels in, nor on the micro-batch size (default context: all 5 in one pass)
     x, y = synth.make_frame_pairs(5, 1080, 1920, seed=21)
-    m = models["bf16"]
     xs, ys = x.cuda(), y.cuda()
-    full = m(xs, ys)
+    small = _fresh_bf16({"NQA_MICRO_IMAGES": "4"})
+    assert small._context(torch.device("cuda:0")).micro_batch(5, 1080, 1920, _lib.PREC_BF16) == 2
+    full = small(xs, ys)
     for i in (0, 4):
-        assert torch.equal(m(xs[i:i + 1], ys[i:i + 1]), full[i:i + 1])
-    assert float(m(xs[:2], xs[:2]).abs().max()) < 1e-6
+        assert torch.equal(small(xs[i:i + 1], ys[i:i + 1]), full[i:i + 1])
+    assert torch.equal(models["bf16"](xs, ys), full)
+    assert float(small(xs[:2], xs[:2]).abs().max()) < 1e-6
 
 
 def test_dists_1080p_against_oracle(models, vgg_weights, alpha_beta):
@@ -178,23 +198,6 @@ def test_dists_1080p_against_oracle(models, vgg_weights, alpha_beta):
             assert rel_err(got, want) < 1e-4
         else:
             assert np.max(np.abs(got - want)) < 2e-3
-
-
-def _fresh_bf16(env):
-    """A bf16 DISTS module whose library context was created under the given environment switches."""
-    import os
-    old = {k: os.environ.get(k) for k in env}
-    os.environ.update(env)
-    try:
-        m = make_dists("bf16")
-        m._context(torch.device("cuda:0"))           # the switches are read when the context is created
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-    return m
 
 
 @pytest.mark.parametrize("shape", [(2, 45, 77), (1, 135, 240), (1, 16, 8), (2, 64, 64)])
