@@ -346,8 +346,14 @@ def main():
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Every rank is done and rank 0 has printed its line.  Leave without the NCCL communicator teardown:
+        # destroy_process_group() was observed to block for minutes under torchrun on the B200 box after the line
+        # had been printed, and the driver times the whole process.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -125,6 +125,25 @@ NQA_API int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_N
                           const float* const feats_y[NQA_NUM_LEVELS], int B, int H, int W, int window,
                           float* score_out, void* stream);
 
+/* Gradient of the DISTS scores w.r.t. the frames: autograd of DISTS.forward (DISTS_pt.py:105-148).
+ * grad_score [B] (device) is d loss / d score_b; grad_x / grad_y [B,3,H,W] fp32 (device) receive d loss / d x, d y.
+ * through_trunk = 1: require_grad=True semantics, the gradient flows through the VGG trunk (13 data-gradient
+ * convolutions on the tensor pipe, L2pooling and statistics backward); through_trunk = 0: the reference's
+ * default (trunk under no_grad), where only the level-0 statistics of the RAW frames are differentiable
+ * (forward_once returns x itself, DISTS_pt.py:103).  The trunk forward is recomputed inside the call
+ * (activation recomputation), so nothing has to be kept between nqa_dists_forward and this call.
+ * precision: NQA_PREC_FP32 or NQA_PREC_BF16.  The alpha/beta gradients follow from the per-channel S1/S2
+ * that nqa_dists_forward already returns. */
+NQA_API int nqa_dists_backward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int precision,
+                               const float* grad_score, int through_trunk, float* grad_x, float* grad_y, void* stream);
+
+/* Gradient of forward_from_feats (DISTS_pt.py:181-208) w.r.t. the 2 x 6 feature tensors (NCHW fp32, same shapes
+ * as the inputs): what model_nr_v8.py:258-265 back-propagates into its decoder. */
+NQA_API int nqa_dists_from_feats_backward(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],
+                                          const float* const feats_y[NQA_NUM_LEVELS], int B, int H, int W,
+                                          const float* grad_score, float* const grad_fx[NQA_NUM_LEVELS],
+                                          float* const grad_fy[NQA_NUM_LEVELS], void* stream);
+
 /* Standalone L2pooling / Downsample on an NCHW fp32 device tensor (DISTS_pt.py:11-25,
  * ADISTS.py:16-31): out[B,C,(H-1)/2+1,(W-1)/2+1] = sqrt(hanning3x3(x^2, stride 2, pad 1) + 1e-12). */
 NQA_API int nqa_l2pool(nqa_ctx* ctx, const float* x, int B, int C, int H, int W, float* out, void* stream);
@@ -145,7 +164,7 @@ NQA_API int nqa_launch_count(nqa_ctx* ctx, uint64_t* launches);
 /* Per-kernel-family device timing with CUDA events recorded on the launching stream around every
  * launch (bench.py's live roofline numbers).  nqa_profile_read synchronises the device, returns the
  * milliseconds and launch counts accumulated since the previous read, and resets them. */
-#define NQA_NUM_KERNEL_FAMILIES 10
+#define NQA_NUM_KERNEL_FAMILIES 11
 enum nqa_kernel_family {
   NQA_K_CONV_TC = 0,  /* tcgen05 implicit-GEMM 3x3 conv + bias + ReLU          */
   NQA_K_CONV1_1 = 1,  /* normalise + conv1_1 (CUDA cores)                      */
@@ -156,7 +175,8 @@ enum nqa_kernel_family {
   NQA_K_LAYOUT = 6,   /* NHWC <-> NCHW conversions                             */
   NQA_K_ADISTS = 7,   /* the whole A-DISTS statistics stage                    */
   NQA_K_POOL_STATS = 8, /* fused L2pooling + DISTS statistics (levels 1..4)    */
-  NQA_K_STAGE1 = 9    /* fused normalise + conv1_1 + conv1_2 (tcgen05)         */
+  NQA_K_STAGE1 = 9,   /* fused normalise + conv1_1 + conv1_2 (tcgen05)         */
+  NQA_K_BACKWARD = 10 /* statistics / pooling / conv1_1 gradient kernels       */
 };
 NQA_API int nqa_profile_enable(nqa_ctx* ctx, int on);
 NQA_API int nqa_profile_read(nqa_ctx* ctx, double ms[NQA_NUM_KERNEL_FAMILIES], uint64_t launches[NQA_NUM_KERNEL_FAMILIES]);

@@ -24,10 +24,10 @@ EXPORTS = (
     "nqa_set_alpha_beta", "nqa_dists_forward", "nqa_dists_forward_host", "nqa_dists_features",
     "nqa_dists_from_feats", "nqa_adists_forward", "nqa_adists_from_feats", "nqa_l2pool",
     "nqa_workspace_bytes", "nqa_launch_count", "nqa_micro_batch", "nqa_conv3x3_relu",
-    "nqa_profile_enable", "nqa_profile_read",
+    "nqa_profile_enable", "nqa_profile_read", "nqa_dists_backward", "nqa_dists_from_feats_backward",
 )
 KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists", "pool_stats",
-                   "stage1")
+                   "stage1", "backward")
 
 
 class NerfQAError(RuntimeError):
@@ -62,6 +62,9 @@ def load_library() -> ctypes.CDLL:
     lib.nqa_adists_forward.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp, vp]
     lib.nqa_adists_from_feats.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ci, ci, fp, vp]
     lib.nqa_l2pool.argtypes = [vp, fp, ci, ci, ci, ci, fp, vp]
+    lib.nqa_dists_backward.argtypes = [vp, fp, fp, ci, ci, ci, ci, fp, ci, fp, fp, vp]
+    lib.nqa_dists_from_feats_backward.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ci, fp,
+                                                  ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     lib.nqa_conv3x3_relu.argtypes = [vp, fp, fp, fp, ci, ci, ci, ci, ci, ci, fp, vp]
     lib.nqa_workspace_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.nqa_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
@@ -197,6 +200,30 @@ class Context:
         s1s2 = torch.empty(b, 2, NUM_CHANNELS, device=dev, dtype=torch.float32)
         _check(self.lib.nqa_dists_from_feats(self.handle, a0, a1, b, h, w, _ptr(score), _ptr(s1s2), _stream(dev)))
         return score, s1s2
+
+    def dists_backward(self, x: torch.Tensor, y: torch.Tensor, precision: int, grad_score: torch.Tensor,
+                       through_trunk: bool):
+        """d loss / d x, d loss / d y ([B,3,H,W] fp32) for d loss / d score = grad_score [B]."""
+        x, y = _as_input(x, "x"), _as_input(y, "y")
+        g = _as_input(grad_score, "grad_score").reshape(-1)
+        b, _, h, w = x.shape
+        if g.numel() != b:
+            raise NerfQAError(f"grad_score must have {b} elements, got {g.numel()}")
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        _check(self.lib.nqa_dists_backward(self.handle, _ptr(x), _ptr(y), b, h, w, precision, _ptr(g),
+                                           1 if through_trunk else 0, _ptr(gx), _ptr(gy), _stream(x.device)))
+        return gx, gy
+
+    def dists_from_feats_backward(self, feats0, feats1, grad_score: torch.Tensor):
+        f0, f1, a0, a1, b, h, w = self._feat_arrays(feats0, feats1)
+        dev = f0[0].device
+        g = _as_input(grad_score, "grad_score").reshape(-1)
+        g0 = [torch.empty_like(f) for f in f0]
+        g1 = [torch.empty_like(f) for f in f1]
+        ga0 = (ctypes.c_void_p * NUM_LEVELS)(*[t.data_ptr() for t in g0])
+        ga1 = (ctypes.c_void_p * NUM_LEVELS)(*[t.data_ptr() for t in g1])
+        _check(self.lib.nqa_dists_from_feats_backward(self.handle, a0, a1, b, h, w, _ptr(g), ga0, ga1, _stream(dev)))
+        return g0, g1
 
     def adists_forward(self, x: torch.Tensor, y: torch.Tensor, window: int, precision: int) -> torch.Tensor:
         if x.shape != y.shape:

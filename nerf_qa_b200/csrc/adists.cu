@@ -310,22 +310,39 @@ window_kernel(const float* __restrict__ fx, const float* __restrict__ fy, int c,
 #pragma unroll
   for (int i = 0; i < RY; ++i) acc_a[i] = acc_b[i] = acc_g[i] = 0.f;
 
-  for (int ch = c_begin; ch < c_end; ++ch) {
+  // software pipeline over channels: the global loads of channel ch+1 are issued right after channel ch's tile
+  // has been written to shared memory and stay in flight during its two filter passes
+  constexpr int NLD = (IN * IN + 255) / 256;
+  float pre_x[NLD], pre_y[NLD];
+  auto fetch = [&](int ch) {
     const float* px = fx + ((size_t)b * c + ch) * h * w;
     const float* py = fy + ((size_t)b * c + ch) * h * w;
-    __syncthreads();  // previous channel's vertical pass has finished reading hb; sx/sy are free
-    for (int idx = threadIdx.x; idx < IN * IN; idx += 256) {
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int idx = threadIdx.x + q * 256;
       const int r = idx / IN, col = idx - r * IN;
       const int gy = oy0 + r, gx = ox0 + col;
-      float vx = 0.f, vy = 0.f;
-      if (gy < h && gx < w) {
-        vx = __ldg(px + (size_t)gy * w + gx);
-        vy = __ldg(py + (size_t)gy * w + gx);
+      pre_x[q] = pre_y[q] = 0.f;
+      if (idx < IN * IN && gy < h && gx < w) {
+        pre_x[q] = __ldg(px + (size_t)gy * w + gx);
+        pre_y[q] = __ldg(py + (size_t)gy * w + gx);
       }
-      sx[r * LDI + col] = vx;
-      sy[r * LDI + col] = vy;
+    }
+  };
+  if (c_begin < c_end) fetch(c_begin);
+  for (int ch = c_begin; ch < c_end; ++ch) {
+    __syncthreads();  // previous channel's vertical pass has finished reading hb; sx/sy are free
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int idx = threadIdx.x + q * 256;
+      if (idx < IN * IN) {
+        const int r = idx / IN, col = idx - r * IN;
+        sx[r * LDI + col] = pre_x[q];
+        sy[r * LDI + col] = pre_y[q];
+      }
     }
     __syncthreads();
+    if (ch + 1 < c_end) fetch(ch + 1);
     if (hr < IN) {
       float o0[RX], o1[RX], o2[RX], o3[RX], o4[RX];
 #pragma unroll

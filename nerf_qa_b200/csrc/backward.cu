@@ -1,0 +1,276 @@
+// Backward pass of the DISTS score w.r.t. the frames / features (row a9 of SURVEY.md §8: DISTS.forward with
+// require_grad=True, DISTS_pt.py:105-148 under autograd; forward_from_feats, DISTS_pt.py:181-208).
+//
+//   score_b = 1 - sum_k sum_c (alpha_c S1 + beta_c S2) / w,   S1 = (2 mx my + c1)/(mx^2 + my^2 + c1),
+//   S2 = (2 cov + c2)/(vx + vy + c2),  mx = E[x], vx = E[x^2] - mx^2, cov = E[xy] - mx my  (per level, image, channel)
+//
+// so the gradient w.r.t. one feature element is AFFINE in the element pair:
+//   d score / d x_i = Px + Qx x_i + R y_i,      d score / d y_i = Py + Qy y_i + R x_i
+// with five coefficients per (image pair, channel) that depend only on the saved moments (stat_coef_kernel).
+// The trunk is differentiated layer by layer: the data gradient of a 3x3 convolution is the same convolution with
+// rotated / transposed weights (the tcgen05 kernels with a masking epilogue, kernels.h ConvEpilogue), L2pooling
+// out = sqrt(sum g x^2 + eps) has d out / d x_j = g x_j / out, and conv1_1 (3 input channels) is differentiated on
+// the CUDA cores together with the input normalisation.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nqa {
+
+// ================================================================================================
+// coefficients: grid = (ceil(1475/256), pairs)
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+stat_coef_kernel(const float* __restrict__ moments, const float* __restrict__ alpha, const float* __restrict__ beta,
+                 const float* __restrict__ grad_score, GradLevels lv, int levels_valid, float* __restrict__ coef) {
+  __shared__ double smd[33];
+  double wpart = 0.0;
+  for (int c = threadIdx.x; c < kTotalChannels; c += 256) wpart += (double)alpha[c] + (double)beta[c];
+  const double wsum = block_sum<double>(wpart, smd);
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= kTotalChannels) return;
+  const int k = c < 3 ? 0 : c < 67 ? 1 : c < 195 ? 2 : c < 451 ? 3 : c < 963 ? 4 : 5;
+  float* out = coef + ((size_t)b * kTotalChannels + c) * 5;
+  if (k >= levels_valid) {
+    out[0] = out[1] = out[2] = out[3] = out[4] = 0.f;
+    return;
+  }
+  const float* m = moments + ((size_t)b * kTotalChannels + c) * 5;
+  const double mx = m[0], my = m[1], vx = m[2], vy = m[3], cov = m[4];
+  const double g = grad_score[b];
+  const double a = -g * (double)alpha[c] / wsum, bb = -g * (double)beta[c] / wsum;
+  const double c1 = 1e-6, c2 = 1e-6, inv_n = lv.inv_n[k];
+  const double n1 = 2.0 * mx * my + c1, d1 = mx * mx + my * my + c1;
+  const double ds1_dmx = (2.0 * my * d1 - n1 * 2.0 * mx) / (d1 * d1);
+  const double ds1_dmy = (2.0 * mx * d1 - n1 * 2.0 * my) / (d1 * d1);
+  const double n2 = 2.0 * cov + c2, d2 = vx + vy + c2;
+  const double ds2_dcov = 2.0 / d2, ds2_dv = -n2 / (d2 * d2);
+  out[0] = (float)((a * ds1_dmx - 2.0 * bb * ds2_dv * mx - bb * ds2_dcov * my) * inv_n);   // Px
+  out[1] = (float)(2.0 * bb * ds2_dv * inv_n);                                             // Qx (= Qy)
+  out[2] = (float)(bb * ds2_dcov * inv_n);                                                 // R
+  out[3] = (float)((a * ds1_dmy - 2.0 * bb * ds2_dv * my - bb * ds2_dcov * mx) * inv_n);   // Py
+  out[4] = out[1];                                                                         // Qy
+}
+
+int launch_stat_coef(const float* moments, const float* alpha, const float* beta, const float* grad_score,
+                     const GradLevels& lv, int levels_valid, int pairs, float* coef, cudaStream_t st) {
+  dim3 grid(ceil_div(kTotalChannels, 256), pairs);
+  stat_coef_kernel<<<grid, 256, 0, st>>>(moments, alpha, beta, grad_score, lv, levels_valid, coef);
+  return 1;
+}
+
+// ================================================================================================
+// planar (NCHW fp32) statistics gradient: level 0 and every level of forward_from_feats.
+// grid = (ceil(hw/1024), C, pairs)
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+stat_grad_planar_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ coef,
+                        int choff, int c, int hw, float* __restrict__ gx, float* __restrict__ gy, int accumulate) {
+  const int ch = blockIdx.y, b = blockIdx.z;
+  const float* k = coef + ((size_t)b * kTotalChannels + choff + ch) * 5;
+  const float px = k[0], qx = k[1], r = k[2], py = k[3], qy = k[4];
+  const size_t base = ((size_t)b * c + ch) * hw;
+  for (int i = blockIdx.x * 1024 + threadIdx.x; i < min(hw, (int)(blockIdx.x + 1) * 1024); i += 256) {
+    const float a = x[base + i], d = y[base + i];
+    const float vx = fmaf(qx, a, fmaf(r, d, px)), vy = fmaf(qy, d, fmaf(r, a, py));
+    if (accumulate) {
+      gx[base + i] += vx;
+      gy[base + i] += vy;
+    } else {
+      gx[base + i] = vx;
+      gy[base + i] = vy;
+    }
+  }
+}
+
+int launch_stat_grad_planar(const float* x, const float* y, const float* coef, int choff, int pairs, int c, int hw,
+                            float* gx, float* gy, bool accumulate, cudaStream_t st) {
+  dim3 grid(ceil_div(hw, 1024), c, pairs);
+  stat_grad_planar_kernel<<<grid, 256, 0, st>>>(x, y, coef, choff, c, hw, gx, gy, accumulate ? 1 : 0);
+  return 1;
+}
+
+// ================================================================================================
+// NHWC level gradient: statistics term (+ L2pooling backward for levels 1..4), masked by the level's own ReLU.
+//   gx_j = [x_j > 0] * ( Px + Qx x_j + R y_j  +  x_j * sum_{o covers j} g(o,j) * gpool_o / pooled_o )
+// thread = (input pixel, 16-byte channel vector); POOL = false for the last level.
+// ================================================================================================
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(256)
+level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* __restrict__ poolx,
+                  const T* __restrict__ pooly, const T* __restrict__ gpoolx, const T* __restrict__ gpooly,
+                  const float* __restrict__ coef, int choff, int pairs, int h, int w, int c, int ho, int wo,
+                  T* __restrict__ gx, T* __restrict__ gy) {
+  constexpr int V = Vec<T>::N;
+  const int groups = c / V;
+  const size_t total = (size_t)pairs * h * w * groups;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    size_t t = idx / groups;
+    const int ix = (int)(t % w); t /= w;
+    const int iy = (int)(t % h);
+    const int b = (int)(t / h);
+    const size_t off = (((size_t)b * h + iy) * w + ix) * c + (size_t)g * V;
+    float x[V], y[V], ox[V], oy[V];
+    Vec<T>::load(fx + off, x);
+    Vec<T>::load(fy + off, y);
+    const float* k = coef + ((size_t)b * kTotalChannels + choff + g * V) * 5;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      ox[i] = fmaf(k[i * 5 + 1], x[i], fmaf(k[i * 5 + 2], y[i], k[i * 5 + 0]));
+      oy[i] = fmaf(k[i * 5 + 4], y[i], fmaf(k[i * 5 + 2], x[i], k[i * 5 + 3]));
+    }
+    if (POOL) {
+      float sx[V], sy[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) sx[i] = sy[i] = 0.f;
+      // pooled outputs whose 3x3 stride-2 window (rows 2o-1..2o+1) contains this pixel: one if the index is
+      // even (centre tap, weight 2), two if it is odd (edge taps, weight 1 each)
+      const int oy0 = iy >> 1, oy1 = (iy & 1) ? oy0 + 1 : oy0;
+      const int ox0 = ix >> 1, ox1 = (ix & 1) ? ox0 + 1 : ox0;
+      const float wy = (iy & 1) ? 1.f : 2.f, wx = (ix & 1) ? 1.f : 2.f;
+      const float wgt = wy * wx * (1.f / 16.f);
+      for (int py = oy0; py <= oy1; ++py) {
+        if (py >= ho) continue;
+        for (int px = ox0; px <= ox1; ++px) {
+          if (px >= wo) continue;
+          const size_t po = (((size_t)b * ho + py) * wo + px) * c + (size_t)g * V;
+          float pvx[V], pvy[V], gvx[V], gvy[V];
+          Vec<T>::load(poolx + po, pvx);
+          Vec<T>::load(pooly + po, pvy);
+          Vec<T>::load(gpoolx + po, gvx);
+          Vec<T>::load(gpooly + po, gvy);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            sx[i] += gvx[i] / pvx[i];      // pooled = sqrt(. + 1e-12) > 0
+            sy[i] += gvy[i] / pvy[i];
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        ox[i] = fmaf(wgt * x[i], sx[i], ox[i]);
+        oy[i] = fmaf(wgt * y[i], sy[i], oy[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      if (!(x[i] > 0.f)) ox[i] = 0.f;
+      if (!(y[i] > 0.f)) oy[i] = 0.f;
+    }
+    Vec<T>::store(gx + off, ox);
+    Vec<T>::store(gy + off, oy);
+  }
+}
+
+template <typename T>
+int launch_level_grad(const T* fx, const T* fy, const T* poolx, const T* pooly, const T* gpoolx, const T* gpooly,
+                      const float* coef, int choff, int pairs, int h, int w, int c, T* gx, T* gy, cudaStream_t st) {
+  const size_t total = (size_t)pairs * h * w * (c / Vec<T>::N);
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (poolx)
+    level_grad_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(fx, fy, poolx, pooly, gpoolx, gpooly, coef, choff, pairs, h, w,
+                                                                c, pooled(h), pooled(w), gx, gy);
+  else
+    level_grad_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(fx, fy, nullptr, nullptr, nullptr, nullptr, coef, choff, pairs,
+                                                                 h, w, c, 0, 0, gx, gy);
+  return 1;
+}
+template int launch_level_grad<float>(const float*, const float*, const float*, const float*, const float*, const float*,
+                                      const float*, int, int, int, int, int, float*, float*, cudaStream_t);
+template int launch_level_grad<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, const bf16*, const bf16*,
+                                     const float*, int, int, int, int, int, bf16*, bf16*, cudaStream_t);
+
+// ================================================================================================
+// conv1_1 backward + input normalisation: gz [n,h,w,64] (gradient w.r.t. the pre-ReLU output of conv1_1, already
+// masked) -> gradient w.r.t. the RAW frames, NCHW fp32 (images [0,nx) -> gx, [nx,n) -> gy).
+// Thread = one input pixel; weights [9][64][3] in shared memory.
+// ================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128)
+conv1_1_bwd_kernel(const T* __restrict__ gz, const float* __restrict__ wb /*[9][64][3]*/, int nx, int h, int w,
+                   float* __restrict__ gx, float* __restrict__ gy) {
+  __shared__ float ws[9 * 64 * 3];
+  for (int i = threadIdx.x; i < 9 * 64 * 3; i += 128) ws[i] = wb[i];
+  __syncthreads();
+  constexpr int V = Vec<T>::N;
+  const int img = blockIdx.z, y = blockIdx.y, x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= w) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int oy = y + 1 - r;
+    if (oy < 0 || oy >= h) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ox = x + 1 - s;
+      if (ox < 0 || ox >= w) continue;
+      const T* src = gz + (((size_t)img * h + oy) * w + ox) * 64;
+      const float* wt = ws + (r * 3 + s) * 64 * 3;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += V) {
+        float v[V];
+        Vec<T>::load(src + c0, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          acc[0] = fmaf(v[i], wt[(c0 + i) * 3 + 0], acc[0]);
+          acc[1] = fmaf(v[i], wt[(c0 + i) * 3 + 1], acc[1]);
+          acc[2] = fmaf(v[i], wt[(c0 + i) * 3 + 2], acc[2]);
+        }
+      }
+    }
+  }
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  float* dst = img < nx ? gx + (size_t)img * 3 * h * w : gy + (size_t)(img - nx) * 3 * h * w;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) dst[((size_t)ci * h + y) * w + x] = acc[ci] / stdv[ci];
+}
+
+template <typename T>
+int launch_conv1_1_bwd(const T* gz, const float* wb, int nx, int n, int h, int w, float* gx, float* gy, cudaStream_t st) {
+  dim3 grid(ceil_div(w, 128), h, n);
+  conv1_1_bwd_kernel<T><<<grid, 128, 0, st>>>(gz, wb, nx, h, w, gx, gy);
+  return 1;
+}
+template int launch_conv1_1_bwd<float>(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
+template int launch_conv1_1_bwd<bf16>(const bf16*, const float*, int, int, int, int, float*, float*, cudaStream_t);
+
+// ================================================================================================
+// weight packing for the data-gradient convolutions
+// ================================================================================================
+// w OIHW [cout][cin][3][3] ->  w_f32 [tap'][cout][cin],  w_hi [cin][tap'][cout] (K-major rows for the tcgen05 B
+// operand), tap' = 8 - tap (180-degree rotation), roles of cin / cout swapped.
+__global__ void pack_w_bwd_kernel(const float* __restrict__ w, int cin, int cout, float* __restrict__ w_f32,
+                                  bf16* __restrict__ w_hi) {
+  const size_t total = (size_t)cout * cin * 9;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 9);
+    const int ci = (int)((i / 9) % cin);
+    const int co = (int)(i / (9 * (size_t)cin));
+    const float v = w[i];
+    const int tb = 8 - tap;
+    w_f32[((size_t)tb * cout + co) * cin + ci] = v;
+    w_hi[(size_t)ci * 9 * cout + (size_t)tb * cout + co] = __float2bfloat16_rn(v);
+  }
+}
+// conv1_1: w [64][3][3][3] -> [tap][co][ci] (indexed by the FORWARD tap: input pixel p feeds output p - shift(tap))
+__global__ void pack_w11_bwd_kernel(const float* __restrict__ w, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 27) return;
+  const int tap = i % 9, ci = (i / 9) % 3, co = i / 27;
+  out[(tap * 64 + co) * 3 + ci] = w[i];
+}
+
+int launch_pack_w_bwd(const float* w_oihw, int cin, int cout, float* w_f32, bf16* w_hi, cudaStream_t st) {
+  pack_w_bwd_kernel<<<1024, 256, 0, st>>>(w_oihw, cin, cout, w_f32, w_hi);
+  return 1;
+}
+int launch_pack_w11_bwd(const float* w_oihw, float* out, cudaStream_t st) {
+  pack_w11_bwd_kernel<<<(64 * 27 + 255) / 256, 256, 0, st>>>(w_oihw, out);
+  return 1;
+}
+
+}  // namespace nqa

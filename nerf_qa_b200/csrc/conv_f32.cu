@@ -107,7 +107,8 @@ constexpr int IN_LD = CK + 1;
 
 __global__ void __launch_bounds__(256)
 conv3x3_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ wpack,
-                   const float* __restrict__ bias, int h, int w, int cin, int cout, int tiles_w) {
+                   const float* __restrict__ bias, int h, int w, int cin, int cout, int tiles_w, int epi,
+                   const float* __restrict__ mask) {
   using namespace f32conv;
   __shared__ float in_s[HALO * IN_LD];
   __shared__ __align__(16) float w_s[9 * CK * BN];
@@ -166,30 +167,42 @@ conv3x3_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const 
       }
     }
   }
-  const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + tx * 4);
+  const float4 bb = epi == kEpiBiasRelu ? *reinterpret_cast<const float4*>(bias + n0 + tx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   const int oy = h0 + row;
   if (oy < h) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int ox = w0 + colbase + i;
       if (ox < w) {
+        const size_t o = (((size_t)img * h + oy) * w + ox) * cout + n0 + tx * 4;
         float4 v;
-        v.x = fmaxf(acc[i][0] + bb.x, 0.f);
-        v.y = fmaxf(acc[i][1] + bb.y, 0.f);
-        v.z = fmaxf(acc[i][2] + bb.z, 0.f);
-        v.w = fmaxf(acc[i][3] + bb.w, 0.f);
-        *reinterpret_cast<float4*>(out + (((size_t)img * h + oy) * w + ox) * cout + n0 + tx * 4) = v;
+        if (epi == kEpiBiasRelu) {
+          v.x = fmaxf(acc[i][0] + bb.x, 0.f);
+          v.y = fmaxf(acc[i][1] + bb.y, 0.f);
+          v.z = fmaxf(acc[i][2] + bb.z, 0.f);
+          v.w = fmaxf(acc[i][3] + bb.w, 0.f);
+        } else {
+          v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          if (epi == kEpiMask) {          // ReLU of the layer below
+            const float4 a = *reinterpret_cast<const float4*>(mask + o);
+            if (!(a.x > 0.f)) v.x = 0.f;
+            if (!(a.y > 0.f)) v.y = 0.f;
+            if (!(a.z > 0.f)) v.z = 0.f;
+            if (!(a.w > 0.f)) v.w = 0.f;
+          }
+        }
+        *reinterpret_cast<float4*>(out + o) = v;
       }
     }
   }
 }
 
 int launch_conv3x3_f32(const float* in, float* out, const float* wpack, const float* bias, int n, int h, int w, int cin,
-                       int cout, cudaStream_t st) {
+                       int cout, cudaStream_t st, int epi, const float* mask) {
   using namespace f32conv;
   const int tiles_w = ceil_div(w, TW), tiles_h = ceil_div(h, TH);
   dim3 grid(tiles_w * tiles_h, cout / BN, n);
-  conv3x3_f32_kernel<<<grid, 256, 0, st>>>(in, out, wpack, bias, h, w, cin, cout, tiles_w);
+  conv3x3_f32_kernel<<<grid, 256, 0, st>>>(in, out, wpack, bias, h, w, cin, cout, tiles_w, epi, mask);
   return 1;
 }
 

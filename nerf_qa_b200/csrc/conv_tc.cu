@@ -367,6 +367,8 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
   // bf16x3 stages are twice as large, so cap its channel tile at 128 to keep >= 3 pipeline stages
   plan->block_n = cout >= 256 ? (split ? 128 : 256) : cout >= 128 ? 128 : 64;
   // thin layers: halo-reuse kernel (A tile fetched once instead of nine times)
+  plan->epi = kEpiBiasRelu;
+  plan->mask = nullptr;
   plan->halo = false;
   plan->pair = false;
   plan->halo_hbw = 10;
@@ -421,6 +423,10 @@ int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st) {
     const int rc = launch_conv3x3_tc_halo(plan, tc::g_sm_count, st);
     if (rc > 0) return rc;
     fprintf(stderr, "nerfqa_b200: halo conv configuration does not fit (cin %d cout %d)\n", plan.cin, plan.cout);
+    return 0;
+  }
+  if (plan.epi != kEpiBiasRelu) {
+    fprintf(stderr, "nerfqa_b200: gradient epilogues need the halo / pair convolution kernels\n");
     return 0;
   }
   if (plan.split) {

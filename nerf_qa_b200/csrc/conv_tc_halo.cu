@@ -35,6 +35,8 @@ struct Params {
   int a_stage_bytes;
   const float* bias;
   bf16* out;
+  int epi;             // ConvEpilogue
+  const bf16* mask;    // kEpiMask: saved activation of the layer below, [n,h,w,cout]
 };
 
 template <int BLOCK_N, bool RESIDENT>
@@ -210,6 +212,9 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const int thi = m_tile % p.tiles_h;
       const int img = m_tile / p.tiles_h;
       const int n0 = n_tile * BLOCK_N;
+      const int py = thi * TH + (m >> 3), px = twi * TW + (m & 7);
+      const bool pix_ok = py < p.h && px < p.w;
+      const size_t pix_off = (((size_t)img * p.h + py) * p.w + px) * p.cout;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -222,12 +227,35 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c64 * 64 + half * 32, r);
           tmem_ld_wait();
+          uint4 mk[4];
+          if (p.epi == kEpiMask) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mk[q] = make_uint4(0u, 0u, 0u, 0u);
+            if (pix_ok) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix_off + n0 + c64 * 64 + half * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) mk[q] = __ldg(mp + q);
+            }
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float v[8];
+            if (p.epi == kEpiBiasRelu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              v[j] = fmaxf(__uint_as_float(r[q * 8 + j]) + bias_s[n0 + c64 * 64 + half * 32 + q * 8 + j], 0.f);
+              for (int j = 0; j < 8; ++j)
+                v[j] = fmaxf(__uint_as_float(r[q * 8 + j]) + bias_s[n0 + c64 * 64 + half * 32 + q * 8 + j], 0.f);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+              if (p.epi == kEpiMask) {      // ReLU of the layer below: pass the gradient where its output was > 0
+                const uint32_t mw[4] = {mk[q].x, mk[q].y, mk[q].z, mk[q].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if ((mw[j] & 0x00007fffu) == 0u) v[2 * j] = 0.f;
+                  if ((mw[j] & 0x7fff0000u) == 0u) v[2 * j + 1] = 0.f;
+                }
+              }
+            }
             uint4 t;
             t.x = Vec<bf16>::pack2(v[0], v[1]);
             t.y = Vec<bf16>::pack2(v[2], v[3]);
@@ -271,7 +299,7 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
   p.num_tiles = plan.n * plan.tiles_h * plan.tiles_w * p.num_n_tiles;
   p.hbw = plan.halo_hbw; p.desc_mode = plan.halo_desc_mode;
   p.a_stage_bytes = (HALO_H * plan.halo_hbw * 128 + 1023) & ~1023;
-  p.bias = plan.bias; p.out = plan.out;
+  p.bias = plan.bias; p.out = plan.out; p.epi = plan.epi; p.mask = plan.mask;
   const int chunks = plan.cin / BLOCK_K;
   const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*bias*/ - STG_BYTES;
   int a_stages, b_stages = 0;

@@ -38,6 +38,8 @@ struct Params {
   int tiles_w, tiles_h, num_n_tiles, num_m_pairs, num_items;
   int hbw, a_stage_bytes;
   const float* bias;
+  int epi;             // ConvEpilogue
+  const bf16* mask;    // kEpiMask: saved activation of the layer below, [n,h,w,cout]
 };
 
 // ---- cluster / cta_group::2 primitives ----------------------------------------------------------------
@@ -267,6 +269,9 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const uint32_t acc_phase = (local >> 1) & 1;
       int n0, img, h0, w0;
       decode(item, n0, img, h0, w0);
+      const int py = h0 + (m >> 3), px = w0 + (m & 7);
+      const bool pix_ok = img < p.n && py < p.h && px < p.w;
+      const size_t pix_off = (((size_t)img * p.h + py) * p.w + px) * p.cout;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -279,12 +284,35 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c64 * 64 + half * 32, r);
           tmem_ld_wait();
+          uint4 mk[4];
+          if (p.epi == kEpiMask) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mk[q] = make_uint4(0u, 0u, 0u, 0u);
+            if (pix_ok) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix_off + n0 + c64 * 64 + half * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) mk[q] = __ldg(mp + q);
+            }
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float v[8];
+            if (p.epi == kEpiBiasRelu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              v[j] = fmaxf(__uint_as_float(r[q * 8 + j]) + bias_s[n0 + c64 * 64 + half * 32 + q * 8 + j], 0.f);
+              for (int j = 0; j < 8; ++j)
+                v[j] = fmaxf(__uint_as_float(r[q * 8 + j]) + bias_s[n0 + c64 * 64 + half * 32 + q * 8 + j], 0.f);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+              if (p.epi == kEpiMask) {      // ReLU of the layer below: pass the gradient where its output was > 0
+                const uint32_t mw[4] = {mk[q].x, mk[q].y, mk[q].z, mk[q].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if ((mw[j] & 0x00007fffu) == 0u) v[2 * j] = 0.f;
+                  if ((mw[j] & 0x7fff0000u) == 0u) v[2 * j + 1] = 0.f;
+                }
+              }
+            }
             uint4 t;
             t.x = Vec<bf16>::pack2(v[0], v[1]);
             t.y = Vec<bf16>::pack2(v[2], v[3]);
@@ -331,7 +359,7 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
   p.num_items = p.num_m_pairs * p.num_n_tiles;
   p.hbw = plan.halo_hbw;
   p.a_stage_bytes = (HALO_H * plan.halo_hbw * 128 + 1023) & ~1023;
-  p.bias = plan.bias;
+  p.bias = plan.bias; p.epi = plan.epi; p.mask = plan.mask;
   const int chunks = plan.cin / BLOCK_K;
   const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*bias*/ - STG_BYTES;
   int a_stages, b_stages = 0;

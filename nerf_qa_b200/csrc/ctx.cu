@@ -64,6 +64,9 @@ struct nqa_ctx {
   float* w_f32[kNumConvs] = {};          // [9][cin][cout]
   bf16* w_hi[kNumConvs] = {};            // [cout][9][cin]
   bf16* w_lo[kNumConvs] = {};            // residual of the bf16 rounding (bf16x3)
+  float* w_bwd_f32[kNumConvs] = {};      // data-gradient weights [9][cout][cin] (rotated taps)
+  bf16* w_bwd_hi[kNumConvs] = {};        // data-gradient weights [cin][9][cout] bf16
+  float* w11_bwd = nullptr;              // conv1_1 backward [9][64][3]
   float* alpha = nullptr;
   float* beta = nullptr;
   CUtensorMap w12_map;                   // conv1_2 weights for the fused stage-1 kernel
@@ -359,19 +362,20 @@ void partial_alloc(nqa_ctx* ctx, int pairs, PartialBufs* pb) {
   pb->terms = static_cast<double*>(ctx->arena.take((size_t)pairs * kTotalChannels * sizeof(double)));
 }
 
-int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float* score, float* s1s2, cudaStream_t st) {
+int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float* score, float* s1s2, cudaStream_t st,
+             float* moments = nullptr, int levels_valid = kNumLevels) {
   int h[kNumLevels], w[kNumLevels];
   level_dims(H, W, h, w);
   FinalizeParams fp;
   for (int k = 0; k < kNumLevels; ++k) {
     fp.lv[k].partials = pb.p[k];
-    fp.lv[k].chunks = pb.chunks[k];
+    fp.lv[k].chunks = k < levels_valid ? pb.chunks[k] : 0;
     fp.lv[k].C = level_channels(k);
     fp.lv[k].choff = level_offset(k);
     fp.lv[k].inv_n = 1.0 / ((double)h[k] * w[k]);
   }
   ProfScope ps(ctx, NQA_K_FINALIZE, st);
-  ctx->launches += launch_dists_finalize(fp, ctx->alpha, ctx->beta, pairs, score, s1s2, nullptr, pb.terms, st);
+  ctx->launches += launch_dists_finalize(fp, ctx->alpha, ctx->beta, pairs, score, s1s2, moments, pb.terms, st);
   return NQA_OK;
 }
 
@@ -438,6 +442,149 @@ int dists_forward_device(nqa_ctx* ctx, const float* x, const float* y, int B, in
   return NQA_OK;
 }
 
+// ---- DISTS backward: one micro-batch ------------------------------------------------------------
+// Recomputes the trunk forward with every activation kept (activation recomputation: nothing survives between the
+// forward and the backward C-ABI calls), then walks the layers back.  See backward.cu for the math.
+template <typename T>
+int conv_layer_bwd(nqa_ctx* ctx, int li, const T* gin, T* gout, int n, int h, int w, int epi, const T* mask, cudaStream_t st);
+template <>
+int conv_layer_bwd<float>(nqa_ctx* ctx, int li, const float* gin, float* gout, int n, int h, int w, int epi,
+                          const float* mask, cudaStream_t st) {
+  ProfScope ps(ctx, NQA_K_CONV_F32, st);
+  ctx->launches += launch_conv3x3_f32(gin, gout, ctx->w_bwd_f32[li], nullptr, n, h, w, kConvCout[li], kConvCin[li], st, epi, mask);
+  return NQA_OK;
+}
+template <>
+int conv_layer_bwd<bf16>(nqa_ctx* ctx, int li, const bf16* gin, bf16* gout, int n, int h, int w, int epi, const bf16* mask,
+                         cudaStream_t st) {
+  ConvTcPlan plan;
+  const char* err = "";
+  // roles of the channel counts are swapped; the bias pointer is only staged (512 floats), never applied
+  if (conv_tc_make_plan(&plan, gin, nullptr, ctx->w_bwd_hi[li], nullptr, ctx->bias[kNumConvs - 1], gout, nullptr, n, h, w,
+                        kConvCout[li], kConvCin[li], false, &err))
+    return fail(NQA_ERR_CUDA, "%s (backward of layer %d, %dx%dx%d)", err, li, n, h, w);
+  plan.epi = epi;
+  plan.mask = mask;
+  ProfScope ps(ctx, NQA_K_CONV_TC, st);
+  const int nl = launch_conv3x3_tc(plan, st);
+  if (nl <= 0) return fail(NQA_ERR_CUDA, "backward convolution of layer %d could not be launched", li);
+  ctx->launches += nl;
+  return NQA_OK;
+}
+
+template <typename T>
+size_t dists_bwd_bytes(const nqa_ctx* ctx, int pairs, int H, int W, int prec) {
+  int h[kNumLevels], w[kNumLevels];
+  level_dims(H, W, h, w);
+  const size_t n = 2 * (size_t)pairs;
+  size_t total = 0;
+  int li = 0;
+  for (int stage = 0; stage < 5; ++stage) {
+    const size_t hw = (size_t)h[stage + 1] * w[stage + 1];
+    for (int j = 0; j < kStageConvs[stage]; ++j, ++li) total += align256(n * hw * kConvCout[li] * sizeof(T));
+    if (stage < 4) total += align256(n * (size_t)h[stage + 2] * w[stage + 2] * kConvCout[li - 1] * sizeof(T));
+  }
+  total += 2 * align256(n * (size_t)H * W * 64 * sizeof(T));                     // gradient ping-pong
+  total += partial_bytes(pairs, H, W, prec, nullptr, false, true);
+  total += 2 * align256((size_t)pairs * kTotalChannels * 5 * sizeof(float)) + align256(pairs * sizeof(float));
+  return total + 8192;
+}
+
+template <typename T>
+int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, int H, int W, int prec,
+                               const float* grad_score, bool through_trunk, float* gx, float* gy, cudaStream_t st) {
+  ctx->arena.reset();
+  int lh[kNumLevels], lw[kNumLevels];
+  level_dims(H, W, lh, lw);
+  const int n = 2 * pairs;
+  PartialBufs pb;
+  partial_bytes(pairs, H, W, prec, &pb, false, true);
+  partial_alloc(ctx, pairs, &pb);
+  float* moments = static_cast<float*>(ctx->arena.take((size_t)pairs * kTotalChannels * 5 * sizeof(float)));
+  float* coef = static_cast<float*>(ctx->arena.take((size_t)pairs * kTotalChannels * 5 * sizeof(float)));
+  float* score_scratch = static_cast<float*>(ctx->arena.take(pairs * sizeof(float)));
+  GradLevels gl;
+  for (int k = 0; k < kNumLevels; ++k) gl.inv_n[k] = 1.0 / ((double)lh[k] * lw[k]);
+
+  {  // level 0: the RAW frames
+    ProfScope ps(ctx, NQA_K_STATS, st);
+    ctx->launches += launch_stats_planar(x, y, pairs, 3, H * W, pb.chunks[0], pb.p[0], st);
+  }
+  T* act[kNumConvs] = {};
+  T* pool[4] = {};
+  if (through_trunk) {
+    int li = 0;
+    const T* cur = nullptr;
+    for (int stage = 0; stage < 5; ++stage) {
+      const int h = lh[stage + 1], w = lw[stage + 1];
+      for (int j = 0; j < kStageConvs[stage]; ++j, ++li) {
+        act[li] = static_cast<T*>(ctx->arena.take((size_t)n * h * w * kConvCout[li] * sizeof(T)));
+        if (li == 0) {
+          conv1_1_layer<T>(ctx, x, y, pairs, n, h, w, act[0], nullptr, st);
+        } else {
+          const int rc = conv_layer<T>(ctx, li, cur, nullptr, act[li], nullptr, n, h, w, prec, st);
+          if (rc != NQA_OK) return rc;
+        }
+        cur = act[li];
+      }
+      const int k = stage + 1, c = level_channels(k);
+      const size_t half = (size_t)pairs * h * w * c;
+      if (stage < 4) {
+        const size_t half_out = (size_t)pairs * lh[k + 1] * lw[k + 1] * c;
+        pool[stage] = static_cast<T*>(ctx->arena.take(2 * half_out * sizeof(T)));
+        ProfScope ps(ctx, NQA_K_POOL_STATS, st);
+        ctx->launches += launch_pool_stats<T>(cur, cur + half, pool[stage], pool[stage] + half_out, pairs, h, w, c, pb.chunks[k],
+                                              pb.p[k], st);
+        cur = pool[stage];
+      } else {
+        ProfScope ps(ctx, NQA_K_STATS, st);
+        ctx->launches += launch_stats_nhwc<T>(cur, cur + half, nullptr, nullptr, pairs, h * w, c, pb.chunks[k], pb.p[k], st);
+      }
+    }
+  }
+  const int levels_valid = through_trunk ? kNumLevels : 1;
+  int rc = finalize(ctx, pb, pairs, H, W, score_scratch, nullptr, st, moments, levels_valid);
+  if (rc != NQA_OK) return rc;
+  ProfScope psb(ctx, NQA_K_BACKWARD, st);
+  ctx->launches += launch_stat_coef(moments, ctx->alpha, ctx->beta, grad_score, gl, levels_valid, pairs, coef, st);
+
+  if (through_trunk) {
+    const size_t gsz = (size_t)n * H * W * 64 * sizeof(T);
+    T* g[2] = {static_cast<T*>(ctx->arena.take(gsz)), static_cast<T*>(ctx->arena.take(gsz))};
+    int cur = 0;
+    {  // last level: statistics gradient only
+      const int h = lh[5], w = lw[5], c = level_channels(5);
+      const size_t half = (size_t)pairs * h * w * c;
+      ctx->launches += launch_level_grad<T>(act[12], act[12] + half, nullptr, nullptr, nullptr, nullptr, coef, level_offset(5),
+                                            pairs, h, w, c, g[cur], g[cur] + half, st);
+    }
+    int li = kNumConvs - 1;
+    for (int stage = 4; stage >= 0; --stage) {
+      const int h = lh[stage + 1], w = lw[stage + 1];
+      for (int j = kStageConvs[stage] - 1; j >= 0; --j, --li) {
+        if (li == 0) break;
+        const bool first = j == 0;                       // input of this conv = pooled output of the stage below
+        rc = conv_layer_bwd<T>(ctx, li, g[cur], g[cur ^ 1], n, h, w, first ? kEpiPlain : kEpiMask, first ? nullptr : act[li - 1], st);
+        if (rc != NQA_OK) return rc;
+        cur ^= 1;
+      }
+      if (stage == 0) break;
+      // g[cur] = gradient w.r.t. the pooled input of this stage -> gradient w.r.t. the pre-ReLU output of the last
+      // conv of the stage below (pooling backward + that level's statistics term + ReLU mask)
+      const int k = stage, hp = lh[k], wp = lw[k], c = level_channels(k);
+      const size_t half = (size_t)pairs * hp * wp * c, half_pool = (size_t)pairs * h * w * c;
+      const T* feat = act[li];                            // li now indexes the last conv of the stage below
+      ctx->launches += launch_level_grad<T>(feat, feat + half, pool[stage - 1], pool[stage - 1] + half_pool, g[cur],
+                                            g[cur] + half_pool, coef, level_offset(k), pairs, hp, wp, c, g[cur ^ 1],
+                                            g[cur ^ 1] + half, st);
+      cur ^= 1;
+    }
+    ctx->launches += launch_conv1_1_bwd<T>(g[cur], ctx->w11_bwd, pairs, n, H, W, gx, gy, st);
+  }
+  ctx->launches += launch_stat_grad_planar(x, y, coef, 0, pairs, 3, H * W, gx, gy, through_trunk, st);
+  return NQA_OK;
+}
+
 int check_ready(nqa_ctx* ctx, bool need_ab) {
   if (!ctx) return fail(NQA_ERR_INVALID, "null context");
   if (!ctx->have_weights) return fail(NQA_ERR_STATE, "VGG weights not set (nqa_set_vgg_weights)");
@@ -494,6 +641,7 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   CUDA_TRY(cudaMalloc(&ctx->beta, kTotalChannels * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ctx->w11, 27 * 64 * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ctx->w11_img, 2 * 64 * 32 * sizeof(bf16)));
+  CUDA_TRY(cudaMalloc(&ctx->w11_bwd, 27 * 64 * sizeof(float)));
   for (int i = 0; i < kNumConvs; ++i) {
     const size_t nw = (size_t)kConvCout[i] * kConvCin[i] * 9;
     CUDA_TRY(cudaMalloc(&ctx->bias[i], kConvCout[i] * sizeof(float)));
@@ -501,6 +649,8 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
       CUDA_TRY(cudaMalloc(&ctx->w_f32[i], nw * sizeof(float)));
       CUDA_TRY(cudaMalloc(&ctx->w_hi[i], nw * sizeof(bf16)));
       CUDA_TRY(cudaMalloc(&ctx->w_lo[i], nw * sizeof(bf16)));
+      CUDA_TRY(cudaMalloc(&ctx->w_bwd_f32[i], nw * sizeof(float)));
+      CUDA_TRY(cudaMalloc(&ctx->w_bwd_hi[i], nw * sizeof(bf16)));
     }
   }
   *out = ctx;
@@ -515,7 +665,10 @@ int nqa_ctx_destroy(nqa_ctx* ctx) {
   cudaFree(ctx->beta);
   cudaFree(ctx->w11);
   cudaFree(ctx->w11_img);
+  cudaFree(ctx->w11_bwd);
   for (int i = 0; i < kNumConvs; ++i) {
+    cudaFree(ctx->w_bwd_f32[i]);
+    cudaFree(ctx->w_bwd_hi[i]);
     cudaFree(ctx->bias[i]);
     cudaFree(ctx->w_f32[i]);
     cudaFree(ctx->w_hi[i]);
@@ -555,8 +708,10 @@ int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const
     if (i == 0) {
       pack_w11_kernel<<<(27 * 64 + 255) / 256, 256>>>(tmp, ctx->w11);
       ctx->launches += launch_pack_w11_tc(tmp, ctx->w11_img, 0);
+      ctx->launches += launch_pack_w11_bwd(tmp, ctx->w11_bwd, 0);
     } else {
       pack_w_kernel<<<1024, 256>>>(tmp, kConvCin[i], kConvCout[i], ctx->w_f32[i], ctx->w_hi[i], ctx->w_lo[i]);
+      ctx->launches += launch_pack_w_bwd(tmp, kConvCin[i], kConvCout[i], ctx->w_bwd_f32[i], ctx->w_bwd_hi[i], 0);
     }
     ctx->launches += 1;
     e = cudaDeviceSynchronize();
@@ -822,6 +977,77 @@ int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVEL
   {
     ProfScope ps(ctx, NQA_K_ADISTS, st);
     ctx->launches += adists_stage(feats_x, feats_y, B, H, W, window, ws, score_out, st);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_dists_backward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int precision,
+                       const float* grad_score, int through_trunk, float* grad_x, float* grad_y, void* stream) {
+  int rc = check_ready(ctx, true);
+  if (rc != NQA_OK) return rc;
+  if (!x || !y || !grad_score || !grad_x || !grad_y) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  if (precision != NQA_PREC_FP32 && precision != NQA_PREC_BF16)
+    return fail(NQA_ERR_INVALID, "the backward pass supports the fp32 and bf16 trunks (got precision %d)", precision);
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int mb = pick_micro_pairs(ctx, B, H, W) / 2;
+  if (mb < 1) mb = 1;
+  const size_t need = precision == NQA_PREC_FP32 ? dists_bwd_bytes<float>(ctx, mb, H, W, precision)
+                                                 : dists_bwd_bytes<bf16>(ctx, mb, H, W, precision);
+  if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
+  const size_t frame = (size_t)3 * H * W;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int pairs = B - b0 < mb ? B - b0 : mb;
+    rc = precision == NQA_PREC_FP32
+             ? dists_backward_micro_batch<float>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, precision, grad_score + b0,
+                                                 through_trunk != 0, grad_x + b0 * frame, grad_y + b0 * frame, st)
+             : dists_backward_micro_batch<bf16>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, precision, grad_score + b0,
+                                                through_trunk != 0, grad_x + b0 * frame, grad_y + b0 * frame, st);
+    if (rc != NQA_OK) return rc;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_dists_from_feats_backward(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],
+                                  const float* const feats_y[NQA_NUM_LEVELS], int B, int H, int W, const float* grad_score,
+                                  float* const grad_fx[NQA_NUM_LEVELS], float* const grad_fy[NQA_NUM_LEVELS], void* stream) {
+  if (!ctx) return fail(NQA_ERR_INVALID, "null context");
+  if (!ctx->have_alpha_beta) return fail(NQA_ERR_STATE, "alpha/beta not set (nqa_set_alpha_beta)");
+  if (!feats_x || !feats_y || !grad_score || !grad_fx || !grad_fy) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  for (int k = 0; k < kNumLevels; ++k)
+    if (!feats_x[k] || !feats_y[k] || !grad_fx[k] || !grad_fy[k]) return fail(NQA_ERR_INVALID, "null pointer for level %d", k);
+  int rc = check_shape(B, H, W);
+  if (rc != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PartialBufs pb;
+  const size_t need = partial_bytes(B, H, W, NQA_PREC_FP32, &pb, true) + 2 * align256((size_t)B * kTotalChannels * 5 * sizeof(float)) +
+                      align256(B * sizeof(float)) + 4096;
+  if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
+  ctx->arena.reset();
+  partial_alloc(ctx, B, &pb);
+  float* moments = static_cast<float*>(ctx->arena.take((size_t)B * kTotalChannels * 5 * sizeof(float)));
+  float* coef = static_cast<float*>(ctx->arena.take((size_t)B * kTotalChannels * 5 * sizeof(float)));
+  float* score_scratch = static_cast<float*>(ctx->arena.take(B * sizeof(float)));
+  int lh[kNumLevels], lw[kNumLevels];
+  level_dims(H, W, lh, lw);
+  GradLevels gl;
+  for (int k = 0; k < kNumLevels; ++k) {
+    gl.inv_n[k] = 1.0 / ((double)lh[k] * lw[k]);
+    ProfScope ps(ctx, NQA_K_STATS, st);
+    ctx->launches += launch_stats_planar(feats_x[k], feats_y[k], B, level_channels(k), lh[k] * lw[k], pb.chunks[k], pb.p[k], st);
+  }
+  rc = finalize(ctx, pb, B, H, W, score_scratch, nullptr, st, moments);
+  if (rc != NQA_OK) return rc;
+  {
+    ProfScope ps(ctx, NQA_K_BACKWARD, st);
+    ctx->launches += launch_stat_coef(moments, ctx->alpha, ctx->beta, grad_score, gl, kNumLevels, B, coef, st);
+    for (int k = 0; k < kNumLevels; ++k)
+      ctx->launches += launch_stat_grad_planar(feats_x[k], feats_y[k], coef, level_offset(k), B, level_channels(k), lh[k] * lw[k],
+                                               grad_fx[k], grad_fy[k], false, st);
   }
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;

@@ -60,6 +60,10 @@ int launch_nchw_to_nhwc(const float* in, T* out, T* out_lo, int n, int c, int h,
 int launch_nhwc_split_to_nchw(const bf16* hi, const bf16* lo, float* out, int n, int c, int h, int w, cudaStream_t st);
 
 // ---- convolutions ---------------------------------------------------------------------------------
+// Epilogue of the 3x3 convolution kernels.  Forward: bias + ReLU.  Backward (data gradient = the same convolution
+// with rotated / transposed weights): either the plain sum (gradient w.r.t. a pooled tensor) or the sum masked by
+// the ReLU of the layer below (mask = that layer's saved output, same shape as this kernel's output).
+enum ConvEpilogue { kEpiBiasRelu = 0, kEpiPlain = 1, kEpiMask = 2 };
 // conv1_1 fused with the input normalisation: images [0,nx) come from x, [nx,n) from y (NCHW fp32);
 // weights packed [27][64] (k = (ci*3 + r)*3 + s), output NHWC [n,h,w,64].  If out_lo != nullptr the output is
 // written as a bf16 hi/lo pair (T must be bf16).
@@ -73,7 +77,7 @@ int launch_conv1_1_tc(const float* x, const float* y, int nx, int n, int h, int 
                       bf16* out, bf16* out_lo, int sm_count, cudaStream_t st);
 // strict fp32 CUDA-core conv: NHWC fp32, weights [9][cin][cout]
 int launch_conv3x3_f32(const float* in, float* out, const float* wpack, const float* bias, int n, int h, int w, int cin,
-                       int cout, cudaStream_t st);
+                       int cout, cudaStream_t st, int epi = kEpiBiasRelu, const float* mask = nullptr);
 
 // tcgen05 implicit-GEMM conv: NHWC bf16 activations, weights [cout][9][cin] bf16 (K-major), fp32 bias.
 // split = bf16x3 mode (hi/lo pairs for activations and weights, three MMAs per k-step).
@@ -92,6 +96,8 @@ struct ConvTcPlan {
   const float* bias;
   bf16* out;
   bf16* out_lo;
+  int epi;             // ConvEpilogue (halo / pair kernels; the plain kernel is forward-only)
+  const bf16* mask;    // kEpiMask: saved activation [n,h,w,cout]
 };
 // Fills the tensor maps; returns 0 on success, nonzero + message on failure.
 int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
@@ -111,6 +117,27 @@ int conv_tc_make_weight_map(CUtensorMap* map, const bf16* wk, int cout, int k, i
 int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, int w, const bf16* w1img,
                         const float* bias1, const CUtensorMap& w2map, const float* bias2, bf16* out, int sm_count,
                         cudaStream_t st);
+
+// ---- backward (backward.cu) -------------------------------------------------------------------------
+struct GradLevels {
+  double inv_n[6];   // 1 / (H_k * W_k)
+};
+// coef[b][c][5] = (Px, Qx, R, Py, Qy): d score_b/d x_i = Px + Qx x_i + R y_i (times grad_score[b], already folded in);
+// channels of levels >= levels_valid get zeros.  moments from launch_dists_finalize.
+int launch_stat_coef(const float* moments, const float* alpha, const float* beta, const float* grad_score,
+                     const GradLevels& lv, int levels_valid, int pairs, float* coef, cudaStream_t st);
+// NCHW fp32 planes of one level: gx (+)= Px + Qx x + R y, gy (+)= Py + Qy y + R x
+int launch_stat_grad_planar(const float* x, const float* y, const float* coef, int choff, int pairs, int c, int hw,
+                            float* gx, float* gy, bool accumulate, cudaStream_t st);
+// NHWC level: statistics gradient (+ L2pooling backward when poolx != nullptr), masked by the level's ReLU
+template <typename T>
+int launch_level_grad(const T* fx, const T* fy, const T* poolx, const T* pooly, const T* gpoolx, const T* gpooly,
+                      const float* coef, int choff, int pairs, int h, int w, int c, T* gx, T* gy, cudaStream_t st);
+// conv1_1 + normalisation backward: gz [n,h,w,64] -> NCHW fp32 frame gradients
+template <typename T>
+int launch_conv1_1_bwd(const T* gz, const float* wb, int nx, int n, int h, int w, float* gx, float* gy, cudaStream_t st);
+int launch_pack_w_bwd(const float* w_oihw, int cin, int cout, float* w_f32, bf16* w_hi, cudaStream_t st);
+int launch_pack_w11_bwd(const float* w_oihw, float* out, cudaStream_t st);
 
 // ---- A-DISTS --------------------------------------------------------------------------------------
 // See adists.cu.

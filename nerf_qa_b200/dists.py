@@ -130,25 +130,68 @@ class _TrunkModule(nn.Module):
         return state
 
 
-class _AlphaBetaCombine(torch.autograd.Function):
-    """score_b = 1 - sum_c (alpha_c S1_bc + beta_c S2_bc) / (sum alpha + sum beta)   (DISTS_pt.py:127-144).
+def _alpha_beta_grads(grad_out, score, s1s2, alpha, beta):
+    """d score_b / d alpha_c = (-S1_bc + (1 - score_b)) / w from the saved per-channel S1/S2 (no feature re-read):
+    the direct term -S1/w plus the shared term through w = sum(alpha) + sum(beta) (DISTS_pt.py:127-144)."""
+    w = alpha.sum() + beta.sum()
+    d = (1.0 - score).unsqueeze(1)                                   # [B,1] = (dist1 + dist2)
+    ga = (grad_out.unsqueeze(1) * (d - s1s2[:, 0]) / w).sum(0)
+    gb = (grad_out.unsqueeze(1) * (d - s1s2[:, 1]) / w).sum(0)
+    return ga.reshape(alpha.shape), gb.reshape(beta.shape)
 
-    Forward returns the kernel's score; backward gives the alpha/beta gradients from the saved per-channel
-    S1/S2 (no feature re-read): d score_b / d alpha_c = (-S1_bc + (1 - score_b)) / w."""
+
+class _DistsScore(torch.autograd.Function):
+    """DISTS.forward under autograd (DISTS_pt.py:105-148).  Forward = nqa_dists_forward; backward =
+    nqa_dists_backward for the frames (through the trunk when require_grad=True, level-0 statistics only
+    otherwise -- the reference's forward_once returns the raw x as level 0 even under no_grad) plus the
+    closed-form alpha/beta gradients."""
 
     @staticmethod
-    def forward(ctx, score, s1s2, alpha, beta):
-        ctx.save_for_backward(score, s1s2, alpha, beta)
-        return score.clone()
+    def forward(ctx, x, y, alpha, beta, lib_ctx, prec, through_trunk):
+        score, s1s2 = lib_ctx.dists_forward(x, y, prec, want_s1s2=True)
+        ctx.save_for_backward(x, y, score, s1s2, alpha, beta)
+        ctx.lib_ctx, ctx.prec, ctx.through_trunk = lib_ctx, prec, through_trunk
+        return score
 
     @staticmethod
     def backward(ctx, grad_out):
-        score, s1s2, alpha, beta = ctx.saved_tensors
-        w = alpha.sum() + beta.sum()
-        d = (1.0 - score).unsqueeze(1)                                   # [B,1] = (dist1 + dist2)
-        ga = (grad_out.unsqueeze(1) * (d - s1s2[:, 0]) / w).sum(0)
-        gb = (grad_out.unsqueeze(1) * (d - s1s2[:, 1]) / w).sum(0)
-        return None, None, ga.reshape(alpha.shape), gb.reshape(beta.shape)
+        x, y, score, s1s2, alpha, beta = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        gx = gy = ga = gb = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gx, gy = ctx.lib_ctx.dists_backward(x, y, ctx.prec, grad_out, ctx.through_trunk)
+            gx = gx if ctx.needs_input_grad[0] else None
+            gy = gy if ctx.needs_input_grad[1] else None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            ga, gb = _alpha_beta_grads(grad_out, score, s1s2, alpha, beta)
+        return gx, gy, ga, gb, None, None, None
+
+
+class _DistsFromFeats(torch.autograd.Function):
+    """forward_from_feats under autograd (DISTS_pt.py:181-208): gradients w.r.t. the 2 x 6 feature tensors
+    (what the NR models back-propagate, model_nr_v8.py:258-265) and alpha/beta."""
+
+    @staticmethod
+    def forward(ctx, alpha, beta, lib_ctx, *feats):
+        f0, f1 = feats[:6], feats[6:]
+        score, s1s2 = lib_ctx.dists_from_feats(f0, f1)
+        ctx.save_for_backward(score, s1s2, alpha, beta, *feats)
+        ctx.lib_ctx = lib_ctx
+        return score
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        score, s1s2, alpha, beta = ctx.saved_tensors[:4]
+        feats = ctx.saved_tensors[4:]
+        grad_out = grad_out.contiguous()
+        ga = gb = None
+        gf = [None] * 12
+        if any(ctx.needs_input_grad[3:]):
+            g0, g1 = ctx.lib_ctx.dists_from_feats_backward(feats[:6], feats[6:], grad_out)
+            gf = [g if need else None for g, need in zip(list(g0) + list(g1), ctx.needs_input_grad[3:])]
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            ga, gb = _alpha_beta_grads(grad_out, score, s1s2, alpha, beta)
+        return (ga, gb, None, *gf)
 
 
 class DISTS(_TrunkModule):
@@ -193,30 +236,37 @@ class DISTS(_TrunkModule):
             ctx.set_alpha_beta(self.alpha, self.beta)
             ctx.ab_key = key
 
-    def _finish(self, score, s1s2, batch_average: bool):
-        if torch.is_grad_enabled() and (self.alpha.requires_grad or self.beta.requires_grad):
-            score = _AlphaBetaCombine.apply(score, s1s2, self.alpha, self.beta)
-        return score.mean() if batch_average else score
 
     # -- scoring ---------------------------------------------------------------------------------
     def forward(self, x, y, require_grad: bool = False, batch_average: bool = False, warp=None, certainty=None):
         """Per-frame DISTS scores ``[B]`` (or their mean).  ``warp`` / ``certainty`` are accepted and ignored
         exactly like the reference (DISTS_pt.py:105)."""
-        if require_grad:
-            raise NotImplementedError("require_grad=True (gradients w.r.t. the frames through the VGG trunk) is not "
-                                      "implemented in nerf_qa_b200 yet; alpha/beta gradients are available")
         ctx = self._context(x.device)
         self._sync_alpha_beta(ctx)
-        score, s1s2 = ctx.dists_forward(x, y, self._prec(), want_s1s2=True)
-        return self._finish(score, s1s2, batch_average)
+        wants_grad = torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or self.alpha.requires_grad
+                                                  or self.beta.requires_grad)
+        if wants_grad:
+            if (x.requires_grad or y.requires_grad) and self.precision == "bf16x3":
+                raise NotImplementedError("gradients w.r.t. the frames are implemented for precision 'fp32' and 'bf16'")
+            # require_grad=False keeps the trunk out of the graph like the reference's torch.no_grad() block; the
+            # level-0 statistics of the raw frames stay differentiable (DISTS_pt.py:103, 109-112)
+            score = _DistsScore.apply(x, y, self.alpha, self.beta, ctx, self._prec(), bool(require_grad))
+        else:
+            score, _ = ctx.dists_forward(x, y, self._prec(), want_s1s2=False)
+        return score.mean() if batch_average else score
 
     def forward_from_feats(self, feats0: Sequence[torch.Tensor], feats1: Sequence[torch.Tensor],
                            batch_average: bool = False):
         """DISTS_pt.py:181-208."""
         ctx = self._context(feats0[0].device)
         self._sync_alpha_beta(ctx)
-        score, s1s2 = ctx.dists_from_feats(feats0, feats1)
-        return self._finish(score, s1s2, batch_average)
+        feats = list(feats0) + list(feats1)
+        if torch.is_grad_enabled() and (self.alpha.requires_grad or self.beta.requires_grad
+                                        or any(f.requires_grad for f in feats)):
+            score = _DistsFromFeats.apply(self.alpha, self.beta, ctx, *feats)
+        else:
+            score, _ = ctx.dists_from_feats(feats0, feats1)
+        return score.mean() if batch_average else score
 
     def score_host(self, x: torch.Tensor, y: torch.Tensor, device: Optional[torch.device] = None) -> torch.Tensor:
         """End-to-end call from HOST tensors (pinned recommended): streams frames to the GPU in micro-batches
