@@ -40,6 +40,9 @@ WORKLOADS = {
                   desc="DISTS batch of 64 synthetic 1920x1080 frame pairs per GPU (BASELINE configs[1])"),
     "adists": dict(pairs=32, metric="adists_1080p_frame_pairs_per_sec",
                    desc="A-DISTS batch of 32 synthetic 1920x1080 frame pairs per GPU (BASELINE configs[2])"),
+    "train": dict(pairs=32, metric="dists_512_fwd_bwd_frame_pairs_per_sec", hw=(512, 512),
+                  desc="DISTS forward+backward (require_grad=True) on 32 synthetic 512x512 crop pairs per GPU "
+                       "(BASELINE configs[4]); a step = scores + d(mean score)/d frames"),
 }
 # algorithmic work per 1080p frame PAIR
 TRUNK_FLOP_PER_PAIR = 2.5386e12
@@ -98,7 +101,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_frames_device(pairs: int, device, seed: int = 0):
+def make_frames_device(pairs: int, device, seed: int = 0, H: int = H, W: int = W):
     """Synthetic "NeRF-like" frames generated on the device: box-blurred noise + the five distortion
     types of nerf_qa_b200.synth, 8 distinct pairs tiled to the batch."""
     import torch.nn.functional as F
@@ -230,15 +233,26 @@ def main():
     pairs = args.pairs or wl["pairs"]
     steps, warmup = args.steps, max(args.warmup, 3)
     peaks = load_peaks()
+    H, W = wl.get("hw", (1080, 1920))
+    train = args.workload == "train"
 
-    model = build_model(args.workload, args.precision, device)
-    x, y = make_frames_device(pairs, device, seed=rank)
+    model = build_model("adists" if args.workload == "adists" else "dists", args.precision, device)
+    x, y = make_frames_device(pairs, device, seed=rank, H=H, W=W)
+    if train:
+        x.requires_grad_(True)
+        y.requires_grad_(True)
     ctx = model._context(device)
     gathered = torch.empty(world * pairs, device=device, dtype=torch.float32) if world > 1 else None
 
     def step():
-        with torch.no_grad():
-            s = model(x, y) if args.workload == "dists" else model(x, y, as_loss=False)
+        if train:
+            x.grad = y.grad = None
+            s = model(x, y, require_grad=True)
+            s.mean().backward()
+            s = s.detach()
+        else:
+            with torch.no_grad():
+                s = model(x, y) if args.workload == "dists" else model(x, y, as_loss=False)
         if world > 1:
             dist.all_gather_into_tensor(gathered, s)     # the path's one collective: per-frame score gather
             return gathered
@@ -284,7 +298,7 @@ def main():
     # ---- end to end through the host-buffer C-ABI call (H2D of the frames + D2H of the scores inside) ----
     e2e = None
     if args.workload == "dists" and not args.no_e2e:
-        xh, yh = x.cpu().pin_memory(), y.cpu().pin_memory()
+        xh, yh = x.detach().cpu().pin_memory(), y.detach().cpu().pin_memory()
         out = torch.empty(pairs, dtype=torch.float32).pin_memory()
         model.score_host(xh, yh, device)                     # warm-up (staging buffers)
         barrier()
@@ -306,7 +320,9 @@ def main():
         # (+ the stand-alone conv1_1 kernel when the fused stage-1 kernel is switched off)
         conv_fams = [prof[k] for k in ("conv_tc", "stage1", "conv1_1") if k in prof]
         tc_ms, tc_launches = sum(v[0] for v in conv_fams), sum(v[1] for v in conv_fams)
-        tc_flop = TRUNK_FLOP_PER_PAIR * pairs * steps
+        # train: forward, recomputed forward inside the backward call, and 12 of 13 data-gradient convolutions
+        flop_pair = TRUNK_FLOP_PER_PAIR * (H * W) / (1080 * 1920) * (3.0 if train else 1.0)
+        tc_flop = flop_pair * pairs * steps
         tc_peak = peaks["bf16_tflops_sustained"] * (1.0 if args.precision == "bf16" else 1.0)
         achieved = tc_flop / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None
         mma_factor = 3.0 if args.precision == "bf16x3" else 1.0
@@ -328,7 +344,7 @@ def main():
             "metric": wl["metric"], "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": wl["desc"], "pairs_per_gpu": pairs, "resolution": "1920x1080",
+            "config": {"workload": wl["desc"], "pairs_per_gpu": pairs, "resolution": f"{W}x{H}",
                        "trunk_precision": args.precision, "vgg16": "random-init (seed 1234), shipped alpha/beta",
                        "micro_batch_pairs": ctx.micro_batch(pairs, H, W, model._prec()),
                        "l2": f"inputs are {2 * pairs * 3 * H * W * 4 / 1e9:.2f} GB per step, larger than the 126 MB L2",
@@ -336,7 +352,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(lsum.item()), "clocks": clocks, "roofline": roofline,
             "kernel_families": families,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not train:
             n = 2 if args.workload == "dists" else 1
             pps, dt_cpu, cores = cpu_reference_pairs_per_sec(args.workload, n, 1 if args.workload == "dists" else 0)
             line["cpu_baseline"] = {"value": pps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
