@@ -83,6 +83,12 @@ NQA_API int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS
  * inside the scoring calls. */
 NQA_API int nqa_set_alpha_beta(nqa_ctx* ctx, const float* alpha, const float* beta);
 
+/* Channel weights used AS GIVEN: score = 1 - sum_c (a_c S1 + b_c S2), no division by the joint sum.  For the
+ * reference's weight-normalisation variants, where the caller forms the effective weights itself and autograd
+ * differentiates that transform: relu / w_sum.detach() / beta.detach() (DISTS_pt_original.py:111-121) and the
+ * softmax over the 2950 logits (DISTS_pt_softmax.py:117-123).  d score_b / d a_c = -S1_bc, d score_b / d b_c = -S2_bc. */
+NQA_API int nqa_set_channel_weights(nqa_ctx* ctx, const float* a, const float* b);
+
 /* DISTS.forward(x, y) (DISTS_pt.py:105-148): per-frame scores.
  *   x, y       device, [B,3,H,W] fp32
  *   score_out  device, [B] fp32

@@ -25,6 +25,7 @@ EXPORTS = (
     "nqa_dists_from_feats", "nqa_adists_forward", "nqa_adists_from_feats", "nqa_l2pool",
     "nqa_workspace_bytes", "nqa_launch_count", "nqa_micro_batch", "nqa_conv3x3_relu",
     "nqa_profile_enable", "nqa_profile_read", "nqa_dists_backward", "nqa_dists_from_feats_backward",
+    "nqa_set_channel_weights",
 )
 KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists", "pool_stats",
                    "stage1", "backward")
@@ -55,6 +56,7 @@ def load_library() -> ctypes.CDLL:
     lib.nqa_ctx_destroy.argtypes = [vp]
     lib.nqa_set_vgg_weights.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     lib.nqa_set_alpha_beta.argtypes = [vp, fp, fp]
+    lib.nqa_set_channel_weights.argtypes = [vp, fp, fp]
     lib.nqa_dists_forward.argtypes = [vp, fp, fp, ci, ci, ci, ci, fp, fp, vp]
     lib.nqa_dists_forward_host.argtypes = [vp, fp, fp, ci, ci, ci, ci, fp]
     lib.nqa_dists_features.argtypes = [vp, fp, ci, ci, ci, ci, ctypes.POINTER(vp), vp]
@@ -142,6 +144,14 @@ class Context:
         b = beta.detach().to(torch.float32).reshape(-1).contiguous()
         assert a.numel() == NUM_CHANNELS and b.numel() == NUM_CHANNELS
         _check(self.lib.nqa_set_alpha_beta(self.handle, _ptr(a), _ptr(b)))
+
+    def set_channel_weights(self, a: torch.Tensor, b: torch.Tensor) -> None:
+        """Effective per-channel weights, used as given (no division by their sum inside the kernels)."""
+        a = a.detach().to(torch.float32).reshape(-1).contiguous()
+        b = b.detach().to(torch.float32).reshape(-1).contiguous()
+        assert a.numel() == NUM_CHANNELS and b.numel() == NUM_CHANNELS
+        _check(self.lib.nqa_set_channel_weights(self.handle, _ptr(a), _ptr(b)))
+        self.ab_key = None
 
     # -- scoring ---------------------------------------------------------------------------------
     def dists_forward(self, x: torch.Tensor, y: torch.Tensor, precision: int, want_s1s2: bool = True):

@@ -21,11 +21,13 @@ namespace nqa {
 // ================================================================================================
 __global__ void __launch_bounds__(256)
 stat_coef_kernel(const float* __restrict__ moments, const float* __restrict__ alpha, const float* __restrict__ beta,
-                 const float* __restrict__ grad_score, GradLevels lv, int levels_valid, float* __restrict__ coef) {
+                 int normalize, const float* __restrict__ grad_score, GradLevels lv, int levels_valid,
+                 float* __restrict__ coef) {
   __shared__ double smd[33];
   double wpart = 0.0;
   for (int c = threadIdx.x; c < kTotalChannels; c += 256) wpart += (double)alpha[c] + (double)beta[c];
-  const double wsum = block_sum<double>(wpart, smd);
+  double wsum = block_sum<double>(wpart, smd);
+  if (!normalize) wsum = 1.0;          // channel weights are used as given (nqa_set_channel_weights)
   const int b = blockIdx.y;
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= kTotalChannels) return;
@@ -52,10 +54,10 @@ stat_coef_kernel(const float* __restrict__ moments, const float* __restrict__ al
   out[4] = out[1];                                                                         // Qy
 }
 
-int launch_stat_coef(const float* moments, const float* alpha, const float* beta, const float* grad_score,
+int launch_stat_coef(const float* moments, const float* alpha, const float* beta, bool normalize, const float* grad_score,
                      const GradLevels& lv, int levels_valid, int pairs, float* coef, cudaStream_t st) {
   dim3 grid(ceil_div(kTotalChannels, 256), pairs);
-  stat_coef_kernel<<<grid, 256, 0, st>>>(moments, alpha, beta, grad_score, lv, levels_valid, coef);
+  stat_coef_kernel<<<grid, 256, 0, st>>>(moments, alpha, beta, normalize ? 1 : 0, grad_score, lv, levels_valid, coef);
   return 1;
 }
 

@@ -58,6 +58,7 @@ struct nqa_ctx {
   int device = 0;
   int sm_count = kNumSMs;
   bool have_weights = false, have_alpha_beta = false;
+  bool ab_normalize = true;              // divide alpha/beta by their joint sum inside the kernels (DISTS_pt.py:127-129)
   float* w11 = nullptr;                  // conv1_1 [27][64] (CUDA-core path)
   bf16* w11_img = nullptr;               // conv1_1 [2][64*32] UMMA operand image (tensor path)
   float* bias[kNumConvs] = {};           // fp32
@@ -375,7 +376,7 @@ int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float
     fp.lv[k].inv_n = 1.0 / ((double)h[k] * w[k]);
   }
   ProfScope ps(ctx, NQA_K_FINALIZE, st);
-  ctx->launches += launch_dists_finalize(fp, ctx->alpha, ctx->beta, pairs, score, s1s2, moments, pb.terms, st);
+  ctx->launches += launch_dists_finalize(fp, ctx->alpha, ctx->beta, ctx->ab_normalize, pairs, score, s1s2, moments, pb.terms, st);
   return NQA_OK;
 }
 
@@ -546,7 +547,7 @@ int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int
   int rc = finalize(ctx, pb, pairs, H, W, score_scratch, nullptr, st, moments, levels_valid);
   if (rc != NQA_OK) return rc;
   ProfScope psb(ctx, NQA_K_BACKWARD, st);
-  ctx->launches += launch_stat_coef(moments, ctx->alpha, ctx->beta, grad_score, gl, levels_valid, pairs, coef, st);
+  ctx->launches += launch_stat_coef(moments, ctx->alpha, ctx->beta, ctx->ab_normalize, grad_score, gl, levels_valid, pairs, coef, st);
 
   if (through_trunk) {
     const size_t gsz = (size_t)n * H * W * 64 * sizeof(T);
@@ -733,7 +734,14 @@ int nqa_set_alpha_beta(nqa_ctx* ctx, const float* alpha, const float* beta) {
   CUDA_TRY(cudaMemcpy(ctx->alpha, alpha, kTotalChannels * sizeof(float), cudaMemcpyDefault));
   CUDA_TRY(cudaMemcpy(ctx->beta, beta, kTotalChannels * sizeof(float), cudaMemcpyDefault));
   ctx->have_alpha_beta = true;
+  ctx->ab_normalize = true;
   return NQA_OK;
+}
+
+int nqa_set_channel_weights(nqa_ctx* ctx, const float* a, const float* b) {
+  const int rc = nqa_set_alpha_beta(ctx, a, b);
+  if (rc == NQA_OK) ctx->ab_normalize = false;
+  return rc;
 }
 
 int nqa_dists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int precision, float* score_out,
@@ -1044,7 +1052,7 @@ int nqa_dists_from_feats_backward(nqa_ctx* ctx, const float* const feats_x[NQA_N
   if (rc != NQA_OK) return rc;
   {
     ProfScope ps(ctx, NQA_K_BACKWARD, st);
-    ctx->launches += launch_stat_coef(moments, ctx->alpha, ctx->beta, grad_score, gl, kNumLevels, B, coef, st);
+    ctx->launches += launch_stat_coef(moments, ctx->alpha, ctx->beta, ctx->ab_normalize, grad_score, gl, kNumLevels, B, coef, st);
     for (int k = 0; k < kNumLevels; ++k)
       ctx->launches += launch_stat_grad_planar(feats_x[k], feats_y[k], coef, level_offset(k), B, level_channels(k), lh[k] * lw[k],
                                                grad_fx[k], grad_fy[k], false, st);

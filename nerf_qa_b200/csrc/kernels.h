@@ -39,8 +39,8 @@ int launch_stats_planar(const float* x, const float* y, int pairs, int c, int hw
 // score[b] = 1 - sum_c (alpha_c/w S1 + beta_c/w S2); optional s1s2[b][2][1475]; optional moments[b][1475][5]
 // (mean x, mean y, var x, var y, cov) for the backward pass.
 // terms: [pairs][1475] fp64 scratch
-int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const float* beta, int pairs, float* score,
-                          float* s1s2, float* moments, double* terms, cudaStream_t st);
+int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const float* beta, bool normalize, int pairs,
+                          float* score, float* s1s2, float* moments, double* terms, cudaStream_t st);
 
 // ---- pooling / layout -----------------------------------------------------------------------------
 template <typename T>
@@ -124,7 +124,7 @@ struct GradLevels {
 };
 // coef[b][c][5] = (Px, Qx, R, Py, Qy): d score_b/d x_i = Px + Qx x_i + R y_i (times grad_score[b], already folded in);
 // channels of levels >= levels_valid get zeros.  moments from launch_dists_finalize.
-int launch_stat_coef(const float* moments, const float* alpha, const float* beta, const float* grad_score,
+int launch_stat_coef(const float* moments, const float* alpha, const float* beta, bool normalize, const float* grad_score,
                      const GradLevels& lv, int levels_valid, int pairs, float* coef, cudaStream_t st);
 // NCHW fp32 planes of one level: gx (+)= Px + Qx x + R y, gy (+)= Py + Qy y + R x
 int launch_stat_grad_planar(const float* x, const float* y, const float* coef, int choff, int pairs, int c, int hw,

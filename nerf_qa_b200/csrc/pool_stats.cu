@@ -238,7 +238,7 @@ dists_terms_kernel(FinalizeParams p, const float* __restrict__ alpha, const floa
 
 __global__ void __launch_bounds__(256)
 dists_score_kernel(const double* __restrict__ terms, const float* __restrict__ alpha, const float* __restrict__ beta,
-                   float* __restrict__ score) {
+                   int normalize, float* __restrict__ score) {
   __shared__ double smd[33];
   const int b = blockIdx.x;
   double wpart = 0.0, tpart = 0.0;
@@ -248,14 +248,14 @@ dists_score_kernel(const double* __restrict__ terms, const float* __restrict__ a
   }
   const double wsum = block_sum<double>(wpart, smd);
   const double total = block_sum<double>(tpart, smd);
-  if (threadIdx.x == 0) score[b] = (float)(1.0 - total / wsum);
+  if (threadIdx.x == 0) score[b] = (float)(1.0 - (normalize ? total / wsum : total));
 }
 
-int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const float* beta, int pairs, float* score,
-                          float* s1s2, float* moments, double* terms, cudaStream_t st) {
+int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const float* beta, bool normalize, int pairs,
+                          float* score, float* s1s2, float* moments, double* terms, cudaStream_t st) {
   dim3 grid(ceil_div(kTotalChannels, kFinCh), pairs);
   dists_terms_kernel<<<grid, kFinCh * kFinLanes, 0, st>>>(p, alpha, beta, terms, s1s2, moments);
-  dists_score_kernel<<<pairs, 256, 0, st>>>(terms, alpha, beta, score);
+  dists_score_kernel<<<pairs, 256, 0, st>>>(terms, alpha, beta, normalize ? 1 : 0, score);
   return 2;
 }
 

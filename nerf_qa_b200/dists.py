@@ -4,7 +4,8 @@ routed through the C-ABI library (hand-written sm_100a kernels).  No eager-PyTor
 tensors raise.
 
 Differences a caller can observe are listed in DESIGN.md ("API deviations"): ``precision=`` selects the
-trunk arithmetic; ``require_grad=True`` (gradients w.r.t. the input frames) is not implemented yet.
+trunk arithmetic.  ``DISTSOriginal`` / ``DISTSSoftmax`` are the reference's ``DISTS_pt_original`` / ``DISTS_pt_softmax``
+weight-normalisation flavours (same kernels, different host-side weight transform).
 """
 from __future__ import annotations
 
@@ -130,67 +131,66 @@ class _TrunkModule(nn.Module):
         return state
 
 
-def _alpha_beta_grads(grad_out, score, s1s2, alpha, beta):
-    """d score_b / d alpha_c = (-S1_bc + (1 - score_b)) / w from the saved per-channel S1/S2 (no feature re-read):
-    the direct term -S1/w plus the shared term through w = sum(alpha) + sum(beta) (DISTS_pt.py:127-144)."""
-    w = alpha.sum() + beta.sum()
-    d = (1.0 - score).unsqueeze(1)                                   # [B,1] = (dist1 + dist2)
-    ga = (grad_out.unsqueeze(1) * (d - s1s2[:, 0]) / w).sum(0)
-    gb = (grad_out.unsqueeze(1) * (d - s1s2[:, 1]) / w).sum(0)
-    return ga.reshape(alpha.shape), gb.reshape(beta.shape)
-
-
-class _DistsScore(torch.autograd.Function):
-    """DISTS.forward under autograd (DISTS_pt.py:105-148).  Forward = nqa_dists_forward; backward =
-    nqa_dists_backward for the frames (through the trunk when require_grad=True, level-0 statistics only
-    otherwise -- the reference's forward_once returns the raw x as level 0 even under no_grad) plus the
-    closed-form alpha/beta gradients."""
+class _WeightedScore(torch.autograd.Function):
+    """score_b = 1 - sum_c (a_c S1_bc + b_c S2_bc) with EFFECTIVE channel weights a, b used as given
+    (nqa_set_channel_weights): the weight normalisation (alpha / (sum alpha + sum beta) in DISTS_pt.py:127-129; relu /
+    detach / softmax in the `_original` / `_softmax` flavours) stays in torch and is differentiated by autograd.
+    Backward: frames through nqa_dists_backward (the whole trunk when require_grad=True, level-0 statistics only
+    otherwise -- the reference's forward_once returns the raw x as level 0 even under no_grad); weights in closed form
+    from the saved per-channel S1/S2: d score_b / d a_c = -S1_bc, d score_b / d b_c = -S2_bc."""
 
     @staticmethod
-    def forward(ctx, x, y, alpha, beta, lib_ctx, prec, through_trunk):
+    def forward(ctx, x, y, a, b, lib_ctx, prec, through_trunk):
+        lib_ctx.set_channel_weights(a, b)
         score, s1s2 = lib_ctx.dists_forward(x, y, prec, want_s1s2=True)
-        ctx.save_for_backward(x, y, score, s1s2, alpha, beta)
+        ctx.save_for_backward(x, y, s1s2, a, b)
         ctx.lib_ctx, ctx.prec, ctx.through_trunk = lib_ctx, prec, through_trunk
         return score
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, y, score, s1s2, alpha, beta = ctx.saved_tensors
+        x, y, s1s2, a, b = ctx.saved_tensors
         grad_out = grad_out.contiguous()
         gx = gy = ga = gb = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            ctx.lib_ctx.set_channel_weights(a, b)
             gx, gy = ctx.lib_ctx.dists_backward(x, y, ctx.prec, grad_out, ctx.through_trunk)
             gx = gx if ctx.needs_input_grad[0] else None
             gy = gy if ctx.needs_input_grad[1] else None
-        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            ga, gb = _alpha_beta_grads(grad_out, score, s1s2, alpha, beta)
+        if ctx.needs_input_grad[2]:
+            ga = -(grad_out.unsqueeze(1) * s1s2[:, 0]).sum(0).reshape(a.shape)
+        if ctx.needs_input_grad[3]:
+            gb = -(grad_out.unsqueeze(1) * s1s2[:, 1]).sum(0).reshape(b.shape)
         return gx, gy, ga, gb, None, None, None
 
 
-class _DistsFromFeats(torch.autograd.Function):
+class _WeightedFromFeats(torch.autograd.Function):
     """forward_from_feats under autograd (DISTS_pt.py:181-208): gradients w.r.t. the 2 x 6 feature tensors
-    (what the NR models back-propagate, model_nr_v8.py:258-265) and alpha/beta."""
+    (what the NR models back-propagate, model_nr_v8.py:258-265) and the effective channel weights."""
 
     @staticmethod
-    def forward(ctx, alpha, beta, lib_ctx, *feats):
-        f0, f1 = feats[:6], feats[6:]
-        score, s1s2 = lib_ctx.dists_from_feats(f0, f1)
-        ctx.save_for_backward(score, s1s2, alpha, beta, *feats)
+    def forward(ctx, a, b, lib_ctx, *feats):
+        lib_ctx.set_channel_weights(a, b)
+        score, s1s2 = lib_ctx.dists_from_feats(feats[:6], feats[6:])
+        ctx.save_for_backward(s1s2, a, b, *feats)
         ctx.lib_ctx = lib_ctx
         return score
 
     @staticmethod
     def backward(ctx, grad_out):
-        score, s1s2, alpha, beta = ctx.saved_tensors[:4]
-        feats = ctx.saved_tensors[4:]
+        s1s2, a, b = ctx.saved_tensors[:3]
+        feats = ctx.saved_tensors[3:]
         grad_out = grad_out.contiguous()
         ga = gb = None
         gf = [None] * 12
         if any(ctx.needs_input_grad[3:]):
+            ctx.lib_ctx.set_channel_weights(a, b)
             g0, g1 = ctx.lib_ctx.dists_from_feats_backward(feats[:6], feats[6:], grad_out)
             gf = [g if need else None for g, need in zip(list(g0) + list(g1), ctx.needs_input_grad[3:])]
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            ga, gb = _alpha_beta_grads(grad_out, score, s1s2, alpha, beta)
+        if ctx.needs_input_grad[0]:
+            ga = -(grad_out.unsqueeze(1) * s1s2[:, 0]).sum(0).reshape(a.shape)
+        if ctx.needs_input_grad[1]:
+            gb = -(grad_out.unsqueeze(1) * s1s2[:, 1]).sum(0).reshape(b.shape)
         return (ga, gb, None, *gf)
 
 
@@ -230,6 +230,14 @@ class DISTS(_TrunkModule):
         self.alpha.data = alpha / weight_sum
         self.beta.data = beta / weight_sum
 
+    def _effective_weights(self):
+        """The per-channel weights the score is formed with (DISTS_pt.py:127-129): alpha, beta over their joint sum.
+        Differentiable torch ops on 2 x 1475 values; the flavours below override this."""
+        w_sum = self.alpha.sum() + self.beta.sum()
+        return self.alpha / w_sum, self.beta / w_sum
+
+    _squeeze_score = False      # DISTS_pt_original returns score.squeeze() (0-d for B = 1)
+
     def _sync_alpha_beta(self, ctx: _lib.Context) -> None:
         key = (self.alpha.data_ptr(), self.alpha._version, self.beta.data_ptr(), self.beta._version)
         if ctx.ab_key != key:
@@ -242,7 +250,6 @@ class DISTS(_TrunkModule):
         """Per-frame DISTS scores ``[B]`` (or their mean).  ``warp`` / ``certainty`` are accepted and ignored
         exactly like the reference (DISTS_pt.py:105)."""
         ctx = self._context(x.device)
-        self._sync_alpha_beta(ctx)
         wants_grad = torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or self.alpha.requires_grad
                                                   or self.beta.requires_grad)
         if wants_grad:
@@ -250,21 +257,36 @@ class DISTS(_TrunkModule):
                 raise NotImplementedError("gradients w.r.t. the frames are implemented for precision 'fp32' and 'bf16'")
             # require_grad=False keeps the trunk out of the graph like the reference's torch.no_grad() block; the
             # level-0 statistics of the raw frames stay differentiable (DISTS_pt.py:103, 109-112)
-            score = _DistsScore.apply(x, y, self.alpha, self.beta, ctx, self._prec(), bool(require_grad))
+            a, b = self._effective_weights()
+            score = _WeightedScore.apply(x, y, a, b, ctx, self._prec(), bool(require_grad))
         else:
+            self._sync_weights_nograd(ctx)
             score, _ = ctx.dists_forward(x, y, self._prec(), want_s1s2=False)
+        if self._squeeze_score:
+            score = score.squeeze()
         return score.mean() if batch_average else score
+
+    def _sync_weights_nograd(self, ctx: _lib.Context) -> None:
+        """Inference: the plain flavour hands raw alpha/beta to the library (it divides by their joint sum in fp64);
+        flavours with their own normalisation upload the effective weights."""
+        if type(self)._effective_weights is DISTS._effective_weights:
+            self._sync_alpha_beta(ctx)
+        else:
+            with torch.no_grad():
+                a, b = self._effective_weights()
+            ctx.set_channel_weights(a, b)
 
     def forward_from_feats(self, feats0: Sequence[torch.Tensor], feats1: Sequence[torch.Tensor],
                            batch_average: bool = False):
         """DISTS_pt.py:181-208."""
         ctx = self._context(feats0[0].device)
-        self._sync_alpha_beta(ctx)
         feats = list(feats0) + list(feats1)
         if torch.is_grad_enabled() and (self.alpha.requires_grad or self.beta.requires_grad
                                         or any(f.requires_grad for f in feats)):
-            score = _DistsFromFeats.apply(self.alpha, self.beta, ctx, *feats)
+            a, b = self._effective_weights()
+            score = _WeightedFromFeats.apply(a, b, ctx, *feats)
         else:
+            self._sync_weights_nograd(ctx)
             score, _ = ctx.dists_from_feats(feats0, feats1)
         return score.mean() if batch_average else score
 
@@ -274,8 +296,93 @@ class DISTS(_TrunkModule):
         does in prep.py:186-190, without staging the whole batch on the device first."""
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         ctx = self._context(dev)
-        self._sync_alpha_beta(ctx)
+        self._sync_weights_nograd(ctx)
         return ctx.dists_forward_host(x, y, self._prec())
+
+
+class _FlavourConfig:
+    """The four knobs the reference's flavours read from the global ``wandb.config`` (DISTS_pt_original.py:69-70,
+    111-118; DISTS_pt_softmax.py:124).  Explicit constructor arguments win; otherwise a live ``wandb.config`` is
+    consulted when wandb is importable; otherwise the reference's argparse defaults (run_final.py:64-70)."""
+    DEFAULTS = {"weight_lower_bound": 1e-4, "alpha_beta_ratio": 2.0, "dists_weight_norm": "off", "detach_beta": "False"}
+
+    def __init__(self, **overrides):
+        self.values = {k: v for k, v in overrides.items() if v is not None}
+
+    def get(self, key):
+        if key in self.values:
+            return self.values[key]
+        try:
+            import wandb
+            cfg = wandb.config
+            if cfg is not None and key in cfg:
+                return cfg[key]
+        except Exception:
+            pass
+        return self.DEFAULTS[key]
+
+
+class DISTSOriginal(DISTS):
+    """``nerf_qa/DISTS_pytorch/DISTS_pt_original.py`` (the FR-training flavour, model_stats.py / model.py): alpha/beta
+    clamped from below at load (:65-72), optional ``relu`` / ``w_sum_detach`` weight normalisation and ``detach_beta``
+    (:111-121), ``score.squeeze()`` (:134), ``project_weights`` with a uniform lower bound (:88-95)."""
+
+    _squeeze_score = True
+
+    def __init__(self, load_weights: bool = True, from_feats: bool = False, precision: str = "bf16",
+                 weight_lower_bound=None, alpha_beta_ratio=None, dists_weight_norm=None, detach_beta=None):
+        super().__init__(load_weights=load_weights, from_feats=from_feats, precision=precision)
+        self.config = _FlavourConfig(weight_lower_bound=weight_lower_bound, alpha_beta_ratio=alpha_beta_ratio,
+                                     dists_weight_norm=dists_weight_norm, detach_beta=detach_beta)
+        if load_weights:
+            self.original_alpha = self.alpha.data.clone()
+            self.original_beta = self.beta.data.clone()
+            lb, ratio = float(self.config.get("weight_lower_bound")), float(self.config.get("alpha_beta_ratio"))
+            self.alpha.data = torch.clamp(self.alpha.data, min=lb * ratio)
+            self.beta.data = torch.clamp(self.beta.data, min=lb)
+
+    def project_weights(self) -> None:
+        lower_bound = torch.zeros_like(self.alpha.data) + float(self.config.get("weight_lower_bound"))
+        alpha = torch.max(self.alpha.data, lower_bound * float(self.config.get("alpha_beta_ratio")))
+        beta = torch.max(self.beta.data, lower_bound)
+        weight_sum = torch.cat([alpha, beta], dim=1).sum()
+        self.alpha.data = alpha / weight_sum
+        self.beta.data = beta / weight_sum
+
+    def _effective_weights(self):
+        modes = str(self.config.get("dists_weight_norm")).split("+")
+        alpha = torch.relu(self.alpha) if "relu" in modes else self.alpha
+        beta = torch.relu(self.beta) if "relu" in modes else self.beta
+        if str(self.config.get("detach_beta")) == "True":
+            beta = beta.detach()
+        w_sum = alpha.sum() + beta.sum()
+        if "w_sum_detach" in modes:
+            w_sum = w_sum.detach()
+        return alpha / w_sum, beta / w_sum
+
+
+class DISTSSoftmax(DISTS):
+    """``nerf_qa/DISTS_pytorch/DISTS_pt_softmax.py``: alpha/beta are logits (initialised to log(max(w, 0) + 1e-10) of
+    the shipped weights, :65-78); the channel weights are the softmax over all 2950 logits (:117-123)."""
+
+    def __init__(self, load_weights: bool = True, from_feats: bool = False, precision: str = "bf16", detach_beta=None):
+        super().__init__(load_weights=load_weights, from_feats=from_feats, precision=precision)
+        self.config = _FlavourConfig(detach_beta=detach_beta)
+        if load_weights:
+            self.original_alpha = self.alpha.data.clone()
+            self.original_beta = self.beta.data.clone()
+            w = torch.cat([self.alpha.data, self.beta.data], dim=1)
+            logits = torch.log(torch.clamp(w, min=0.0) + 1e-10)
+            a_logits, b_logits = torch.split(logits, [self.alpha.shape[1], self.beta.shape[1]], dim=1)
+            self.alpha.data = a_logits.contiguous()
+            self.beta.data = b_logits.contiguous()
+
+    def _effective_weights(self):
+        w = torch.softmax(torch.cat([self.alpha, self.beta], dim=1), dim=1)
+        a, b = torch.split(w, self.alpha.shape[1], dim=1)
+        if str(self.config.get("detach_beta")) == "True":
+            b = b.detach()
+        return a, b
 
 
 def prepare_image(image, resize: bool = True, keep_aspect_ratio: bool = False) -> torch.Tensor:

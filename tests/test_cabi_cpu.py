@@ -97,17 +97,29 @@ def test_project_weights_matches_oracle():
 
 
 def test_alpha_beta_backward_formula():
-    """The autograd glue around the kernel's (score, S1, S2) equals autograd through the plain expression."""
-    from nerf_qa_b200.dists import _AlphaBetaCombine
+    """The autograd glue around the kernel's (score, S1, S2): closed-form gradients w.r.t. the effective channel
+    weights, chained by autograd through the weight normalisation, equal autograd through the plain expression
+    (DISTS_pt.py:127-144).  The library context is replaced by a stand-in that evaluates the same formula."""
+    from nerf_qa_b200.dists import _WeightedScore
     g = torch.Generator().manual_seed(0)
     s1s2 = torch.rand(3, 2, 1475, generator=g, dtype=torch.float64)
+
+    class FakeCtx:
+        def set_channel_weights(self, a, b):
+            self.a, self.b = a.detach().flatten(), b.detach().flatten()
+
+        def dists_forward(self, x, y, prec, want_s1s2=True):
+            return 1 - ((s1s2[:, 0] * self.a).sum(1) + (s1s2[:, 1] * self.b).sum(1)), s1s2
+
     alpha = torch.rand(1, 1475, 1, 1, generator=g, dtype=torch.float64, requires_grad=True)
     beta = torch.rand(1, 1475, 1, 1, generator=g, dtype=torch.float64, requires_grad=True)
     w = alpha.sum() + beta.sum()
     plain = 1 - ((s1s2[:, 0] * alpha.flatten()).sum(1) + (s1s2[:, 1] * beta.flatten()).sum(1)) / w
     coef = torch.tensor([1.0, -2.0, 0.5], dtype=torch.float64)
     ga, gb = torch.autograd.grad((plain * coef).sum(), [alpha, beta])
-    out = _AlphaBetaCombine.apply(plain.detach(), s1s2, alpha, beta)
+    x = torch.zeros(3, 3, 4, 4, dtype=torch.float64)
+    out = _WeightedScore.apply(x, x, alpha / w, beta / w, FakeCtx(), 0, False)
+    torch.testing.assert_close(out, plain.detach())
     ga2, gb2 = torch.autograd.grad((out * coef).sum(), [alpha, beta])
     torch.testing.assert_close(ga2, ga)
     torch.testing.assert_close(gb2, gb)

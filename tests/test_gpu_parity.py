@@ -324,3 +324,34 @@ def test_training_step_shape_512(models):
         l2 = float((a - b).norm() / a.norm())
         print(f"[parity] 512x512 frame gradient bf16 vs fp32: max err / max|g| = {err:.3e}, rel L2 = {l2:.3e}")
         assert l2 < 0.12 and err < 0.3
+
+
+# ---- weight-normalisation flavours (DISTS_pt_original.py, DISTS_pt_softmax.py) against the reference's own outputs ----
+@pytest.mark.parametrize("name", ["flavour_original_relu", "flavour_original_relu_wsumdetach_detachbeta", "flavour_softmax"])
+def test_flavours_match_reference(golden, name):
+    import warnings
+    from tests._util import load_synth_vgg
+    from tests.test_flavours_cpu import CASES
+    g = golden(name)
+    cls, cfg = CASES[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = load_synth_vgg(cls(precision="fp32", **cfg)).cuda().eval()
+    b, h, w, seed = (int(v) for v in g["shape"])
+    x, y = synth.make_frame_pairs(b, h, w, seed=seed)
+    with torch.enable_grad():
+        s = m(x.cuda(), y.cuda())
+        (s * torch.from_numpy(g["coeffs"]).cuda()).sum().backward()
+    report(f"{name} score", s.detach().cpu().numpy(), g["score"])
+    assert rel_err(s.detach().cpu().numpy(), g["score"]) < 1e-4
+    ga = m.alpha.grad.flatten().cpu().numpy()
+    gb = m.beta.grad.flatten().cpu().numpy() if m.beta.grad is not None else np.zeros_like(g["grad_beta"])
+    for nm, got, want in (("alpha", ga, g["grad_alpha"]), ("beta", gb, g["grad_beta"])):
+        scale = max(float(np.abs(want).max()), 1e-12)
+        err = float(np.abs(got - want).max()) / scale
+        print(f"[parity] {name} d loss/d {nm}: max err / max|g| = {err:.3e}")
+        assert err < 2e-3
+    with torch.no_grad():
+        one = m(x[:1].cuda(), y[:1].cuda())
+        assert one.dim() == int(g["score_b1_ndim"])                   # _original squeezes to 0-d, _softmax keeps [1]
+        assert abs(float(one) - float(g["score"][0])) < 1e-4 * abs(float(g["score"][0]))
