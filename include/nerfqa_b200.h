@@ -125,6 +125,11 @@ NQA_API int nqa_dists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NU
 NQA_API int nqa_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window,
                        int precision, float* score_out, void* stream);
 
+/* ADISTS.forward(as_map=True) (ADISTS.py:163,188-193): additionally writes the full-resolution map
+ * 1 - sum_k bilinear(D_map_k -> (H, W), align_corners=False) to map_out [B,H,W] (device).  map_out may be NULL. */
+NQA_API int nqa_adists_map(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int precision,
+                           float* score_out, float* map_out, void* stream);
+
 /* The statistics half of ADISTS.forward (ADISTS.py:147-197) from six NCHW fp32 device tensors per
  * image (the reference's forward_once format, level 0 = the raw frames). */
 NQA_API int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],

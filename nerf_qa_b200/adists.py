@@ -54,9 +54,12 @@ class ADISTS(_TrunkModule):
         """``as_loss=False`` -> per-frame scores ``[B]``; ``as_loss=True`` (the reference default) -> the scalar
         ``1 - mean_b D`` (ADISTS.py:192-197).  Asymmetric: probability maps and entropy weights come from ``x``."""
         assert x.shape == y.shape                                  # ADISTS.py:138
-        if as_map:
-            raise NotImplementedError("as_map=True (full-resolution distance map) is not implemented in nerf_qa_b200")
         ctx = self._context(x.device)
+        if as_map:
+            # ADISTS.py:163,189: D_map_full is [B,H,W] and each level adds a [B,1,H,W] tensor, so for B > 1 the
+            # reference's result broadcasts to [B,B,H,W] with the per-sample map repeated along dim 1 (upstream quirk)
+            _, dmap = ctx.adists_map(x, y, self.window_size, self._prec())
+            return dmap if x.shape[0] == 1 else dmap.expand(-1, x.shape[0], -1, -1)
         score = ctx.adists_forward(x, y, self.window_size, self._prec())
         if as_loss:
             return score.mean()        # 1 - mean(D) == mean(1 - D)

@@ -29,6 +29,7 @@ constexpr int kRedBlocks = 128;  // blocks per frame pair in the map reductions
 
 struct Taps {
   float g[kAdistsMaxWindow];
+  float2 g2[kAdistsMaxWindow];   // (g, g): operand of the packed f32x2 FMAs of the window kernel
 };
 
 struct LvlScal {   // per (pair, level) scalars of the ps chain
@@ -289,17 +290,15 @@ window_kernel(const float* __restrict__ fx, const float* __restrict__ fy, int c,
   extern __shared__ float smem[];
   float* sx = smem;
   float* sy = sx + IN * LDI;
-  float* hb = sy + IN * LDI;      // [5][IN][LDH]
+  float2* hb01 = reinterpret_cast<float2*>(sy + IN * LDI + ((2 * IN * LDI) & 1));   // [IN][LDH] (G_h x, G_h y), 8-byte aligned
+  float2* hb23 = hb01 + IN * LDH;                                                  // [IN][LDH] (G_h x^2, G_h y^2)
+  float* hb4 = reinterpret_cast<float*>(hb23 + IN * LDH);                          // [IN][LDH] G_h xy
 
   const int tile = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
   const int oy0 = (tile / tiles_x) * WT, ox0 = (tile % tiles_x) * WT;
   const int c_per = ceil_div(c, csplit);
   const int c_begin = split * c_per, c_end = min(c, c_begin + c_per);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  float g[WIN];
-#pragma unroll
-  for (int t = 0; t < WIN; ++t) g[t] = taps.g[t];
 
   // horizontal role: column group jg (8 output columns), input row hr
   const int jg = warp & 3, hr = (warp >> 2) * 32 + lane;
@@ -343,69 +342,72 @@ window_kernel(const float* __restrict__ fx, const float* __restrict__ fy, int c,
     }
     __syncthreads();
     if (ch + 1 < c_end) fetch(ch + 1);
+    // The five filtered planes are carried as two packed pairs (x, y), (x^2, y^2) and one scalar (x y): the sm_100
+    // f32x2 FMAs halve the issue slots of the 21-tap passes (the kernel is issue-bound), same IEEE arithmetic per lane.
     if (hr < IN) {
-      float o0[RX], o1[RX], o2[RX], o3[RX], o4[RX];
+      float2 o01[RX], o23[RX];
+      float o4[RX];
 #pragma unroll
-      for (int j = 0; j < RX; ++j) o0[j] = o1[j] = o2[j] = o3[j] = o4[j] = 0.f;
+      for (int j = 0; j < RX; ++j) { o01[j] = o23[j] = make_float2(0.f, 0.f); o4[j] = 0.f; }
       const float* rx = sx + hr * LDI + jg * RX;
       const float* ry = sy + hr * LDI + jg * RX;
 #pragma unroll
       for (int t = 0; t < RX + WIN - 1; ++t) {
-        const float a = rx[t], d = ry[t];
-        const float aa = a * a, dd = d * d, ad = a * d;
+        const float2 ad = make_float2(rx[t], ry[t]);
+        const float2 sq = __fmul2_rn(ad, ad);
+        const float cr = ad.x * ad.y;
 #pragma unroll
         for (int j = 0; j < RX; ++j) {
           if (t - j >= 0 && t - j < WIN) {
-            const float gw = g[t - j];
-            o0[j] = fmaf(gw, a, o0[j]);
-            o1[j] = fmaf(gw, d, o1[j]);
-            o2[j] = fmaf(gw, aa, o2[j]);
-            o3[j] = fmaf(gw, dd, o3[j]);
-            o4[j] = fmaf(gw, ad, o4[j]);
+            o01[j] = __ffma2_rn(taps.g2[t - j], ad, o01[j]);
+            o23[j] = __ffma2_rn(taps.g2[t - j], sq, o23[j]);
+            o4[j] = fmaf(taps.g[t - j], cr, o4[j]);
           }
         }
       }
-      float* hrow = hb + hr * LDH + jg * RX;
+      float2* h01 = hb01 + hr * LDH + jg * RX;
+      float2* h23 = hb23 + hr * LDH + jg * RX;
+      float* h4 = hb4 + hr * LDH + jg * RX;
 #pragma unroll
       for (int j = 0; j < RX; ++j) {
-        hrow[0 * IN * LDH + j] = o0[j];
-        hrow[1 * IN * LDH + j] = o1[j];
-        hrow[2 * IN * LDH + j] = o2[j];
-        hrow[3 * IN * LDH + j] = o3[j];
-        hrow[4 * IN * LDH + j] = o4[j];
+        h01[j] = o01[j];
+        h23[j] = o23[j];
+        h4[j] = o4[j];
       }
     }
     __syncthreads();
-    float v[5][RY];
+    float2 v01[RY], v23[RY];
+    float v4[RY];
 #pragma unroll
-    for (int k = 0; k < 5; ++k)
-#pragma unroll
-      for (int i = 0; i < RY; ++i) v[k][i] = 0.f;
+    for (int i = 0; i < RY; ++i) { v01[i] = v23[i] = make_float2(0.f, 0.f); v4[i] = 0.f; }
 #pragma unroll
     for (int t = 0; t < RY + WIN - 1; ++t) {
+      const float2 a01 = hb01[(vi0 + t) * LDH + vj];
+      const float2 a23 = hb23[(vi0 + t) * LDH + vj];
+      const float a4 = hb4[(vi0 + t) * LDH + vj];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const float hv = hb[(k * IN + vi0 + t) * LDH + vj];
-#pragma unroll
-        for (int i = 0; i < RY; ++i)
-          if (t - i >= 0 && t - i < WIN) v[k][i] = fmaf(g[t - i], hv, v[k][i]);
-      }
+      for (int i = 0; i < RY; ++i)
+        if (t - i >= 0 && t - i < WIN) {
+          v01[i] = __ffma2_rn(taps.g2[t - i], a01, v01[i]);
+          v23[i] = __ffma2_rn(taps.g2[t - i], a23, v23[i]);
+          v4[i] = fmaf(taps.g[t - i], a4, v4[i]);
+        }
     }
     const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * 8;
     const float ax = (float)cs[0], ay = (float)cs[1];
     const float wc = wt[(size_t)b * kTotalChannels + choff + ch];
 #pragma unroll
     for (int i = 0; i < RY; ++i) {
-      const float mxr = v[0][i], myr = v[1][i];
+      const float mxr = v01[i].x, myr = v01[i].y;
       const float mx = ax * mxr, my = ay * myr;
-      const float vx = ax * ax * v[2][i] - mx * mx;
-      const float vy = ay * ay * v[3][i] - my * my;
-      const float cov = ax * ay * v[4][i] - mx * my;
+      const float vx = ax * ax * v23[i].x - mx * mx;
+      const float vy = ay * ay * v23[i].y - my * my;
+      const float cov = ax * ay * v4[i] - mx * my;
       const float t_ = (2.f * mx * my + 1e-6f) / (mx * mx + my * my + 1e-6f);
       const float s_ = (2.f * cov + 1e-6f) / (vx + vy + 1e-6f);
       acc_a[i] = fmaf(wc, t_, acc_a[i]);
       acc_b[i] = fmaf(wc, s_, acc_b[i]);
-      acc_g[i] += (v[2][i] - mxr * mxr) / (mxr + 1e-12f);   // compute_prob, raw features (ADISTS.py:81-84)
+      acc_g[i] += (v23[i].x - mxr * mxr) / (mxr + 1e-12f);   // compute_prob, raw features (ADISTS.py:81-84)
     }
   }
   const size_t mbase = ((size_t)b * csplit + split) * oh * ow;
@@ -458,7 +460,7 @@ global_level_kernel(int c, int choff, const double* __restrict__ chan, const flo
 // level; the last block of each frame pair combines the block partials in index order.
 // ================================================================================================
 struct MapArgs {
-  const float* amap; const float* bmap; const float* gmap;   // [pairs][csplit][on]
+  const float* amap; const float* bmap; float* gmap;   // [pairs][csplit][on]
   int csplit, on, oh, ow, c;
   const float* prev;     // coarser ps_prod [pairs][ph*pw], or nullptr = ones
   int ph, pw;
@@ -467,6 +469,7 @@ struct MapArgs {
   int level;
   double* red;           // [pairs][kRedBlocks][4]
   unsigned int* cnt;     // [pairs]
+  int store_d;           // as_map: keep the per-pixel D value in slot 0 of gmap
 };
 
 __device__ inline float map_sum(const float* m, int csplit, int on, int b, int i) {
@@ -606,7 +609,9 @@ prod_store_kernel(MapArgs a) {
     const float p = (pr - sc.pmin) / (sc.pmax - sc.pmin + 1e-12f);
     a.ps_out[(size_t)b * a.on + i] = p;
     const float av = map_sum(a.amap, a.csplit, a.on, b, i), bv = map_sum(a.bmap, a.csplit, a.on, b, i);
-    s += (double)((1.f - p) * av + p * bv);
+    const float dv = (1.f - p) * av + p * bv;
+    if (a.store_d) a.gmap[(size_t)b * a.csplit * a.on + i] = dv;   // gamma of pixel i is no longer needed (same thread read it)
+    s += (double)dv;
   }
   const double ts = block_sum<double>(s, redd);
   const double vals[4] = {ts, 0.0, 0.0, 0.0};
@@ -637,6 +642,39 @@ __global__ void final_kernel(const LvlScal* __restrict__ scal, int pairs, float*
   score[b] = 1.f - d;
 }
 
+// (7) as_map (ADISTS.py:163,188-190,192-193): 1 - sum_k bilinear(D_map_k -> (H, W), align_corners=False)
+struct DMapLevels {
+  const float* dmap[kNumLevels];   // windowed levels: [pairs][csplit][oh*ow], slot 0 holds D; fallback levels: unused
+  int oh[kNumLevels], ow[kNumLevels], csplit[kNumLevels], windowed[kNumLevels];
+};
+
+__device__ inline float bilinear_ac_false(const float* p, int ih, int iw, int oy, int ox, int oh, int ow) {
+  // torch upsample_bilinear2d, align_corners=False: src = (dst + 0.5) * in/out - 0.5, clamped at 0
+  const float sy = (float)ih / (float)oh, sx = (float)iw / (float)ow;
+  const float fy = fmaxf(((float)oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf(((float)ox + 0.5f) * sx - 0.5f, 0.f);
+  const int y0 = min((int)fy, ih - 1), x0 = min((int)fx, iw - 1);
+  const int y1 = min(y0 + 1, ih - 1), x1 = min(x0 + 1, iw - 1);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * p[y0 * iw + x0] + lx * p[y0 * iw + x1]) + ly * (hx * p[y1 * iw + x0] + lx * p[y1 * iw + x1]);
+}
+
+__global__ void __launch_bounds__(256)
+as_map_kernel(DMapLevels lv, const LvlScal* __restrict__ scal, int H, int W, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < H * W; i += gridDim.x * 256) {
+    const int oy = i / W, ox = i - oy * W;
+    float acc = 0.f;
+    for (int k = kNumLevels - 1; k >= 0; --k) {
+      if (lv.windowed[k])
+        acc += bilinear_ac_false(lv.dmap[k] + (size_t)b * lv.csplit[k] * lv.oh[k] * lv.ow[k], lv.oh[k], lv.ow[k], oy, ox, H, W);
+      else
+        acc += scal[(size_t)b * kNumLevels + k].d;   // 1x1 map
+    }
+    out[(size_t)b * H * W + i] = 1.f - acc;
+  }
+}
+
 Taps make_taps(int window) {
   // ADISTS.gaussian (ADISTS.py:102-104): exp in double, stored as fp32, normalised in fp32
   Taps t;
@@ -649,6 +687,7 @@ Taps make_taps(int window) {
     sum += t.g[i];
   }
   for (int i = 0; i < window; ++i) t.g[i] = t.g[i] / sum;
+  for (int i = 0; i < kAdistsMaxWindow; ++i) t.g2[i] = make_float2(t.g[i], t.g[i]);
   return t;
 }
 
@@ -657,7 +696,7 @@ int launch_window(const LevelPlan& L, const float* fx, const float* fy, int pair
                   const Taps& taps, float* amap, float* bmap, float* gmap, cudaStream_t st) {
   constexpr int IN = WT + WIN - 1;
   constexpr int LDI = IN | 1;
-  constexpr size_t smem = (size_t)(2 * IN * LDI + 5 * IN * (WT + 1)) * sizeof(float);
+  constexpr size_t smem = (size_t)(2 * IN * LDI + 5 * IN * (WT + 1) + 2) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(window_kernel<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -676,7 +715,7 @@ bool adists_window_supported(int window) { return window == 21 || window == 11 |
 size_t adists_workspace_bytes(int pairs, int H, int W, int window) { return make_plan(pairs, H, W, window).total; }
 
 int adists_stage(const float* const fx[6], const float* const fy[6], int pairs, int H, int W, int window, void* ws,
-                 float* score, cudaStream_t st) {
+                 float* score, cudaStream_t st, float* map_out) {
   const Plan p = make_plan(pairs, H, W, window);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
@@ -734,6 +773,7 @@ int adists_stage(const float* const fx[6], const float* const fy[6], int pairs, 
     a.csplit = L.csplit; a.on = L.on; a.oh = L.oh; a.ow = L.ow; a.c = L.c;
     a.prev = prev; a.ph = ph; a.pw = pw;
     a.ps_out = F(L.off_ps); a.scal = scal; a.level = k; a.red = red; a.cnt = cnt;
+    a.store_d = map_out ? 1 : 0;
     if (L.windowed) {
       int nblk = ceil_div(L.on, 256 * 4);
       if (nblk > kRedBlocks) nblk = kRedBlocks;
@@ -751,6 +791,18 @@ int adists_stage(const float* const fx[6], const float* const fy[6], int pairs, 
   }
   final_kernel<<<ceil_div(pairs, 128), 128, 0, st>>>(scal, pairs, score);
   ++launches;
+  if (map_out) {
+    DMapLevels dl;
+    for (int k = 0; k < kNumLevels; ++k) {
+      const LevelPlan& L = p.lv[k];
+      dl.dmap[k] = F(L.off_g); dl.oh[k] = L.oh; dl.ow[k] = L.ow; dl.csplit[k] = L.csplit; dl.windowed[k] = L.windowed ? 1 : 0;
+    }
+    int nblk = ceil_div(H * W, 256 * 4);
+    if (nblk > 2048) nblk = 2048;
+    dim3 grid(nblk, pairs);
+    as_map_kernel<<<grid, 256, 0, st>>>(dl, scal, H, W, map_out);
+    ++launches;
+  }
   return launches;
 }
 

@@ -786,10 +786,13 @@ int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_hos
   if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
   float* d_scores = ctx->stage_in[0] + 2 * (size_t)mb * frame;
 
+  // The first chunk is small so that the copy/compute pipeline fills quickly (its H2D copy is the only one that is
+  // not hidden behind compute); scores do not depend on the chunking (batch-independent reductions).
   int it = 0;
-  for (int b0 = 0; b0 < B; b0 += mb, ++it) {
+  for (int b0 = 0; b0 < B; ++it) {
     const int slot = it & 1;
-    const int pairs = B - b0 < mb ? B - b0 : mb;
+    const int want = it == 0 ? (mb > 2 ? 2 : mb) : mb;
+    const int pairs = B - b0 < want ? B - b0 : want;
     float* dx = ctx->stage_in[slot];
     float* dy = dx + (size_t)mb * frame;
     if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0));
@@ -802,6 +805,7 @@ int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_hos
              : dists_micro_batch<bf16>(ctx, dx, dy, pairs, H, W, precision, d_scores + b0, nullptr, ctx->compute_stream);
     if (rc != NQA_OK) return rc;
     CUDA_TRY(cudaEventRecord(ctx->ev_consumed[slot], ctx->compute_stream));
+    b0 += pairs;
   }
   CUDA_TRY(cudaMemcpyAsync(score_host, d_scores, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, ctx->compute_stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->compute_stream));
@@ -900,7 +904,7 @@ static size_t adists_feat_bytes(int pairs, int H, int W) {
 
 template <typename T>
 static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int prec,
-                       float* score_out, cudaStream_t st) {
+                       float* score_out, float* map_out, cudaStream_t st) {
   int mb = pick_micro_pairs(ctx, B, H, W) / 2;
   if (mb < 1) mb = 1;
   int rc = ensure_arena(ctx, trunk_bytes<T>(2 * mb, H, W, prec) + adists_feat_bytes(mb, H, W) +
@@ -935,7 +939,8 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
       fy[k] = planar[k] + (size_t)pairs * level_channels(k) * lh[k] * lw[k];
     }
     ProfScope ps(ctx, NQA_K_ADISTS, st);
-    ctx->launches += adists_stage(fx, fy, pairs, H, W, window, ws, score_out + b0, st);
+    ctx->launches += adists_stage(fx, fy, pairs, H, W, window, ws, score_out + b0, st,
+                                  map_out ? map_out + (size_t)b0 * H * W : nullptr);
   }
   return NQA_OK;
 }
@@ -952,6 +957,11 @@ extern "C" {
 
 int nqa_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int precision,
                        float* score_out, void* stream) {
+  return nqa_adists_map(ctx, x, y, B, H, W, window, precision, score_out, nullptr, stream);
+}
+
+int nqa_adists_map(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int precision,
+                   float* score_out, float* map_out, void* stream) {
   int rc = check_ready(ctx, false);
   if (rc != NQA_OK) return rc;
   if (!x || !y || !score_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
@@ -960,8 +970,8 @@ int nqa_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int 
   if ((rc = check_window(window)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, score_out, st)
-                                  : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, score_out, st);
+  rc = precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, score_out, map_out, st)
+                                  : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, score_out, map_out, st);
   if (rc != NQA_OK) return rc;
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;

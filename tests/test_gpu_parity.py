@@ -355,3 +355,20 @@ def test_flavours_match_reference(golden, name):
         one = m(x[:1].cuda(), y[:1].cuda())
         assert one.dim() == int(g["score_b1_ndim"])                   # _original squeezes to 0-d, _softmax keeps [1]
         assert abs(float(one) - float(g["score"][0])) < 1e-4 * abs(float(g["score"][0]))
+
+
+@pytest.mark.parametrize("name", ["adists_map_96x128", "adists_map_176"])
+def test_adists_as_map_matches_reference(amodels, golden, name):
+    g = golden(name)
+    b, h, w, seed = (int(v) for v in g["shape"])
+    x, y = synth.make_frame_pairs(b, h, w, seed=seed)
+    m = amodels["fp32"]
+    one = m(x[:1].cuda(), y[:1].cuda(), as_loss=False, as_map=True).cpu().numpy()
+    assert one.shape == g["map_b1"].shape
+    err = float(np.abs(one - g["map_b1"]).max())
+    print(f"[parity] A-DISTS as_map {name}: max|abs| {err:.3e} (map range {g['map_b1'].min():.3f}..{g['map_b1'].max():.3f})")
+    assert err < 2e-5
+    two = m(x.cuda(), y.cuda(), as_loss=False, as_map=True)
+    assert tuple(two.shape) == tuple(int(v) for v in g["map_b2_shape"])      # [B,B,H,W]: the upstream broadcast quirk
+    assert float((two[1, 0].cpu() - torch.from_numpy(g["map_b2_sample1"])).abs().max()) < 2e-5
+    assert torch.equal(two[1, 0], two[1, 1])
