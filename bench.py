@@ -48,6 +48,28 @@ WORKLOADS = {
 TRUNK_FLOP_PER_PAIR = 2.5386e12
 
 
+def load_conv_traffic():
+    """DRAM bytes per launch of the trunk-convolution family from the committed `ncu --set full` capture of the same
+    bench command (profiles/r1m_ncu_full_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of every
+    stage1 / pair / halo kernel of one 16-frame micro-batch, averaged over those launches)."""
+    path = os.path.join(ROOT, "profiles", "r1m_ncu_full_summary.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        cols = d["columns"]
+        kn, rd, wr = cols.index("Kernel Name"), cols.index("dram__bytes_read.sum"), cols.index("dram__bytes_write.sum")
+        rows = [r for r in d["rows"] if any(t in r[kn] for t in ("stage1_fused", "conv3x3_tc_pair", "conv3x3_tc_halo"))]
+        # the capture covers a little more than one micro-batch: keep the first 12 conv launches (1 fused + 11)
+        rows = rows[:12]
+        if len(rows) < 12:
+            return None
+        total_gb = sum(float(r[rd]) + float(r[wr]) for r in rows)
+        return {"bytes_per_launch": total_gb * 1e9 / len(rows), "launches_in_capture": len(rows),
+                "source": "profiles/r1m_ncu_full_summary.json (ncu --set full, bench.py --pairs 8, 16 frames per launch)"}
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -339,6 +361,13 @@ def main():
             "share_of_step": tc_ms / total_prof_ms if total_prof_ms > 0 else None,
             "traffic": None,
         }
+        tr = load_conv_traffic() if (args.workload == "dists" and args.precision == "bf16") else None
+        if tr is not None:
+            roofline["traffic"] = tr["bytes_per_launch"]
+            roofline["traffic_source"] = tr["source"]
+            # algorithmic HBM bytes of the same 12 launches: frames in (fp32), every conv output written once (bf16),
+            # every conv input except the fused stage's read once
+            roofline["traffic_note"] = "DRAM bytes per conv launch (avg of the 12 trunk launches of one 8-pair micro-batch)"
         families = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in prof.items() if v[1]}
         line = {
             "metric": wl["metric"], "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": steps,
