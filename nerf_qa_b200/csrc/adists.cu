@@ -25,6 +25,7 @@ namespace nqa {
 namespace {
 
 constexpr int WT = 32;           // window kernel: 32x32 output pixels per block
+constexpr int kChan = 10;        // doubles per (pair, channel) in the chan table
 constexpr int kRedBlocks = 128;  // blocks per frame pair in the map reductions
 
 struct Taps {
@@ -89,7 +90,7 @@ Plan make_plan(int pairs, int H, int W, int window) {
     L.off_g = take((size_t)pairs * L.csplit * L.on * sizeof(float));
     L.off_ps = take((size_t)pairs * L.on * sizeof(float));
   }
-  p.off_chan = take((size_t)pairs * kTotalChannels * 8 * sizeof(double));
+  p.off_chan = take((size_t)pairs * kTotalChannels * kChan * sizeof(double));
   p.off_e = take((size_t)pairs * kTotalChannels * sizeof(double));
   p.off_wt = take((size_t)pairs * kTotalChannels * sizeof(float));
   p.off_scal = take((size_t)pairs * kNumLevels * sizeof(LvlScal));
@@ -149,7 +150,8 @@ sums7_kernel(const float* __restrict__ x, const float* __restrict__ y, int c, in
   }
 }
 
-// chan[b][1475][8] (double): 1/max(||x||,eps), 1/max(||y||,eps), entropy scale, mean x, mean y, E[x^2], E[y^2], E[xy]
+// chan[b][1475][kChan] (double): 1/max(||x||,eps), 1/max(||y||,eps), max(||relu x||,eps), mean x, mean y, E[x^2], E[y^2],
+// E[xy], sum_hw(relu x / max(||relu x||,eps))
 struct SumLevels {
   const float* partials[kNumLevels];
   int chunks[kNumLevels];
@@ -170,11 +172,11 @@ chan_kernel(SumLevels sl, double* __restrict__ chan) {
     const double n = (double)sl.hw[k];
     const double eps = 1e-12;
     const double nx = fmax(sqrt(s[2]), eps), ny = fmax(sqrt(s[3]), eps), nr = fmax(sqrt(s[6]), eps);
-    const double a = 1.0 / nr;
-    double* o = chan + ((size_t)b * kTotalChannels + c) * 8;
+    double* o = chan + ((size_t)b * kTotalChannels + c) * kChan;
     o[0] = 1.0 / nx;
     o[1] = 1.0 / ny;
-    o[2] = a / (a * s[5] + eps);   // p = relu(x) * o[2]  (ADISTS.py:130-132)
+    o[2] = nr;                     // p = (relu(x) / o[2]) / (o[8] + 1e-12)  (ADISTS.py:130-132), formed in fp32 like
+    o[8] = s[5] / nr;              // the reference so that degenerate 1x1 maps give exactly p = 1 and zero entropy
     o[3] = s[0] / n;
     o[4] = s[1] / n;
     o[5] = s[2] / n;
@@ -194,10 +196,11 @@ entropy_kernel(const float* __restrict__ x, int c, int hw, int chunks, int choff
   const int per = ceil_div(ceil_div(hw, chunks), 4) * 4;
   const int p0 = chunk * per, p1 = min(hw, p0 + per);
   const float* px = x + ((size_t)b * c + ch) * hw;
-  const float scale = (float)chan[((size_t)b * kTotalChannels + choff + ch) * 8 + 2];
+  const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * kChan;
+  const float nr = (float)cs[2], den = (float)cs[8] + 1e-12f;
   float s = 0.f;
   auto acc = [&](float a) {
-    const float p = fmaxf(a, 0.f) * scale;
+    const float p = (fmaxf(a, 0.f) / nr) / den;      // same fp32 operation order as the reference (two IEEE divisions)
     s -= p * log2f(p + 1e-12f);
   };
   const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & 15) == 0);
@@ -393,7 +396,7 @@ window_kernel(const float* __restrict__ fx, const float* __restrict__ fy, int c,
           v4[i] = fmaf(taps.g[t - i], a4, v4[i]);
         }
     }
-    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * 8;
+    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * kChan;
     const float ax = (float)cs[0], ay = (float)cs[1];
     const float wc = wt[(size_t)b * kTotalChannels + choff + ch];
 #pragma unroll
@@ -432,7 +435,7 @@ global_level_kernel(int c, int choff, const double* __restrict__ chan, const flo
   const int b = blockIdx.x;
   double pa = 0, pb = 0, pg = 0;
   for (int ch = threadIdx.x; ch < c; ch += 256) {
-    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * 8;
+    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * kChan;
     const double ax = cs[0], ay = cs[1];
     const double mxr = cs[3], myr = cs[4];
     const double mx = ax * mxr, my = ay * myr;

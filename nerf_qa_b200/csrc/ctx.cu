@@ -156,6 +156,19 @@ void level_dims(int H, int W, int (&h)[kNumLevels], int (&w)[kNumLevels]) {
   }
 }
 
+// Largest activation of the trunk per image, in elements.  For ordinary frames that is relu1_x (64 x H x W); once a
+// pyramid dimension is stuck at 1 the channel doubling wins (a 1x1 frame has 512 values at levels 4 and 5).
+size_t max_act_elems(int H, int W) {
+  int h[kNumLevels], w[kNumLevels];
+  level_dims(H, W, h, w);
+  size_t m = 0;
+  for (int k = 1; k < kNumLevels; ++k) {
+    const size_t e = (size_t)level_channels(k) * h[k] * w[k];
+    if (e > m) m = e;
+  }
+  return m;
+}
+
 int check_shape(int B, int H, int W) {
   if (B < 1) return fail(NQA_ERR_SHAPE, "batch size %d < 1", B);
   if (H < 1 || W < 1) return fail(NQA_ERR_SHAPE, "image size %dx%d is empty", H, W);
@@ -210,13 +223,13 @@ struct TrunkBufs {
 
 template <typename T>
 size_t trunk_bytes(int n, int H, int W, int prec) {
-  const size_t big = align256((size_t)n * H * W * 64 * sizeof(T));
+  const size_t big = align256((size_t)n * max_act_elems(H, W) * sizeof(T));
   return 2 * big * carriers(prec) + 4096;
 }
 
 template <typename T>
 void trunk_alloc(nqa_ctx* ctx, TrunkBufs<T>* b, int n, int H, int W, int prec) {
-  const size_t big = (size_t)n * H * W * 64 * sizeof(T);
+  const size_t big = (size_t)n * max_act_elems(H, W) * sizeof(T);
   for (int i = 0; i < 2; ++i) {
     b->ping[i] = static_cast<T*>(ctx->arena.take(big));
     if (prec == NQA_PREC_BF16X3) b->ping_lo[i] = static_cast<T*>(ctx->arena.take(big));
@@ -351,7 +364,7 @@ size_t partial_bytes(int pairs, int H, int W, int prec, PartialBufs* pb /* may b
                        : (fused_pool && k < kNumLevels - 1) ? pool_stats_chunks(h[k], w[k], c, elem_bytes(prec))
                                                             : stats_chunks_nhwc(h[k] * w[k], c, elem_bytes(prec), pairs);
     if (pb) pb->chunks[k] = chunks;
-    total += align256((size_t)pairs * chunks * 5 * c * sizeof(float));
+    total += align256(((size_t)pairs * chunks * 5 * c + (size_t)pairs * 2 * c) * sizeof(float));   // partial sums + pivots
   }
   total += align256((size_t)pairs * kTotalChannels * sizeof(double));
   return total + 4096;
@@ -359,7 +372,7 @@ size_t partial_bytes(int pairs, int H, int W, int prec, PartialBufs* pb /* may b
 
 void partial_alloc(nqa_ctx* ctx, int pairs, PartialBufs* pb) {
   for (int k = 0; k < kNumLevels; ++k)
-    pb->p[k] = static_cast<float*>(ctx->arena.take((size_t)pairs * pb->chunks[k] * 5 * level_channels(k) * sizeof(float)));
+    pb->p[k] = static_cast<float*>(ctx->arena.take(((size_t)pairs * pb->chunks[k] * 5 + (size_t)pairs * 2) * level_channels(k) * sizeof(float)));
   pb->terms = static_cast<double*>(ctx->arena.take((size_t)pairs * kTotalChannels * sizeof(double)));
 }
 
@@ -370,6 +383,7 @@ int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float
   FinalizeParams fp;
   for (int k = 0; k < kNumLevels; ++k) {
     fp.lv[k].partials = pb.p[k];
+    fp.lv[k].piv = pb.p[k] + (size_t)pairs * pb.chunks[k] * 5 * level_channels(k);
     fp.lv[k].chunks = k < levels_valid ? pb.chunks[k] : 0;
     fp.lv[k].C = level_channels(k);
     fp.lv[k].choff = level_offset(k);
@@ -485,7 +499,7 @@ size_t dists_bwd_bytes(const nqa_ctx* ctx, int pairs, int H, int W, int prec) {
     for (int j = 0; j < kStageConvs[stage]; ++j, ++li) total += align256(n * hw * kConvCout[li] * sizeof(T));
     if (stage < 4) total += align256(n * (size_t)h[stage + 2] * w[stage + 2] * kConvCout[li - 1] * sizeof(T));
   }
-  total += 2 * align256(n * (size_t)H * W * 64 * sizeof(T));                     // gradient ping-pong
+  total += 2 * align256(n * max_act_elems(H, W) * sizeof(T));                     // gradient ping-pong
   total += partial_bytes(pairs, H, W, prec, nullptr, false, true);
   total += 2 * align256((size_t)pairs * kTotalChannels * 5 * sizeof(float)) + align256(pairs * sizeof(float));
   return total + 8192;
@@ -550,7 +564,7 @@ int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int
   ctx->launches += launch_stat_coef(moments, ctx->alpha, ctx->beta, ctx->ab_normalize, grad_score, gl, levels_valid, pairs, coef, st);
 
   if (through_trunk) {
-    const size_t gsz = (size_t)n * H * W * 64 * sizeof(T);
+    const size_t gsz = (size_t)n * max_act_elems(H, W) * sizeof(T);
     T* g[2] = {static_cast<T*>(ctx->arena.take(gsz)), static_cast<T*>(ctx->arena.take(gsz))};
     int cur = 0;
     {  // last level: statistics gradient only

@@ -14,9 +14,14 @@ typedef __nv_bfloat16 bf16;
 
 // ---- statistics -----------------------------------------------------------------------------------
 // Partial sums of one pyramid level: partials[((b*chunks + chunk)*5 + s)*C + c], s in
-// {sum x, sum y, sum x^2, sum y^2, sum x*y}; fp32 per chunk, combined in fp64 by the finalize kernel.
+// {sum x', sum y', sum x'^2, sum y'^2, sum x'*y'}; fp32 per chunk, combined in fp64 by the finalize kernel.
+// x' = x - pivot_x, y' = y - pivot_y with the channel's FIRST pixel as pivot (stored behind the partial sums at
+// partials + pairs*chunks*5*C + (b*2 + {0,1})*C + c): variances and covariances are shift invariant, the shifted
+// one-pass formula has no cancellation against the mean (a constant map gives exactly zero like the reference's
+// two-pass variance, DISTS_pt.py:137-139), and the mean is pivot + E[x'].
 struct LevelPartials {
   const float* partials;
+  const float* piv;   // [pairs][2][C] pivots (first pixel of x / y per channel): the sums are of (x - piv_x), (y - piv_y)
   int chunks;
   int C;
   int choff;     // first channel of this level inside the 1475-vector

@@ -34,6 +34,22 @@ stats_nhwc_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* _
     const size_t off = (size_t)b * hw * c + (size_t)g * V;
     const T* px = fx + off;
     const T* py = fy + off;
+    // pivots = the channel's first pixel (kernels.h: shifted one-pass sums)
+    float pvx[V], pvy[V];
+    Vec<T>::load(px, pvx);
+    Vec<T>::load(py, pvy);
+    if (SPLIT) {
+      float lx[V], ly[V];
+      Vec<T>::load(fx_lo + off, lx);
+      Vec<T>::load(fy_lo + off, ly);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { pvx[i] += lx[i]; pvy[i] += ly[i]; }
+    }
+    if (chunk == 0 && pl == 0) {
+      float* piv = partials + (size_t)gridDim.y * chunks * 5 * c + (size_t)b * 2 * c + (size_t)g * V;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { piv[i] = pvx[i]; piv[c + i] = pvy[i]; }
+    }
 #pragma unroll 4
     for (int p = p0 + pl; p < p1; p += ppi) {
       float vx[V], vy[V];
@@ -46,6 +62,8 @@ stats_nhwc_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* _
 #pragma unroll
         for (int i = 0; i < V; ++i) { vx[i] += lx[i]; vy[i] += ly[i]; }
       }
+#pragma unroll
+      for (int i = 0; i < V; ++i) { vx[i] -= pvx[i]; vy[i] -= pvy[i]; }
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         sx[i] += vx[i];
@@ -118,6 +136,12 @@ stats_planar_kernel(const float* __restrict__ x, const float* __restrict__ y, in
   const int p0 = chunk * per, p1 = min(hw, p0 + per);
   const float* px = x + ((size_t)b * c + ch) * hw;
   const float* py = y + ((size_t)b * c + ch) * hw;
+  const float pvx = __ldg(px), pvy = __ldg(py);   // pivots = the channel's first pixel (kernels.h: shifted one-pass sums)
+  if (chunk == 0 && threadIdx.x == 0) {
+    float* piv = partials + (size_t)gridDim.z * chunks * 5 * c + (size_t)b * 2 * c;
+    piv[ch] = pvx;
+    piv[c + ch] = pvy;
+  }
   float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(py) & 15) == 0);
@@ -127,7 +151,9 @@ stats_planar_kernel(const float* __restrict__ x, const float* __restrict__ y, in
     const float4* qy = reinterpret_cast<const float4*>(py + p0);
 #pragma unroll 4
     for (int i = threadIdx.x; i < n4; i += 256) {
-      const float4 a = __ldcs(qx + i), d = __ldcs(qy + i);
+      float4 a = __ldcs(qx + i), d = __ldcs(qy + i);
+      a.x -= pvx; a.y -= pvx; a.z -= pvx; a.w -= pvx;
+      d.x -= pvy; d.y -= pvy; d.z -= pvy; d.w -= pvy;
       s[0] += (a.x + a.y) + (a.z + a.w);
       s[1] += (d.x + d.y) + (d.z + d.w);
       s[2] += fmaf(a.x, a.x, a.y * a.y) + fmaf(a.z, a.z, a.w * a.w);
@@ -135,12 +161,12 @@ stats_planar_kernel(const float* __restrict__ x, const float* __restrict__ y, in
       s[4] += fmaf(a.x, d.x, a.y * d.y) + fmaf(a.z, d.z, a.w * d.w);
     }
     for (int p = p0 + n4 * 4 + threadIdx.x; p < p1; p += 256) {
-      const float a = px[p], d = py[p];
+      const float a = px[p] - pvx, d = py[p] - pvy;
       s[0] += a; s[1] += d; s[2] = fmaf(a, a, s[2]); s[3] = fmaf(d, d, s[3]); s[4] = fmaf(a, d, s[4]);
     }
   } else {
     for (int p = p0 + threadIdx.x; p < p1; p += 256) {
-      const float a = px[p], d = py[p];
+      const float a = px[p] - pvx, d = py[p] - pvy;
       s[0] += a; s[1] += d; s[2] = fmaf(a, a, s[2]); s[3] = fmaf(d, d, s[3]); s[4] = fmaf(a, d, s[4]);
     }
   }
@@ -218,9 +244,12 @@ dists_terms_kernel(FinalizeParams p, const float* __restrict__ alpha, const floa
       for (int l = 1; l < kFinLanes; ++l) t += sm[l][cl][i];
       s[i] = t;
     }
-    const double mx = s[0] * lv.inv_n, my = s[1] * lv.inv_n;
-    const double vx = s[2] * lv.inv_n - mx * mx, vy = s[3] * lv.inv_n - my * my;
-    const double cov = s[4] * lv.inv_n - mx * my;
+    // sums are of the pivot-shifted values: variances / covariance are shift invariant, the mean adds the pivot back
+    const double dx = s[0] * lv.inv_n, dy = s[1] * lv.inv_n;
+    const double vx = s[2] * lv.inv_n - dx * dx, vy = s[3] * lv.inv_n - dy * dy;
+    const double cov = s[4] * lv.inv_n - dx * dy;
+    const float* piv = lv.piv + (size_t)b * 2 * lv.C + (c - lv.choff);
+    const double mx = (double)piv[0] + dx, my = (double)piv[lv.C] + dy;
     const double c1 = 1e-6, c2 = 1e-6;
     const double s1 = (2.0 * mx * my + c1) / (mx * mx + my * my + c1);
     const double s2 = (2.0 * cov + c2) / (vx + vy + c2);
@@ -398,6 +427,20 @@ pool_stats_kernel(const T* __restrict__ fx, const T* __restrict__ fy, T* __restr
     const T* bx = fx + ioff;
     const T* by = fy + ioff;
     const bool c0 = 2 * ox - 1 >= 0, c2 = 2 * ox + 1 < w;   // column 2ox always exists
+    // pivots = the channel's first pixel, negated (kernels.h: shifted one-pass sums)
+    float2 npx[2], npy[2];
+    Vec4<T>::load(bx, npx);
+    Vec4<T>::load(by, npy);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && pl == 0) {
+      float* piv = partials + (size_t)gridDim.z * chunks * 5 * c + (size_t)b * 2 * c + (size_t)g * V;
+      piv[0] = npx[0].x; piv[1] = npx[0].y; piv[2] = npx[1].x; piv[3] = npx[1].y;
+      piv[c + 0] = npy[0].x; piv[c + 1] = npy[0].y; piv[c + 2] = npy[1].x; piv[c + 3] = npy[1].y;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      npx[i] = make_float2(-npx[i].x, -npx[i].y);
+      npy[i] = make_float2(-npy[i].x, -npy[i].y);
+    }
 
     // horizontal [1 2 1] of squares of input row iy for both images (+ statistics on the owned columns)
     // rx / ry point at column 2ox of the input row; rows outside the image contribute zeros
@@ -419,11 +462,14 @@ pool_stats_kernel(const T* __restrict__ fx, const T* __restrict__ fy, T* __restr
         hx[i] = __ffma2_rn(x0[i], x0[i], __ffma2_rn(two2, xx1, xx2));
         hy[i] = __ffma2_rn(y0[i], y0[i], __ffma2_rn(two2, yy1, yy2));
         if (own) {
-          s[0][i] = __fadd2_rn(s[0][i], __fadd2_rn(x1[i], x2[i]));
-          s[1][i] = __fadd2_rn(s[1][i], __fadd2_rn(y1[i], y2[i]));
-          s[2][i] = __fadd2_rn(s[2][i], __fadd2_rn(xx1, xx2));
-          s[3][i] = __fadd2_rn(s[3][i], __fadd2_rn(yy1, yy2));
-          s[4][i] = __fadd2_rn(s[4][i], __ffma2_rn(x1[i], y1[i], __fmul2_rn(x2[i], y2[i])));
+          // column 2ox+1 outside the image must not be counted: its shifted value is forced to zero
+          const float2 dx1 = __fadd2_rn(x1[i], npx[i]), dy1 = __fadd2_rn(y1[i], npy[i]);
+          const float2 dx2 = c2 ? __fadd2_rn(x2[i], npx[i]) : zero2, dy2 = c2 ? __fadd2_rn(y2[i], npy[i]) : zero2;
+          s[0][i] = __fadd2_rn(s[0][i], __fadd2_rn(dx1, dx2));
+          s[1][i] = __fadd2_rn(s[1][i], __fadd2_rn(dy1, dy2));
+          s[2][i] = __ffma2_rn(dx2, dx2, __ffma2_rn(dx1, dx1, s[2][i]));
+          s[3][i] = __ffma2_rn(dy2, dy2, __ffma2_rn(dy1, dy1, s[3][i]));
+          s[4][i] = __ffma2_rn(dx2, dy2, __ffma2_rn(dx1, dy1, s[4][i]));
         }
       }
     };
