@@ -448,3 +448,33 @@ def test_constant_frames_have_exactly_zero_variance(models, vgg_weights, alpha_b
         assert rel_err(got, want) < tol
     got = models["bf16"](x.cuda(), y.cuda()).cpu().numpy()
     assert np.max(np.abs(got - want)) < 2e-3
+
+
+def test_large_frames_and_ragged_batches(models):
+    """Sizes beyond BASELINE's: one 2160x3840 pair (size-independent properties: identical frames -> 0, symmetry) and a
+    batch that is not a multiple of the micro-batch at a small size (every frame equals its single-frame score)."""
+    m = models["bf16"]
+    x, y = synth.make_frame_pairs(1, 2160, 3840, seed=53)
+    xs, ys = x.cuda(), y.cuda()
+    s = m(xs, ys)
+    assert torch.isfinite(s).all() and 0.0 < float(s) < 1.0
+    assert float(m(xs, xs).abs().max()) < 1e-6
+    assert torch.allclose(m(ys, xs), s, rtol=1e-5, atol=1e-7)
+    del xs, ys
+    x, y = synth.make_frame_pairs(37, 72, 104, seed=59)
+    xs, ys = x.cuda(), y.cuda()
+    full = m(xs, ys)
+    assert full.shape == (37,)
+    for i in (0, 17, 36):
+        assert torch.equal(m(xs[i:i + 1], ys[i:i + 1]), full[i:i + 1])
+
+
+def test_invalid_inputs_are_rejected(models, amodels):
+    m = models["bf16"]
+    x = torch.rand(2, 3, 32, 32, device="cuda")
+    with pytest.raises(_lib.NerfQAError):
+        m(x[:0], x[:0])                                   # empty batch
+    with pytest.raises(_lib.NerfQAError):
+        m(x[:, :1], x[:, :1])                             # not RGB
+    with pytest.raises(AssertionError):
+        amodels["bf16"](x, x[:, :, :16], as_loss=False)   # ADISTS.py:138 asserts equal shapes
