@@ -130,6 +130,14 @@ NQA_API int nqa_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int
 NQA_API int nqa_adists_map(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int precision,
                            float* score_out, float* map_out, void* stream);
 
+/* DISTS and A-DISTS scores of the same batch from ONE trunk evaluation: what prep.py:186-190 /
+ * test2_prep.py:151-155 compute with two model calls (four trunk forwards per pair in the reference).  The DISTS
+ * scores are bit-identical to nqa_dists_forward; the A-DISTS scores equal nqa_adists_forward up to the rounding of the
+ * pooled activations (the fused pool + moments kernel replaces the stand-alone pooling kernel).  Needs VGG weights and
+ * alpha/beta. */
+NQA_API int nqa_dists_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window,
+                                     int precision, float* dists_out, float* adists_out, void* stream);
+
 /* The statistics half of ADISTS.forward (ADISTS.py:147-197) from six NCHW fp32 device tensors per
  * image (the reference's forward_once format, level 0 = the raw frames). */
 NQA_API int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],

@@ -25,7 +25,7 @@ EXPORTS = (
     "nqa_dists_from_feats", "nqa_adists_forward", "nqa_adists_from_feats", "nqa_l2pool",
     "nqa_workspace_bytes", "nqa_launch_count", "nqa_micro_batch", "nqa_conv3x3_relu",
     "nqa_profile_enable", "nqa_profile_read", "nqa_dists_backward", "nqa_dists_from_feats_backward",
-    "nqa_set_channel_weights", "nqa_adists_map",
+    "nqa_set_channel_weights", "nqa_adists_map", "nqa_dists_adists_forward",
 )
 KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists", "pool_stats",
                    "stage1", "backward")
@@ -62,6 +62,7 @@ def load_library() -> ctypes.CDLL:
     lib.nqa_dists_features.argtypes = [vp, fp, ci, ci, ci, ci, ctypes.POINTER(vp), vp]
     lib.nqa_dists_from_feats.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ci, fp, fp, vp]
     lib.nqa_adists_forward.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp, vp]
+    lib.nqa_dists_adists_forward.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp, fp, vp]
     lib.nqa_adists_map.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp, fp, vp]
     lib.nqa_adists_from_feats.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ci, ci, fp, vp]
     lib.nqa_l2pool.argtypes = [vp, fp, ci, ci, ci, ci, fp, vp]
@@ -247,6 +248,18 @@ class Context:
         _check(self.lib.nqa_adists_forward(self.handle, _ptr(x), _ptr(y), b, h, w, window, precision, _ptr(score),
                                            _stream(x.device)))
         return score
+
+    def dists_adists_forward(self, x: torch.Tensor, y: torch.Tensor, window: int, precision: int):
+        """(DISTS [B], A-DISTS [B]) from one trunk evaluation."""
+        if x.shape != y.shape:
+            raise NerfQAError(f"shape mismatch: x {tuple(x.shape)} vs y {tuple(y.shape)}")
+        x, y = _as_input(x, "x"), _as_input(y, "y")
+        b, _, h, w = x.shape
+        d = torch.empty(b, device=x.device, dtype=torch.float32)
+        a = torch.empty(b, device=x.device, dtype=torch.float32)
+        _check(self.lib.nqa_dists_adists_forward(self.handle, _ptr(x), _ptr(y), b, h, w, window, precision, _ptr(d), _ptr(a),
+                                                 _stream(x.device)))
+        return d, a
 
     def adists_map(self, x: torch.Tensor, y: torch.Tensor, window: int, precision: int):
         """(scores [B], map [B,1,H,W]) of ADISTS.forward(as_map=True)."""

@@ -916,13 +916,18 @@ static size_t adists_feat_bytes(int pairs, int H, int W) {
   return total + 4096;
 }
 
+// dists_out != nullptr: the same trunk pass also feeds the DISTS statistics (fused pool + moments kernel), so a
+// scorer that wants both metrics for a batch (prep.py:186-190) runs the VGG trunk once instead of twice.
 template <typename T>
 static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int prec,
-                       float* score_out, float* map_out, cudaStream_t st) {
+                       float* score_out, float* map_out, cudaStream_t st, float* dists_out = nullptr) {
   int mb = pick_micro_pairs(ctx, B, H, W) / 2;
   if (mb < 1) mb = 1;
+  const bool with_dists = dists_out != nullptr;
+  const bool fused_pool = with_dists && prec != NQA_PREC_BF16X3;
   int rc = ensure_arena(ctx, trunk_bytes<T>(2 * mb, H, W, prec) + adists_feat_bytes(mb, H, W) +
-                                 adists_workspace_bytes(mb, H, W, window));
+                                 adists_workspace_bytes(mb, H, W, window) +
+                                 (with_dists ? partial_bytes(mb, H, W, prec, nullptr, false, fused_pool) : 0));
   if (rc != NQA_OK) return rc;
   int lh[kNumLevels], lw[kNumLevels];
   level_dims(H, W, lh, lw);
@@ -938,12 +943,33 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     void* ws = ctx->arena.take(adists_workspace_bytes(pairs, H, W, window));
     const float* xb = x + b0 * frame;
     const float* yb = y + b0 * frame;
+    PartialBufs pb;
+    if (with_dists) {
+      partial_bytes(pairs, H, W, prec, &pb, false, fused_pool);
+      partial_alloc(ctx, pairs, &pb);
+      ProfScope ps(ctx, NQA_K_STATS, st);
+      ctx->launches += launch_stats_planar(xb, yb, pairs, 3, H * W, pb.chunks[0], pb.p[0], st);
+    }
     rc = run_trunk<T>(ctx, xb, yb, pairs, 2 * pairs, H, W, prec, bufs, st,
-                      [&](int k, const T* f, const T* f_lo, int h, int w, T*) {
-                        level_to_nchw<T>(ctx, f, f_lo, planar[k], 2 * pairs, level_channels(k), h, w, st);
+                      [&](int k, const T* f, const T* f_lo, int h, int w, T* pooled_dst) {
+                        const int c = level_channels(k);
+                        level_to_nchw<T>(ctx, f, f_lo, planar[k], 2 * pairs, c, h, w, st);
+                        if (!with_dists) return false;
+                        const size_t half = (size_t)pairs * h * w * c;
+                        if (fused_pool && pooled_dst) {
+                          const size_t half_out = (size_t)pairs * pooled(h) * pooled(w) * c;
+                          ProfScope ps(ctx, NQA_K_POOL_STATS, st);
+                          ctx->launches += launch_pool_stats<T>(f, f + half, pooled_dst, pooled_dst + half_out, pairs, h, w, c,
+                                                                pb.chunks[k], pb.p[k], st);
+                          return true;
+                        }
+                        ProfScope ps(ctx, NQA_K_STATS, st);
+                        ctx->launches += launch_stats_nhwc<T>(f, f + half, f_lo, f_lo ? f_lo + half : nullptr, pairs, h * w, c,
+                                                             pb.chunks[k], pb.p[k], st);
                         return false;
                       });
     if (rc != NQA_OK) return rc;
+    if (with_dists && (rc = finalize(ctx, pb, pairs, H, W, dists_out + b0, nullptr, st)) != NQA_OK) return rc;
     const float* fx[kNumLevels];
     const float* fy[kNumLevels];
     fx[0] = xb;
@@ -986,6 +1012,23 @@ int nqa_adists_map(nqa_ctx* ctx, const float* x, const float* y, int B, int H, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rc = precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, score_out, map_out, st)
                                   : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, score_out, map_out, st);
+  if (rc != NQA_OK) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_dists_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int precision,
+                             float* dists_out, float* adists_out, void* stream) {
+  int rc = check_ready(ctx, true);
+  if (rc != NQA_OK) return rc;
+  if (!x || !y || !dists_out || !adists_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  if ((rc = check_prec(precision)) != NQA_OK) return rc;
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  if ((rc = check_window(window)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, adists_out, nullptr, st, dists_out)
+                                  : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, adists_out, nullptr, st, dists_out);
   if (rc != NQA_OK) return rc;
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;

@@ -290,6 +290,15 @@ class DISTS(_TrunkModule):
             score, _ = ctx.dists_from_feats(feats0, feats1)
         return score.mean() if batch_average else score
 
+    def score_with_adists(self, x: torch.Tensor, y: torch.Tensor, window_size: int = 21):
+        """(DISTS [B], A-DISTS [B]) of the batch from ONE trunk evaluation -- the pair of calls prep.py:186-190 /
+        test2_prep.py:151-155 make per batch (``adists_model(ref, render, as_loss=False)``, ``dists_model(ref,
+        render)``), whose trunks are the same VGG16.  DISTS is bit-identical to ``forward``; A-DISTS equals ``ADISTS.forward``
+        up to the rounding of the pooled activations."""
+        ctx = self._context(x.device)
+        self._sync_weights_nograd(ctx)
+        return ctx.dists_adists_forward(x, y, window_size, self._prec())
+
     def score_host(self, x: torch.Tensor, y: torch.Tensor, device: Optional[torch.device] = None) -> torch.Tensor:
         """End-to-end call from HOST tensors (pinned recommended): streams frames to the GPU in micro-batches
         overlapped with compute and returns CPU scores — what ``model(ref.to(device), dist.to(device)).cpu()``

@@ -478,3 +478,17 @@ def test_invalid_inputs_are_rejected(models, amodels):
         m(x[:, :1], x[:, :1])                             # not RGB
     with pytest.raises(AssertionError):
         amodels["bf16"](x, x[:, :, :16], as_loss=False)   # ADISTS.py:138 asserts equal shapes
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_shared_trunk_scores_match_separate_calls(models, amodels, prec):
+    """One trunk evaluation for both metrics (prep.py:186-190 makes two model calls per batch)."""
+    x, y = synth.make_frame_pairs(3, 176, 208, seed=61)
+    xs, ys = x.cuda(), y.cuda()
+    d, a = models[prec].score_with_adists(xs, ys)
+    assert torch.equal(d, models[prec](xs, ys))
+    want_a = amodels[prec](xs, ys, as_loss=False)
+    report(f"shared-trunk A-DISTS vs separate ({prec})", a.cpu().numpy(), want_a.cpu().numpy())
+    # the fused pool + moments kernel (separable sums, MUFU sqrt before the bf16 rounding) replaces the stand-alone pooling
+    # kernel on this path: pooled bf16 activations can differ in the last bit
+    assert torch.allclose(a, want_a, rtol=1e-4, atol=(1e-4 if prec == "bf16" else 2e-6))
