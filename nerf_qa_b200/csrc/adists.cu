@@ -24,6 +24,41 @@ namespace nqa {
 
 namespace {
 
+// feature planes are fp32 (level 0 = raw frames, forward_from_feats, fp32 trunk) or bf16 (bf16 trunk: half the bytes)
+__device__ inline float ldf(const float* p) { return __ldg(p); }
+__device__ inline float ldf(const bf16* p) { return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16); }
+// Two adjacent plane elements as they come out of one load.  The window kernel keeps them RAW in registers while the
+// loads are in flight and only unpacks when it writes the tile to shared memory one channel later (touching a loaded
+// register earlier -- e.g. the bf16 -> fp32 shift -- would stall the warp on the load right away).
+template <typename TI> struct Raw2;
+template <> struct Raw2<float> {
+  typedef float2 type;
+  __device__ static inline type zero() { return make_float2(0.f, 0.f); }
+  __device__ static inline type load(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  __device__ static inline type one(float a, float b) { return make_float2(a, b); }
+  __device__ static inline void unpack(type t, float& a, float& b) { a = t.x; b = t.y; }
+};
+template <> struct Raw2<bf16> {
+  typedef uint32_t type;
+  __device__ static inline type zero() { return 0u; }
+  __device__ static inline type load(const bf16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  __device__ static inline type one(float a, float b) {   // a, b are exact bf16 values
+    return (__float_as_uint(a) >> 16) | (__float_as_uint(b) & 0xffff0000u);
+  }
+  __device__ static inline void unpack(type t, float& a, float& b) {
+    a = __uint_as_float(t << 16); b = __uint_as_float(t & 0xffff0000u);
+  }
+};
+__device__ inline void ld4(const float* p, float (&v)[4]) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ inline void ld4(const bf16* p, float (&v)[4]) {
+  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+
 constexpr int WT = 32;           // window kernel: 32x32 output pixels per block
 constexpr int kChan = 10;        // doubles per (pair, channel) in the chan table
 constexpr int kRedBlocks = 128;  // blocks per frame pair in the map reductions
@@ -104,14 +139,16 @@ Plan make_plan(int pairs, int H, int W, int window) {
 // (1) per-(pair, channel) sums over the map: x, y, x^2, y^2, xy, relu(x), relu(x)^2
 // grid = (chunks, C, pairs); partial[((b*chunks + chunk)*7 + s)*C + ch]
 // ================================================================================================
+template <typename TI>
 __global__ void __launch_bounds__(256)
-sums7_kernel(const float* __restrict__ x, const float* __restrict__ y, int c, int hw, int chunks,
+sums7_kernel(const TI* __restrict__ x, const TI* __restrict__ y, int c, int hw, int chunks,
              float* __restrict__ partials) {
   const int chunk = blockIdx.x, ch = blockIdx.y, b = blockIdx.z;
   const int per = ceil_div(ceil_div(hw, chunks), 4) * 4;
   const int p0 = chunk * per, p1 = min(hw, p0 + per);
-  const float* px = x + ((size_t)b * c + ch) * hw;
-  const float* py = y + ((size_t)b * c + ch) * hw;
+  const TI* px = x + ((size_t)b * c + ch) * hw;
+  const TI* py = y + ((size_t)b * c + ch) * hw;
+  constexpr uintptr_t kAlign = 4 * sizeof(TI) - 1;
   float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   auto acc = [&](float a, float d) {
     const float r = fmaxf(a, 0.f);
@@ -119,20 +156,20 @@ sums7_kernel(const float* __restrict__ x, const float* __restrict__ y, int c, in
     s[2] = fmaf(a, a, s[2]); s[3] = fmaf(d, d, s[3]); s[4] = fmaf(a, d, s[4]);
     s[5] += r; s[6] = fmaf(r, r, s[6]);
   };
-  const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(py) & 15) == 0);
+  const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & kAlign) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(py) & kAlign) == 0);
   if (vec_ok && p1 > p0) {
     const int n4 = (p1 - p0) / 4;
-    const float4* qx = reinterpret_cast<const float4*>(px + p0);
-    const float4* qy = reinterpret_cast<const float4*>(py + p0);
 #pragma unroll 2
     for (int i = threadIdx.x; i < n4; i += 256) {
-      const float4 a = __ldg(qx + i), d = __ldg(qy + i);
-      acc(a.x, d.x); acc(a.y, d.y); acc(a.z, d.z); acc(a.w, d.w);
+      float a[4], d[4];
+      ld4(px + p0 + 4 * i, a);
+      ld4(py + p0 + 4 * i, d);
+      acc(a[0], d[0]); acc(a[1], d[1]); acc(a[2], d[2]); acc(a[3], d[3]);
     }
-    for (int p = p0 + n4 * 4 + threadIdx.x; p < p1; p += 256) acc(px[p], py[p]);
+    for (int p = p0 + n4 * 4 + threadIdx.x; p < p1; p += 256) acc(ldf(px + p), ldf(py + p));
   } else {
-    for (int p = p0 + threadIdx.x; p < p1; p += 256) acc(px[p], py[p]);
+    for (int p = p0 + threadIdx.x; p < p1; p += 256) acc(ldf(px + p), ldf(py + p));
   }
   __shared__ float sm[7][8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -189,32 +226,37 @@ chan_kernel(SumLevels sl, double* __restrict__ chan) {
 // (2) entropy of the first image's channels: E_c = -sum_hw p log2(p + 1e-12)   (ADISTS.py:133)
 // grid = (chunks, C, pairs); partial[(b*chunks + chunk)*C + ch]
 // ================================================================================================
+template <typename TI>
 __global__ void __launch_bounds__(256)
-entropy_kernel(const float* __restrict__ x, int c, int hw, int chunks, int choff, const double* __restrict__ chan,
+entropy_kernel(const TI* __restrict__ x, int c, int hw, int chunks, int choff, const double* __restrict__ chan,
                float* __restrict__ partials) {
   const int chunk = blockIdx.x, ch = blockIdx.y, b = blockIdx.z;
   const int per = ceil_div(ceil_div(hw, chunks), 4) * 4;
   const int p0 = chunk * per, p1 = min(hw, p0 + per);
-  const float* px = x + ((size_t)b * c + ch) * hw;
+  const TI* px = x + ((size_t)b * c + ch) * hw;
   const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * kChan;
   const float nr = (float)cs[2], den = (float)cs[8] + 1e-12f;
+  const float scale = (float)(1.0 / ((double)nr * (double)den));
+  const bool exact = hw == 1;   // a 1x1 map: the reference's (relu(x)/||relu(x)||)/(sum + 1e-12) is exactly 1 (or 0), its
+                                // entropy exactly 0, and the channel normalisation that follows turns any rounding into O(1)
   float s = 0.f;
   auto acc = [&](float a) {
-    const float p = (fmaxf(a, 0.f) / nr) / den;      // same fp32 operation order as the reference (two IEEE divisions)
+    const float r = fmaxf(a, 0.f);
+    const float p = exact ? (r / nr) / den : r * scale;
     s -= p * log2f(p + 1e-12f);
   };
-  const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & 15) == 0);
+  const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & (4 * sizeof(TI) - 1)) == 0);
   if (vec_ok && p1 > p0) {
     const int n4 = (p1 - p0) / 4;
-    const float4* qx = reinterpret_cast<const float4*>(px + p0);
 #pragma unroll 2
     for (int i = threadIdx.x; i < n4; i += 256) {
-      const float4 a = __ldg(qx + i);
-      acc(a.x); acc(a.y); acc(a.z); acc(a.w);
+      float a[4];
+      ld4(px + p0 + 4 * i, a);
+      acc(a[0]); acc(a[1]); acc(a[2]); acc(a[3]);
     }
-    for (int p = p0 + n4 * 4 + threadIdx.x; p < p1; p += 256) acc(px[p]);
+    for (int p = p0 + n4 * 4 + threadIdx.x; p < p1; p += 256) acc(ldf(px + p));
   } else {
-    for (int p = p0 + threadIdx.x; p < p1; p += 256) acc(px[p]);
+    for (int p = p0 + threadIdx.x; p < p1; p += 256) acc(ldf(px + p));
   }
   __shared__ float sm[33];
   const float tot = block_sum<float>(s, sm);
@@ -279,9 +321,9 @@ weights_kernel(EntLevels el, float* __restrict__ wt) {
 // pass in registers, then per-pixel T, S, gamma accumulated over channels.
 // grid = (tiles_x*tiles_y, csplit, pairs); out maps [pairs][csplit][oh*ow].
 // ================================================================================================
-template <int WIN>
+template <int WIN, typename TI>
 __global__ void __launch_bounds__(256, 2)
-window_kernel(const float* __restrict__ fx, const float* __restrict__ fy, int c, int h, int w, int oh, int ow,
+window_kernel(const TI* __restrict__ fx, const TI* __restrict__ fy, int c, int h, int w, int oh, int ow,
               int tiles_x, int csplit, int choff, const double* __restrict__ chan, const float* __restrict__ wt,
               Taps taps, float* __restrict__ amap, float* __restrict__ bmap, float* __restrict__ gmap) {
   constexpr int IN = WT + WIN - 1;
@@ -314,20 +356,34 @@ window_kernel(const float* __restrict__ fx, const float* __restrict__ fy, int c,
 
   // software pipeline over channels: the global loads of channel ch+1 are issued right after channel ch's tile
   // has been written to shared memory and stay in flight during its two filter passes
-  constexpr int NLD = (IN * IN + 255) / 256;
-  float pre_x[NLD], pre_y[NLD];
+  // the tile is fetched as element PAIRS (one 4- or 8-byte load per two pixels) when the rows allow it (even width =>
+  // even global column, aligned planes); IN is even, so a pair never straddles a tile row
+  static_assert(IN % 2 == 0, "pair loads assume an even tile width");
+  constexpr int NPAIR = IN * IN / 2;
+  constexpr int NLD = (NPAIR + 255) / 256;
+  const bool pair_ok = (w & 1) == 0 && (reinterpret_cast<uintptr_t>(fx) & (2 * sizeof(TI) - 1)) == 0 &&
+                       (reinterpret_cast<uintptr_t>(fy) & (2 * sizeof(TI) - 1)) == 0;
+  typedef Raw2<TI> R2;
+  typename R2::type pre_x[NLD], pre_y[NLD];
   auto fetch = [&](int ch) {
-    const float* px = fx + ((size_t)b * c + ch) * h * w;
-    const float* py = fy + ((size_t)b * c + ch) * h * w;
+    const TI* px = fx + ((size_t)b * c + ch) * h * w;
+    const TI* py = fy + ((size_t)b * c + ch) * h * w;
 #pragma unroll
     for (int q = 0; q < NLD; ++q) {
       const int idx = threadIdx.x + q * 256;
-      const int r = idx / IN, col = idx - r * IN;
+      const int r = idx / (IN / 2), col = 2 * (idx - r * (IN / 2));
       const int gy = oy0 + r, gx = ox0 + col;
-      pre_x[q] = pre_y[q] = 0.f;
-      if (idx < IN * IN && gy < h && gx < w) {
-        pre_x[q] = __ldg(px + (size_t)gy * w + gx);
-        pre_y[q] = __ldg(py + (size_t)gy * w + gx);
+      pre_x[q] = pre_y[q] = R2::zero();
+      if (idx < NPAIR && gy < h && gx < w) {
+        const size_t o = (size_t)gy * w + gx;
+        if (pair_ok) {
+          pre_x[q] = R2::load(px + o);
+          pre_y[q] = R2::load(py + o);
+        } else {                                    // odd width: scalar loads (rare; latency is exposed here)
+          const bool two = gx + 1 < w;
+          pre_x[q] = R2::one(ldf(px + o), two ? ldf(px + o + 1) : 0.f);
+          pre_y[q] = R2::one(ldf(py + o), two ? ldf(py + o + 1) : 0.f);
+        }
       }
     }
   };
@@ -337,10 +393,15 @@ window_kernel(const float* __restrict__ fx, const float* __restrict__ fy, int c,
 #pragma unroll
     for (int q = 0; q < NLD; ++q) {
       const int idx = threadIdx.x + q * 256;
-      if (idx < IN * IN) {
-        const int r = idx / IN, col = idx - r * IN;
-        sx[r * LDI + col] = pre_x[q];
-        sy[r * LDI + col] = pre_y[q];
+      if (idx < NPAIR) {
+        const int r = idx / (IN / 2), col = 2 * (idx - r * (IN / 2));
+        float a0, a1, d0, d1;
+        R2::unpack(pre_x[q], a0, a1);
+        R2::unpack(pre_y[q], d0, d1);
+        sx[r * LDI + col] = a0;
+        sx[r * LDI + col + 1] = a1;
+        sy[r * LDI + col] = d0;
+        sy[r * LDI + col + 1] = d1;
       }
     }
     __syncthreads();
@@ -694,19 +755,19 @@ Taps make_taps(int window) {
   return t;
 }
 
-template <int WIN>
-int launch_window(const LevelPlan& L, const float* fx, const float* fy, int pairs, const double* chan, const float* wt,
+template <int WIN, typename TI>
+int launch_window(const LevelPlan& L, const TI* fx, const TI* fy, int pairs, const double* chan, const float* wt,
                   const Taps& taps, float* amap, float* bmap, float* gmap, cudaStream_t st) {
   constexpr int IN = WT + WIN - 1;
   constexpr int LDI = IN | 1;
   constexpr size_t smem = (size_t)(2 * IN * LDI + 5 * IN * (WT + 1) + 2) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(window_kernel<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(window_kernel<WIN, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
   dim3 grid(L.tiles_x * L.tiles_y, L.csplit, pairs);
-  window_kernel<WIN><<<grid, 256, smem, st>>>(fx, fy, L.c, L.h, L.w, L.oh, L.ow, L.tiles_x, L.csplit, L.choff, chan, wt,
+  window_kernel<WIN, TI><<<grid, 256, smem, st>>>(fx, fy, L.c, L.h, L.w, L.oh, L.ow, L.tiles_x, L.csplit, L.choff, chan, wt,
                                              taps, amap, bmap, gmap);
   return 1;
 }
@@ -717,8 +778,36 @@ bool adists_window_supported(int window) { return window == 21 || window == 11 |
 
 size_t adists_workspace_bytes(int pairs, int H, int W, int window) { return make_plan(pairs, H, W, window).total; }
 
-int adists_stage(const float* const fx[6], const float* const fy[6], int pairs, int H, int W, int window, void* ws,
-                 float* score, cudaStream_t st, float* map_out) {
+namespace {
+template <typename TI>
+int level_front(const LevelPlan& L, const TI* x, const TI* y, int pairs, float* sums, cudaStream_t st) {
+  dim3 grid(L.chunks, L.c, pairs);
+  sums7_kernel<TI><<<grid, 256, 0, st>>>(x, y, L.c, L.hw, L.chunks, sums);
+  return 1;
+}
+template <typename TI>
+int level_entropy(const LevelPlan& L, const TI* x, int pairs, const double* chan, float* ent, cudaStream_t st) {
+  dim3 grid(L.chunks, L.c, pairs);
+  entropy_kernel<TI><<<grid, 256, 0, st>>>(x, L.c, L.hw, L.chunks, L.choff, chan, ent);
+  return 1;
+}
+template <typename TI>
+int level_window(int window, const LevelPlan& L, const TI* x, const TI* y, int pairs, const double* chan, const float* wt,
+                 const Taps& taps, float* amap, float* bmap, float* gmap, cudaStream_t st) {
+  switch (window) {
+    case 21: return launch_window<21, TI>(L, x, y, pairs, chan, wt, taps, amap, bmap, gmap, st);
+    case 11: return launch_window<11, TI>(L, x, y, pairs, chan, wt, taps, amap, bmap, gmap, st);
+    default: return launch_window<7, TI>(L, x, y, pairs, chan, wt, taps, amap, bmap, gmap, st);
+  }
+}
+}  // namespace
+
+int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
+                 void* ws, float* score, cudaStream_t st, float* map_out) {
+  // level 0 (the raw frames) is always fp32; levels 1..5 are bf16 planes when feats_bf16
+  auto is16 = [&](int k) { return feats_bf16 && k > 0; };
+  auto F32 = [](const void* p) { return static_cast<const float*>(p); };
+  auto B16 = [](const void* p) { return static_cast<const bf16*>(p); };
   const Plan p = make_plan(pairs, H, W, window);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
@@ -736,9 +825,8 @@ int adists_stage(const float* const fx[6], const float* const fy[6], int pairs, 
   EntLevels el;
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
-    dim3 grid(L.chunks, L.c, pairs);
-    sums7_kernel<<<grid, 256, 0, st>>>(fx[k], fy[k], L.c, L.hw, L.chunks, F(L.off_sum));
-    ++launches;
+    launches += is16(k) ? level_front<bf16>(L, B16(fx[k]), B16(fy[k]), pairs, F(L.off_sum), st)
+                        : level_front<float>(L, F32(fx[k]), F32(fy[k]), pairs, F(L.off_sum), st);
     sl.partials[k] = F(L.off_sum); sl.chunks[k] = L.chunks; sl.hw[k] = L.hw;
     el.partials[k] = F(L.off_ent); el.chunks[k] = L.chunks;
   }
@@ -746,9 +834,8 @@ int adists_stage(const float* const fx[6], const float* const fy[6], int pairs, 
   ++launches;
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
-    dim3 grid(L.chunks, L.c, pairs);
-    entropy_kernel<<<grid, 256, 0, st>>>(fx[k], L.c, L.hw, L.chunks, L.choff, chan, F(L.off_ent));
-    ++launches;
+    launches += is16(k) ? level_entropy<bf16>(L, B16(fx[k]), pairs, chan, F(L.off_ent), st)
+                        : level_entropy<float>(L, F32(fx[k]), pairs, chan, F(L.off_ent), st);
   }
   weights_kernel<<<pairs, 256, 0, st>>>(el, wt);
   ++launches;
@@ -756,11 +843,10 @@ int adists_stage(const float* const fx[6], const float* const fy[6], int pairs, 
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
     if (L.windowed) {
-      switch (window) {
-        case 21: launches += launch_window<21>(L, fx[k], fy[k], pairs, chan, wt, taps, F(L.off_a), F(L.off_b), F(L.off_g), st); break;
-        case 11: launches += launch_window<11>(L, fx[k], fy[k], pairs, chan, wt, taps, F(L.off_a), F(L.off_b), F(L.off_g), st); break;
-        default: launches += launch_window<7>(L, fx[k], fy[k], pairs, chan, wt, taps, F(L.off_a), F(L.off_b), F(L.off_g), st); break;
-      }
+      launches += is16(k) ? level_window<bf16>(window, L, B16(fx[k]), B16(fy[k]), pairs, chan, wt, taps, F(L.off_a), F(L.off_b),
+                                               F(L.off_g), st)
+                          : level_window<float>(window, L, F32(fx[k]), F32(fy[k]), pairs, chan, wt, taps, F(L.off_a), F(L.off_b),
+                                                F(L.off_g), st);
     } else {
       global_level_kernel<<<pairs, 256, 0, st>>>(L.c, L.choff, chan, wt, F(L.off_a), F(L.off_b), F(L.off_g));
       ++launches;

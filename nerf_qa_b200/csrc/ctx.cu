@@ -908,11 +908,11 @@ int nqa_dists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS
 // A-DISTS keeps all six levels of both images alive (the entropy weights are global over the 1475
 // channels), as planar fp32 -- the layout its window kernels want and the reference's own
 // forward_once format -- so its micro-batch is smaller than the DISTS one.
-static size_t adists_feat_bytes(int pairs, int H, int W) {
+static size_t adists_feat_bytes(int pairs, int H, int W, size_t elem = sizeof(float)) {
   int h[kNumLevels], w[kNumLevels];
   level_dims(H, W, h, w);
   size_t total = 0;
-  for (int k = 1; k < kNumLevels; ++k) total += align256((size_t)2 * pairs * level_channels(k) * h[k] * w[k] * sizeof(float));
+  for (int k = 1; k < kNumLevels; ++k) total += align256((size_t)2 * pairs * level_channels(k) * h[k] * w[k] * elem);
   return total + 4096;
 }
 
@@ -925,7 +925,10 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
   if (mb < 1) mb = 1;
   const bool with_dists = dists_out != nullptr;
   const bool fused_pool = with_dists && prec != NQA_PREC_BF16X3;
-  int rc = ensure_arena(ctx, trunk_bytes<T>(2 * mb, H, W, prec) + adists_feat_bytes(mb, H, W) +
+  // bf16 trunk: the planes the statistics read are bf16 too (exact copies of the activations, half the bytes)
+  const bool planes16 = std::is_same<T, bf16>::value && prec == NQA_PREC_BF16;
+  const size_t pelem = planes16 ? sizeof(bf16) : sizeof(float);
+  int rc = ensure_arena(ctx, trunk_bytes<T>(2 * mb, H, W, prec) + adists_feat_bytes(mb, H, W, pelem) +
                                  adists_workspace_bytes(mb, H, W, window) +
                                  (with_dists ? partial_bytes(mb, H, W, prec, nullptr, false, fused_pool) : 0));
   if (rc != NQA_OK) return rc;
@@ -937,9 +940,9 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     ctx->arena.reset();
     TrunkBufs<T> bufs;
     trunk_alloc<T>(ctx, &bufs, 2 * pairs, H, W, prec);
-    float* planar[kNumLevels] = {};
+    char* planar[kNumLevels] = {};
     for (int k = 1; k < kNumLevels; ++k)
-      planar[k] = static_cast<float*>(ctx->arena.take((size_t)2 * pairs * level_channels(k) * lh[k] * lw[k] * sizeof(float)));
+      planar[k] = static_cast<char*>(ctx->arena.take((size_t)2 * pairs * level_channels(k) * lh[k] * lw[k] * pelem));
     void* ws = ctx->arena.take(adists_workspace_bytes(pairs, H, W, window));
     const float* xb = x + b0 * frame;
     const float* yb = y + b0 * frame;
@@ -953,7 +956,13 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     rc = run_trunk<T>(ctx, xb, yb, pairs, 2 * pairs, H, W, prec, bufs, st,
                       [&](int k, const T* f, const T* f_lo, int h, int w, T* pooled_dst) {
                         const int c = level_channels(k);
-                        level_to_nchw<T>(ctx, f, f_lo, planar[k], 2 * pairs, c, h, w, st);
+                        if (planes16) {
+                          ProfScope ps(ctx, NQA_K_LAYOUT, st);
+                          ctx->launches += launch_nhwc_to_nchw_bf16(reinterpret_cast<const bf16*>(f), reinterpret_cast<bf16*>(planar[k]),
+                                                                    2 * pairs, c, h, w, st);
+                        } else {
+                          level_to_nchw<T>(ctx, f, f_lo, reinterpret_cast<float*>(planar[k]), 2 * pairs, c, h, w, st);
+                        }
                         if (!with_dists) return false;
                         const size_t half = (size_t)pairs * h * w * c;
                         if (fused_pool && pooled_dst) {
@@ -970,16 +979,16 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
                       });
     if (rc != NQA_OK) return rc;
     if (with_dists && (rc = finalize(ctx, pb, pairs, H, W, dists_out + b0, nullptr, st)) != NQA_OK) return rc;
-    const float* fx[kNumLevels];
-    const float* fy[kNumLevels];
+    const void* fx[kNumLevels];
+    const void* fy[kNumLevels];
     fx[0] = xb;
     fy[0] = yb;
     for (int k = 1; k < kNumLevels; ++k) {
       fx[k] = planar[k];
-      fy[k] = planar[k] + (size_t)pairs * level_channels(k) * lh[k] * lw[k];
+      fy[k] = planar[k] + (size_t)pairs * level_channels(k) * lh[k] * lw[k] * pelem;
     }
     ProfScope ps(ctx, NQA_K_ADISTS, st);
-    ctx->launches += adists_stage(fx, fy, pairs, H, W, window, ws, score_out + b0, st,
+    ctx->launches += adists_stage(fx, fy, planes16, pairs, H, W, window, ws, score_out + b0, st,
                                   map_out ? map_out + (size_t)b0 * H * W : nullptr);
   }
   return NQA_OK;
@@ -1051,7 +1060,10 @@ int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVEL
   void* ws = ctx->arena.take(adists_workspace_bytes(B, H, W, window));
   {
     ProfScope ps(ctx, NQA_K_ADISTS, st);
-    ctx->launches += adists_stage(feats_x, feats_y, B, H, W, window, ws, score_out, st);
+    const void* vx[kNumLevels];
+    const void* vy[kNumLevels];
+    for (int k = 0; k < kNumLevels; ++k) { vx[k] = feats_x[k]; vy[k] = feats_y[k]; }
+    ctx->launches += adists_stage(vx, vy, false, B, H, W, window, ws, score_out, st);
   }
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;

@@ -61,6 +61,7 @@ template <typename T>
 int launch_nhwc_to_nchw(const T* in, float* out, int n, int c, int h, int w, cudaStream_t st);
 template <typename T>
 int launch_nchw_to_nhwc(const float* in, T* out, T* out_lo, int n, int c, int h, int w, cudaStream_t st);
+int launch_nhwc_to_nchw_bf16(const bf16* in, bf16* out, int n, int c, int h, int w, cudaStream_t st);
 // bf16x3 carrier: hi = bf16(v), lo = bf16(v - hi)
 int launch_nhwc_split_to_nchw(const bf16* hi, const bf16* lo, float* out, int n, int c, int h, int w, cudaStream_t st);
 

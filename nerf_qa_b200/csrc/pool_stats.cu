@@ -599,9 +599,9 @@ int launch_l2pool_nchw(const float* in, float* out, int n, int c, int h, int w, 
 // NHWC (internal) -> NCHW fp32 (API surface of forward_once), tiled transpose through smem.
 // grid = (ceil(hw/32), ceil(c/32), n), block = (32, 8).
 // ================================================================================================
-template <typename T, bool SPLIT>
+template <typename T, bool SPLIT, typename TO>
 __global__ void __launch_bounds__(256)
-nhwc_to_nchw_kernel(const T* __restrict__ in, const T* __restrict__ in_lo, float* __restrict__ out, int c, int hw) {
+nhwc_to_nchw_kernel(const T* __restrict__ in, const T* __restrict__ in_lo, TO* __restrict__ out, int c, int hw) {
   __shared__ float tile[32][33];
   const int img = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -617,10 +617,10 @@ nhwc_to_nchw_kernel(const T* __restrict__ in, const T* __restrict__ in_lo, float
     tile[i][threadIdx.x] = v;
   }
   __syncthreads();
-  float* dst = out + (size_t)img * c * hw;
+  TO* dst = out + (size_t)img * c * hw;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int ch = c0 + i, p = p0 + threadIdx.x;
-    if (p < hw && ch < c) dst[(size_t)ch * hw + p] = tile[threadIdx.x][i];
+    if (p < hw && ch < c) dst[(size_t)ch * hw + p] = from_float<TO>(tile[threadIdx.x][i]);
   }
 }
 
@@ -662,16 +662,53 @@ template <typename T>
 int launch_nhwc_to_nchw(const T* in, float* out, int n, int c, int h, int w, cudaStream_t st) {
   const int hw = h * w;
   dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
-  nhwc_to_nchw_kernel<T, false><<<grid, block, 0, st>>>(in, nullptr, out, c, hw);
+  nhwc_to_nchw_kernel<T, false, float><<<grid, block, 0, st>>>(in, nullptr, out, c, hw);
   return 1;
 }
 template int launch_nhwc_to_nchw<float>(const float*, float*, int, int, int, int, cudaStream_t);
 template int launch_nhwc_to_nchw<bf16>(const bf16*, float*, int, int, int, int, cudaStream_t);
 
+// bf16 NHWC -> bf16 planes (A-DISTS statistics of the bf16 trunk: exact copies, half the bytes of fp32 planes).
+// Tile = 64 pixels x 64 channels; loads are channel pairs (4 bytes per lane, 128 bytes per warp), stores are pixel
+// pairs (4 bytes per lane along the plane).  grid = (ceil(hw/64), c/64, n), block = (32, 8).  c % 64 == 0.
+__global__ void __launch_bounds__(256)
+nhwc_to_planes_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int c, int hw) {
+  __shared__ uint32_t tile[64][33];   // [pixel][channel pair]
+  const int img = blockIdx.z;
+  const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (size_t)img * hw * c);
+  for (int i = threadIdx.y; i < 64; i += 8) {
+    const int p = p0 + i;
+    tile[i][threadIdx.x] = p < hw ? __ldg(src + ((size_t)p * c + c0) / 2 + threadIdx.x) : 0u;
+  }
+  __syncthreads();
+  bf16* dst = out + (size_t)img * c * hw;
+  const bool even = (hw & 1) == 0;     // 4-byte stores need even plane sizes (plane starts stay 4-byte aligned)
+  for (int ch = threadIdx.y; ch < 64; ch += 8) {
+    const int pp = threadIdx.x, p = p0 + 2 * pp;
+    const uint32_t a = tile[2 * pp][ch >> 1], b = tile[2 * pp + 1][ch >> 1];
+    const uint32_t lo = (ch & 1) ? (a >> 16) : (a & 0xffffu), hi = (ch & 1) ? (b >> 16) : (b & 0xffffu);
+    unsigned short* row = reinterpret_cast<unsigned short*>(dst + (size_t)(c0 + ch) * hw);
+    if (even && p + 1 < hw) {
+      *reinterpret_cast<uint32_t*>(row + p) = lo | (hi << 16);
+    } else {
+      if (p < hw) row[p] = (unsigned short)lo;
+      if (p + 1 < hw) row[p + 1] = (unsigned short)hi;
+    }
+  }
+}
+
+int launch_nhwc_to_nchw_bf16(const bf16* in, bf16* out, int n, int c, int h, int w, cudaStream_t st) {
+  const int hw = h * w;
+  dim3 grid(ceil_div(hw, 64), c / 64, n), block(32, 8);
+  nhwc_to_planes_bf16_kernel<<<grid, block, 0, st>>>(in, out, c, hw);
+  return 1;
+}
+
 int launch_nhwc_split_to_nchw(const bf16* hi, const bf16* lo, float* out, int n, int c, int h, int w, cudaStream_t st) {
   const int hw = h * w;
   dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
-  nhwc_to_nchw_kernel<bf16, true><<<grid, block, 0, st>>>(hi, lo, out, c, hw);
+  nhwc_to_nchw_kernel<bf16, true, float><<<grid, block, 0, st>>>(hi, lo, out, c, hw);
   return 1;
 }
 
