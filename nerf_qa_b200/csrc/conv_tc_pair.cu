@@ -14,6 +14,8 @@
 //   * every TMA load (both CTAs) signals the LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2 with
 //     the mapa-translated barrier address); the leader's elected lane issues all MMAs and releases smem slots /
 //     publishes accumulators to BOTH CTAs with tcgen05.commit ... .multicast::cluster;
+//   * accumulators form a ring over all 512 TMEM columns (2 x N=256 or 4 x N=128), so the epilogue latency of the short
+//     N=128 tiles (cross-CTA hand-offs included) stays hidden behind the MMAs of the next tiles;
 //   * each CTA's epilogue warps read their own 128 TMEM lanes, add bias, ReLU, stage through swizzled shared
 //     memory and TMA-store their own tile; the follower's warps hand the accumulator back with a remote
 //     mbarrier.arrive on the leader's tmem_empty barrier.
@@ -91,6 +93,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_out, const Params p, int a_stages, int b_stages) {
   constexpr int HALF_N = BLOCK_N / 2;
+  constexpr int ACC = 512 / BLOCK_N;                              // accumulator ring in TMEM: 2 x 256 or 4 x 128 columns
+  constexpr int ACC_LOG2 = ACC == 4 ? 2 : 1;
   constexpr int B_TILE = HALF_N * BLOCK_K * 2;                   // this CTA's half of one tap's weight tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -105,10 +109,10 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   uint64_t* a_empty = bars + 4;            // [4]  local, multicast commit
   uint64_t* b_full = bars + 8;             // [8]  leader's copy (ring) / [0] = weights loaded (resident)
   uint64_t* b_empty = bars + 16;           // [8]  local, multicast commit
-  uint64_t* tmem_full = bars + 24;         // [2]  local, multicast commit
-  uint64_t* tmem_empty = bars + 26;        // [2]  leader's copy: 4 epilogue warps of each CTA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
-  float* bias_s = reinterpret_cast<float*>(tail + 256);
+  uint64_t* tmem_full = bars + 24;         // [4]  local, multicast commit
+  uint64_t* tmem_empty = bars + 28;        // [4]  leader's copy: 4 epilogue warps of each CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  float* bias_s = reinterpret_cast<float*>(tail + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1-D grid with cluster dims (2,1,1): %cluster_ctarank == blockIdx.x & 1; derived from blockIdx so that the
@@ -124,13 +128,13 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     prefetch_tmap(&tmap_out);
     for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    for (int a = 0; a < 4; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)(2 * BLOCK_N))
+                 "r"((uint32_t)(ACC * BLOCK_N))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
@@ -207,8 +211,8 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       uint32_t aph = 0, bph = 0;
       int local = 0;
       for (int item = cluster_id; item < p.num_items; item += num_clusters, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
+        const int acc = local & (ACC - 1);
+        const uint32_t acc_phase = (local >> ACC_LOG2) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -265,8 +269,8 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const bool elected = warp == 2 && lane == 0;
     int local = 0, sub = 0;
     for (int item = cluster_id; item < p.num_items; item += num_clusters, ++local) {
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
+      const int acc = local & (ACC - 1);
+      const uint32_t acc_phase = (local >> ACC_LOG2) & 1;
       int n0, img, h0, w0;
       decode(item, n0, img, h0, w0);
       const int py = h0 + (m >> 3), px = w0 + (m & 7);
@@ -342,7 +346,7 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   cluster_sync_all();                      // the peer may still signal barriers in this CTA's shared memory
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N))
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(ACC * BLOCK_N))
                  : "memory");
   }
 }
@@ -361,7 +365,7 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
   p.a_stage_bytes = (HALO_H * plan.halo_hbw * 128 + 1023) & ~1023;
   p.bias = plan.bias; p.epi = plan.epi; p.mask = plan.mask;
   const int chunks = plan.cin / BLOCK_K;
-  const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*bias*/ - STG_BYTES;
+  const int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - 2048 /*bias*/ - STG_BYTES;
   int a_stages, b_stages = 0;
   if (RESIDENT) {
     const int wbytes = chunks * 9 * B_TILE;
@@ -374,7 +378,7 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
     if (b_stages > 8) b_stages = 8;
     if (b_stages < 3) return -1;
   }
-  const int smem = STG_BYTES + a_stages * p.a_stage_bytes + (RESIDENT ? chunks * 9 : b_stages) * B_TILE + 1024 + 256 + 2048;
+  const int smem = STG_BYTES + a_stages * p.a_stage_bytes + (RESIDENT ? chunks * 9 : b_stages) * B_TILE + 1024 + 512 + 2048;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     cudaFuncSetAttribute(conv3x3_tc_pair_kernel<BLOCK_N, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
