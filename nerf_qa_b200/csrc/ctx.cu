@@ -77,6 +77,13 @@ struct nqa_ctx {
   Arena arena;
   uint64_t launches = 0;
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+  // Optional second lane (NQA_LANES=2): consecutive micro-batches alternate between two internal streams so that the
+  // HBM-bound pooling / statistics kernels of one micro-batch share the SMs with the tensor-bound convolutions of
+  // the other.  Measured on B200: no gain (428 vs 430 pairs/s) -- the step runs at the 1000 W power cap, the overlap
+  // only lowers the SM clock (1556 vs 1610 MHz): the path is energy-bound, not latency-bound.  Default: one lane.
+  int lanes = 1;
+  cudaStream_t lane_stream[2] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {};
   cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
   float* stage_in[2] = {};               // device staging for the host path
   size_t stage_cap = 0;
@@ -441,17 +448,39 @@ int dists_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, i
 int dists_forward_device(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int prec, float* score,
                          float* s1s2, cudaStream_t st) {
   const int mb = pick_micro_pairs(ctx, B, H, W);
-  const size_t need = prec == NQA_PREC_FP32 ? dists_mb_bytes<float>(ctx, mb, H, W, prec) : dists_mb_bytes<bf16>(ctx, mb, H, W, prec);
-  int rc = ensure_arena(ctx, need);
+  const size_t need = align256(prec == NQA_PREC_FP32 ? dists_mb_bytes<float>(ctx, mb, H, W, prec)
+                                                     : dists_mb_bytes<bf16>(ctx, mb, H, W, prec));
+  const int n_mb = ceil_div(B, mb);
+  const int lanes = (ctx->lanes > 1 && n_mb > 1) ? 2 : 1;
+  int rc = ensure_arena(ctx, lanes * need);
   if (rc != NQA_OK) return rc;
   const size_t frame = (size_t)3 * H * W;
-  for (int b0 = 0; b0 < B; b0 += mb) {
+  if (lanes > 1) {   // fork: both lanes start after everything already enqueued on the caller's stream
+    CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+    for (int l = 0; l < 2; ++l) CUDA_TRY(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
+  }
+  const Arena whole = ctx->arena;
+  int it = 0;
+  for (int b0 = 0; b0 < B; b0 += mb, ++it) {
     const int pairs = B - b0 < mb ? B - b0 : mb;
     float* s12 = s1s2 ? s1s2 + (size_t)b0 * 2 * kTotalChannels : nullptr;
+    const int lane = lanes > 1 ? (it & 1) : 0;
+    cudaStream_t ls = lanes > 1 ? ctx->lane_stream[lane] : st;
+    // each lane owns one half of the arena (dists_micro_batch resets and carves ctx->arena)
+    ctx->arena.base = whole.base + (size_t)lane * need;
+    ctx->arena.cap = need;
+    ctx->arena.used = 0;
     rc = prec == NQA_PREC_FP32
-             ? dists_micro_batch<float>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, prec, score + b0, s12, st)
-             : dists_micro_batch<bf16>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, prec, score + b0, s12, st);
+             ? dists_micro_batch<float>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, prec, score + b0, s12, ls)
+             : dists_micro_batch<bf16>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, prec, score + b0, s12, ls);
+    ctx->arena = whole;
     if (rc != NQA_OK) return rc;
+  }
+  if (lanes > 1) {   // join
+    for (int l = 0; l < 2; ++l) {
+      CUDA_TRY(cudaEventRecord(ctx->ev_join[l], ctx->lane_stream[l]));
+      CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join[l], 0));
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;
@@ -646,6 +675,12 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   if (const char* e = getenv("NQA_STAGE1_FUSED")) ctx->fuse_stage1 = atoi(e) != 0;
   if (const char* e = getenv("NQA_POOL_STATS_FUSED")) ctx->fuse_pool_stats = atoi(e) != 0;
   if (const char* e = getenv("NQA_MICRO_IMAGES")) ctx->micro_images = atoi(e) > 0 ? atoi(e) : 16;
+  if (const char* e = getenv("NQA_LANES")) ctx->lanes = atoi(e) == 2 ? 2 : 1;
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->lane_stream[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
@@ -697,6 +732,11 @@ int nqa_ctx_destroy(nqa_ctx* ctx) {
   }
   for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->lane_stream[i]) cudaStreamDestroy(ctx->lane_stream[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
   cudaGetLastError();
