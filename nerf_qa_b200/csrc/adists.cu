@@ -761,11 +761,7 @@ int launch_window(const LevelPlan& L, const TI* fx, const TI* fy, int pairs, con
   constexpr int IN = WT + WIN - 1;
   constexpr int LDI = IN | 1;
   constexpr size_t smem = (size_t)(2 * IN * LDI + 5 * IN * (WT + 1) + 2) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(window_kernel<WIN, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  ensure_dynamic_smem(window_kernel<WIN, TI>, (int)smem);
   dim3 grid(L.tiles_x * L.tiles_y, L.csplit, pairs);
   window_kernel<WIN, TI><<<grid, 256, smem, st>>>(fx, fy, L.c, L.h, L.w, L.oh, L.ow, L.tiles_x, L.csplit, L.choff, chan, wt,
                                              taps, amap, bmap, gmap);

@@ -5,6 +5,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace nqa {
 
 constexpr int kNumLevels = 6;
@@ -18,6 +22,25 @@ __host__ __device__ constexpr int level_channels(int k) {
 __host__ __device__ constexpr int level_offset(int k) {
   return k == 0 ? 0 : k == 1 ? 3 : k == 2 ? 67 : k == 3 ? 195 : k == 4 ? 451 : 963;
 }
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE and per KERNEL: remember the largest request per
+// (kernel entry point, device) so that a process holding contexts on several GPUs configures each of them.
+inline void ensure_dynamic_smem_impl(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> granted;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  int& g = granted[std::make_pair(kernel, dev)];
+  if (bytes > g) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    g = bytes;
+  }
+}
+template <typename K>
+inline void ensure_dynamic_smem(K kernel, int bytes) {
+  ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 __host__ __device__ inline int pooled(int n) { return (n - 1) / 2 + 1; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

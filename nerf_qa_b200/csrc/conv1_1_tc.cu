@@ -277,12 +277,11 @@ int launch_conv1_1_tc(const float* x, const float* y, int nx, int n, int h, int 
   const int a_stage = A_BYTES * (split ? 2 : 1);
   const int smem = STAGES * a_stage + 2 * W_BYTES + NOUT * 4 + 256 + 128;
   const int grid = p.num_tiles < 2 * sm_count ? p.num_tiles : 2 * sm_count;   // two resident CTAs per SM
-  static bool attr[2] = {false, false};
   if (split) {
-    if (!attr[1]) { cudaFuncSetAttribute(conv1_1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr[1] = true; }
+    ensure_dynamic_smem(conv1_1_tc_kernel<true>, smem);
     conv1_1_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(p);
   } else {
-    if (!attr[0]) { cudaFuncSetAttribute(conv1_1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr[0] = true; }
+    ensure_dynamic_smem(conv1_1_tc_kernel<false>, smem);
     conv1_1_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(p);
   }
   return 1;

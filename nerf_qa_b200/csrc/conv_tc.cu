@@ -327,11 +327,7 @@ static bool encode_w_map(CUtensorMap* map, const bf16* ptr, int cout, int k, int
 template <int BLOCK_N, bool SPLIT>
 static int launch_impl(const ConvTcPlan& plan, cudaStream_t st) {
   using C = Cfg<BLOCK_N, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    attr_set = true;
-  }
+  ensure_dynamic_smem(conv3x3_tc_kernel<BLOCK_N, SPLIT>, C::SMEM_BYTES);
   Params p;
   p.n = plan.n; p.h = plan.h; p.w = plan.w; p.cin = plan.cin; p.cout = plan.cout;
   p.tw_log2 = plan.tw_log2; p.tiles_w = plan.tiles_w; p.tiles_h = plan.tiles_h;

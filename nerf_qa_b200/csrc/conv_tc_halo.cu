@@ -315,11 +315,7 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
     if (b_stages < 3) return -1;
   }
   const int smem = STG_BYTES + a_stages * p.a_stage_bytes + (RESIDENT ? chunks * 9 : b_stages) * B_TILE + 1024 + 256 + 2048;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaFuncSetAttribute(conv3x3_tc_halo_kernel<BLOCK_N, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_smem = smem;
-  }
+  ensure_dynamic_smem(conv3x3_tc_halo_kernel<BLOCK_N, RESIDENT>, smem);
   int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
   if (RESIDENT) grid -= grid % p.num_n_tiles;
   conv3x3_tc_halo_kernel<BLOCK_N, RESIDENT><<<grid, NUM_THREADS, smem, st>>>(plan.tmap_a, plan.tmap_b, plan.tmap_out, p, a_stages,

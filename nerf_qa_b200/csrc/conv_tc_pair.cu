@@ -379,11 +379,7 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
     if (b_stages < 3) return -1;
   }
   const int smem = STG_BYTES + a_stages * p.a_stage_bytes + (RESIDENT ? chunks * 9 : b_stages) * B_TILE + 1024 + 512 + 2048;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaFuncSetAttribute(conv3x3_tc_pair_kernel<BLOCK_N, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_smem = smem;
-  }
+  ensure_dynamic_smem(conv3x3_tc_pair_kernel<BLOCK_N, RESIDENT>, smem);
   int clusters = sm_count / 2;
   if (p.num_items < clusters) clusters = p.num_items;
   if (RESIDENT && clusters > p.num_n_tiles) clusters -= clusters % p.num_n_tiles;

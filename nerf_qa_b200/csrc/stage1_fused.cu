@@ -396,11 +396,7 @@ int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, in
   p.tiles_h = ceil_div(h, TH);
   p.num_tiles = n * p.tiles_h * p.tiles_w;
   p.w1img = w1img; p.bias1 = bias1; p.bias2 = bias2; p.out = out;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(stage1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    attr = true;
-  }
+  ensure_dynamic_smem(stage1_fused_kernel, SMEM_BYTES);
   const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
   stage1_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(w2map, outmap, p);
   return 1;

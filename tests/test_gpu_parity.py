@@ -492,3 +492,19 @@ def test_shared_trunk_scores_match_separate_calls(models, amodels, prec):
     # the fused pool + moments kernel (separable sums, MUFU sqrt before the bf16 rounding) replaces the stand-alone pooling
     # kernel on this path: pooled bf16 activations can differ in the last bit
     assert torch.allclose(a, want_a, rtol=1e-4, atol=(1e-4 if prec == "bf16" else 2e-6))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """One library context per device inside ONE process (the reference's .to(device) pattern); per-device kernel
+    attributes (dynamic shared memory) and device guards must not leak between them."""
+    x, y = synth.make_frame_pairs(2, 135, 240, seed=67)
+    m = make_dists("bf16", device="cuda:0")
+    s0 = m(x.to("cuda:0"), y.to("cuda:0")).cpu()
+    m1 = make_dists("bf16", device="cuda:1")
+    s1 = m1(x.to("cuda:1"), y.to("cuda:1")).cpu()
+    assert torch.equal(s0, s1)
+    a1 = make_adists("bf16", device="cuda:1")
+    a0 = make_adists("bf16", device="cuda:0")
+    assert torch.equal(a1(x.to("cuda:1"), y.to("cuda:1"), as_loss=False).cpu(), a0(x.to("cuda:0"), y.to("cuda:0"), as_loss=False).cpu())
+    assert torch.cuda.current_device() == 0
