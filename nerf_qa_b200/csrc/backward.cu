@@ -32,9 +32,10 @@ stat_coef_kernel(const float* __restrict__ moments, const float* __restrict__ al
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= kTotalChannels) return;
   const int k = c < 3 ? 0 : c < 67 ? 1 : c < 195 ? 2 : c < 451 ? 3 : c < 963 ? 4 : 5;
-  float* out = coef + ((size_t)b * kTotalChannels + c) * 5;
+  float* out = coef + (size_t)b * 5 * kCoefStride + coef_offset(k) + (c - level_offset(k));   // out[q * kCoefStride]
   if (k >= levels_valid) {
-    out[0] = out[1] = out[2] = out[3] = out[4] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) out[q * kCoefStride] = 0.f;
     return;
   }
   const float* m = moments + ((size_t)b * kTotalChannels + c) * 5;
@@ -47,11 +48,11 @@ stat_coef_kernel(const float* __restrict__ moments, const float* __restrict__ al
   const double ds1_dmy = (2.0 * mx * d1 - n1 * 2.0 * my) / (d1 * d1);
   const double n2 = 2.0 * cov + c2, d2 = vx + vy + c2;
   const double ds2_dcov = 2.0 / d2, ds2_dv = -n2 / (d2 * d2);
-  out[0] = (float)((a * ds1_dmx - 2.0 * bb * ds2_dv * mx - bb * ds2_dcov * my) * inv_n);   // Px
-  out[1] = (float)(2.0 * bb * ds2_dv * inv_n);                                             // Qx (= Qy)
-  out[2] = (float)(bb * ds2_dcov * inv_n);                                                 // R
-  out[3] = (float)((a * ds1_dmy - 2.0 * bb * ds2_dv * my - bb * ds2_dcov * mx) * inv_n);   // Py
-  out[4] = out[1];                                                                         // Qy
+  out[0 * kCoefStride] = (float)((a * ds1_dmx - 2.0 * bb * ds2_dv * mx - bb * ds2_dcov * my) * inv_n);   // Px
+  out[1 * kCoefStride] = (float)(2.0 * bb * ds2_dv * inv_n);                                             // Qx (= Qy)
+  out[2 * kCoefStride] = (float)(bb * ds2_dcov * inv_n);                                                 // R
+  out[3 * kCoefStride] = (float)((a * ds1_dmy - 2.0 * bb * ds2_dv * my - bb * ds2_dcov * mx) * inv_n);   // Py
+  out[4 * kCoefStride] = out[1 * kCoefStride];                                                           // Qy
 }
 
 int launch_stat_coef(const float* moments, const float* alpha, const float* beta, bool normalize, const float* grad_score,
@@ -67,10 +68,10 @@ int launch_stat_coef(const float* moments, const float* alpha, const float* beta
 // ================================================================================================
 __global__ void __launch_bounds__(256)
 stat_grad_planar_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ coef,
-                        int choff, int c, int hw, float* __restrict__ gx, float* __restrict__ gy, int accumulate) {
+                        int level, int c, int hw, float* __restrict__ gx, float* __restrict__ gy, int accumulate) {
   const int ch = blockIdx.y, b = blockIdx.z;
-  const float* k = coef + ((size_t)b * kTotalChannels + choff + ch) * 5;
-  const float px = k[0], qx = k[1], r = k[2], py = k[3], qy = k[4];
+  const float* k = coef + (size_t)b * 5 * kCoefStride + coef_offset(level) + ch;
+  const float px = k[0], qx = k[kCoefStride], r = k[2 * kCoefStride], py = k[3 * kCoefStride], qy = k[4 * kCoefStride];
   const size_t base = ((size_t)b * c + ch) * hw;
   for (int i = blockIdx.x * 1024 + threadIdx.x; i < min(hw, (int)(blockIdx.x + 1) * 1024); i += 256) {
     const float a = x[base + i], d = y[base + i];
@@ -85,10 +86,10 @@ stat_grad_planar_kernel(const float* __restrict__ x, const float* __restrict__ y
   }
 }
 
-int launch_stat_grad_planar(const float* x, const float* y, const float* coef, int choff, int pairs, int c, int hw,
+int launch_stat_grad_planar(const float* x, const float* y, const float* coef, int level, int pairs, int c, int hw,
                             float* gx, float* gy, bool accumulate, cudaStream_t st) {
   dim3 grid(ceil_div(hw, 1024), c, pairs);
-  stat_grad_planar_kernel<<<grid, 256, 0, st>>>(x, y, coef, choff, c, hw, gx, gy, accumulate ? 1 : 0);
+  stat_grad_planar_kernel<<<grid, 256, 0, st>>>(x, y, coef, level, c, hw, gx, gy, accumulate ? 1 : 0);
   return 1;
 }
 
@@ -99,10 +100,9 @@ int launch_stat_grad_planar(const float* x, const float* y, const float* coef, i
 // ================================================================================================
 template <typename T, bool POOL>
 __global__ void __launch_bounds__(256)
-level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* __restrict__ poolx,
-                  const T* __restrict__ pooly, const T* __restrict__ gpoolx, const T* __restrict__ gpooly,
-                  const float* __restrict__ coef, int choff, int pairs, int h, int w, int c, int ho, int wo,
-                  T* __restrict__ gx, T* __restrict__ gy) {
+level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* __restrict__ qpoolx,
+                  const T* __restrict__ qpooly, const float* __restrict__ coef, int level, int pairs, int h, int w, int c,
+                  int ho, int wo, T* __restrict__ gx, T* __restrict__ gy) {
   constexpr int V = Vec<T>::N;
   const int groups = c / V;
   const size_t total = (size_t)pairs * h * w * groups;
@@ -116,11 +116,21 @@ level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* _
     float x[V], y[V], ox[V], oy[V];
     Vec<T>::load(fx + off, x);
     Vec<T>::load(fy + off, y);
-    const float* k = coef + ((size_t)b * kTotalChannels + choff + g * V) * 5;
+    // five coefficient vectors of this (pair, channel group): 16-byte loads from the padded table
+    const float* k = coef + (size_t)b * 5 * kCoefStride + coef_offset(level) + g * V;
+    float kp[V], kq[V], kr[V], kpy[V], kqy[V];
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      *reinterpret_cast<float4*>(kp + i) = __ldg(reinterpret_cast<const float4*>(k + i));
+      *reinterpret_cast<float4*>(kq + i) = __ldg(reinterpret_cast<const float4*>(k + kCoefStride + i));
+      *reinterpret_cast<float4*>(kr + i) = __ldg(reinterpret_cast<const float4*>(k + 2 * kCoefStride + i));
+      *reinterpret_cast<float4*>(kpy + i) = __ldg(reinterpret_cast<const float4*>(k + 3 * kCoefStride + i));
+      *reinterpret_cast<float4*>(kqy + i) = __ldg(reinterpret_cast<const float4*>(k + 4 * kCoefStride + i));
+    }
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      ox[i] = fmaf(k[i * 5 + 1], x[i], fmaf(k[i * 5 + 2], y[i], k[i * 5 + 0]));
-      oy[i] = fmaf(k[i * 5 + 4], y[i], fmaf(k[i * 5 + 2], x[i], k[i * 5 + 3]));
+      ox[i] = fmaf(kq[i], x[i], fmaf(kr[i], y[i], kp[i]));
+      oy[i] = fmaf(kqy[i], y[i], fmaf(kr[i], x[i], kpy[i]));
     }
     if (POOL) {
       float sx[V], sy[V];
@@ -137,16 +147,11 @@ level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* _
         for (int px = ox0; px <= ox1; ++px) {
           if (px >= wo) continue;
           const size_t po = (((size_t)b * ho + py) * wo + px) * c + (size_t)g * V;
-          float pvx[V], pvy[V], gvx[V], gvy[V];
-          Vec<T>::load(poolx + po, pvx);
-          Vec<T>::load(pooly + po, pvy);
-          Vec<T>::load(gpoolx + po, gvx);
-          Vec<T>::load(gpooly + po, gvy);
+          float qx[V], qy[V];
+          Vec<T>::load(qpoolx + po, qx);      // = d loss / d pooled  /  pooled  (kEpiDivide epilogue)
+          Vec<T>::load(qpooly + po, qy);
 #pragma unroll
-          for (int i = 0; i < V; ++i) {
-            sx[i] += gvx[i] / pvx[i];      // pooled = sqrt(. + 1e-12) > 0
-            sy[i] += gvy[i] / pvy[i];
-          }
+          for (int i = 0; i < V; ++i) { sx[i] += qx[i]; sy[i] += qy[i]; }
         }
       }
 #pragma unroll
@@ -166,38 +171,39 @@ level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* _
 }
 
 template <typename T>
-int launch_level_grad(const T* fx, const T* fy, const T* poolx, const T* pooly, const T* gpoolx, const T* gpooly,
-                      const float* coef, int choff, int pairs, int h, int w, int c, T* gx, T* gy, cudaStream_t st) {
+int launch_level_grad(const T* fx, const T* fy, const T* qpoolx, const T* qpooly, const float* coef, int level, int pairs,
+                      int h, int w, int c, T* gx, T* gy, cudaStream_t st) {
   const size_t total = (size_t)pairs * h * w * (c / Vec<T>::N);
   size_t blocks = (total + 255) / 256;
   const size_t cap = (size_t)kNumSMs * 32;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (poolx)
-    level_grad_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(fx, fy, poolx, pooly, gpoolx, gpooly, coef, choff, pairs, h, w,
-                                                                c, pooled(h), pooled(w), gx, gy);
+  if (qpoolx)
+    level_grad_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(fx, fy, qpoolx, qpooly, coef, level, pairs, h, w, c, pooled(h),
+                                                                pooled(w), gx, gy);
   else
-    level_grad_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(fx, fy, nullptr, nullptr, nullptr, nullptr, coef, choff, pairs,
-                                                                 h, w, c, 0, 0, gx, gy);
+    level_grad_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(fx, fy, nullptr, nullptr, coef, level, pairs, h, w, c, 0, 0, gx,
+                                                                 gy);
   return 1;
 }
-template int launch_level_grad<float>(const float*, const float*, const float*, const float*, const float*, const float*,
-                                      const float*, int, int, int, int, int, float*, float*, cudaStream_t);
-template int launch_level_grad<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, const bf16*, const bf16*,
-                                     const float*, int, int, int, int, int, bf16*, bf16*, cudaStream_t);
+template int launch_level_grad<float>(const float*, const float*, const float*, const float*, const float*, int, int, int, int,
+                                      int, float*, float*, cudaStream_t);
+template int launch_level_grad<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, const float*, int, int, int, int, int,
+                                     bf16*, bf16*, cudaStream_t);
 
 // ================================================================================================
 // conv1_1 backward + input normalisation: gz [n,h,w,64] (gradient w.r.t. the pre-ReLU output of conv1_1, already
 // masked) -> gradient w.r.t. the RAW frames, NCHW fp32 (images [0,nx) -> gx, [nx,n) -> gy).
-// Thread = one input pixel; weights [9][64][3] in shared memory.
+// Weights [9][64][3] arrive as a kernel parameter (constant bank).
 // ================================================================================================
+// Thread = one input pixel.  ncu on B200 (512x512, 32 images, bf16): weights as scalar shared-memory reads 2.9 ms per
+// launch, this version (weights as compile-time offsets into the constant bank) 2.1 ms.  Two pixels per thread with
+// float4 weights from shared memory, and staging the gradient rows in shared memory, were tried and did not move the
+// step time; the kernel is far from the FP32 roofline (0.4 ms) -- a tensor-core N=16 variant is the next step.
 template <typename T>
 __global__ void __launch_bounds__(128)
-conv1_1_bwd_kernel(const T* __restrict__ gz, const float* __restrict__ wb /*[9][64][3]*/, int nx, int h, int w,
+conv1_1_bwd_kernel(const T* __restrict__ gz, const __grid_constant__ Conv11BwdWeights wb, int nx, int h, int w,
                    float* __restrict__ gx, float* __restrict__ gy) {
-  __shared__ float ws[9 * 64 * 3];
-  for (int i = threadIdx.x; i < 9 * 64 * 3; i += 128) ws[i] = wb[i];
-  __syncthreads();
   constexpr int V = Vec<T>::N;
   const int img = blockIdx.z, y = blockIdx.y, x = blockIdx.x * 128 + threadIdx.x;
   if (x >= w) return;
@@ -211,16 +217,15 @@ conv1_1_bwd_kernel(const T* __restrict__ gz, const float* __restrict__ wb /*[9][
       const int ox = x + 1 - s;
       if (ox < 0 || ox >= w) continue;
       const T* src = gz + (((size_t)img * h + oy) * w + ox) * 64;
-      const float* wt = ws + (r * 3 + s) * 64 * 3;
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += V) {
         float v[V];
         Vec<T>::load(src + c0, v);
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          acc[0] = fmaf(v[i], wt[(c0 + i) * 3 + 0], acc[0]);
-          acc[1] = fmaf(v[i], wt[(c0 + i) * 3 + 1], acc[1]);
-          acc[2] = fmaf(v[i], wt[(c0 + i) * 3 + 2], acc[2]);
+        for (int i = 0; i < V; ++i) {     // weights: compile-time offsets into the constant bank
+          acc[0] = fmaf(v[i], wb.w[r * 3 + s][c0 + i][0], acc[0]);
+          acc[1] = fmaf(v[i], wb.w[r * 3 + s][c0 + i][1], acc[1]);
+          acc[2] = fmaf(v[i], wb.w[r * 3 + s][c0 + i][2], acc[2]);
         }
       }
     }
@@ -232,13 +237,14 @@ conv1_1_bwd_kernel(const T* __restrict__ gz, const float* __restrict__ wb /*[9][
 }
 
 template <typename T>
-int launch_conv1_1_bwd(const T* gz, const float* wb, int nx, int n, int h, int w, float* gx, float* gy, cudaStream_t st) {
+int launch_conv1_1_bwd(const T* gz, const Conv11BwdWeights& wb, int nx, int n, int h, int w, float* gx, float* gy,
+                       cudaStream_t st) {
   dim3 grid(ceil_div(w, 128), h, n);
   conv1_1_bwd_kernel<T><<<grid, 128, 0, st>>>(gz, wb, nx, h, w, gx, gy);
   return 1;
 }
-template int launch_conv1_1_bwd<float>(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
-template int launch_conv1_1_bwd<bf16>(const bf16*, const float*, int, int, int, int, float*, float*, cudaStream_t);
+template int launch_conv1_1_bwd<float>(const float*, const Conv11BwdWeights&, int, int, int, int, float*, float*, cudaStream_t);
+template int launch_conv1_1_bwd<bf16>(const bf16*, const Conv11BwdWeights&, int, int, int, int, float*, float*, cudaStream_t);
 
 // ================================================================================================
 // weight packing for the data-gradient convolutions

@@ -189,6 +189,9 @@ conv3x3_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const 
             if (!(a.y > 0.f)) v.y = 0.f;
             if (!(a.z > 0.f)) v.z = 0.f;
             if (!(a.w > 0.f)) v.w = 0.f;
+          } else if (epi == kEpiDivide) { // gradient w.r.t. a pooled tensor, handed on as grad / pooled
+            const float4 a = *reinterpret_cast<const float4*>(mask + o);
+            v.x /= a.x; v.y /= a.y; v.z /= a.z; v.w /= a.w;
           }
         }
         *reinterpret_cast<float4*>(out + o) = v;

@@ -228,7 +228,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c64 * 64 + half * 32, r);
           tmem_ld_wait();
           uint4 mk[4];
-          if (p.epi == kEpiMask) {
+          if (p.epi == kEpiMask || p.epi == kEpiDivide) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) mk[q] = make_uint4(0u, 0u, 0u, 0u);
             if (pix_ok) {
@@ -247,12 +247,19 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+              const uint32_t mw[4] = {mk[q].x, mk[q].y, mk[q].z, mk[q].w};
               if (p.epi == kEpiMask) {      // ReLU of the layer below: pass the gradient where its output was > 0
-                const uint32_t mw[4] = {mk[q].x, mk[q].y, mk[q].z, mk[q].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   if ((mw[j] & 0x00007fffu) == 0u) v[2 * j] = 0.f;
                   if ((mw[j] & 0x7fff0000u) == 0u) v[2 * j + 1] = 0.f;
+                }
+              } else if (p.epi == kEpiDivide) {   // gradient w.r.t. a pooled tensor, handed on as grad / pooled
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float d0 = __uint_as_float(mw[j] << 16), d1 = __uint_as_float(mw[j] & 0xffff0000u);
+                  v[2 * j] = pix_ok ? v[2 * j] / d0 : 0.f;
+                  v[2 * j + 1] = pix_ok ? v[2 * j + 1] / d1 : 0.f;
                 }
               }
             }

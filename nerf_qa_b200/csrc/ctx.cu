@@ -67,7 +67,8 @@ struct nqa_ctx {
   bf16* w_lo[kNumConvs] = {};            // residual of the bf16 rounding (bf16x3)
   float* w_bwd_f32[kNumConvs] = {};      // data-gradient weights [9][cout][cin] (rotated taps)
   bf16* w_bwd_hi[kNumConvs] = {};        // data-gradient weights [cin][9][cout] bf16
-  float* w11_bwd = nullptr;              // conv1_1 backward [9][64][3]
+  float* w11_bwd = nullptr;              // conv1_1 backward [9][64][3] (device staging of the packed weights)
+  Conv11BwdWeights w11_bwd_host;         // the same, passed to the backward kernel as a parameter (constant bank)
   float* alpha = nullptr;
   float* beta = nullptr;
   CUtensorMap w12_map;                   // conv1_2 weights for the fused stage-1 kernel
@@ -530,7 +531,8 @@ size_t dists_bwd_bytes(const nqa_ctx* ctx, int pairs, int H, int W, int prec) {
   }
   total += 2 * align256(n * max_act_elems(H, W) * sizeof(T));                     // gradient ping-pong
   total += partial_bytes(pairs, H, W, prec, nullptr, false, true);
-  total += 2 * align256((size_t)pairs * kTotalChannels * 5 * sizeof(float)) + align256(pairs * sizeof(float));
+  total += align256((size_t)pairs * kTotalChannels * 5 * sizeof(float)) + align256((size_t)pairs * 5 * kCoefStride * sizeof(float)) +
+           align256(pairs * sizeof(float));
   return total + 8192;
 }
 
@@ -545,7 +547,7 @@ int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int
   partial_bytes(pairs, H, W, prec, &pb, false, true);
   partial_alloc(ctx, pairs, &pb);
   float* moments = static_cast<float*>(ctx->arena.take((size_t)pairs * kTotalChannels * 5 * sizeof(float)));
-  float* coef = static_cast<float*>(ctx->arena.take((size_t)pairs * kTotalChannels * 5 * sizeof(float)));
+  float* coef = static_cast<float*>(ctx->arena.take((size_t)pairs * 5 * kCoefStride * sizeof(float)));
   float* score_scratch = static_cast<float*>(ctx->arena.take(pairs * sizeof(float)));
   GradLevels gl;
   for (int k = 0; k < kNumLevels; ++k) gl.inv_n[k] = 1.0 / ((double)lh[k] * lw[k]);
@@ -599,16 +601,19 @@ int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int
     {  // last level: statistics gradient only
       const int h = lh[5], w = lw[5], c = level_channels(5);
       const size_t half = (size_t)pairs * h * w * c;
-      ctx->launches += launch_level_grad<T>(act[12], act[12] + half, nullptr, nullptr, nullptr, nullptr, coef, level_offset(5),
-                                            pairs, h, w, c, g[cur], g[cur] + half, st);
+      ctx->launches += launch_level_grad<T>(act[12], act[12] + half, nullptr, nullptr, coef, 5, pairs, h, w, c, g[cur],
+                                            g[cur] + half, st);
     }
     int li = kNumConvs - 1;
     for (int stage = 4; stage >= 0; --stage) {
       const int h = lh[stage + 1], w = lw[stage + 1];
       for (int j = kStageConvs[stage] - 1; j >= 0; --j, --li) {
         if (li == 0) break;
-        const bool first = j == 0;                       // input of this conv = pooled output of the stage below
-        rc = conv_layer_bwd<T>(ctx, li, g[cur], g[cur ^ 1], n, h, w, first ? kEpiPlain : kEpiMask, first ? nullptr : act[li - 1], st);
+        // first conv of a stage: its input is the pooled output of the stage below; the gradient w.r.t. that tensor
+        // is handed on as grad / pooled (the only form the pooling backward needs)
+        const bool first = j == 0;
+        rc = conv_layer_bwd<T>(ctx, li, g[cur], g[cur ^ 1], n, h, w, first ? kEpiDivide : kEpiMask,
+                               first ? pool[stage - 1] : act[li - 1], st);
         if (rc != NQA_OK) return rc;
         cur ^= 1;
       }
@@ -618,14 +623,13 @@ int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int
       const int k = stage, hp = lh[k], wp = lw[k], c = level_channels(k);
       const size_t half = (size_t)pairs * hp * wp * c, half_pool = (size_t)pairs * h * w * c;
       const T* feat = act[li];                            // li now indexes the last conv of the stage below
-      ctx->launches += launch_level_grad<T>(feat, feat + half, pool[stage - 1], pool[stage - 1] + half_pool, g[cur],
-                                            g[cur] + half_pool, coef, level_offset(k), pairs, hp, wp, c, g[cur ^ 1],
+      ctx->launches += launch_level_grad<T>(feat, feat + half, g[cur], g[cur] + half_pool, coef, k, pairs, hp, wp, c, g[cur ^ 1],
                                             g[cur ^ 1] + half, st);
       cur ^= 1;
     }
-    ctx->launches += launch_conv1_1_bwd<T>(g[cur], ctx->w11_bwd, pairs, n, H, W, gx, gy, st);
+    ctx->launches += launch_conv1_1_bwd<T>(g[cur], ctx->w11_bwd_host, pairs, n, H, W, gx, gy, st);
   }
-  ctx->launches += launch_stat_grad_planar(x, y, coef, 0, pairs, 3, H * W, gx, gy, through_trunk, st);
+  ctx->launches += launch_stat_grad_planar(x, y, coef, 0, pairs, 3, H * W, gx, gy, through_trunk, st);   // level 0
   return NQA_OK;
 }
 
@@ -776,6 +780,7 @@ int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const
     }
   }
   cudaFree(tmp);
+  CUDA_TRY(cudaMemcpy(&ctx->w11_bwd_host, ctx->w11_bwd, sizeof(Conv11BwdWeights), cudaMemcpyDeviceToHost));
   if (conv_tc_make_weight_map(&ctx->w12_map, ctx->w_hi[1], 64, 9 * 64, 64) != 0)
     return fail(NQA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the conv1_2 weights");
   ctx->have_weights = true;
@@ -1151,13 +1156,13 @@ int nqa_dists_from_feats_backward(nqa_ctx* ctx, const float* const feats_x[NQA_N
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PartialBufs pb;
-  const size_t need = partial_bytes(B, H, W, NQA_PREC_FP32, &pb, true) + 2 * align256((size_t)B * kTotalChannels * 5 * sizeof(float)) +
-                      align256(B * sizeof(float)) + 4096;
+  const size_t need = partial_bytes(B, H, W, NQA_PREC_FP32, &pb, true) + align256((size_t)B * kTotalChannels * 5 * sizeof(float)) +
+                      align256((size_t)B * 5 * kCoefStride * sizeof(float)) + align256(B * sizeof(float)) + 4096;
   if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
   ctx->arena.reset();
   partial_alloc(ctx, B, &pb);
   float* moments = static_cast<float*>(ctx->arena.take((size_t)B * kTotalChannels * 5 * sizeof(float)));
-  float* coef = static_cast<float*>(ctx->arena.take((size_t)B * kTotalChannels * 5 * sizeof(float)));
+  float* coef = static_cast<float*>(ctx->arena.take((size_t)B * 5 * kCoefStride * sizeof(float)));
   float* score_scratch = static_cast<float*>(ctx->arena.take(B * sizeof(float)));
   int lh[kNumLevels], lw[kNumLevels];
   level_dims(H, W, lh, lw);
@@ -1173,7 +1178,7 @@ int nqa_dists_from_feats_backward(nqa_ctx* ctx, const float* const feats_x[NQA_N
     ProfScope ps(ctx, NQA_K_BACKWARD, st);
     ctx->launches += launch_stat_coef(moments, ctx->alpha, ctx->beta, ctx->ab_normalize, grad_score, gl, kNumLevels, B, coef, st);
     for (int k = 0; k < kNumLevels; ++k)
-      ctx->launches += launch_stat_grad_planar(feats_x[k], feats_y[k], coef, level_offset(k), B, level_channels(k), lh[k] * lw[k],
+      ctx->launches += launch_stat_grad_planar(feats_x[k], feats_y[k], coef, k, B, level_channels(k), lh[k] * lw[k],
                                                grad_fx[k], grad_fy[k], false, st);
   }
   CUDA_TRY(cudaGetLastError());

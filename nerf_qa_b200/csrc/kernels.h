@@ -69,7 +69,10 @@ int launch_nhwc_split_to_nchw(const bf16* hi, const bf16* lo, float* out, int n,
 // Epilogue of the 3x3 convolution kernels.  Forward: bias + ReLU.  Backward (data gradient = the same convolution
 // with rotated / transposed weights): either the plain sum (gradient w.r.t. a pooled tensor) or the sum masked by
 // the ReLU of the layer below (mask = that layer's saved output, same shape as this kernel's output).
-enum ConvEpilogue { kEpiBiasRelu = 0, kEpiPlain = 1, kEpiMask = 2 };
+// kEpiDivide: the sum divided by a saved tensor of the output's shape -- the data gradient w.r.t. an L2-pooled tensor
+// is only ever used as grad / pooled (backward of the square root), so the quotient is formed once here instead of in
+// each of the up to nine input pixels of the pooling window.
+enum ConvEpilogue { kEpiBiasRelu = 0, kEpiPlain = 1, kEpiMask = 2, kEpiDivide = 3 };
 // conv1_1 fused with the input normalisation: images [0,nx) come from x, [nx,n) from y (NCHW fp32);
 // weights packed [27][64] (k = (ci*3 + r)*3 + s), output NHWC [n,h,w,64].  If out_lo != nullptr the output is
 // written as a bf16 hi/lo pair (T must be bf16).
@@ -103,7 +106,7 @@ struct ConvTcPlan {
   bf16* out;
   bf16* out_lo;
   int epi;             // ConvEpilogue (halo / pair kernels; the plain kernel is forward-only)
-  const bf16* mask;    // kEpiMask: saved activation [n,h,w,cout]
+  const bf16* mask;    // kEpiMask / kEpiDivide: saved activation [n,h,w,cout]
 };
 // Fills the tensor maps; returns 0 on success, nonzero + message on failure.
 int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
@@ -128,20 +131,27 @@ int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, in
 struct GradLevels {
   double inv_n[6];   // 1 / (H_k * W_k)
 };
-// coef[b][c][5] = (Px, Qx, R, Py, Qy): d score_b/d x_i = Px + Qx x_i + R y_i (times grad_score[b], already folded in);
-// channels of levels >= levels_valid get zeros.  moments from launch_dists_finalize.
+// Coefficient table coef[b][q][kCoefStride], q in (Px, Qx, R, Py, Qy): d score_b/d x_i = Px + Qx x_i + R y_i (times
+// grad_score[b], already folded in).  Level k's channels start at coef_offset(k), padded to multiples of 8 so that the
+// NHWC kernel reads its 4 / 8 channels as 16-byte vectors.  Channels of levels >= levels_valid get zeros.
+constexpr int kCoefStride = 1536;
+__host__ __device__ constexpr int coef_offset(int k) { return k == 0 ? 0 : k == 1 ? 8 : k == 2 ? 72 : k == 3 ? 200 : k == 4 ? 456 : 968; }
 int launch_stat_coef(const float* moments, const float* alpha, const float* beta, bool normalize, const float* grad_score,
                      const GradLevels& lv, int levels_valid, int pairs, float* coef, cudaStream_t st);
 // NCHW fp32 planes of one level: gx (+)= Px + Qx x + R y, gy (+)= Py + Qy y + R x
-int launch_stat_grad_planar(const float* x, const float* y, const float* coef, int choff, int pairs, int c, int hw,
+int launch_stat_grad_planar(const float* x, const float* y, const float* coef, int level, int pairs, int c, int hw,
                             float* gx, float* gy, bool accumulate, cudaStream_t st);
-// NHWC level: statistics gradient (+ L2pooling backward when poolx != nullptr), masked by the level's ReLU
+// NHWC level: statistics gradient (+ L2pooling backward when qpoolx != nullptr), masked by the level's ReLU.
+// qpoolx / qpooly: (gradient w.r.t. the pooled tensor) / (pooled tensor), as written by a kEpiDivide convolution.
 template <typename T>
-int launch_level_grad(const T* fx, const T* fy, const T* poolx, const T* pooly, const T* gpoolx, const T* gpooly,
-                      const float* coef, int choff, int pairs, int h, int w, int c, T* gx, T* gy, cudaStream_t st);
-// conv1_1 + normalisation backward: gz [n,h,w,64] -> NCHW fp32 frame gradients
+int launch_level_grad(const T* fx, const T* fy, const T* qpoolx, const T* qpooly, const float* coef, int level, int pairs,
+                      int h, int w, int c, T* gx, T* gy, cudaStream_t st);
+// conv1_1 + normalisation backward: gz [n,h,w,64] -> NCHW fp32 frame gradients.  The 9x64x3 weights travel as a kernel
+// parameter (constant bank: every thread reads the same weight at the same time, no shared-memory traffic).
+struct Conv11BwdWeights { float w[9][64][3]; };
 template <typename T>
-int launch_conv1_1_bwd(const T* gz, const float* wb, int nx, int n, int h, int w, float* gx, float* gy, cudaStream_t st);
+int launch_conv1_1_bwd(const T* gz, const Conv11BwdWeights& wb, int nx, int n, int h, int w, float* gx, float* gy,
+                       cudaStream_t st);
 int launch_pack_w_bwd(const float* w_oihw, int cin, int cout, float* w_f32, bf16* w_hi, cudaStream_t st);
 int launch_pack_w11_bwd(const float* w_oihw, float* out, cudaStream_t st);
 
