@@ -365,25 +365,41 @@ window_kernel(const TI* __restrict__ fx, const TI* __restrict__ fy, int c, int h
                        (reinterpret_cast<uintptr_t>(fy) & (2 * sizeof(TI) - 1)) == 0;
   typedef Raw2<TI> R2;
   typename R2::type pre_x[NLD], pre_y[NLD];
+  // Pair path: UNCONDITIONAL loads from a clamped address (a load under a branch makes the compiler wait for it at the
+  // reconvergence point, which serialises the NLD global-load latencies of a channel); the out-of-image elements are
+  // zeroed when the tile is written to shared memory.  Offsets and validity do not depend on the channel.
+  uint32_t pre_valid = 0;
+  int pre_off[NLD];
+#pragma unroll
+  for (int q = 0; q < NLD; ++q) {
+    const int idx = threadIdx.x + q * 256;
+    const int r = idx / (IN / 2), col = 2 * (idx - r * (IN / 2));
+    const int gy = oy0 + r, gx = ox0 + col;
+    if (idx < NPAIR && gy < h && gx < w) pre_valid |= 1u << q;
+    pre_off[q] = min(gy, h - 1) * w + min(gx, max(w - 2, 0));
+  }
   auto fetch = [&](int ch) {
     const TI* px = fx + ((size_t)b * c + ch) * h * w;
     const TI* py = fy + ((size_t)b * c + ch) * h * w;
+    if (pair_ok) {
 #pragma unroll
-    for (int q = 0; q < NLD; ++q) {
+      for (int q = 0; q < NLD; ++q) {
+        pre_x[q] = R2::load(px + pre_off[q]);
+        pre_y[q] = R2::load(py + pre_off[q]);
+      }
+      return;
+    }
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {                 // odd width: scalar loads (rare; latency is exposed here)
       const int idx = threadIdx.x + q * 256;
       const int r = idx / (IN / 2), col = 2 * (idx - r * (IN / 2));
       const int gy = oy0 + r, gx = ox0 + col;
       pre_x[q] = pre_y[q] = R2::zero();
       if (idx < NPAIR && gy < h && gx < w) {
         const size_t o = (size_t)gy * w + gx;
-        if (pair_ok) {
-          pre_x[q] = R2::load(px + o);
-          pre_y[q] = R2::load(py + o);
-        } else {                                    // odd width: scalar loads (rare; latency is exposed here)
-          const bool two = gx + 1 < w;
-          pre_x[q] = R2::one(ldf(px + o), two ? ldf(px + o + 1) : 0.f);
-          pre_y[q] = R2::one(ldf(py + o), two ? ldf(py + o + 1) : 0.f);
-        }
+        const bool two = gx + 1 < w;
+        pre_x[q] = R2::one(ldf(px + o), two ? ldf(px + o + 1) : 0.f);
+        pre_y[q] = R2::one(ldf(py + o), two ? ldf(py + o + 1) : 0.f);
       }
     }
   };
@@ -398,6 +414,7 @@ window_kernel(const TI* __restrict__ fx, const TI* __restrict__ fy, int c, int h
         float a0, a1, d0, d1;
         R2::unpack(pre_x[q], a0, a1);
         R2::unpack(pre_y[q], d0, d1);
+        if (!((pre_valid >> q) & 1)) a0 = a1 = d0 = d1 = 0.f;
         sx[r * LDI + col] = a0;
         sx[r * LDI + col + 1] = a1;
         sy[r * LDI + col] = d0;

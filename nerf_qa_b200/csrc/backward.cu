@@ -101,89 +101,92 @@ int launch_stat_grad_planar(const float* x, const float* y, const float* coef, i
 template <typename T, bool POOL>
 __global__ void __launch_bounds__(256)
 level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* __restrict__ qpoolx,
-                  const T* __restrict__ qpooly, const float* __restrict__ coef, int level, int pairs, int h, int w, int c,
-                  int ho, int wo, T* __restrict__ gx, T* __restrict__ gy) {
+                  const T* __restrict__ qpooly, const float* __restrict__ coef, int level, int h, int w, int c,
+                  int groups_log2, int ho, int wo, T* __restrict__ gx, T* __restrict__ gy) {
+  // grid = (ceil(w * groups / 256), h, pairs): no divisions in the index math, 32-bit offsets inside an image
   constexpr int V = Vec<T>::N;
-  const int groups = c / V;
-  const size_t total = (size_t)pairs * h * w * groups;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    size_t t = idx / groups;
-    const int ix = (int)(t % w); t /= w;
-    const int iy = (int)(t % h);
-    const int b = (int)(t / h);
-    const size_t off = (((size_t)b * h + iy) * w + ix) * c + (size_t)g * V;
-    float x[V], y[V], ox[V], oy[V];
-    Vec<T>::load(fx + off, x);
-    Vec<T>::load(fy + off, y);
-    // five coefficient vectors of this (pair, channel group): 16-byte loads from the padded table
-    const float* k = coef + (size_t)b * 5 * kCoefStride + coef_offset(level) + g * V;
-    float kp[V], kq[V], kr[V], kpy[V], kqy[V];
-#pragma unroll
-    for (int i = 0; i < V; i += 4) {
-      *reinterpret_cast<float4*>(kp + i) = __ldg(reinterpret_cast<const float4*>(k + i));
-      *reinterpret_cast<float4*>(kq + i) = __ldg(reinterpret_cast<const float4*>(k + kCoefStride + i));
-      *reinterpret_cast<float4*>(kr + i) = __ldg(reinterpret_cast<const float4*>(k + 2 * kCoefStride + i));
-      *reinterpret_cast<float4*>(kpy + i) = __ldg(reinterpret_cast<const float4*>(k + 3 * kCoefStride + i));
-      *reinterpret_cast<float4*>(kqy + i) = __ldg(reinterpret_cast<const float4*>(k + 4 * kCoefStride + i));
-    }
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      ox[i] = fmaf(kq[i], x[i], fmaf(kr[i], y[i], kp[i]));
-      oy[i] = fmaf(kqy[i], y[i], fmaf(kr[i], x[i], kpy[i]));
-    }
-    if (POOL) {
-      float sx[V], sy[V];
-#pragma unroll
-      for (int i = 0; i < V; ++i) sx[i] = sy[i] = 0.f;
-      // pooled outputs whose 3x3 stride-2 window (rows 2o-1..2o+1) contains this pixel: one if the index is
-      // even (centre tap, weight 2), two if it is odd (edge taps, weight 1 each)
-      const int oy0 = iy >> 1, oy1 = (iy & 1) ? oy0 + 1 : oy0;
-      const int ox0 = ix >> 1, ox1 = (ix & 1) ? ox0 + 1 : ox0;
-      const float wy = (iy & 1) ? 1.f : 2.f, wx = (ix & 1) ? 1.f : 2.f;
-      const float wgt = wy * wx * (1.f / 16.f);
-      for (int py = oy0; py <= oy1; ++py) {
-        if (py >= ho) continue;
-        for (int px = ox0; px <= ox1; ++px) {
-          if (px >= wo) continue;
-          const size_t po = (((size_t)b * ho + py) * wo + px) * c + (size_t)g * V;
-          float qx[V], qy[V];
-          Vec<T>::load(qpoolx + po, qx);      // = d loss / d pooled  /  pooled  (kEpiDivide epilogue)
-          Vec<T>::load(qpooly + po, qy);
-#pragma unroll
-          for (int i = 0; i < V; ++i) { sx[i] += qx[i]; sy[i] += qy[i]; }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        ox[i] = fmaf(wgt * x[i], sx[i], ox[i]);
-        oy[i] = fmaf(wgt * y[i], sy[i], oy[i]);
-      }
-    }
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int g = idx & ((1 << groups_log2) - 1), ix = idx >> groups_log2;
+  if (ix >= w) return;
+  const int iy = blockIdx.y, b = blockIdx.z;
+  const size_t off = (((size_t)b * h + iy) * w + ix) * c + (size_t)g * V;
+  float x[V], y[V], ox[V], oy[V];
+  Vec<T>::load(fx + off, x);
+  Vec<T>::load(fy + off, y);
+  float sx[V], sy[V];
+  if (POOL) {
+    // Pooled outputs whose 3x3 stride-2 window (rows 2o-1..2o+1) contains this pixel: one if the index is even
+    // (centre tap, weight 2), two if it is odd (edge taps, weight 1 each).  All four candidate loads are issued
+    // unconditionally from clamped addresses and weighted by 0/1 (loads under branches would serialise their latencies).
+    const int oy0 = iy >> 1, ox0 = ix >> 1;
+    const float my0 = oy0 < ho ? 1.f : 0.f, my1 = ((iy & 1) && oy0 + 1 < ho) ? 1.f : 0.f;
+    const float mx0 = ox0 < wo ? 1.f : 0.f, mx1 = ((ix & 1) && ox0 + 1 < wo) ? 1.f : 0.f;
+    const int cy0 = min(oy0, ho - 1), cy1 = min(oy0 + 1, ho - 1), cx0 = min(ox0, wo - 1), cx1 = min(ox0 + 1, wo - 1);
+    const T* qx = qpoolx + (size_t)b * ho * wo * c + (size_t)g * V;
+    const T* qy = qpooly + (size_t)b * ho * wo * c + (size_t)g * V;
+    const int o00 = (cy0 * wo + cx0) * c, o01 = (cy0 * wo + cx1) * c, o10 = (cy1 * wo + cx0) * c, o11 = (cy1 * wo + cx1) * c;
+    float a00[V], a01[V], a10[V], a11[V], d00[V], d01[V], d10[V], d11[V];
+    Vec<T>::load(qx + o00, a00);        // = d loss / d pooled  /  pooled  (kEpiDivide epilogue)
+    Vec<T>::load(qx + o01, a01);
+    Vec<T>::load(qx + o10, a10);
+    Vec<T>::load(qx + o11, a11);
+    Vec<T>::load(qy + o00, d00);
+    Vec<T>::load(qy + o01, d01);
+    Vec<T>::load(qy + o10, d10);
+    Vec<T>::load(qy + o11, d11);
+    const float m00 = my0 * mx0, m01 = my0 * mx1, m10 = my1 * mx0, m11 = my1 * mx1;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      if (!(x[i] > 0.f)) ox[i] = 0.f;
-      if (!(y[i] > 0.f)) oy[i] = 0.f;
+      sx[i] = fmaf(m11, a11[i], fmaf(m10, a10[i], fmaf(m01, a01[i], m00 * a00[i])));
+      sy[i] = fmaf(m11, d11[i], fmaf(m10, d10[i], fmaf(m01, d01[i], m00 * d00[i])));
     }
-    Vec<T>::store(gx + off, ox);
-    Vec<T>::store(gy + off, oy);
   }
+  // five coefficient vectors of this (pair, channel group): 16-byte loads from the padded table
+  const float* k = coef + (size_t)b * 5 * kCoefStride + coef_offset(level) + g * V;
+  float kp[V], kq[V], kr[V], kpy[V], kqy[V];
+#pragma unroll
+  for (int i = 0; i < V; i += 4) {
+    *reinterpret_cast<float4*>(kp + i) = __ldg(reinterpret_cast<const float4*>(k + i));
+    *reinterpret_cast<float4*>(kq + i) = __ldg(reinterpret_cast<const float4*>(k + kCoefStride + i));
+    *reinterpret_cast<float4*>(kr + i) = __ldg(reinterpret_cast<const float4*>(k + 2 * kCoefStride + i));
+    *reinterpret_cast<float4*>(kpy + i) = __ldg(reinterpret_cast<const float4*>(k + 3 * kCoefStride + i));
+    *reinterpret_cast<float4*>(kqy + i) = __ldg(reinterpret_cast<const float4*>(k + 4 * kCoefStride + i));
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    ox[i] = fmaf(kq[i], x[i], fmaf(kr[i], y[i], kp[i]));
+    oy[i] = fmaf(kqy[i], y[i], fmaf(kr[i], x[i], kpy[i]));
+  }
+  if (POOL) {
+    const float wgt = ((iy & 1) ? 1.f : 2.f) * ((ix & 1) ? 1.f : 2.f) * (1.f / 16.f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      ox[i] = fmaf(wgt * x[i], sx[i], ox[i]);
+      oy[i] = fmaf(wgt * y[i], sy[i], oy[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    if (!(x[i] > 0.f)) ox[i] = 0.f;
+    if (!(y[i] > 0.f)) oy[i] = 0.f;
+  }
+  Vec<T>::store(gx + off, ox);
+  Vec<T>::store(gy + off, oy);
 }
 
 template <typename T>
 int launch_level_grad(const T* fx, const T* fy, const T* qpoolx, const T* qpooly, const float* coef, int level, int pairs,
                       int h, int w, int c, T* gx, T* gy, cudaStream_t st) {
-  const size_t total = (size_t)pairs * h * w * (c / Vec<T>::N);
-  size_t blocks = (total + 255) / 256;
-  const size_t cap = (size_t)kNumSMs * 32;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
+  const int groups = c / Vec<T>::N;            // 8 .. 128, a power of two for every VGG level
+  int groups_log2 = 0;
+  while ((1 << groups_log2) < groups) ++groups_log2;
+  if ((1 << groups_log2) != groups || h > 65535 || pairs > 65535) return 0;
+  const dim3 grid((unsigned)((w * groups + 255) / 256), (unsigned)h, (unsigned)pairs);
   if (qpoolx)
-    level_grad_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(fx, fy, qpoolx, qpooly, coef, level, pairs, h, w, c, pooled(h),
-                                                                pooled(w), gx, gy);
+    level_grad_kernel<T, true><<<grid, 256, 0, st>>>(fx, fy, qpoolx, qpooly, coef, level, h, w, c, groups_log2, pooled(h),
+                                                    pooled(w), gx, gy);
   else
-    level_grad_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(fx, fy, nullptr, nullptr, coef, level, pairs, h, w, c, 0, 0, gx,
-                                                                 gy);
+    level_grad_kernel<T, false><<<grid, 256, 0, st>>>(fx, fy, nullptr, nullptr, coef, level, h, w, c, groups_log2, 0, 0, gx, gy);
   return 1;
 }
 template int launch_level_grad<float>(const float*, const float*, const float*, const float*, const float*, int, int, int, int,
@@ -260,7 +263,7 @@ __global__ void pack_w_bwd_kernel(const float* __restrict__ w, int cin, int cout
     const int co = (int)(i / (9 * (size_t)cin));
     const float v = w[i];
     const int tb = 8 - tap;
-    w_f32[((size_t)tb * cout + co) * cin + ci] = v;
+    if (w_f32) w_f32[((size_t)tb * cout + co) * cin + ci] = v;
     w_hi[(size_t)ci * 9 * cout + (size_t)tb * cout + co] = __float2bfloat16_rn(v);
   }
 }

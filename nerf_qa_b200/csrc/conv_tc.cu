@@ -365,6 +365,8 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
   // thin layers: halo-reuse kernel (A tile fetched once instead of nine times)
   plan->epi = kEpiBiasRelu;
   plan->mask = nullptr;
+  plan->fg_x = plan->fg_y = nullptr;
+  plan->fg_nx = 0;
   plan->halo = false;
   plan->pair = false;
   plan->halo_hbw = 10;
@@ -409,6 +411,10 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
 }
 
 int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st) {
+  if (plan.epi == kEpiFrameGrad && !(plan.halo && !plan.pair)) {
+    fprintf(stderr, "nerfqa_b200: the frame-gradient epilogue needs the halo convolution kernel\n");
+    return 0;
+  }
   if (plan.pair) {
     const int rc = launch_conv3x3_tc_pair(plan, tc::g_sm_count, st);
     if (rc > 0) return rc;

@@ -37,6 +37,9 @@ struct Params {
   bf16* out;
   int epi;             // ConvEpilogue
   const bf16* mask;    // kEpiMask: saved activation of the layer below, [n,h,w,cout]
+  float* fg_x;         // kEpiFrameGrad
+  float* fg_y;
+  int fg_nx;
 };
 
 template <int BLOCK_N, bool RESIDENT>
@@ -217,6 +220,23 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const size_t pix_off = (((size_t)img * p.h + py) * p.w + px) * p.cout;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (p.epi == kEpiFrameGrad) {                   // three fp32 planes per image; no staging, no TMA store
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (pix_ok) {
+          const size_t hw = (size_t)p.h * p.w;
+          float* dst = img < p.fg_nx ? p.fg_x + (size_t)img * 3 * hw : p.fg_y + (size_t)(img - p.fg_nx) * 3 * hw;
+          const size_t o = (size_t)py * p.w + px;
+          dst[o] = __uint_as_float(r[0]) / 0.229f;
+          dst[hw + o] = __uint_as_float(r[1]) / 0.224f;
+          dst[2 * hw + o] = __uint_as_float(r[2]) / 0.225f;
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c64 = 0; c64 < BLOCK_N / 64; ++c64, ++sub) {
         uint8_t* stg = stg_smem + (sub & 1) * (128 * 128);
@@ -307,6 +327,8 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
   p.hbw = plan.halo_hbw; p.desc_mode = plan.halo_desc_mode;
   p.a_stage_bytes = (HALO_H * plan.halo_hbw * 128 + 1023) & ~1023;
   p.bias = plan.bias; p.out = plan.out; p.epi = plan.epi; p.mask = plan.mask;
+  p.fg_x = plan.fg_x; p.fg_y = plan.fg_y; p.fg_nx = plan.fg_nx;
+  if (plan.epi == kEpiFrameGrad && (BLOCK_N != 64 || plan.cout != 64)) return -1;
   const int chunks = plan.cin / BLOCK_K;
   const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*bias*/ - STG_BYTES;
   int a_stages, b_stages = 0;

@@ -69,9 +69,14 @@ struct nqa_ctx {
   bf16* w_bwd_hi[kNumConvs] = {};        // data-gradient weights [cin][9][cout] bf16
   float* w11_bwd = nullptr;              // conv1_1 backward [9][64][3] (device staging of the packed weights)
   Conv11BwdWeights w11_bwd_host;         // the same, passed to the backward kernel as a parameter (constant bank)
+  bf16* w11_bwd_hi = nullptr;            // conv1_1 data-gradient weights for the tensor pipe: [64 (3 used)][9][64] bf16
+  bool conv11_bwd_tc = true;             // NQA_CONV11_BWD_TC=0: CUDA-core conv1_1 backward in the bf16 trunk too
   float* alpha = nullptr;
   float* beta = nullptr;
-  CUtensorMap w12_map;                   // conv1_2 weights for the fused stage-1 kernel
+  CUtensorMap w12_map;                   // conv1_2 weights for the fused stage-1 kernel, box {64, 64}
+  CUtensorMap w12_map_pair;              // the same with box {64, 32}: CTA-pair version (each CTA holds half the channels)
+  bool stage1_pair = false;              // NQA_STAGE1_PAIR=1: fused stage 1 on CTA pairs (measured slower: DESIGN.md §4)
+  bool stage1_a2_linear = true;          // NQA_STAGE1_A2_LINEAR=0: relu1_1 tile in the 128-byte-swizzled layout
   bool fuse_stage1 = true;               // NQA_STAGE1_FUSED=0 falls back to conv1_1 + conv1_2 kernels
   int micro_images = 16;                 // full-HD-equivalent images per trunk pass (NQA_MICRO_IMAGES)
   bool fuse_pool_stats = true;           // NQA_POOL_STATS_FUSED=0 falls back to separate pooling / statistics kernels
@@ -303,8 +308,10 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
       if (li == 0 && std::is_same<T, bf16>::value && !split && ctx->fuse_stage1) {
         // normalise + conv1_1 + conv1_2 in one kernel; relu1_1 never reaches HBM
         ProfScope ps(ctx, NQA_K_STAGE1, st);
-        const int nl = launch_stage1_fused(x, y, nx, n, h, w, ctx->w11_img, ctx->bias[0], ctx->w12_map, ctx->bias[1],
-                                           reinterpret_cast<bf16*>(bufs.ping[1]), ctx->sm_count, st);
+        const bool pair = ctx->stage1_pair && (ctx->sm_count & 1) == 0;
+        const int nl = launch_stage1_fused(x, y, nx, n, h, w, ctx->w11_img, ctx->bias[0], pair ? ctx->w12_map_pair : ctx->w12_map,
+                                           ctx->bias[1], reinterpret_cast<bf16*>(bufs.ping[1]), ctx->sm_count, pair,
+                                           ctx->stage1_a2_linear, st);
         if (nl <= 0) return fail(NQA_ERR_CUDA, "stage-1 kernel: cuTensorMapEncodeTiled failed (%dx%dx%d)", n, h, w);
         ctx->launches += nl;
         cur = 1;
@@ -517,6 +524,38 @@ int conv_layer_bwd<bf16>(nqa_ctx* ctx, int li, const bf16* gin, bf16* gout, int 
   return NQA_OK;
 }
 
+// Backward of conv1_1 + input normalisation: gz = gradient w.r.t. the pre-ReLU conv1_1 output, NHWC [n,H,W,64];
+// writes the frame gradients (planes).  bf16 trunk: the halo convolution kernel with the three input channels as
+// output rows and the kEpiFrameGrad epilogue (the CUDA-core kernel is ~2.5x slower); fp32 trunk: CUDA cores.
+template <typename T>
+int conv1_1_bwd(nqa_ctx* ctx, const T* gz, T* scratch, int pairs, int n, int H, int W, float* gx, float* gy, cudaStream_t st);
+template <>
+int conv1_1_bwd<float>(nqa_ctx* ctx, const float* gz, float*, int pairs, int n, int H, int W, float* gx, float* gy,
+                       cudaStream_t st) {
+  ctx->launches += launch_conv1_1_bwd<float>(gz, ctx->w11_bwd_host, pairs, n, H, W, gx, gy, st);
+  return NQA_OK;
+}
+template <>
+int conv1_1_bwd<bf16>(nqa_ctx* ctx, const bf16* gz, bf16* scratch, int pairs, int n, int H, int W, float* gx, float* gy,
+                      cudaStream_t st) {
+  ConvTcPlan plan;
+  const char* err = "";
+  if (ctx->conv11_bwd_tc &&
+      conv_tc_make_plan(&plan, gz, nullptr, ctx->w11_bwd_hi, nullptr, ctx->bias[kNumConvs - 1], scratch, nullptr, n, H, W, 64, 64,
+                        false, &err) == 0 &&
+      plan.halo && !plan.pair) {
+    plan.epi = kEpiFrameGrad;
+    plan.fg_x = gx; plan.fg_y = gy; plan.fg_nx = pairs;
+    ProfScope ps(ctx, NQA_K_CONV_TC, st);
+    const int nl = launch_conv3x3_tc(plan, st);
+    if (nl <= 0) return fail(NQA_ERR_CUDA, "backward convolution of conv1_1 could not be launched");
+    ctx->launches += nl;
+    return NQA_OK;
+  }
+  ctx->launches += launch_conv1_1_bwd<bf16>(gz, ctx->w11_bwd_host, pairs, n, H, W, gx, gy, st);
+  return NQA_OK;
+}
+
 template <typename T>
 size_t dists_bwd_bytes(const nqa_ctx* ctx, int pairs, int H, int W, int prec) {
   int h[kNumLevels], w[kNumLevels];
@@ -601,8 +640,10 @@ int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int
     {  // last level: statistics gradient only
       const int h = lh[5], w = lw[5], c = level_channels(5);
       const size_t half = (size_t)pairs * h * w * c;
-      ctx->launches += launch_level_grad<T>(act[12], act[12] + half, nullptr, nullptr, coef, 5, pairs, h, w, c, g[cur],
-                                            g[cur] + half, st);
+      const int nl = launch_level_grad<T>(act[12], act[12] + half, nullptr, nullptr, coef, 5, pairs, h, w, c, g[cur],
+                                          g[cur] + half, st);
+      if (nl <= 0) return fail(NQA_ERR_INVALID, "level gradient: unsupported shape %dx%dx%d", h, w, c);
+      ctx->launches += nl;
     }
     int li = kNumConvs - 1;
     for (int stage = 4; stage >= 0; --stage) {
@@ -623,11 +664,14 @@ int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int
       const int k = stage, hp = lh[k], wp = lw[k], c = level_channels(k);
       const size_t half = (size_t)pairs * hp * wp * c, half_pool = (size_t)pairs * h * w * c;
       const T* feat = act[li];                            // li now indexes the last conv of the stage below
-      ctx->launches += launch_level_grad<T>(feat, feat + half, g[cur], g[cur] + half_pool, coef, k, pairs, hp, wp, c, g[cur ^ 1],
-                                            g[cur ^ 1] + half, st);
+      const int nl = launch_level_grad<T>(feat, feat + half, g[cur], g[cur] + half_pool, coef, k, pairs, hp, wp, c, g[cur ^ 1],
+                                          g[cur ^ 1] + half, st);
+      if (nl <= 0) return fail(NQA_ERR_INVALID, "level gradient: unsupported shape %dx%dx%d", hp, wp, c);
+      ctx->launches += nl;
       cur ^= 1;
     }
-    ctx->launches += launch_conv1_1_bwd<T>(g[cur], ctx->w11_bwd_host, pairs, n, H, W, gx, gy, st);
+    rc = conv1_1_bwd<T>(ctx, g[cur], g[cur ^ 1], pairs, n, H, W, gx, gy, st);
+    if (rc != NQA_OK) return rc;
   }
   ctx->launches += launch_stat_grad_planar(x, y, coef, 0, pairs, 3, H * W, gx, gy, through_trunk, st);   // level 0
   return NQA_OK;
@@ -678,6 +722,9 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   conv_tc_set_sm_count(ctx->sm_count);
   if (const char* e = getenv("NQA_STAGE1_FUSED")) ctx->fuse_stage1 = atoi(e) != 0;
   if (const char* e = getenv("NQA_POOL_STATS_FUSED")) ctx->fuse_pool_stats = atoi(e) != 0;
+  if (const char* e = getenv("NQA_STAGE1_PAIR")) ctx->stage1_pair = atoi(e) != 0;
+  if (const char* e = getenv("NQA_CONV11_BWD_TC")) ctx->conv11_bwd_tc = atoi(e) != 0;
+  if (const char* e = getenv("NQA_STAGE1_A2_LINEAR")) ctx->stage1_a2_linear = atoi(e) != 0;
   if (const char* e = getenv("NQA_MICRO_IMAGES")) ctx->micro_images = atoi(e) > 0 ? atoi(e) : 16;
   if (const char* e = getenv("NQA_LANES")) ctx->lanes = atoi(e) == 2 ? 2 : 1;
   for (int i = 0; i < 2; ++i) {
@@ -696,6 +743,8 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   CUDA_TRY(cudaMalloc(&ctx->w11, 27 * 64 * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ctx->w11_img, 2 * 64 * 32 * sizeof(bf16)));
   CUDA_TRY(cudaMalloc(&ctx->w11_bwd, 27 * 64 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&ctx->w11_bwd_hi, 64 * 9 * 64 * sizeof(bf16)));
+  CUDA_TRY(cudaMemset(ctx->w11_bwd_hi, 0, 64 * 9 * 64 * sizeof(bf16)));
   for (int i = 0; i < kNumConvs; ++i) {
     const size_t nw = (size_t)kConvCout[i] * kConvCin[i] * 9;
     CUDA_TRY(cudaMalloc(&ctx->bias[i], kConvCout[i] * sizeof(float)));
@@ -720,6 +769,7 @@ int nqa_ctx_destroy(nqa_ctx* ctx) {
   cudaFree(ctx->w11);
   cudaFree(ctx->w11_img);
   cudaFree(ctx->w11_bwd);
+  cudaFree(ctx->w11_bwd_hi);
   for (int i = 0; i < kNumConvs; ++i) {
     cudaFree(ctx->w_bwd_f32[i]);
     cudaFree(ctx->w_bwd_hi[i]);
@@ -768,6 +818,8 @@ int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const
       pack_w11_kernel<<<(27 * 64 + 255) / 256, 256>>>(tmp, ctx->w11);
       ctx->launches += launch_pack_w11_tc(tmp, ctx->w11_img, 0);
       ctx->launches += launch_pack_w11_bwd(tmp, ctx->w11_bwd, 0);
+      // rows ci = 0..2 of the [64][9][64] tensor-pipe image (the other rows stay zero)
+      ctx->launches += launch_pack_w_bwd(tmp, 3, 64, nullptr, ctx->w11_bwd_hi, 0);
     } else {
       pack_w_kernel<<<1024, 256>>>(tmp, kConvCin[i], kConvCout[i], ctx->w_f32[i], ctx->w_hi[i], ctx->w_lo[i]);
       ctx->launches += launch_pack_w_bwd(tmp, kConvCin[i], kConvCout[i], ctx->w_bwd_f32[i], ctx->w_bwd_hi[i], 0);
@@ -781,7 +833,8 @@ int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const
   }
   cudaFree(tmp);
   CUDA_TRY(cudaMemcpy(&ctx->w11_bwd_host, ctx->w11_bwd, sizeof(Conv11BwdWeights), cudaMemcpyDeviceToHost));
-  if (conv_tc_make_weight_map(&ctx->w12_map, ctx->w_hi[1], 64, 9 * 64, 64) != 0)
+  if (conv_tc_make_weight_map(&ctx->w12_map_pair, ctx->w_hi[1], 64, 9 * 64, 32) != 0 ||
+      conv_tc_make_weight_map(&ctx->w12_map, ctx->w_hi[1], 64, 9 * 64, 64) != 0)
     return fail(NQA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the conv1_2 weights");
   ctx->have_weights = true;
   return NQA_OK;

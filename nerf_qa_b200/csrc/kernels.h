@@ -72,7 +72,11 @@ int launch_nhwc_split_to_nchw(const bf16* hi, const bf16* lo, float* out, int n,
 // kEpiDivide: the sum divided by a saved tensor of the output's shape -- the data gradient w.r.t. an L2-pooled tensor
 // is only ever used as grad / pooled (backward of the square root), so the quotient is formed once here instead of in
 // each of the up to nine input pixels of the pooling window.
-enum ConvEpilogue { kEpiBiasRelu = 0, kEpiPlain = 1, kEpiMask = 2, kEpiDivide = 3 };
+// kEpiFrameGrad (halo kernel, 64-channel tile): backward of conv1_1 + input normalisation.  The weights are the
+// rotated conv1_1 filters with the three input channels as output rows 0..2 (rows 3..63 zero); the epilogue writes
+// sum / std[ci] as fp32 PLANES into the frame gradients (images [0,nx) -> fg_x, the rest -> fg_y) instead of an NHWC
+// tensor.
+enum ConvEpilogue { kEpiBiasRelu = 0, kEpiPlain = 1, kEpiMask = 2, kEpiDivide = 3, kEpiFrameGrad = 4 };
 // conv1_1 fused with the input normalisation: images [0,nx) come from x, [nx,n) from y (NCHW fp32);
 // weights packed [27][64] (k = (ci*3 + r)*3 + s), output NHWC [n,h,w,64].  If out_lo != nullptr the output is
 // written as a bf16 hi/lo pair (T must be bf16).
@@ -107,6 +111,9 @@ struct ConvTcPlan {
   bf16* out_lo;
   int epi;             // ConvEpilogue (halo / pair kernels; the plain kernel is forward-only)
   const bf16* mask;    // kEpiMask / kEpiDivide: saved activation [n,h,w,cout]
+  float* fg_x;         // kEpiFrameGrad: frame gradients, NCHW fp32 [nx,3,h,w] / [n-nx,3,h,w]
+  float* fg_y;
+  int fg_nx;
 };
 // Fills the tensor maps; returns 0 on success, nonzero + message on failure.
 int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
@@ -124,8 +131,8 @@ int conv_tc_make_weight_map(CUtensorMap* map, const bf16* wk, int cout, int k, i
 // Fused VGG stage 1 (bf16 trunk): normalise + conv1_1 + ReLU + conv1_2 + ReLU, relu1_1 stays on chip
 // (stage1_fused.cu).  w1img from launch_pack_w11_tc, w2map from conv_tc_make_weight_map(.., 64, 576, 64).
 int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, int w, const bf16* w1img,
-                        const float* bias1, const CUtensorMap& w2map, const float* bias2, bf16* out, int sm_count,
-                        cudaStream_t st);
+                        const float* bias1, const CUtensorMap& w2map, const float* bias2, bf16* out, int sm_count, bool pair,
+                        bool a2_linear, cudaStream_t st);
 
 // ---- backward (backward.cu) -------------------------------------------------------------------------
 struct GradLevels {

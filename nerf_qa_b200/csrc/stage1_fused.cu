@@ -16,6 +16,13 @@
 // Everything is double-buffered (im2col rows, both accumulators, halo tile) and handed over with mbarriers, so the
 // conv1_1 MMAs + mid epilogue of tile i+1 overlap the conv1_2 MMAs of tile i.  Persistent grid = #SMs.
 //
+// PAIR = true runs the same pipeline on a cluster of two CTAs (one TPC): each CTA keeps its own tile, producers and
+// epilogues, but every tcgen05.mma is a cta_group::2 instruction issued by the leader for both tiles (M = 256) and each
+// CTA holds only half of the conv1_1 / conv1_2 weights (32 of the 64 output channels).  At N = 64 a single-CTA MMA costs
+// ~95 cycles of shared-memory operand fetch (128 A rows + 64 B rows) against 32 cycles of math; the pair fetches
+// 128 + 32 rows per SM.  Barriers the MMA warp waits on live in the leader CTA (the follower arrives remotely), the ones
+// it signals are multicast to both CTAs.
+//
 // Reference semantics: DISTS_pt.py:92 (normalise), vgg16.features[0:4] (DISTS_pt.py:36-37), ADISTS.py:113-114.
 #include "common.cuh"
 #include "kernels.h"
@@ -52,6 +59,41 @@ constexpr int OFF_BIAS = OFF_STG + 2 * 128 * 128;
 constexpr int OFF_BARS = OFF_BIAS + 2 * C * 4;
 constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024 /*align slack*/;
 
+// ---- cluster / cta_group::2 primitives (PAIR) --------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
 struct Params {
   const float* x;
   const float* y;
@@ -63,9 +105,26 @@ struct Params {
   bf16* out;           // relu1_2, NHWC [n, h, w, 64]
 };
 
+template <bool PAIR, bool A2_LINEAR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out,
                     const Params p) {
+  // work units: single CTA -> one tile per unit; PAIR -> two consecutive tiles per unit, tile 2u + rank for this CTA
+  // (1-D grid with cluster dims (2,1,1): rank = blockIdx.x & 1, derived from blockIdx so that it is warp-uniform)
+  const uint32_t rank = PAIR ? (blockIdx.x & 1) : 0;
+  const bool leader = rank == 0;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_units = PAIR ? (p.num_tiles + 1) / 2 : p.num_tiles;
+  auto tile_of = [&](int unit) { return PAIR ? 2 * unit + (int)rank : unit; };
+  constexpr int NW = PAIR ? 2 : 1;                    // CTAs whose threads arrive on the leader's barriers
+  constexpr int CH = PAIR ? C / 2 : C;                // output channels whose weights this CTA holds
+  constexpr int W2_SLICE = CH * 64 * 2;               // bytes per tap
+  // arrive on a barrier the (leader's) MMA warp waits on
+  auto arrive_mma = [&](uint64_t* bar) {
+    if (PAIR) mbar_arrive_cluster(map_to_rank(bar, 0));
+    else mbar_arrive(bar);
+  };
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a2_s = smem + OFF_A2;
@@ -89,8 +148,9 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < W1_BYTES / 16; i += NUM_THREADS)
-    reinterpret_cast<uint4*>(w1_s)[i] = reinterpret_cast<const uint4*>(p.w1img)[i];
+  // conv1_1 weights: rows [rank*CH, rank*CH + CH) of the [64 x 32] no-swizzle image (8-row groups of 512 bytes)
+  for (int i = threadIdx.x; i < (CH * KPAD * 2) / 16; i += NUM_THREADS)
+    reinterpret_cast<uint4*>(w1_s)[i] = reinterpret_cast<const uint4*>(p.w1img)[rank * ((CH * KPAD * 2) / 16) + i];
   if (threadIdx.x < C) {
     bias1_s[threadIdx.x] = p.bias1[threadIdx.x];
     bias2_s[threadIdx.x] = p.bias2[threadIdx.x];
@@ -99,27 +159,35 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
     prefetch_tmap(&tmap_w2);
     prefetch_tmap(&tmap_out);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&a1_full[s], HROWS);
+      mbar_init(&a1_full[s], NW * (NUM_PRODUCERS / 32));
       mbar_init(&a1_empty[s], 1);
       mbar_init(&d1_full[s], 1);
-      mbar_init(&d1_empty[s], 4);
-      mbar_init(&a2_full[s], 128);
+      mbar_init(&d1_empty[s], NW * 4);
+      mbar_init(&a2_full[s], NW * 4);
       mbar_init(&a2_empty[s], 1);
       mbar_init(&d2_full[s], 1);
-      mbar_init(&d2_empty[s], 4);
+      mbar_init(&d2_empty[s], NW * 4);
     }
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // w1 written through the generic proxy
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();              // barrier inits, w1 and the TMEM allocation of both CTAs are in place
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -158,13 +226,17 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
     auto fetch = [&](int tile) {
       int img, h0, w0;
       decode(tile, img, h0, w0);
+      const bool tile_ok = tile < p.num_tiles;        // PAIR: the last unit of an odd tile count carries a padding tile
+      if (!tile_ok) img = p.n - 1;
       const float* src = img < p.nx ? p.x + (size_t)img * 3 * p.h * p.w : p.y + (size_t)(img - p.nx) * 3 * p.h * p.w;
+      // Unconditional loads from a clamped address: a load under a branch makes the compiler wait for it at the
+      // reconvergence point, which serialises the four global-load latencies of a tile.
 #pragma unroll
       for (int j = 0; j < LPT; ++j) {
         const int gy = h0 - 2 + e_rr[j], gx = w0 - 2 + e_cc[j];
-        pre_ok[j] = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-        pre[j] = 0.f;
-        if (pre_ok[j]) pre[j] = __ldg(src + e_plane[j] + (size_t)gy * p.w + gx);
+        pre_ok[j] = tile_ok && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+        const int cy = min(max(gy, 0), p.h - 1), cx = min(max(gx, 0), p.w - 1);
+        pre[j] = __ldg(src + e_plane[j] + (size_t)cy * p.w + cx);
       }
     };
     auto stash = [&](int buf) {
@@ -176,17 +248,17 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
       }
     };
     const int hr = pt / HW, hc = pt - hr * HW;
-    int tile = blockIdx.x;
-    if (tile < p.num_tiles) {
-      fetch(tile);
+    int unit = unit0;
+    if (unit < num_units) {
+      fetch(tile_of(unit));
       stash(0);
     }
     named_bar_sync(1, NUM_PRODUCERS);
-    for (int local = 0; tile < p.num_tiles; ++local, tile += gridDim.x) {
+    for (int local = 0; unit < num_units; ++local, unit += unit_stride) {
       const int s = local & 1;
       const uint32_t ph = (local >> 1) & 1;
-      const int next = tile + gridDim.x;
-      if (next < p.num_tiles) fetch(next);          // global loads in flight while this tile's rows are built
+      const int next = unit + unit_stride;
+      if (next < num_units) fetch(tile_of(next));   // global loads in flight while this tile's rows are built
       if (pt < HROWS) {
         const float* src = in_s + s * IN_ELEMS + hr * IW + hc;
         float v[KPAD];
@@ -210,73 +282,98 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
           *reinterpret_cast<uint4*>(dst + noswz_offset_bytes(pt, kc)) = t;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&a1_full[s]);
       }
-      if (next < p.num_tiles) stash(s ^ 1);
+      __syncwarp();
+      if (lane == 0) arrive_mma(&a1_full[s]);        // one arrival per producer warp
+      if (next < num_units) stash(s ^ 1);
       named_bar_sync(1, NUM_PRODUCERS);
     }
   } else if (warp == MMA_WARP) {
-    // =============================== MMA issuer (whole warp, one elected lane issues) ===============================
+    // =============================== MMA issuer (whole warp, one elected lane issues; leader CTA only) ===============
+    // conv1_2 weights of this CTA's channels: box {64 k, CH rows} per tap; PAIR: both CTAs' bytes are counted on the
+    // leader's barrier
     if (elect_one()) {
-      mbar_expect_tx(w_full, 9 * W2_TILE);
-      for (int tap = 0; tap < 9; ++tap) tma_load_2d(w2_s + tap * W2_TILE, &tmap_w2, w_full, tap * C, 0);
+      if (PAIR) {
+        if (leader) mbar_expect_tx(w_full, 2 * 9 * W2_SLICE);
+        const uint32_t bar = map_to_rank(w_full, 0);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d_pair(w2_s + tap * W2_SLICE, &tmap_w2, bar, tap * C, (int)rank * CH);
+      } else {
+        mbar_expect_tx(w_full, 9 * W2_SLICE);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(w2_s + tap * W2_SLICE, &tmap_w2, w_full, tap * C, 0);
+      }
     }
     __syncwarp();
-    constexpr uint32_t idesc = make_idesc(128, C);
-    const uint64_t w1_desc = make_desc_noswz(smem_u32(w1_s));
-    const uint64_t w2_desc = make_desc_sw128(smem_u32(w2_s), 1024, 0);
-    auto conv1_1 = [&](int local) {
-      const int s = local & 1;
-      const uint32_t ph = (local >> 1) & 1;
-      mbar_wait(&d1_empty[s], ph ^ 1);
-      mbar_wait(&a1_full[s], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t a1_desc = make_desc_noswz(smem_u32(a1_s + s * A1_BYTES));
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc(PAIR ? 256 : 128, C);
+      const uint64_t w1_desc = make_desc_noswz(smem_u32(w1_s));
+      const uint64_t w2_desc = make_desc_sw128(smem_u32(w2_s), 1024, 0);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+        if (PAIR) umma_bf16_pair(d, a, b, idesc, acc);
+        else umma_bf16(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (PAIR) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
+      auto conv1_1 = [&](int local) {
+        const int s = local & 1;
+        const uint32_t ph = (local >> 1) & 1;
+        mbar_wait(&d1_empty[s], ph ^ 1);
+        mbar_wait(&a1_full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a1_desc = make_desc_noswz(smem_u32(a1_s + s * A1_BYTES));
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
+          for (int half = 0; half < 2; ++half)
 #pragma unroll
-          for (int k = 0; k < KPAD / 16; ++k)   // descriptor address field counts 16-byte units
-            umma_bf16(tmem_base + s * 128 + half * 64, a1_desc + (uint64_t)((half * (A1_BYTES / 2) + k * 256) >> 4),
-                      w1_desc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
-        umma_commit(&a1_empty[s]);
-        umma_commit(&d1_full[s]);
-      }
-      __syncwarp();
-    };
-    int n_local = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) ++n_local;
-    if (n_local > 0) conv1_1(0);
-    mbar_wait(w_full, 0);
-    tc_fence_after();
-    for (int local = 0; local < n_local; ++local) {
-      if (local + 1 < n_local) conv1_1(local + 1);
-      const int s = local & 1;
-      const uint32_t ph = (local >> 1) & 1;
-      mbar_wait(&d2_empty[s], ph ^ 1);
-      mbar_wait(&a2_full[s], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t a2_desc = make_desc_sw128(smem_u32(a2_s + s * A2_BYTES), HW * 128, 0);
-        const uint32_t d2 = tmem_base + 256 + s * C;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int r = tap / 3, q = tap - r * 3;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d2, a2_desc + (uint64_t)((r * HW + q) * 8 + k * 2), w2_desc + (uint64_t)((tap * W2_TILE) / 16 + k * 2),
-                      idesc, (tap > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < KPAD / 16; ++k)   // descriptor address field counts 16-byte units
+              mma(tmem_base + s * 128 + half * 64, a1_desc + (uint64_t)((half * (A1_BYTES / 2) + k * 256) >> 4),
+                  w1_desc + (uint64_t)((k * 256) >> 4), k > 0 ? 1u : 0u);
+          commit(&a1_empty[s]);
+          commit(&d1_full[s]);
         }
-        umma_commit(&a2_empty[s]);
-        umma_commit(&d2_full[s]);
+        __syncwarp();
+      };
+      int n_local = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_stride) ++n_local;
+      if (n_local > 0) conv1_1(0);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      for (int local = 0; local < n_local; ++local) {
+        if (local + 1 < n_local) conv1_1(local + 1);
+        const int s = local & 1;
+        const uint32_t ph = (local >> 1) & 1;
+        mbar_wait(&d2_empty[s], ph ^ 1);
+        mbar_wait(&a2_full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          // A2_LINEAR: relu1_1 halo tile stored without swizzle as [8-channel chunk][halo row][16 B]: a K=16 slice of
+          // an 8-pixel row group is two contiguous 128-byte lines (LBO = HROWS*16 between chunks, SBO = HW*16 between
+          // pixel rows of the tile); a tap shift is still a plain start-address offset.
+          const uint64_t a2_desc = A2_LINEAR
+              ? make_desc_noswz_strided(smem_u32(a2_s + s * A2_BYTES), HROWS * 16, HW * 16)
+              : make_desc_sw128(smem_u32(a2_s + s * A2_BYTES), HW * 128, 0);
+          const uint32_t d2 = tmem_base + 256 + s * C;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, q = tap - r * 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma(d2, a2_desc + (uint64_t)(A2_LINEAR ? (r * HW + q) + k * 2 * HROWS : (r * HW + q) * 8 + k * 2), w2_desc + (uint64_t)((tap * W2_SLICE) / 16 + k * 2),
+                  (tap > 0 || k > 0) ? 1u : 0u);
+          }
+          commit(&a2_empty[s]);
+          commit(&d2_full[s]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp < FIN_WARP0) {
     // =============================== mid epilogue: relu1_1 halo tile -> shared memory ===============================
     const int quarter = warp & 3;
     int local = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++local) {
+      const int tile = tile_of(unit);
       const int s = local & 1;
       const uint32_t ph = (local >> 1) & 1;
       int img, h0, w0;
@@ -310,16 +407,19 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
               t.z = Vec<bf16>::pack2(v[4], v[5]);
               t.w = Vec<bf16>::pack2(v[6], v[7]);
               const int chunk = ch * 4 + j;                      // 16-byte chunk = 8 channels
-              *reinterpret_cast<uint4*>(a2 + row * 128 + ((chunk ^ (row & 7)) << 4)) = t;
+              *reinterpret_cast<uint4*>(a2 + (A2_LINEAR ? chunk * (HROWS * 16) + row * 16
+                                                        : row * 128 + ((chunk ^ (row & 7)) << 4))) = t;
             }
           }
         }
       }
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&d1_empty[s]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-      mbar_arrive(&a2_full[s]);
+      __syncwarp();
+      if (lane == 0) {
+        arrive_mma(&d1_empty[s]);
+        arrive_mma(&a2_full[s]);
+      }
     }
   } else {
     // =============================== final epilogue: relu1_2 -> shared memory -> TMA store ===============================
@@ -331,11 +431,12 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
     const bool elected = warp == FIN_WARP0 && lane == 0;
     uint8_t* stg_s = smem + OFF_STG;
     int local = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++local) {
+      const int tile = tile_of(unit);
       const int s = local & 1;
       const uint32_t ph = (local >> 1) & 1;
       int img, h0, w0;
-      decode(tile, img, h0, w0);
+      decode(tile, img, h0, w0);                       // a padding tile decodes to img == n: the TMA store clips it away
       mbar_wait(&d2_full[s], ph);
       tc_fence_after();
       if (elected) tma_store_wait_read<1>();          // the store issued two tiles ago has read staging buffer s
@@ -361,7 +462,7 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&d2_empty[s]);
+      if (lane == 0) arrive_mma(&d2_empty[s]);
       fence_proxy_async_smem();
       named_bar_sync(3, 128);
       if (elected) {
@@ -374,19 +475,24 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();              // the peer may still signal barriers in this CTA's shared memory
   if (warp == MMA_WARP) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
 }  // namespace s1
 
-// w2map: 2-D tensor map over the conv1_2 weights [64][9*64] bf16 with box {64, 64}, SWIZZLE_128B
-// (conv_tc_make_weight_map).  Returns the number of launches (0 if the output tensor map cannot be encoded).
+// w2map: 2-D tensor map over the conv1_2 weights [64][9*64] bf16, SWIZZLE_128B, with box {64, 64} (single CTA) or
+// {64, 32} (pair = true: cluster of two CTAs, each holding half of the output channels).  Returns the number of launches
+// (0 if the output tensor map cannot be encoded or the launch fails).
 int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, int w, const bf16* w1img,
-                        const float* bias1, const CUtensorMap& w2map, const float* bias2, bf16* out, int sm_count,
-                        cudaStream_t st) {
+                        const float* bias1, const CUtensorMap& w2map, const float* bias2, bf16* out, int sm_count, bool pair,
+                        bool a2_linear, cudaStream_t st) {
   CUtensorMap outmap;
   if (conv_tc_make_act_map(&outmap, out, n, h, w, s1::C, s1::TW, s1::TH) != 0) return 0;
   using namespace s1;
@@ -396,9 +502,30 @@ int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, in
   p.tiles_h = ceil_div(h, TH);
   p.num_tiles = n * p.tiles_h * p.tiles_w;
   p.w1img = w1img; p.bias1 = bias1; p.bias2 = bias2; p.out = out;
-  ensure_dynamic_smem(stage1_fused_kernel, SMEM_BYTES);
+  if (pair) {
+    auto kern = a2_linear ? stage1_fused_kernel<true, true> : stage1_fused_kernel<true, false>;
+    ensure_dynamic_smem(kern, SMEM_BYTES);
+    const int units = (p.num_tiles + 1) / 2;
+    int clusters = sm_count / 2;
+    if (units < clusters) clusters = units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, w2map, outmap, p) == cudaSuccess ? 1 : 0;
+  }
+  auto kern = a2_linear ? stage1_fused_kernel<false, true> : stage1_fused_kernel<false, false>;
+  ensure_dynamic_smem(kern, SMEM_BYTES);
   const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-  stage1_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(w2map, outmap, p);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(w2map, outmap, p);
   return 1;
 }
 

@@ -138,6 +138,16 @@ __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t smem_addr) {
   return d;                          // layout_type 0 = no swizzle
 }
 
+// K-major, no swizzle, explicit strides: element (row, 8-element k chunk) at (row >> 3) * sbo + kchunk * lbo + (row & 7) * 16.
+__device__ __forceinline__ uint64_t make_desc_noswz_strided(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=bf16 (bits 7, 10), both
 // K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {

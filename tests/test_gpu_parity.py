@@ -200,13 +200,17 @@ def test_dists_1080p_against_oracle(models, vgg_weights, alpha_beta):
             assert np.max(np.abs(got - want)) < 2e-3
 
 
-@pytest.mark.parametrize("shape", [(2, 45, 77), (1, 135, 240), (1, 16, 8), (2, 64, 64)])
-def test_fused_stage1_is_bit_identical_to_two_kernels(shape):
-    """The fused normalise+conv1_1+conv1_2 kernel rounds relu1_1 to bf16 in shared memory exactly like the
-    two-kernel path rounds it on its way to HBM, and accumulates in the same order: features must be equal."""
+@pytest.mark.parametrize("pair,linear", [("0", "1"), ("0", "0"), ("1", "1"), ("1", "0")])
+@pytest.mark.parametrize("shape", [(2, 45, 77), (1, 135, 240), (1, 16, 8), (2, 64, 64), (3, 40, 16), (5, 270, 480)])
+def test_fused_stage1_is_bit_identical_to_two_kernels(shape, pair, linear):
+    """The fused normalise+conv1_1+conv1_2 kernel (on CTA pairs or on single CTAs, relu1_1 tile in the linear or in the
+    128-byte-swizzled shared-memory layout) rounds relu1_1 to bf16 in shared
+    memory exactly like the two-kernel path rounds it on its way to HBM, and accumulates in the same order: features
+    must be equal.  (3, 40, 16) has an odd tile count: the last CTA pair carries a padding tile."""
     b, h, w = shape
     x, _ = synth.make_frame_pairs(b, h, w, seed=7)
-    fused = _fresh_bf16({"NQA_STAGE1_FUSED": "1"}).forward_once(x.cuda())
+    fused = _fresh_bf16({"NQA_STAGE1_FUSED": "1", "NQA_STAGE1_PAIR": pair,
+                         "NQA_STAGE1_A2_LINEAR": linear}).forward_once(x.cuda())
     plain = _fresh_bf16({"NQA_STAGE1_FUSED": "0"}).forward_once(x.cuda())
     for k in range(1, 6):
         assert torch.equal(fused[k], plain[k]), f"level {k}"
