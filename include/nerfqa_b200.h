@@ -156,6 +156,22 @@ NQA_API int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_N
 NQA_API int nqa_dists_backward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int precision,
                                const float* grad_score, int through_trunk, float* grad_x, float* grad_y, void* stream);
 
+/* The same forward / backward pair with the trunk activations KEPT between the two calls -- what torch autograd does
+ * for DISTS.forward(require_grad=True) (DISTS_pt.py:105-148; the training loop run_final.py:168-229 calls backward right
+ * after forward) -- instead of recomputing them: one trunk forward less per training step.
+ * nqa_dists_forward_saved = nqa_dists_forward (scores, optional per-channel S1/S2) + the 13 conv outputs, 4 pooled
+ * tensors and moments of every micro-batch stored in a library-owned tape buffer (142 MB per 512x512 image in bf16;
+ * buffers are reused between steps).  *tape_out receives a handle, or 0 when the tape would exceed the limit
+ * (NQA_TAPE_MAX_MB, default 65536) or cannot be allocated: the scores are still computed and the caller differentiates
+ * with nqa_dists_backward.  nqa_dists_backward_saved consumes the tape (through_trunk = 1 semantics; x, y are the
+ * same frames, needed for the level-0 term) and releases it; nqa_tape_release drops a tape that will not be
+ * differentiated.  Forward and backward must be enqueued on the same stream.  precision: fp32 or bf16. */
+NQA_API int nqa_dists_forward_saved(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int precision,
+                                    float* score_out, float* s1s2_out, unsigned long long* tape_out, void* stream);
+NQA_API int nqa_dists_backward_saved(nqa_ctx* ctx, unsigned long long tape, const float* x, const float* y,
+                                     const float* grad_score, float* grad_x, float* grad_y, void* stream);
+NQA_API int nqa_tape_release(nqa_ctx* ctx, unsigned long long tape);
+
 /* Gradient of forward_from_feats (DISTS_pt.py:181-208) w.r.t. the 2 x 6 feature tensors (NCHW fp32, same shapes
  * as the inputs): what model_nr_v8.py:258-265 back-propagates into its decoder. */
 NQA_API int nqa_dists_from_feats_backward(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],

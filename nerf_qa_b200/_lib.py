@@ -25,7 +25,8 @@ EXPORTS = (
     "nqa_dists_from_feats", "nqa_adists_forward", "nqa_adists_from_feats", "nqa_l2pool",
     "nqa_workspace_bytes", "nqa_launch_count", "nqa_micro_batch", "nqa_conv3x3_relu",
     "nqa_profile_enable", "nqa_profile_read", "nqa_dists_backward", "nqa_dists_from_feats_backward",
-    "nqa_set_channel_weights", "nqa_adists_map", "nqa_dists_adists_forward",
+    "nqa_set_channel_weights", "nqa_adists_map", "nqa_dists_adists_forward", "nqa_dists_forward_saved",
+    "nqa_dists_backward_saved", "nqa_tape_release",
 )
 KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists", "pool_stats",
                    "stage1", "backward")
@@ -67,6 +68,9 @@ def load_library() -> ctypes.CDLL:
     lib.nqa_adists_from_feats.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ci, ci, fp, vp]
     lib.nqa_l2pool.argtypes = [vp, fp, ci, ci, ci, ci, fp, vp]
     lib.nqa_dists_backward.argtypes = [vp, fp, fp, ci, ci, ci, ci, fp, ci, fp, fp, vp]
+    lib.nqa_dists_forward_saved.argtypes = [vp, fp, fp, ci, ci, ci, ci, fp, fp, ctypes.POINTER(ctypes.c_ulonglong), vp]
+    lib.nqa_dists_backward_saved.argtypes = [vp, ctypes.c_ulonglong, fp, fp, fp, fp, fp, vp]
+    lib.nqa_tape_release.argtypes = [vp, ctypes.c_ulonglong]
     lib.nqa_dists_from_feats_backward.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ci, fp,
                                                   ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     lib.nqa_conv3x3_relu.argtypes = [vp, fp, fp, fp, ci, ci, ci, ci, ci, ci, fp, vp]
@@ -108,6 +112,25 @@ def level_shapes(b: int, h: int, w: int):
         h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         shapes.append((b, c, h, w))
     return shapes
+
+
+class ActivationTape:
+    """Handle of the activations ``Context.dists_forward_saved`` kept in the library; released when it is consumed by
+    ``dists_backward_saved`` or garbage-collected (a forward that is never differentiated)."""
+
+    def __init__(self, ctx: "Context", tape_id: int):
+        self.ctx, self.id = ctx, tape_id
+
+    def release(self):
+        if self.id and self.ctx.handle is not None:
+            self.ctx.lib.nqa_tape_release(self.ctx.handle, self.id)
+        self.id = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class Context:
@@ -224,6 +247,32 @@ class Context:
         gx, gy = torch.empty_like(x), torch.empty_like(y)
         _check(self.lib.nqa_dists_backward(self.handle, _ptr(x), _ptr(y), b, h, w, precision, _ptr(g),
                                            1 if through_trunk else 0, _ptr(gx), _ptr(gy), _stream(x.device)))
+        return gx, gy
+
+    def dists_forward_saved(self, x: torch.Tensor, y: torch.Tensor, precision: int):
+        """``(score, s1s2, tape)``: the forward with the trunk activations kept for ``dists_backward_saved``.  ``tape`` is
+        None when the library declined to keep them (too large); differentiate with ``dists_backward`` then."""
+        x, y = _as_input(x, "x"), _as_input(y, "y")
+        if x.shape != y.shape or x.dim() != 4 or x.shape[1] != 3:
+            raise NerfQAError(f"expected two [B,3,H,W] batches of the same shape, got {tuple(x.shape)} / {tuple(y.shape)}")
+        b, _, h, w = x.shape
+        score = torch.empty(b, device=x.device, dtype=torch.float32)
+        s1s2 = torch.empty(b, 2, NUM_CHANNELS, device=x.device, dtype=torch.float32)
+        tape = ctypes.c_ulonglong(0)
+        _check(self.lib.nqa_dists_forward_saved(self.handle, _ptr(x), _ptr(y), b, h, w, precision, _ptr(score), _ptr(s1s2),
+                                                ctypes.byref(tape), _stream(x.device)))
+        return score, s1s2, (ActivationTape(self, tape.value) if tape.value else None)
+
+    def dists_backward_saved(self, tape: "ActivationTape", x: torch.Tensor, y: torch.Tensor, grad_score: torch.Tensor):
+        """Frame gradients from a tape (consumes it)."""
+        x, y = _as_input(x, "x"), _as_input(y, "y")
+        g = _as_input(grad_score, "grad_score").reshape(-1)
+        if g.numel() != x.shape[0]:
+            raise NerfQAError(f"grad_score must have {x.shape[0]} elements, got {g.numel()}")
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        tape_id, tape.id = tape.id, 0          # consumed by the call whatever its outcome
+        _check(self.lib.nqa_dists_backward_saved(self.handle, tape_id, _ptr(x), _ptr(y), _ptr(g), _ptr(gx), _ptr(gy),
+                                                 _stream(x.device)))
         return gx, gy
 
     def dists_from_feats_backward(self, feats0, feats1, grad_score: torch.Tensor):

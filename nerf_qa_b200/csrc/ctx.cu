@@ -54,6 +54,27 @@ struct Arena {
   }
 };
 
+struct TapeBuf {
+  char* base = nullptr;
+  size_t cap = 0;
+  bool in_use = false;
+};
+// Activations a backward walk needs: the 13 conv outputs, the 4 pooled tensors and the per-channel moments of one
+// micro-batch.  They live either in the workspace arena (activation recomputation inside nqa_dists_backward) or in a
+// tape buffer that survives from nqa_dists_forward_saved to nqa_dists_backward_saved.
+struct SavedActs {
+  void* act[kNumConvs] = {};
+  void* pool[4] = {};
+  float* moments = nullptr;
+  int pairs = 0;
+};
+struct Tape {
+  unsigned long long id = 0;
+  int buf = -1;
+  int B = 0, H = 0, W = 0, prec = 0, mb = 0;
+  std::vector<SavedActs> chunks;   // one per micro-batch of mb pairs
+};
+
 struct nqa_ctx {
   int device = 0;
   int sm_count = kNumSMs;
@@ -70,6 +91,10 @@ struct nqa_ctx {
   float* w11_bwd = nullptr;              // conv1_1 backward [9][64][3] (device staging of the packed weights)
   Conv11BwdWeights w11_bwd_host;         // the same, passed to the backward kernel as a parameter (constant bank)
   bf16* w11_bwd_hi = nullptr;            // conv1_1 data-gradient weights for the tensor pipe: [64 (3 used)][9][64] bf16
+  std::vector<TapeBuf> tape_bufs;        // device buffers of the activation tapes (reused between training steps)
+  std::vector<Tape> tapes;               // live tapes
+  unsigned long long next_tape = 1;
+  size_t tape_limit = (size_t)64 << 30;  // NQA_TAPE_MAX_MB: above this the saved-activation forward declines (tape 0)
   bool conv11_bwd_tc = true;             // NQA_CONV11_BWD_TC=0: CUDA-core conv1_1 backward in the bf16 trunk too
   float* alpha = nullptr;
   float* beta = nullptr;
@@ -556,8 +581,9 @@ int conv1_1_bwd<bf16>(nqa_ctx* ctx, const bf16* gz, bf16* scratch, int pairs, in
   return NQA_OK;
 }
 
+
 template <typename T>
-size_t dists_bwd_bytes(const nqa_ctx* ctx, int pairs, int H, int W, int prec) {
+size_t saved_bytes(int pairs, int H, int W) {
   int h[kNumLevels], w[kNumLevels];
   level_dims(H, W, h, w);
   const size_t n = 2 * (size_t)pairs;
@@ -568,59 +594,66 @@ size_t dists_bwd_bytes(const nqa_ctx* ctx, int pairs, int H, int W, int prec) {
     for (int j = 0; j < kStageConvs[stage]; ++j, ++li) total += align256(n * hw * kConvCout[li] * sizeof(T));
     if (stage < 4) total += align256(n * (size_t)h[stage + 2] * w[stage + 2] * kConvCout[li - 1] * sizeof(T));
   }
-  total += 2 * align256(n * max_act_elems(H, W) * sizeof(T));                     // gradient ping-pong
-  total += partial_bytes(pairs, H, W, prec, nullptr, false, true);
-  total += align256((size_t)pairs * kTotalChannels * 5 * sizeof(float)) + align256((size_t)pairs * 5 * kCoefStride * sizeof(float)) +
-           align256(pairs * sizeof(float));
-  return total + 8192;
+  return total + align256((size_t)pairs * kTotalChannels * 5 * sizeof(float)) + 4096;
+}
+
+// workspace of one micro-batch besides the saved activations: statistics partials, coefficient table, gradient ping-pong
+template <typename T>
+size_t bwd_work_bytes(int pairs, int H, int W, int prec) {
+  const size_t n = 2 * (size_t)pairs;
+  return 2 * align256(n * max_act_elems(H, W) * sizeof(T)) + partial_bytes(pairs, H, W, prec, nullptr, false, true) +
+         align256((size_t)pairs * 5 * kCoefStride * sizeof(float)) + align256(pairs * sizeof(float)) + 8192;
 }
 
 template <typename T>
-int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, int H, int W, int prec,
-                               const float* grad_score, bool through_trunk, float* gx, float* gy, cudaStream_t st) {
-  ctx->arena.reset();
+size_t dists_bwd_bytes(const nqa_ctx*, int pairs, int H, int W, int prec) {
+  return saved_bytes<T>(pairs, H, W) + bwd_work_bytes<T>(pairs, H, W, prec);
+}
+
+// Trunk forward of one micro-batch with every activation kept in `store` (not the fused stage-1 kernel: relu1_1 is
+// needed by the backward), statistics and scores as in dists_micro_batch.  Statistics partials come from ctx->arena
+// (the caller resets it).
+template <typename T>
+int trunk_forward_keep(nqa_ctx* ctx, Arena& store, const float* x, const float* y, int pairs, int H, int W, int prec,
+                       bool through_trunk, SavedActs* sv, float* score, float* s1s2, cudaStream_t st) {
   int lh[kNumLevels], lw[kNumLevels];
   level_dims(H, W, lh, lw);
   const int n = 2 * pairs;
   PartialBufs pb;
   partial_bytes(pairs, H, W, prec, &pb, false, true);
   partial_alloc(ctx, pairs, &pb);
-  float* moments = static_cast<float*>(ctx->arena.take((size_t)pairs * kTotalChannels * 5 * sizeof(float)));
-  float* coef = static_cast<float*>(ctx->arena.take((size_t)pairs * 5 * kCoefStride * sizeof(float)));
-  float* score_scratch = static_cast<float*>(ctx->arena.take(pairs * sizeof(float)));
-  GradLevels gl;
-  for (int k = 0; k < kNumLevels; ++k) gl.inv_n[k] = 1.0 / ((double)lh[k] * lw[k]);
-
+  sv->pairs = pairs;
+  sv->moments = static_cast<float*>(store.take((size_t)pairs * kTotalChannels * 5 * sizeof(float)));
   {  // level 0: the RAW frames
     ProfScope ps(ctx, NQA_K_STATS, st);
     ctx->launches += launch_stats_planar(x, y, pairs, 3, H * W, pb.chunks[0], pb.p[0], st);
   }
-  T* act[kNumConvs] = {};
-  T* pool[4] = {};
   if (through_trunk) {
     int li = 0;
     const T* cur = nullptr;
     for (int stage = 0; stage < 5; ++stage) {
       const int h = lh[stage + 1], w = lw[stage + 1];
       for (int j = 0; j < kStageConvs[stage]; ++j, ++li) {
-        act[li] = static_cast<T*>(ctx->arena.take((size_t)n * h * w * kConvCout[li] * sizeof(T)));
+        T* out = static_cast<T*>(store.take((size_t)n * h * w * kConvCout[li] * sizeof(T)));
+        sv->act[li] = out;
         if (li == 0) {
-          conv1_1_layer<T>(ctx, x, y, pairs, n, h, w, act[0], nullptr, st);
+          conv1_1_layer<T>(ctx, x, y, pairs, n, h, w, out, nullptr, st);
         } else {
-          const int rc = conv_layer<T>(ctx, li, cur, nullptr, act[li], nullptr, n, h, w, prec, st);
+          const int rc = conv_layer<T>(ctx, li, cur, nullptr, out, nullptr, n, h, w, prec, st);
           if (rc != NQA_OK) return rc;
         }
-        cur = act[li];
+        cur = out;
       }
       const int k = stage + 1, c = level_channels(k);
       const size_t half = (size_t)pairs * h * w * c;
       if (stage < 4) {
         const size_t half_out = (size_t)pairs * lh[k + 1] * lw[k + 1] * c;
-        pool[stage] = static_cast<T*>(ctx->arena.take(2 * half_out * sizeof(T)));
+        T* pooled_t = static_cast<T*>(store.take(2 * half_out * sizeof(T)));
+        sv->pool[stage] = pooled_t;
         ProfScope ps(ctx, NQA_K_POOL_STATS, st);
-        ctx->launches += launch_pool_stats<T>(cur, cur + half, pool[stage], pool[stage] + half_out, pairs, h, w, c, pb.chunks[k],
-                                              pb.p[k], st);
-        cur = pool[stage];
+        ctx->launches += launch_pool_stats<T>(cur, cur + half, pooled_t, pooled_t + half_out, pairs, h, w, c, pb.chunks[k], pb.p[k],
+                                              st);
+        cur = pooled_t;
       } else {
         ProfScope ps(ctx, NQA_K_STATS, st);
         ctx->launches += launch_stats_nhwc<T>(cur, cur + half, nullptr, nullptr, pairs, h * w, c, pb.chunks[k], pb.p[k], st);
@@ -628,10 +661,25 @@ int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int
     }
   }
   const int levels_valid = through_trunk ? kNumLevels : 1;
-  int rc = finalize(ctx, pb, pairs, H, W, score_scratch, nullptr, st, moments, levels_valid);
-  if (rc != NQA_OK) return rc;
+  return finalize(ctx, pb, pairs, H, W, score, s1s2, st, sv->moments, levels_valid);
+}
+
+// Walks the layers back from the saved activations of one micro-batch.  See backward.cu for the math.
+template <typename T>
+int trunk_backward_walk(nqa_ctx* ctx, const float* x, const float* y, int pairs, int H, int W, const SavedActs& sv,
+                        const float* grad_score, bool through_trunk, float* gx, float* gy, cudaStream_t st) {
+  int lh[kNumLevels], lw[kNumLevels];
+  level_dims(H, W, lh, lw);
+  const int n = 2 * pairs;
+  T* const* act = reinterpret_cast<T* const*>(sv.act);
+  T* const* pool = reinterpret_cast<T* const*>(sv.pool);
+  float* coef = static_cast<float*>(ctx->arena.take((size_t)pairs * 5 * kCoefStride * sizeof(float)));
+  GradLevels gl;
+  for (int k = 0; k < kNumLevels; ++k) gl.inv_n[k] = 1.0 / ((double)lh[k] * lw[k]);
+  const int levels_valid = through_trunk ? kNumLevels : 1;
+  int rc = NQA_OK;
   ProfScope psb(ctx, NQA_K_BACKWARD, st);
-  ctx->launches += launch_stat_coef(moments, ctx->alpha, ctx->beta, ctx->ab_normalize, grad_score, gl, levels_valid, pairs, coef, st);
+  ctx->launches += launch_stat_coef(sv.moments, ctx->alpha, ctx->beta, ctx->ab_normalize, grad_score, gl, levels_valid, pairs, coef, st);
 
   if (through_trunk) {
     const size_t gsz = (size_t)n * max_act_elems(H, W) * sizeof(T);
@@ -675,6 +723,76 @@ int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int
   }
   ctx->launches += launch_stat_grad_planar(x, y, coef, 0, pairs, 3, H * W, gx, gy, through_trunk, st);   // level 0
   return NQA_OK;
+}
+
+// ---- DISTS backward by activation recomputation: one micro-batch ------------------------------------------------
+// Recomputes the trunk forward with every activation kept in the arena (nothing survives between nqa_dists_forward and
+// nqa_dists_backward), then walks the layers back.
+template <typename T>
+int dists_backward_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, int H, int W, int prec,
+                               const float* grad_score, bool through_trunk, float* gx, float* gy, cudaStream_t st) {
+  ctx->arena.reset();
+  float* score_scratch = static_cast<float*>(ctx->arena.take(pairs * sizeof(float)));
+  SavedActs sv;
+  int rc = trunk_forward_keep<T>(ctx, ctx->arena, x, y, pairs, H, W, prec, through_trunk, &sv, score_scratch, nullptr, st);
+  if (rc != NQA_OK) return rc;
+  return trunk_backward_walk<T>(ctx, x, y, pairs, H, W, sv, grad_score, through_trunk, gx, gy, st);
+}
+
+// ---- tape: activations kept from nqa_dists_forward_saved to nqa_dists_backward_saved -----------------------------
+Tape* find_tape(nqa_ctx* ctx, unsigned long long id) {
+  for (auto& t : ctx->tapes)
+    if (t.id == id) return &t;
+  return nullptr;
+}
+
+void release_tape(nqa_ctx* ctx, unsigned long long id) {
+  for (size_t i = 0; i < ctx->tapes.size(); ++i)
+    if (ctx->tapes[i].id == id) {
+      ctx->tape_bufs[ctx->tapes[i].buf].in_use = false;
+      ctx->tapes.erase(ctx->tapes.begin() + i);
+      return;
+    }
+}
+
+// Index of a free tape buffer of at least `bytes` (smallest that fits, else a new allocation); -1 if the tape limit
+// would be exceeded or the allocation fails (the caller then falls back to activation recomputation).
+int acquire_tape_buf(nqa_ctx* ctx, size_t bytes) {
+  int best = -1;
+  size_t held = 0;
+  for (size_t i = 0; i < ctx->tape_bufs.size(); ++i) {
+    const TapeBuf& b = ctx->tape_bufs[i];
+    held += b.cap;
+    if (!b.in_use && b.cap >= bytes && (best < 0 || b.cap < ctx->tape_bufs[best].cap)) best = (int)i;
+  }
+  if (best >= 0) {
+    ctx->tape_bufs[best].in_use = true;
+    return best;
+  }
+  // drop idle buffers that are too small before growing
+  for (size_t i = 0; i < ctx->tape_bufs.size(); ++i) {
+    TapeBuf& b = ctx->tape_bufs[i];
+    if (!b.in_use && b.base) {
+      cudaDeviceSynchronize();
+      cudaFree(b.base);
+      held -= b.cap;
+      b.base = nullptr;
+      b.cap = 0;
+    }
+  }
+  if (held + bytes > ctx->tape_limit) return -1;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  for (size_t i = 0; i < ctx->tape_bufs.size(); ++i)
+    if (!ctx->tape_bufs[i].base) {
+      ctx->tape_bufs[i] = TapeBuf{static_cast<char*>(p), bytes, true};
+      return (int)i;
+    }
+  ctx->tape_bufs.push_back(TapeBuf{static_cast<char*>(p), bytes, true});
+  return (int)ctx->tape_bufs.size() - 1;
 }
 
 int check_ready(nqa_ctx* ctx, bool need_ab) {
@@ -724,6 +842,7 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   if (const char* e = getenv("NQA_POOL_STATS_FUSED")) ctx->fuse_pool_stats = atoi(e) != 0;
   if (const char* e = getenv("NQA_STAGE1_PAIR")) ctx->stage1_pair = atoi(e) != 0;
   if (const char* e = getenv("NQA_CONV11_BWD_TC")) ctx->conv11_bwd_tc = atoi(e) != 0;
+  if (const char* e = getenv("NQA_TAPE_MAX_MB")) ctx->tape_limit = (size_t)atoll(e) << 20;
   if (const char* e = getenv("NQA_STAGE1_A2_LINEAR")) ctx->stage1_a2_linear = atoi(e) != 0;
   if (const char* e = getenv("NQA_MICRO_IMAGES")) ctx->micro_images = atoi(e) > 0 ? atoi(e) : 16;
   if (const char* e = getenv("NQA_LANES")) ctx->lanes = atoi(e) == 2 ? 2 : 1;
@@ -770,6 +889,7 @@ int nqa_ctx_destroy(nqa_ctx* ctx) {
   cudaFree(ctx->w11_img);
   cudaFree(ctx->w11_bwd);
   cudaFree(ctx->w11_bwd_hi);
+  for (auto& b : ctx->tape_bufs) cudaFree(b.base);
   for (int i = 0; i < kNumConvs; ++i) {
     cudaFree(ctx->w_bwd_f32[i]);
     cudaFree(ctx->w_bwd_hi[i]);
@@ -1193,6 +1313,104 @@ int nqa_dists_backward(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     if (rc != NQA_OK) return rc;
   }
   CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_dists_forward_saved(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int precision,
+                            float* score_out, float* s1s2_out, unsigned long long* tape_out, void* stream) {
+  int rc = check_ready(ctx, true);
+  if (rc != NQA_OK) return rc;
+  if (!x || !y || !score_out || !tape_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  if (precision != NQA_PREC_FP32 && precision != NQA_PREC_BF16)
+    return fail(NQA_ERR_INVALID, "the backward pass supports the fp32 and bf16 trunks (got precision %d)", precision);
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  *tape_out = 0;
+  int mb = pick_micro_pairs(ctx, B, H, W) / 2;
+  if (mb < 1) mb = 1;
+  const bool f32 = precision == NQA_PREC_FP32;
+  size_t tape_bytes = 0;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int pairs = B - b0 < mb ? B - b0 : mb;
+    tape_bytes += align256(f32 ? saved_bytes<float>(pairs, H, W) : saved_bytes<bf16>(pairs, H, W));
+  }
+  const int buf = acquire_tape_buf(ctx, tape_bytes);
+  if (buf < 0)   // does not fit: plain forward, the caller differentiates by recomputation (nqa_dists_backward)
+    return dists_forward_device(ctx, x, y, B, H, W, precision, score_out, s1s2_out, st);
+  const size_t need = partial_bytes(mb, H, W, precision, nullptr, false, true) + 8192;
+  if ((rc = ensure_arena(ctx, need)) != NQA_OK) {
+    ctx->tape_bufs[buf].in_use = false;
+    return rc;
+  }
+  Tape tape;
+  tape.id = ctx->next_tape++;
+  tape.buf = buf;
+  tape.B = B; tape.H = H; tape.W = W; tape.prec = precision; tape.mb = mb;
+  Arena store;
+  store.base = ctx->tape_bufs[buf].base;
+  store.cap = ctx->tape_bufs[buf].cap;
+  const size_t frame = (size_t)3 * H * W;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int pairs = B - b0 < mb ? B - b0 : mb;
+    ctx->arena.reset();
+    SavedActs sv;
+    float* s12 = s1s2_out ? s1s2_out + (size_t)b0 * 2 * kTotalChannels : nullptr;
+    rc = f32 ? trunk_forward_keep<float>(ctx, store, x + b0 * frame, y + b0 * frame, pairs, H, W, precision, true, &sv,
+                                         score_out + b0, s12, st)
+             : trunk_forward_keep<bf16>(ctx, store, x + b0 * frame, y + b0 * frame, pairs, H, W, precision, true, &sv,
+                                        score_out + b0, s12, st);
+    if (rc != NQA_OK) {
+      ctx->tape_bufs[buf].in_use = false;
+      return rc;
+    }
+    tape.chunks.push_back(sv);
+  }
+  if (store.used > store.cap) {   // cannot happen (saved_bytes is the sum of the same takes); refuse to hand out the tape
+    ctx->tape_bufs[buf].in_use = false;
+    return fail(NQA_ERR_STATE, "activation tape overflow (%zu > %zu bytes)", store.used, store.cap);
+  }
+  CUDA_TRY(cudaGetLastError());
+  ctx->tapes.push_back(tape);
+  *tape_out = tape.id;
+  return NQA_OK;
+}
+
+int nqa_dists_backward_saved(nqa_ctx* ctx, unsigned long long tape_id, const float* x, const float* y, const float* grad_score,
+                             float* grad_x, float* grad_y, void* stream) {
+  int rc = check_ready(ctx, true);
+  if (rc != NQA_OK) return rc;
+  if (!x || !y || !grad_score || !grad_x || !grad_y) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  Tape* tp = find_tape(ctx, tape_id);
+  if (!tp) return fail(NQA_ERR_STATE, "unknown or already consumed activation tape %llu", tape_id);
+  const Tape tape = *tp;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool f32 = tape.prec == NQA_PREC_FP32;
+  const int B = tape.B, H = tape.H, W = tape.W, mb = tape.mb;
+  const size_t need = f32 ? bwd_work_bytes<float>(mb, H, W, tape.prec) : bwd_work_bytes<bf16>(mb, H, W, tape.prec);
+  if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
+  const size_t frame = (size_t)3 * H * W;
+  int chunk = 0;
+  for (int b0 = 0; b0 < B; b0 += mb, ++chunk) {
+    const int pairs = B - b0 < mb ? B - b0 : mb;
+    ctx->arena.reset();
+    const SavedActs& sv = tape.chunks[chunk];
+    rc = f32 ? trunk_backward_walk<float>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, sv, grad_score + b0, true,
+                                          grad_x + b0 * frame, grad_y + b0 * frame, st)
+             : trunk_backward_walk<bf16>(ctx, x + b0 * frame, y + b0 * frame, pairs, H, W, sv, grad_score + b0, true,
+                                         grad_x + b0 * frame, grad_y + b0 * frame, st);
+    if (rc != NQA_OK) break;
+  }
+  release_tape(ctx, tape_id);   // the buffer is reused by later calls on the same stream order
+  if (rc != NQA_OK) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_tape_release(nqa_ctx* ctx, unsigned long long tape_id) {
+  if (!ctx) return fail(NQA_ERR_INVALID, "null context");
+  release_tape(ctx, tape_id);
   return NQA_OK;
 }
 

@@ -142,7 +142,13 @@ class _WeightedScore(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, a, b, lib_ctx, prec, through_trunk):
         lib_ctx.set_channel_weights(a, b)
-        score, s1s2 = lib_ctx.dists_forward(x, y, prec, want_s1s2=True)
+        ctx.tape = None
+        if through_trunk and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and prec != _lib.PREC_BF16X3:
+            # like torch autograd: keep the trunk activations for the backward (the library declines -> tape None ->
+            # activation recomputation in nqa_dists_backward)
+            score, s1s2, ctx.tape = lib_ctx.dists_forward_saved(x, y, prec)
+        else:
+            score, s1s2 = lib_ctx.dists_forward(x, y, prec, want_s1s2=True)
         ctx.save_for_backward(x, y, s1s2, a, b)
         ctx.lib_ctx, ctx.prec, ctx.through_trunk = lib_ctx, prec, through_trunk
         return score
@@ -154,7 +160,10 @@ class _WeightedScore(torch.autograd.Function):
         gx = gy = ga = gb = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             ctx.lib_ctx.set_channel_weights(a, b)
-            gx, gy = ctx.lib_ctx.dists_backward(x, y, ctx.prec, grad_out, ctx.through_trunk)
+            if ctx.tape is not None and ctx.tape.id:
+                gx, gy = ctx.lib_ctx.dists_backward_saved(ctx.tape, x, y, grad_out)
+            else:                               # no tape, or a second backward through a retained graph
+                gx, gy = ctx.lib_ctx.dists_backward(x, y, ctx.prec, grad_out, ctx.through_trunk)
             gx = gx if ctx.needs_input_grad[0] else None
             gy = gy if ctx.needs_input_grad[1] else None
         if ctx.needs_input_grad[2]:

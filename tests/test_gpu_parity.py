@@ -276,6 +276,80 @@ def test_frame_gradients_through_trunk_match_oracle(models, vgg_weights, alpha_b
         assert l2 < tol and err < (10 * tol if prec == "fp32" else 3 * tol)
 
 
+def _fresh(prec, env):
+    """A DISTS module whose library context was created under the given environment switches."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        m = make_dists(prec)
+        m._context(torch.device("cuda:0"))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return m
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_saved_activation_backward_equals_recomputation(prec):
+    """require_grad=True keeps the trunk activations between forward and backward (nqa_dists_forward_saved /
+    nqa_dists_backward_saved); with the tape disabled the backward recomputes them.  Same kernels on the same data:
+    scores and gradients must be identical.  NQA_MICRO_IMAGES=1 splits the 3 pairs into 3 micro-batches."""
+    x, y = synth.make_frame_pairs(3, 540, 960, seed=29)
+    coeffs = torch.tensor([1.0, -2.0, 0.5]).cuda()
+    out = []
+    for env in ({"NQA_MICRO_IMAGES": "1"}, {"NQA_MICRO_IMAGES": "1", "NQA_TAPE_MAX_MB": "0"}):
+        m = _fresh(prec, env)
+        xs, ys = x.cuda().requires_grad_(True), y.cuda().requires_grad_(True)
+        with torch.enable_grad():
+            s = m(xs, ys, require_grad=True)
+            (s * coeffs).sum().backward()
+        out.append((s.detach().clone(), xs.grad.clone(), ys.grad.clone()))
+    with torch.no_grad():
+        plain = _fresh(prec, {})(x.cuda(), y.cuda())
+    assert torch.equal(out[0][0], out[1][0])
+    # the inference path normalises alpha/beta inside the kernel, the autograd path in torch: same score up to rounding
+    torch.testing.assert_close(out[0][0], plain, rtol=1e-5, atol=1e-7)
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    assert float(out[0][1].abs().max()) > 0
+
+
+def test_activation_tape_lifecycle(models):
+    """A tape that is never differentiated is released with the autograd graph; a second backward through a retained
+    graph falls back to recomputation; a consumed tape cannot be used twice through the C-ABI."""
+    m = models["bf16"]
+    ctx = m._context(torch.device("cuda:0"))
+    x, y = synth.make_frame_pairs(2, 128, 160, seed=37)
+    xs, ys = x.cuda().requires_grad_(True), y.cuda().requires_grad_(True)
+    torch.cuda.synchronize()
+    with torch.enable_grad():
+        m(xs, ys, require_grad=True)                      # warm the buffers
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(20):                                   # forwards without backward must not pile up tapes
+        with torch.enable_grad():
+            s = m(xs, ys, require_grad=True)
+        del s
+    assert torch.cuda.mem_get_info()[0] >= free0 - (64 << 20)
+    with torch.enable_grad():
+        s = m(xs, ys, require_grad=True)
+        s.sum().backward(retain_graph=True)
+        g1 = xs.grad.clone()
+        s.sum().backward()
+    torch.testing.assert_close(xs.grad, 2 * g1, rtol=1e-5, atol=0)
+    score, s1s2, tape = ctx.dists_forward_saved(x.cuda(), y.cuda(), _lib.PREC_BF16)
+    assert tape is not None
+    tape_id = tape.id
+    g = torch.ones(2, device="cuda")
+    ctx.dists_backward_saved(tape, x.cuda(), y.cuda(), g)
+    assert tape.id == 0
+    stale = _lib.ActivationTape(ctx, tape_id)
+    with pytest.raises(_lib.NerfQAError, match="tape"):
+        ctx.dists_backward_saved(stale, x.cuda(), y.cuda(), g)
+
+
 def test_frame_gradients_without_require_grad_are_level0_only(models, vgg_weights, alpha_beta):
     x, y = synth.make_frame_pairs(2, 64, 64, seed=17)
     ws, bs = vgg_weights
