@@ -102,23 +102,29 @@ conv1_1_tc_kernel(const Params p) {
       const int ox = twi * TILE_M + row;
       const float* src = img < p.nx ? p.x + (size_t)img * 3 * p.h * p.w : p.y + (size_t)(img - p.nx) * 3 * p.h * p.w;
 
+      // All 27 loads are issued unconditionally from clamped addresses and normalised / zeroed afterwards: a load
+      // under a branch makes the compiler wait for it at the reconvergence point (27 serial latencies per pixel).
       float v[KPAD];
+      uint32_t okmask = 0;
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int iy = oy - 1 + r;
           const bool rowok = iy >= 0 && iy < p.h;
-          const float* rp = src + ((size_t)ci * p.h + (rowok ? iy : 0)) * p.w;
+          const float* rp = src + ((size_t)ci * p.h + min(max(iy, 0), p.h - 1)) * p.w;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
             const int ix = ox - 1 + s;
-            float val = 0.f;
-            if (rowok && ix >= 0 && ix < p.w) val = (__ldg(rp + ix) - mean[ci]) / stdv[ci];
-            v[(ci * 3 + r) * 3 + s] = val;
+            if (rowok && ix >= 0 && ix < p.w) okmask |= 1u << ((ci * 3 + r) * 3 + s);
+            v[(ci * 3 + r) * 3 + s] = __ldg(rp + min(max(ix, 0), p.w - 1));
           }
         }
       }
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int k = ci * 9; k < ci * 9 + 9; ++k) v[k] = ((okmask >> k) & 1) ? (v[k] - mean[ci]) / stdv[ci] : 0.f;
 #pragma unroll
       for (int k = 27; k < KPAD; ++k) v[k] = 0.f;
 

@@ -295,66 +295,63 @@ int launch_dists_finalize(const FinalizeParams& p, const float* alpha, const flo
 template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(256)
 l2pool_nhwc_kernel(const T* __restrict__ in, const T* __restrict__ in_lo, T* __restrict__ out, T* __restrict__ out_lo,
-                   int n, int h, int w, int c, int ho, int wo) {
+                   int h, int w, int c, int groups, int ho, int wo) {
+  // grid = (ceil(wo * groups / 256), ho, n): one division per thread, none in 64 bits.  The nine taps are loaded
+  // unconditionally from clamped addresses with weight 0 outside the image (loads under branches serialise).
   constexpr int V = Vec<T>::N;
-  const int groups = c / V;
-  const size_t total = (size_t)n * ho * wo * groups;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    size_t t = idx / groups;
-    const int ox = (int)(t % wo); t /= wo;
-    const int oy = (int)(t % ho);
-    const int img = (int)(t / ho);
-    float acc[V];
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int ox = idx / groups, g = idx - ox * groups;
+  if (ox >= wo) return;
+  const int oy = blockIdx.y, img = blockIdx.z;
+  float acc[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] = 0.f;
-    const size_t boff = (size_t)img * h * w * c + (size_t)g * V;
-    const T* base = in + boff;
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  const size_t boff = (size_t)img * h * w * c + (size_t)g * V;
+  const T* base = in + boff;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int iy = 2 * oy - 1 + r;
-      if (iy < 0 || iy >= h) continue;
+  for (int r = 0; r < 3; ++r) {
+    const int iy = 2 * oy - 1 + r;
+    const bool rowok = iy >= 0 && iy < h;
+    const int cy = min(max(iy, 0), h - 1);
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ix = 2 * ox - 1 + s;
-        if (ix < 0 || ix >= w) continue;
-        const float wt = ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * (1.f / 16.f);
-        float v[V];
-        Vec<T>::load(base + ((size_t)iy * w + ix) * c, v);
-        if (SPLIT) {
-          float l[V];
-          Vec<T>::load(in_lo + boff + ((size_t)iy * w + ix) * c, l);
+    for (int s = 0; s < 3; ++s) {
+      const int ix = 2 * ox - 1 + s;
+      const bool ok = rowok && ix >= 0 && ix < w;
+      const int cx = min(max(ix, 0), w - 1);
+      const float wt = ok ? ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * (1.f / 16.f) : 0.f;
+      float v[V];
+      Vec<T>::load(base + ((size_t)cy * w + cx) * c, v);
+      if (SPLIT) {
+        float l[V];
+        Vec<T>::load(in_lo + boff + ((size_t)cy * w + cx) * c, l);
 #pragma unroll
-          for (int i = 0; i < V; ++i) v[i] += l[i];
-        }
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = fmaf(wt, v[i] * v[i], acc[i]);
+        for (int i = 0; i < V; ++i) v[i] += l[i];
       }
-    }
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] = sqrtf(acc[i] + 1e-12f);
-    const size_t ooff = (((size_t)img * ho + oy) * wo + ox) * c + (size_t)g * V;
-    Vec<T>::store(out + ooff, acc);
-    if (SPLIT) {
-      float l[V];
-#pragma unroll
-      for (int i = 0; i < V; ++i) l[i] = acc[i] - to_float(from_float<T>(acc[i]));
-      Vec<T>::store(out_lo + ooff, l);
+      for (int i = 0; i < V; ++i) acc[i] = fmaf(wt, v[i] * v[i], acc[i]);
     }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = sqrtf(acc[i] + 1e-12f);
+  const size_t ooff = (((size_t)img * ho + oy) * wo + ox) * c + (size_t)g * V;
+  Vec<T>::store(out + ooff, acc);
+  if (SPLIT) {
+    float l[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) l[i] = acc[i] - to_float(from_float<T>(acc[i]));
+    Vec<T>::store(out_lo + ooff, l);
   }
 }
 
 template <typename T>
 int launch_l2pool_nhwc(const T* in, const T* in_lo, T* out, T* out_lo, int n, int h, int w, int c, cudaStream_t st) {
-  const int ho = pooled(h), wo = pooled(w);
-  const size_t total = (size_t)n * ho * wo * (c / Vec<T>::N);
-  size_t blocks = (total + 255) / 256;
-  const size_t cap = (size_t)kNumSMs * 32;
-  if (blocks > cap) blocks = cap;
+  const int ho = pooled(h), wo = pooled(w), groups = c / Vec<T>::N;
+  if (ho > 65535 || n > 65535) return 0;
+  const dim3 grid((unsigned)((wo * groups + 255) / 256), (unsigned)ho, (unsigned)n);
   if (in_lo)
-    l2pool_nhwc_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(in, in_lo, out, out_lo, n, h, w, c, ho, wo);
+    l2pool_nhwc_kernel<T, true><<<grid, 256, 0, st>>>(in, in_lo, out, out_lo, h, w, c, groups, ho, wo);
   else
-    l2pool_nhwc_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(in, nullptr, out, nullptr, n, h, w, c, ho, wo);
+    l2pool_nhwc_kernel<T, false><<<grid, 256, 0, st>>>(in, nullptr, out, nullptr, h, w, c, groups, ho, wo);
   return 1;
 }
 template int launch_l2pool_nhwc<float>(const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
