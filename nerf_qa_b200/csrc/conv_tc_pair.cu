@@ -55,7 +55,10 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (release at CTA scope): the .release.cluster form compiles to MEMBAR.ALL + ERRBAR in front of
+  // the arrive, which also waits for the thread's global loads in flight.  Shared-memory writes the peer's MMA reads
+  // are ordered by the fence.proxy.async that precedes the arrive; TMEM reads by tcgen05.fence::before_thread_sync.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
                                                  int c2, int c3) {
