@@ -12,7 +12,7 @@ $(SRC_DIR)/%.o: $(SRC_DIR)/%.cu $(SRC_DIR)/common.cuh $(SRC_DIR)/tc_common.cuh $
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) -shared -cudart static -o $@ $(OBJS)
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o $@ $(OBJS)
 
 clean:
 	rm -f $(OBJS) $(LIB)
