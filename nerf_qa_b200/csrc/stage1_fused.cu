@@ -45,8 +45,12 @@ constexpr int W2_TILE = C * 64 * 2;            // 8 KB per tap
 constexpr int W1_BYTES = C * KPAD * 2;         // 4 KB
 constexpr int NUM_PRODUCERS = 192;             // warps 0..5
 constexpr int MMA_WARP = 6;                    // warp 6: TMEM alloc, weight TMA, MMA issue
-constexpr int FIN_WARP0 = 11;                  // mid epilogue = warps 7..10, final = 11..14 (distinct warp%4 each)
-constexpr int NUM_THREADS = 15 * 32;
+// mid epilogue: warps 7..10 take halo rows 0..127 (TMEM lane quarters 3,0,1,2), warps 12 and 13 rows 128..179
+// (quarters 0 and 1 of the second accumulator half); warp 11 would own an empty quarter and idles.  Final epilogue =
+// warps 14..17 (distinct warp%4 each: a warp may only read the TMEM lanes 32*(warp%4)..+31).
+constexpr int FIN_WARP0 = 14;
+constexpr int NUM_MID_WARPS = 6;
+constexpr int NUM_THREADS = 18 * 32;
 constexpr uint32_t TMEM_COLS = 512;            // D1: 2 x 128 columns, D2: 2 x 64 columns at 256
 
 constexpr int OFF_A2 = 0;
@@ -165,8 +169,8 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
       mbar_init(&a1_full[s], NW * (NUM_PRODUCERS / 32));
       mbar_init(&a1_empty[s], 1);
       mbar_init(&d1_full[s], 1);
-      mbar_init(&d1_empty[s], NW * 4);
-      mbar_init(&a2_full[s], NW * 4);
+      mbar_init(&d1_empty[s], NW * NUM_MID_WARPS);
+      mbar_init(&a2_full[s], NW * NUM_MID_WARPS);
       mbar_init(&a2_empty[s], 1);
       mbar_init(&d2_full[s], 1);
       mbar_init(&d2_empty[s], NW * 4);
@@ -374,7 +378,9 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
   } else if (warp < FIN_WARP0) {
     // =============================== mid epilogue: relu1_1 halo tile -> shared memory ===============================
     const int quarter = warp & 3;
+    const int half = warp >= 11 ? 1 : 0;
     int local = 0;
+    if (warp != 11)
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++local) {
       const int tile = tile_of(unit);
       const int s = local & 1;
@@ -385,10 +391,8 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
       mbar_wait(&a2_empty[s], ph ^ 1);
       tc_fence_after();
       uint8_t* a2 = a2_s + s * A2_BYTES;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      {
         const int row = half * 128 + quarter * 32 + lane;
-        if (half * 128 + quarter * 32 >= HROWS) break;          // warp-uniform
         const int rr = row / HW, cc = row - rr * HW;
         const int gy = h0 - 1 + rr, gx = w0 - 1 + cc;
         const bool inside = row < HROWS && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
