@@ -13,6 +13,10 @@ namespace nqa {
 
 constexpr int kNumLevels = 6;
 constexpr int kNumConvs = 13;
+// 1 / std of the ImageNet normalisation (DISTS_pt.py:52, 92), correctly rounded: the bf16 trunks multiply by the
+// reciprocal (the fused and the stand-alone conv1_1 kernels use the same constants and stay bit-identical); the fp32
+// trunk divides like the reference.
+constexpr float kInvStd0 = 1.f / 0.229f, kInvStd1 = 1.f / 0.224f, kInvStd2 = 1.f / 0.225f;
 constexpr int kTotalChannels = 1475;
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

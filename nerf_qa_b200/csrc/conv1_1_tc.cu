@@ -89,7 +89,7 @@ conv1_1_tc_kernel(const Params p) {
     const int set = warp >> 2;
     const int row = threadIdx.x & 127;
     const float mean[3] = {0.485f, 0.456f, 0.406f};
-    const float stdv[3] = {0.229f, 0.224f, 0.225f};
+    const float inv_std[3] = {kInvStd0, kInvStd1, kInvStd2};
     for (int local = set;; local += NUM_PRODUCER_SETS) {
       const int tile = blockIdx.x + local * gridDim.x;
       if (tile >= p.num_tiles) break;
@@ -124,7 +124,7 @@ conv1_1_tc_kernel(const Params p) {
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int k = ci * 9; k < ci * 9 + 9; ++k) v[k] = ((okmask >> k) & 1) ? (v[k] - mean[ci]) / stdv[ci] : 0.f;
+        for (int k = ci * 9; k < ci * 9 + 9; ++k) v[k] = ((okmask >> k) & 1) ? (v[k] - mean[ci]) * inv_std[ci] : 0.f;
 #pragma unroll
       for (int k = 27; k < KPAD; ++k) v[k] = 0.f;
 

@@ -198,13 +198,32 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode = [&](int tile, int& img, int& h0, int& w0) {
-    const int twi = tile % p.tiles_w;
-    int t = tile / p.tiles_w;
-    const int thi = t % p.tiles_h;
-    img = t / p.tiles_h;
-    h0 = thi * TH;
-    w0 = twi * TW;
+  // Tile walker: (image, tile row, tile column) of this CTA's tiles without a division per tile -- the per-tile
+  // stride is decomposed once and added with carries.
+  struct Walk {
+    int tile, tw, th, img;
+  };
+  const int tile_first = tile_of(unit0), tile_step = PAIR ? 2 * unit_stride : unit_stride;
+  const int step_tw = tile_step % p.tiles_w, step_th = (tile_step / p.tiles_w) % p.tiles_h,
+            step_img = tile_step / (p.tiles_w * p.tiles_h);
+  auto walk_begin = [&]() {
+    Walk k;
+    k.tile = tile_first;
+    k.tw = tile_first % p.tiles_w;
+    const int t = tile_first / p.tiles_w;
+    k.th = t % p.tiles_h;
+    k.img = t / p.tiles_h;
+    return k;
+  };
+  auto walk_next = [&](Walk& k) {
+    k.tile += tile_step;
+    k.tw += step_tw;
+    const int c0 = k.tw >= p.tiles_w ? 1 : 0;
+    k.tw -= c0 ? p.tiles_w : 0;
+    k.th += step_th + c0;
+    const int c1 = k.th >= p.tiles_h ? 1 : 0;
+    k.th -= c1 ? p.tiles_h : 0;
+    k.img += step_img + c1;
   };
 
   if (warp < MMA_WARP) {
@@ -214,7 +233,7 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
     // tile-independent part of the patch addressing: element e = (ci, rr, cc) of the 3 x 20 x 12 patch
     int e_rr[LPT], e_cc[LPT];
     size_t e_plane[LPT];
-    float e_mean[LPT], e_std[LPT];
+    float e_mean[LPT], e_inv[LPT];
 #pragma unroll
     for (int j = 0; j < LPT; ++j) {
       const int e = pt + j * NUM_PRODUCERS;
@@ -224,16 +243,16 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
       e_cc[j] = rem - (rem / IW) * IW;
       e_plane[j] = (size_t)ci * p.h * p.w;
       e_mean[j] = ci == 0 ? 0.485f : ci == 1 ? 0.456f : 0.406f;
-      e_std[j] = ci == 0 ? 0.229f : ci == 1 ? 0.224f : 0.225f;
+      e_inv[j] = ci == 0 ? kInvStd0 : ci == 1 ? kInvStd1 : kInvStd2;
     }
     // fetch() only ISSUES the global loads (raw values, no arithmetic on them), so they stay in flight while the
     // current tile's rows are built; stash() normalises and writes them to shared memory one tile later.
     float pre[LPT];
     bool pre_ok[LPT];
-    auto fetch = [&](int tile) {
-      int img, h0, w0;
-      decode(tile, img, h0, w0);
-      const bool tile_ok = tile < p.num_tiles;        // PAIR: the last unit of an odd tile count carries a padding tile
+    auto fetch = [&](const Walk& k) {
+      int img = k.img;
+      const int h0 = k.th * TH, w0 = k.tw * TW;
+      const bool tile_ok = k.tile < p.num_tiles;        // PAIR: the last unit of an odd tile count carries a padding tile
       if (!tile_ok) img = p.n - 1;
       const float* src = img < p.nx ? p.x + (size_t)img * 3 * p.h * p.w : p.y + (size_t)(img - p.nx) * 3 * p.h * p.w;
       // Unconditional loads from a clamped address: a load under a branch makes the compiler wait for it at the
@@ -251,13 +270,14 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
       for (int j = 0; j < LPT; ++j) {
         const int e = pt + j * NUM_PRODUCERS;
         // zero padding applies to the NORMALISED tensor
-        if (e < IN_ELEMS) in_s[buf * IN_ELEMS + e] = pre_ok[j] ? (pre[j] - e_mean[j]) / e_std[j] : 0.f;
+        if (e < IN_ELEMS) in_s[buf * IN_ELEMS + e] = pre_ok[j] ? (pre[j] - e_mean[j]) * e_inv[j] : 0.f;
       }
     };
     const int hr = pt / HW, hc = pt - hr * HW;
     int unit = unit0;
+    Walk wk = walk_begin();
     if (unit < num_units) {
-      fetch(tile_of(unit));
+      fetch(wk);
       stash(0);
     }
     named_bar_sync(1, NUM_PRODUCERS);
@@ -265,7 +285,10 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
       const int s = local & 1;
       const uint32_t ph = (local >> 1) & 1;
       const int next = unit + unit_stride;
-      if (next < num_units) fetch(tile_of(next));   // global loads in flight while this tile's rows are built
+      if (next < num_units) {                       // global loads in flight while this tile's rows are built
+        walk_next(wk);
+        fetch(wk);
+      }
       if (pt < HROWS) {
         const float* src = in_s + s * IN_ELEMS + hr * IW + hc;
         float v[KPAD];
@@ -380,13 +403,12 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
     const int quarter = warp & 3;
     const int half = warp >= 11 ? 1 : 0;
     int local = 0;
+    Walk wk = walk_begin();
     if (warp != 11)
-    for (int unit = unit0; unit < num_units; unit += unit_stride, ++local) {
-      const int tile = tile_of(unit);
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++local, walk_next(wk)) {
       const int s = local & 1;
       const uint32_t ph = (local >> 1) & 1;
-      int img, h0, w0;
-      decode(tile, img, h0, w0);
+      const int h0 = wk.th * TH, w0 = wk.tw * TW;
       mbar_wait(&d1_full[s], ph);
       mbar_wait(&a2_empty[s], ph ^ 1);
       tc_fence_after();
@@ -438,12 +460,11 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
     const bool elected = warp == FIN_WARP0 && lane == 0;
     uint8_t* stg_s = smem + OFF_STG;
     int local = 0;
-    for (int unit = unit0; unit < num_units; unit += unit_stride, ++local) {
-      const int tile = tile_of(unit);
+    Walk wk = walk_begin();
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++local, walk_next(wk)) {
       const int s = local & 1;
       const uint32_t ph = (local >> 1) & 1;
-      int img, h0, w0;
-      decode(tile, img, h0, w0);                       // a padding tile decodes to img == n: the TMA store clips it away
+      const int img = wk.img, h0 = wk.th * TH, w0 = wk.tw * TW;   // a padding tile has img == n: the TMA store clips it away
       mbar_wait(&d2_full[s], ph);
       tc_fence_after();
       if (elected) tma_store_wait_read<1>();          // the store issued two tiles ago has read staging buffer s

@@ -1,0 +1,7 @@
+#!/bin/bash
+cd /root/repo
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/r49_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/r49_tests.log
+timeout 500 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:stage1_fused -s 1 -c 1 python scripts/s1_once.py 2>&1 | grep -E "gpu__time|pipe_tensor"
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r49_bench.log 2>&1
+grep -o "\"value\": [0-9.]*\|\"stage1\": {[^}]*}\|\"conv_tc\": {[^}]*}\|sm_mhz\": [0-9.]*" gpurun_out/r49_bench.log
