@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 conv1_1_tc_kernel(const Params p) {
   constexpr int A_STAGE = A_BYTES * (SPLIT ? 2 : 1);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  // aligned by OFFSET from the __shared__ array (a round trip through uintptr_t would turn every access into a generic
+  // LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127);
   uint8_t* a_smem = smem;                                   // [STAGES][A_STAGE]
   uint8_t* w_smem = smem + STAGES * A_STAGE;                // hi (+ lo)
   float* bias_s = reinterpret_cast<float*>(w_smem + 2 * W_BYTES);

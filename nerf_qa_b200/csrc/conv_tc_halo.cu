@@ -48,7 +48,9 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                        const __grid_constant__ CUtensorMap tmap_out, const Params p, int a_stages, int b_stages) {
   constexpr int B_TILE = BLOCK_N * BLOCK_K * 2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by OFFSET from the __shared__ array (a round trip through uintptr_t would turn every access into a generic
+  // LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   const int chunks = p.cin / BLOCK_K;
   uint8_t* stg_smem = smem;                                      // [2][128 x 128 B] output staging for the TMA store
   uint8_t* a_smem = smem + STG_BYTES;                            // [a_stages][a_stage_bytes]

@@ -100,7 +100,9 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   constexpr int ACC_LOG2 = ACC == 4 ? 2 : 1;
   constexpr int B_TILE = HALF_N * BLOCK_K * 2;                   // this CTA's half of one tap's weight tile
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by OFFSET from the __shared__ array (a round trip through uintptr_t would turn every access into a generic
+  // LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   const int chunks = p.cin / BLOCK_K;
   uint8_t* stg_smem = smem;
   uint8_t* a_smem = smem + STG_BYTES;

@@ -133,7 +133,9 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
     else mbar_arrive(bar);
   };
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by OFFSET from the __shared__ array (a round trip through uintptr_t would turn every access into a generic
+  // LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   uint8_t* a2_s = smem + OFF_A2;
   uint8_t* w2_s = smem + OFF_W2;
   uint8_t* a1_s = smem + OFF_A1;
