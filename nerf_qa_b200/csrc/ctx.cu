@@ -100,7 +100,7 @@ struct nqa_ctx {
   float* beta = nullptr;
   CUtensorMap w12_map;                   // conv1_2 weights for the fused stage-1 kernel, box {64, 64}
   CUtensorMap w12_map_pair;              // the same with box {64, 32}: CTA-pair version (each CTA holds half the channels)
-  bool stage1_pair = false;              // NQA_STAGE1_PAIR=1: fused stage 1 on CTA pairs (measured slower: DESIGN.md §4)
+  bool stage1_pair = true;               // NQA_STAGE1_PAIR=0: fused stage 1 on single CTAs instead of CTA pairs
   bool stage1_a2_linear = true;          // NQA_STAGE1_A2_LINEAR=0: relu1_1 tile in the 128-byte-swizzled layout
   bool fuse_stage1 = true;               // NQA_STAGE1_FUSED=0 falls back to conv1_1 + conv1_2 kernels
   int micro_images = 16;                 // full-HD-equivalent images per trunk pass (NQA_MICRO_IMAGES)
