@@ -337,7 +337,7 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
         const int nl = launch_stage1_fused(x, y, nx, n, h, w, ctx->w11_img, ctx->bias[0], pair ? ctx->w12_map_pair : ctx->w12_map,
                                            ctx->bias[1], reinterpret_cast<bf16*>(bufs.ping[1]), ctx->sm_count, pair,
                                            ctx->stage1_a2_linear, st);
-        if (nl <= 0) return fail(NQA_ERR_CUDA, "stage-1 kernel: cuTensorMapEncodeTiled failed (%dx%dx%d)", n, h, w);
+        if (nl <= 0) return fail(NQA_ERR_CUDA, "stage-1 kernel: tensor map or cluster launch failed (%dx%dx%d)", n, h, w);
         ctx->launches += nl;
         cur = 1;
         ++li;
