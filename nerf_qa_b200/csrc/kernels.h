@@ -53,6 +53,11 @@ int launch_l2pool_nhwc(const T* in, const T* in_lo, T* out, T* out_lo, int n, in
 // L2pooling of x and y features fused with the level's DISTS moment sums (one read of the level).
 // chunks = pool_stats_chunks(h, w, c, sizeof(T)) partial-sum slots per pair.
 int pool_stats_chunks(int h, int w, int c, int elem_bytes);
+void pool_stats_plan(int h, int w, int c, int elem_bytes, int* rows_per_block, int* col_blocks, int* strips);
+// TMA-fed version for bf16 levels with x and y in one tensor (fy == fx + pairs*h*w*c): same results bit for bit
+// (pool_stats_tma.cu).  Returns 0 if the configuration is not served.
+int launch_pool_stats_tma(const bf16* fx, const bf16* fy, bf16* px_out, bf16* py_out, int pairs, int h, int w, int c, int chunks,
+                          float* partials, cudaStream_t st);
 template <typename T>
 int launch_pool_stats(const T* fx, const T* fy, T* px_out, T* py_out, int pairs, int h, int w, int c, int chunks,
                       float* partials, cudaStream_t st);

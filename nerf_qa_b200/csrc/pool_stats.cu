@@ -544,6 +544,13 @@ int pool_stats_chunks(int h, int w, int c, int elem_bytes) {
 template <typename T>
 int launch_pool_stats(const T* fx, const T* fy, T* px_out, T* py_out, int pairs, int h, int w, int c, int chunks,
                       float* partials, cudaStream_t st) {
+  if constexpr (std::is_same<T, bf16>::value) {
+    const char* e = getenv("NQA_POOL_STATS_TMA");     // default on; 0 selects the register-fed kernel
+    if (!e || atoi(e) != 0) {
+      const int rc = launch_pool_stats_tma(fx, fy, px_out, py_out, pairs, h, w, c, chunks, partials, st);
+      if (rc > 0) return rc;
+    }
+  }
   int r, cb, strips;
   pool_stats_plan(h, w, c, (int)sizeof(T), &r, &cb, &strips);
   dim3 grid(cb, strips, pairs);

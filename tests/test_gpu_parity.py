@@ -216,6 +216,27 @@ def test_fused_stage1_is_bit_identical_to_two_kernels(shape, pair, linear):
         assert torch.equal(fused[k], plain[k]), f"level {k}"
 
 
+@pytest.mark.parametrize("shape", [(2, 135, 240), (1, 45, 77), (3, 64, 64), (1, 270, 481)])
+def test_tma_fed_pool_stats_is_bit_identical(models, shape):
+    """pool_stats_tma_kernel (rows staged by TMA in a shared-memory ring) does the same arithmetic in the same order as
+    the register-fed pool_stats_kernel: scores and per-channel S1/S2 must be equal bit for bit (odd sizes exercise the
+    zero-filled borders: column -1, the missing last row / column)."""
+    import os
+    b, h, w = shape
+    x, y = synth.make_frame_pairs(b, h, w, seed=41)
+    ctx = models["bf16"]._context(torch.device("cuda:0"))
+    models["bf16"](x.cuda(), y.cuda())                    # uploads alpha / beta into the context
+    out = []
+    for flag in ("1", "0"):
+        os.environ["NQA_POOL_STATS_TMA"] = flag
+        try:
+            out.append(ctx.dists_forward(x.cuda(), y.cuda(), _lib.PREC_BF16, want_s1s2=True))
+        finally:
+            os.environ.pop("NQA_POOL_STATS_TMA", None)
+    assert torch.equal(out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1])
+
+
 @pytest.mark.parametrize("prec", ["bf16", "fp32"])
 def test_fused_pool_stats_matches_separate_kernels(prec):
     import os
