@@ -47,7 +47,7 @@ pool_stats_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __re
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  const int stage_bytes = 2 * nchunk * box_bytes;
+  const int stage_bytes = (2 * nchunk * box_bytes + 1023) & ~1023;   // 1024-aligned stages: same swizzle phases in each
   __shared__ uint64_t full[STAGES];
   __shared__ float red[256 * V];
 
@@ -97,14 +97,19 @@ pool_stats_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __re
   // this thread's 8 bytes inside a 128-byte pixel row of its 64-channel chunk (128-byte swizzle: chunk ^ (row & 7))
   const int q64 = g >> 4, j16 = (g & 15) >> 1, half8 = (g & 1) * 8;
   const uint32_t box_x = (uint32_t)(q64 * box_bytes), box_y = (uint32_t)((nchunk + q64) * box_bytes);
-  // boxes are packed at 128-byte granularity: the swizzle phase of a pixel row is taken from its ABSOLUTE shared-memory
-  // address (bits 7..9), which is what the TMA unit XORs into bits 4..6
-  const uint32_t ring_addr = smem_u32(ring);
-  auto lds8 = [&](const uint8_t* stage, uint32_t box, int m) {
-    const uint32_t off = (uint32_t)(stage - ring) + box + m * 128;
-    const uint32_t phase = ((ring_addr + off) >> 7) & 7;
-    return *reinterpret_cast<const uint2*>(ring + off + ((j16 ^ phase) << 4) + half8);
-  };
+  // Boxes are packed at 128-byte granularity inside 1024-aligned stages: the swizzle phase of a pixel row is bits 7..9
+  // of its offset in the stage (what the TMA unit XORs into bits 4..6 of the ABSOLUTE address).  The twelve offsets a
+  // thread reads per row pair (2 images x 2 rows x 3 columns) do not depend on the stage: computed once.
+  uint32_t off_x[2][3], off_y[2][3];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const uint32_t ax_ = box_x + (uint32_t)(r * BW + 2 * pl + k) * 128, ay_ = box_y + (uint32_t)(r * BW + 2 * pl + k) * 128;
+      off_x[r][k] = ax_ + ((j16 ^ ((ax_ >> 7) & 7)) << 4) + half8;
+      off_y[r][k] = ay_ + ((j16 ^ ((ay_ >> 7) & 7)) << 4) + half8;
+    }
+  auto lds8 = [&](const uint8_t* stage, uint32_t off) { return *reinterpret_cast<const uint2*>(stage + off); };
 
   // horizontal [1 2 1] of squares of one staged input row for both images (+ statistics on the owned columns)
   auto row = [&](const uint8_t* stage, int r, bool in_image, bool own, float2 (&hx)[2], float2 (&hy)[2]) {
@@ -112,14 +117,13 @@ pool_stats_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __re
       hx[0] = hx[1] = hy[0] = hy[1] = zero2;
       return;
     }
-    const int m = r * BW + 2 * pl;
     float2 x0[2], x1[2], x2[2], y0[2], y1[2], y2[2];
-    unpack4(lds8(stage, box_x, m), x0);
-    unpack4(lds8(stage, box_x, m + 1), x1);
-    unpack4(lds8(stage, box_x, m + 2), x2);
-    unpack4(lds8(stage, box_y, m), y0);
-    unpack4(lds8(stage, box_y, m + 1), y1);
-    unpack4(lds8(stage, box_y, m + 2), y2);
+    unpack4(lds8(stage, off_x[r][0]), x0);
+    unpack4(lds8(stage, off_x[r][1]), x1);
+    unpack4(lds8(stage, off_x[r][2]), x2);
+    unpack4(lds8(stage, off_y[r][0]), y0);
+    unpack4(lds8(stage, off_y[r][1]), y1);
+    unpack4(lds8(stage, off_y[r][2]), y2);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const float2 xx1 = __fmul2_rn(x1[i], x1[i]), yy1 = __fmul2_rn(y1[i], y1[i]);
@@ -214,7 +218,7 @@ int launch_pool_stats_tma(const bf16* fx, const bf16* fy, bf16* px_out, bf16* py
   const int box_bytes = 128 * bw * 2;
   CUtensorMap map;
   if (conv_tc_make_act_map(&map, fx, 2 * pairs, h, w, c, bw, 2) != 0) return 0;
-  const int smem = STAGES * 2 * (c / 64) * box_bytes + 1024;
+  const int smem = STAGES * ((2 * (c / 64) * box_bytes + 1023) & ~1023) + 1024;
   ensure_dynamic_smem(pool_stats_tma_kernel, smem);
   dim3 grid(cb, strips, pairs);
   pool_stats_tma_kernel<<<grid, 256, smem, st>>>(map, fx, fy, px_out, py_out, pairs, h, w, c, pooled(h), pooled(w), r, chunks,
