@@ -50,9 +50,9 @@ TRUNK_FLOP_PER_PAIR = 2.5386e12
 
 def load_conv_traffic():
     """DRAM bytes per launch of the trunk-convolution family from the committed `ncu --set full` capture of the same
-    bench command (profiles/r1y_ncu_full_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of every
+    bench command (profiles/r1z_ncu_full_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of every
     stage1 / pair / halo kernel of one 16-frame micro-batch, averaged over those launches)."""
-    path = os.path.join(ROOT, "profiles", "r1y_ncu_full_summary.json")
+    path = os.path.join(ROOT, "profiles", "r1z_ncu_full_summary.json")
     try:
         with open(path) as f:
             d = json.load(f)
@@ -65,7 +65,7 @@ def load_conv_traffic():
             return None
         total_gb = sum(float(r[rd]) + float(r[wr]) for r in rows)
         return {"bytes_per_launch": total_gb * 1e9 / len(rows), "launches_in_capture": len(rows),
-                "source": "profiles/r1y_ncu_full_summary.json (ncu --set full, bench.py --pairs 8, 16 frames per launch)"}
+                "source": "profiles/r1z_ncu_full_summary.json (ncu --set full, bench.py --pairs 8, 16 frames per launch)"}
     except Exception:
         return None
 
