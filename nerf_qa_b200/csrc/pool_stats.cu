@@ -673,39 +673,55 @@ template int launch_nhwc_to_nchw<float>(const float*, float*, int, int, int, int
 template int launch_nhwc_to_nchw<bf16>(const bf16*, float*, int, int, int, int, cudaStream_t);
 
 // bf16 NHWC -> bf16 planes (A-DISTS statistics of the bf16 trunk: exact copies, half the bytes of fp32 planes).
-// Tile = 64 pixels x 64 channels; loads are channel pairs (4 bytes per lane, 128 bytes per warp), stores are pixel
-// pairs (4 bytes per lane along the plane).  grid = (ceil(hw/64), c/64, n), block = (32, 8).  c % 64 == 0.
+// Tile = 256 pixels x 64 channels per block: all eight 16-byte loads of a thread are issued up front (32 KB per block
+// in flight), the tile is transposed through shared memory as 32-bit channel pairs, and each plane receives 512
+// contiguous bytes per block (pixel pairs, 4 bytes per lane, 128 bytes per warp store).
+// grid = (ceil(hw/256), c/64, n), block = 256.  c % 64 == 0.
+constexpr int kPlaneTile = 256;
 __global__ void __launch_bounds__(256)
 nhwc_to_planes_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int c, int hw) {
-  __shared__ uint32_t tile[64][33];   // [pixel][channel pair]
+  __shared__ uint32_t tile[kPlaneTile][33];   // [pixel][channel pair]
   const int img = blockIdx.z;
-  const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (size_t)img * hw * c);
-  for (int i = threadIdx.y; i < 64; i += 8) {
-    const int p = p0 + i;
-    tile[i][threadIdx.x] = p < hw ? __ldg(src + ((size_t)p * c + c0) / 2 + threadIdx.x) : 0u;
+  const int p0 = blockIdx.x * kPlaneTile, c0 = blockIdx.y * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bf16* src = in + (size_t)img * hw * c + c0;
+  // load: one 16-byte chunk (8 channels) per lane, 4 pixels per warp instruction
+  const int lp = lane >> 3, lc = lane & 7;
+  uint4 v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int p = p0 + (k * 8 + warp) * 4 + lp;
+    v[k] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)min(p, hw - 1) * c) + lc);   // clamped, unconditional
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t* row = &tile[(k * 8 + warp) * 4 + lp][lc * 4];
+    row[0] = v[k].x; row[1] = v[k].y; row[2] = v[k].z; row[3] = v[k].w;
   }
   __syncthreads();
   bf16* dst = out + (size_t)img * c * hw;
   const bool even = (hw & 1) == 0;     // 4-byte stores need even plane sizes (plane starts stay 4-byte aligned)
-  for (int ch = threadIdx.y; ch < 64; ch += 8) {
-    const int pp = threadIdx.x, p = p0 + 2 * pp;
-    const uint32_t a = tile[2 * pp][ch >> 1], b = tile[2 * pp + 1][ch >> 1];
-    const uint32_t lo = (ch & 1) ? (a >> 16) : (a & 0xffffu), hi = (ch & 1) ? (b >> 16) : (b & 0xffffu);
+  for (int ch = warp; ch < 64; ch += 8) {
     unsigned short* row = reinterpret_cast<unsigned short*>(dst + (size_t)(c0 + ch) * hw);
-    if (even && p + 1 < hw) {
-      *reinterpret_cast<uint32_t*>(row + p) = lo | (hi << 16);
-    } else {
-      if (p < hw) row[p] = (unsigned short)lo;
-      if (p + 1 < hw) row[p + 1] = (unsigned short)hi;
+#pragma unroll
+    for (int q = 0; q < kPlaneTile / 64; ++q) {
+      const int pp = q * 32 + lane, p = p0 + 2 * pp;
+      const uint32_t a = tile[2 * pp][ch >> 1], b = tile[2 * pp + 1][ch >> 1];
+      const uint32_t lo = (ch & 1) ? (a >> 16) : (a & 0xffffu), hi = (ch & 1) ? (b >> 16) : (b & 0xffffu);
+      if (even && p + 1 < hw) {
+        *reinterpret_cast<uint32_t*>(row + p) = lo | (hi << 16);
+      } else {
+        if (p < hw) row[p] = (unsigned short)lo;
+        if (p + 1 < hw) row[p + 1] = (unsigned short)hi;
+      }
     }
   }
 }
 
 int launch_nhwc_to_nchw_bf16(const bf16* in, bf16* out, int n, int c, int h, int w, cudaStream_t st) {
   const int hw = h * w;
-  dim3 grid(ceil_div(hw, 64), c / 64, n), block(32, 8);
-  nhwc_to_planes_bf16_kernel<<<grid, block, 0, st>>>(in, out, c, hw);
+  dim3 grid(ceil_div(hw, kPlaneTile), c / 64, n);
+  nhwc_to_planes_bf16_kernel<<<grid, 256, 0, st>>>(in, out, c, hw);
   return 1;
 }
 
