@@ -61,7 +61,7 @@ __device__ inline void ld4(const bf16* p, float (&v)[4]) {
 
 constexpr int WT = 32;           // window kernel: 32x32 output pixels per block
 constexpr int kChan = 10;        // doubles per (pair, channel) in the chan table
-constexpr int kRedBlocks = 128;  // blocks per frame pair in the map reductions
+constexpr int kRedBlocks = 512;  // blocks per frame pair in the map reductions (latency-bound gathers: fill the machine)
 
 struct Taps {
   float g[kAdistsMaxWindow];
@@ -243,7 +243,9 @@ entropy_kernel(const TI* __restrict__ x, int c, int hw, int chunks, int choff, c
   auto acc = [&](float a) {
     const float r = fmaxf(a, 0.f);
     const float p = exact ? (r / nr) / den : r * scale;
-    s -= p * log2f(p + 1e-12f);
+    // bf16 planes (2e-3 tolerance): the MUFU logarithm (2^-22 relative away from 1, tiny absolute error near 1, where
+    // p log p vanishes anyway) instead of the 20-instruction libm path this kernel was bound by
+    s -= p * (sizeof(TI) == 2 ? __log2f(p + 1e-12f) : log2f(p + 1e-12f));
   };
   const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(px) & (4 * sizeof(TI) - 1)) == 0);
   if (vec_ok && p1 > p0) {
@@ -877,7 +879,7 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
     a.ps_out = F(L.off_ps); a.scal = scal; a.level = k; a.red = red; a.cnt = cnt;
     a.store_d = map_out ? 1 : 0;
     if (L.windowed) {
-      int nblk = ceil_div(L.on, 256 * 4);
+      int nblk = ceil_div(L.on, 256 * 2);
       if (nblk > kRedBlocks) nblk = kRedBlocks;
       if (nblk < 1) nblk = 1;
       dim3 grid(nblk, pairs);
