@@ -123,3 +123,63 @@ def test_alpha_beta_backward_formula():
     ga2, gb2 = torch.autograd.grad((out * coef).sum(), [alpha, beta])
     torch.testing.assert_close(ga2, ga)
     torch.testing.assert_close(gb2, gb)
+
+
+def test_autograd_glue_routes_frame_gradients_through_the_activation_tape():
+    """_WeightedScore keeps the activations (dists_forward_saved) only when a frame needs a gradient through the trunk,
+    consumes the tape in the first backward, recomputes in a second backward through a retained graph, and falls
+    back to recomputation when the library declines the tape.  The library context is a stand-in that records calls."""
+    from nerf_qa_b200.dists import _WeightedScore
+    from nerf_qa_b200 import _lib
+
+    class Tape:
+        def __init__(self):
+            self.id = 7
+
+    class FakeCtx:
+        def __init__(self, give_tape):
+            self.calls, self.give_tape = [], give_tape
+
+        def set_channel_weights(self, a, b):
+            pass
+
+        def _out(self, x):
+            return torch.zeros(x.shape[0]), torch.zeros(x.shape[0], 2, 1475)
+
+        def dists_forward(self, x, y, prec, want_s1s2=True):
+            self.calls.append("forward")
+            return self._out(x)
+
+        def dists_forward_saved(self, x, y, prec):
+            self.calls.append("forward_saved")
+            return (*self._out(x), Tape() if self.give_tape else None)
+
+        def dists_backward_saved(self, tape, x, y, g):
+            self.calls.append("backward_saved")
+            tape.id = 0
+            return torch.ones_like(x), torch.ones_like(y)
+
+        def dists_backward(self, x, y, prec, g, through_trunk):
+            self.calls.append(f"backward_recompute(through_trunk={through_trunk})")
+            return torch.ones_like(x), torch.ones_like(y)
+
+    a = torch.rand(1, 1475, 1, 1)
+    b = torch.rand(1, 1475, 1, 1)
+
+    def run(ctx, through_trunk, frames_need_grad, backwards=1):
+        x = torch.zeros(2, 3, 4, 4, requires_grad=frames_need_grad)
+        y = torch.zeros(2, 3, 4, 4)
+        w = a.clone().requires_grad_(True)
+        out = _WeightedScore.apply(x, y, w, b, ctx, _lib.PREC_BF16, through_trunk)
+        for i in range(backwards):
+            out.sum().backward(retain_graph=i + 1 < backwards)
+        return ctx.calls
+
+    assert run(FakeCtx(True), True, True) == ["forward_saved", "backward_saved"]
+    assert run(FakeCtx(True), True, True, backwards=2) == ["forward_saved", "backward_saved",
+                                                           "backward_recompute(through_trunk=True)"]
+    assert run(FakeCtx(False), True, True) == ["forward_saved", "backward_recompute(through_trunk=True)"]
+    # the reference's default (trunk under no_grad): level-0 gradient only, nothing to keep
+    assert run(FakeCtx(True), False, True) == ["forward", "backward_recompute(through_trunk=False)"]
+    # only the channel weights need gradients: closed form from S1 / S2, no backward call into the library
+    assert run(FakeCtx(True), True, False) == ["forward"]
