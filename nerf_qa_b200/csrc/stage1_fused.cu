@@ -6,22 +6,24 @@
 //      (K = 27 padded to 32, bf16, canonical no-swizzle K-major layout) of the 18 x 10 halo of conv1_1 outputs
 //      that conv1_2 needs;
 //   2. one thread issues 4 tcgen05.mma (2 x M=128, N=64, K=2x16) -> 256 x 64 fp32 in TMEM (180 rows used);
-//   3. four "mid" epilogue warps read that accumulator, add bias, ReLU, zero the pixels outside the image (the zero
-//      padding of conv1_2), round to bf16 and write the halo tile into shared memory in exactly the 128-byte-swizzled
-//      K-major layout TMA would have produced (one 128-byte row per pixel = 64 channels);
+//   3. six "mid" epilogue warps (four for halo rows 0..127, two for rows 128..179, so that both accumulator halves
+//      drain in parallel) read that accumulator, add bias, ReLU, zero the pixels outside the image (the zero padding
+//      of conv1_2), round to bf16 and write the halo tile into shared memory as a K-major UMMA operand: linear
+//      [8-channel chunk][halo row][16 B] by default, or the 128-byte-swizzled layout TMA would have produced;
 //   4. the same MMA thread issues the 36 tcgen05.mma of conv1_2 (9 taps x 4 k-steps, M=128, N=64): the A operand of
 //      tap (r, s) is the halo tile viewed through a descriptor shifted by (10 r + s) rows, 8-row groups 10 rows apart;
 //      the 72 KB of conv1_2 weights stay resident in shared memory (TMA, loaded once per CTA);
-//   5. four "final" epilogue warps: tcgen05.ld -> +bias -> ReLU -> bf16 -> NHWC global stores.
+//   5. four "final" epilogue warps: tcgen05.ld -> +bias -> ReLU -> bf16 -> swizzled staging tile -> one TMA store.
 // Everything is double-buffered (im2col rows, both accumulators, halo tile) and handed over with mbarriers, so the
 // conv1_1 MMAs + mid epilogue of tile i+1 overlap the conv1_2 MMAs of tile i.  Persistent grid = #SMs.
 //
 // PAIR = true runs the same pipeline on a cluster of two CTAs (one TPC): each CTA keeps its own tile, producers and
 // epilogues, but every tcgen05.mma is a cta_group::2 instruction issued by the leader for both tiles (M = 256) and each
-// CTA holds only half of the conv1_1 / conv1_2 weights (32 of the 64 output channels).  At N = 64 a single-CTA MMA costs
-// ~95 cycles of shared-memory operand fetch (128 A rows + 64 B rows) against 32 cycles of math; the pair fetches
-// 128 + 32 rows per SM.  Barriers the MMA warp waits on live in the leader CTA (the follower arrives remotely), the ones
-// it signals are multicast to both CTAs.
+// CTA holds only half of the conv1_1 / conv1_2 weights (32 of the 64 output channels): 128 + 32 operand rows fetched
+// per SM and MMA instead of 128 + 64 (2.46 vs 2.72 ms per 16 frames, 54% vs 48% tensor-pipe activity; DESIGN.md §4 has
+// the history -- the pair only paid off once the producers and the mid epilogue were no longer the limiters).
+// Barriers the MMA warp waits on live in the leader CTA (the follower arrives remotely), the ones it signals are
+// multicast to both CTAs.
 //
 // Reference semantics: DISTS_pt.py:92 (normalise), vgg16.features[0:4] (DISTS_pt.py:36-37), ADISTS.py:113-114.
 #include "common.cuh"
