@@ -183,3 +183,38 @@ def test_autograd_glue_routes_frame_gradients_through_the_activation_tape():
     assert run(FakeCtx(True), False, True) == ["forward", "backward_recompute(through_trunk=False)"]
     # only the channel weights need gradients: closed form from S1 / S2, no backward call into the library
     assert run(FakeCtx(True), True, False) == ["forward"]
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "score_frames")
+    libdir = os.path.join(root, "nerf_qa_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "score_frames.c"), "-L", libdir, "-lnerfqa_b200",
+                    f"-Wl,-rpath,{libdir}", "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """include/nerfqa_b200.h compiles as strict C99 and examples/score_frames.c links against the shared library; without
+    a GPU the program must stop at context creation with the no-fallback error (exit code 2), never compute on the CPU."""
+    import subprocess
+    import torch
+    exe = _build_c_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("covered by the GPU test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2, (r.stdout, r.stderr)
+    assert "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_consumer_scores_frames_through_the_c_abi(tmp_path):
+    """The plain-C consumer scores host frames with nqa_dists_forward_host and checks DISTS(x,x) = 0 and symmetry."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe, "3", "135", "240"], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert r.stdout.strip().endswith("OK")
