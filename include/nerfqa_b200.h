@@ -19,6 +19,9 @@
  *     a workspace arena that grows on demand (no allocation after warm-up at a fixed shape);
  *   - calls on one context are not thread-safe (same contract as a torch nn.Module); use one
  *     context per GPU, one process (or thread) per GPU;
+ *   - calls on one context may use different streams: the context orders them itself (an event is recorded on
+ *     the stream of every call and the next call on another stream waits for it), because the workspace arena, the
+ *     channel weights and the staging buffers are shared; independent work belongs on separate contexts;
  *   - there is NO CPU fallback: without a CUDA device every compute call fails with NQA_ERR_CUDA.
  */
 #ifndef NERFQA_B200_H
@@ -89,6 +92,14 @@ NQA_API int nqa_set_alpha_beta(nqa_ctx* ctx, const float* alpha, const float* be
  * softmax over the 2950 logits (DISTS_pt_softmax.py:117-123).  d score_b / d a_c = -S1_bc, d score_b / d b_c = -S2_bc. */
 NQA_API int nqa_set_channel_weights(nqa_ctx* ctx, const float* a, const float* b);
 
+/* Stream-ordered forms of the two setters: the 2 x 5.9 KB are copied with cudaMemcpyAsync on `stream`, after the
+ * work already enqueued there -- e.g. the torch ops that just produced alpha / beta (DISTS_pt.py:127-129 reads the
+ * live parameters in every forward) -- and before scoring calls enqueued later on any stream of this context.  The
+ * source must stay valid until the copy has run (device tensors: stream-ordered; pageable host memory: staged before
+ * the call returns).  The synchronous forms above return after the copy has completed. */
+NQA_API int nqa_set_alpha_beta_async(nqa_ctx* ctx, const float* alpha, const float* beta, void* stream);
+NQA_API int nqa_set_channel_weights_async(nqa_ctx* ctx, const float* a, const float* b, void* stream);
+
 /* DISTS.forward(x, y) (DISTS_pt.py:105-148): per-frame scores.
  *   x, y       device, [B,3,H,W] fp32
  *   score_out  device, [B] fp32
@@ -130,6 +141,19 @@ NQA_API int nqa_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int
 NQA_API int nqa_adists_map(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int precision,
                            float* score_out, float* map_out, void* stream);
 
+/* nqa_adists_forward plus the intermediates of ADISTS.forward, for level-by-level parity checks against the reference
+ * (all device pointers, each may be NULL):
+ *   weights_out      [B,1475]  the clamped, renormalised entropy channel weights (ADISTS.py:127-135,152-160);
+ *   level_terms_out  [B,6]     D_k = mean_hw sum_c w_c((1 - ps_k) T + ps_k S) per level; score = 1 - sum_k D_k
+ *                              (ADISTS.py:165-191);
+ *   ps_out[k]        [B, e_k]  the structure-probability map ps_x[k] of compute_prob (ADISTS.py:71-100), row-major
+ *                              (h_k - window + 1) x (w_k - window + 1), or one value for a level smaller than the
+ *                              window; e_k from nqa_adists_ps_elems. */
+NQA_API int nqa_adists_parts(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int precision,
+                             float* score_out, float* weights_out, float* level_terms_out,
+                             float* const ps_out[NQA_NUM_LEVELS], void* stream);
+NQA_API int nqa_adists_ps_elems(int H, int W, int window, int level, size_t* elems);
+
 /* DISTS and A-DISTS scores of the same batch from ONE trunk evaluation: what prep.py:186-190 /
  * test2_prep.py:151-155 compute with two model calls (four trunk forwards per pair in the reference).  The DISTS
  * scores are bit-identical to nqa_dists_forward; the A-DISTS scores equal nqa_adists_forward up to the rounding of the
@@ -137,6 +161,17 @@ NQA_API int nqa_adists_map(nqa_ctx* ctx, const float* x, const float* y, int B, 
  * alpha/beta. */
 NQA_API int nqa_dists_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window,
                                      int precision, float* dists_out, float* adists_out, void* stream);
+
+/* Host-buffer forms (see nqa_dists_forward_host): the loop prep.py:181-190 runs per batch --
+ * `adists_model(ref.to(device), render.to(device), as_loss=False)` and `dists_model(ref, render)` followed by
+ * `.cpu()` -- with the frames streamed host -> device in micro-batches on a copy stream that overlaps the compute
+ * stream.  x_host / y_host [B,3,H,W] and the score vectors [B] are host pointers (pinned memory gives the full PCIe
+ * rate); the calls return when the scores are in host memory.  nqa_dists_adists_forward_host gives both metrics from
+ * one trunk evaluation (needs alpha/beta). */
+NQA_API int nqa_adists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W, int window,
+                                    int precision, float* score_host);
+NQA_API int nqa_dists_adists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W,
+                                          int window, int precision, float* dists_host, float* adists_host);
 
 /* The statistics half of ADISTS.forward (ADISTS.py:147-197) from six NCHW fp32 device tensors per
  * image (the reference's forward_once format, level 0 = the raw frames). */

@@ -26,7 +26,8 @@ EXPORTS = (
     "nqa_workspace_bytes", "nqa_launch_count", "nqa_micro_batch", "nqa_conv3x3_relu",
     "nqa_profile_enable", "nqa_profile_read", "nqa_dists_backward", "nqa_dists_from_feats_backward",
     "nqa_set_channel_weights", "nqa_adists_map", "nqa_dists_adists_forward", "nqa_dists_forward_saved",
-    "nqa_dists_backward_saved", "nqa_tape_release",
+    "nqa_dists_backward_saved", "nqa_tape_release", "nqa_set_alpha_beta_async", "nqa_set_channel_weights_async",
+    "nqa_adists_forward_host", "nqa_dists_adists_forward_host", "nqa_adists_parts", "nqa_adists_ps_elems",
 )
 KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists", "pool_stats",
                    "stage1", "backward")
@@ -58,12 +59,18 @@ def load_library() -> ctypes.CDLL:
     lib.nqa_set_vgg_weights.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     lib.nqa_set_alpha_beta.argtypes = [vp, fp, fp]
     lib.nqa_set_channel_weights.argtypes = [vp, fp, fp]
+    lib.nqa_set_alpha_beta_async.argtypes = [vp, fp, fp, vp]
+    lib.nqa_set_channel_weights_async.argtypes = [vp, fp, fp, vp]
+    lib.nqa_adists_forward_host.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp]
+    lib.nqa_dists_adists_forward_host.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp, fp]
     lib.nqa_dists_forward.argtypes = [vp, fp, fp, ci, ci, ci, ci, fp, fp, vp]
     lib.nqa_dists_forward_host.argtypes = [vp, fp, fp, ci, ci, ci, ci, fp]
     lib.nqa_dists_features.argtypes = [vp, fp, ci, ci, ci, ci, ctypes.POINTER(vp), vp]
     lib.nqa_dists_from_feats.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ci, fp, fp, vp]
     lib.nqa_adists_forward.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp, vp]
     lib.nqa_dists_adists_forward.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp, fp, vp]
+    lib.nqa_adists_parts.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp, fp, fp, ctypes.POINTER(vp), vp]
+    lib.nqa_adists_ps_elems.argtypes = [ci, ci, ci, ci, ctypes.POINTER(ctypes.c_size_t)]
     lib.nqa_adists_map.argtypes = [vp, fp, fp, ci, ci, ci, ci, ci, fp, fp, vp]
     lib.nqa_adists_from_feats.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ci, ci, fp, vp]
     lib.nqa_l2pool.argtypes = [vp, fp, ci, ci, ci, ci, fp, vp]
@@ -168,15 +175,23 @@ class Context:
         a = alpha.detach().to(torch.float32).reshape(-1).contiguous()
         b = beta.detach().to(torch.float32).reshape(-1).contiguous()
         assert a.numel() == NUM_CHANNELS and b.numel() == NUM_CHANNELS
-        _check(self.lib.nqa_set_alpha_beta(self.handle, _ptr(a), _ptr(b)))
+        self._set_weights(self.lib.nqa_set_alpha_beta, self.lib.nqa_set_alpha_beta_async, a, b)
 
     def set_channel_weights(self, a: torch.Tensor, b: torch.Tensor) -> None:
         """Effective per-channel weights, used as given (no division by their sum inside the kernels)."""
         a = a.detach().to(torch.float32).reshape(-1).contiguous()
         b = b.detach().to(torch.float32).reshape(-1).contiguous()
         assert a.numel() == NUM_CHANNELS and b.numel() == NUM_CHANNELS
-        _check(self.lib.nqa_set_channel_weights(self.handle, _ptr(a), _ptr(b)))
-        self.ab_key = None
+        self._set_weights(self.lib.nqa_set_channel_weights, self.lib.nqa_set_channel_weights_async, a, b)
+
+    def _set_weights(self, sync_fn, async_fn, a: torch.Tensor, b: torch.Tensor) -> None:
+        """Device tensors: stream-ordered copy on torch's current stream (behind the ops that produced them, ahead of
+        the scoring call that follows); the caching allocator keeps the sources alive in stream order.  Host tensors:
+        the synchronous form."""
+        if a.is_cuda and b.is_cuda:
+            _check(async_fn(self.handle, _ptr(a), _ptr(b), _stream(self.device)))
+        else:
+            _check(sync_fn(self.handle, _ptr(a), _ptr(b)))
 
     # -- scoring ---------------------------------------------------------------------------------
     def dists_forward(self, x: torch.Tensor, y: torch.Tensor, precision: int, want_s1s2: bool = True):
@@ -204,6 +219,34 @@ class Context:
             out = torch.empty(b, dtype=torch.float32).pin_memory()
         _check(self.lib.nqa_dists_forward_host(self.handle, _ptr(x), _ptr(y), b, h, w, precision, _ptr(out)))
         return out
+
+    def _host_pair(self, x: torch.Tensor, y: torch.Tensor, what: str):
+        if x.is_cuda or y.is_cuda:
+            raise NerfQAError(f"{what} takes host tensors")
+        if x.shape != y.shape or x.dim() != 4 or x.shape[1] != 3:
+            raise NerfQAError(f"expected two [B,3,H,W] host tensors, got {tuple(x.shape)} / {tuple(y.shape)}")
+        return x.to(torch.float32).contiguous(), y.to(torch.float32).contiguous()
+
+    def adists_forward_host(self, x: torch.Tensor, y: torch.Tensor, window: int, precision: int,
+                            out: Optional[torch.Tensor] = None):
+        """A-DISTS per-frame scores from CPU fp32 frames (pinned for full PCIe rate); returns a CPU tensor."""
+        x, y = self._host_pair(x, y, "adists_forward_host")
+        b, _, h, w = x.shape
+        if out is None:
+            out = torch.empty(b, dtype=torch.float32).pin_memory()
+        _check(self.lib.nqa_adists_forward_host(self.handle, _ptr(x), _ptr(y), b, h, w, window, precision, _ptr(out)))
+        return out
+
+    def dists_adists_forward_host(self, x: torch.Tensor, y: torch.Tensor, window: int, precision: int,
+                                  out: Optional[Sequence[torch.Tensor]] = None):
+        """(DISTS [B], A-DISTS [B]) from CPU fp32 frames through one trunk evaluation; CPU tensors."""
+        x, y = self._host_pair(x, y, "dists_adists_forward_host")
+        b, _, h, w = x.shape
+        d, a = out if out is not None else (torch.empty(b, dtype=torch.float32).pin_memory(),
+                                            torch.empty(b, dtype=torch.float32).pin_memory())
+        _check(self.lib.nqa_dists_adists_forward_host(self.handle, _ptr(x), _ptr(y), b, h, w, window, precision,
+                                                      _ptr(d), _ptr(a)))
+        return d, a
 
     def features(self, x: torch.Tensor, precision: int):
         if x.dim() != 4 or x.shape[1] != 3:
@@ -297,6 +340,29 @@ class Context:
         _check(self.lib.nqa_adists_forward(self.handle, _ptr(x), _ptr(y), b, h, w, window, precision, _ptr(score),
                                            _stream(x.device)))
         return score
+
+    def adists_parts(self, x: torch.Tensor, y: torch.Tensor, window: int, precision: int):
+        """(scores [B], channel weights [B,1475], per-level terms [B,6], ps maps: six [B,1,oh_k,ow_k] tensors) -- the
+        intermediates of ADISTS.forward for level-by-level parity checks."""
+        if x.shape != y.shape:
+            raise AssertionError(f"shape mismatch: x {tuple(x.shape)} vs y {tuple(y.shape)}")
+        x, y = _as_input(x, "x"), _as_input(y, "y")
+        b, _, h, w = x.shape
+        dev = x.device
+        score = torch.empty(b, device=dev, dtype=torch.float32)
+        wts = torch.empty(b, NUM_CHANNELS, device=dev, dtype=torch.float32)
+        terms = torch.empty(b, NUM_LEVELS, device=dev, dtype=torch.float32)
+        ps = []
+        for k, (_, _, hk, wk) in enumerate(level_shapes(b, h, w)):
+            n = ctypes.c_size_t()
+            _check(self.lib.nqa_adists_ps_elems(h, w, window, k, ctypes.byref(n)))
+            shape = (b, 1, hk - window + 1, wk - window + 1) if n.value > 1 or (hk == window and wk == window) else (b, 1, 1, 1)
+            assert shape[2] * shape[3] == n.value
+            ps.append(torch.empty(shape, device=dev, dtype=torch.float32))
+        arr = (ctypes.c_void_p * NUM_LEVELS)(*[p.data_ptr() for p in ps])
+        _check(self.lib.nqa_adists_parts(self.handle, _ptr(x), _ptr(y), b, h, w, window, precision, _ptr(score), _ptr(wts),
+                                         _ptr(terms), arr, _stream(dev)))
+        return score, wts, terms, ps
 
     def dists_adists_forward(self, x: torch.Tensor, y: torch.Tensor, window: int, precision: int):
         """(DISTS [B], A-DISTS [B]) from one trunk evaluation."""

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .dists import _TrunkModule, build_vgg_stages, try_load_pretrained_vgg, L2pooling
+from .dists import _TrunkModule, _refuse_grad, build_vgg_stages, try_load_pretrained_vgg, L2pooling
 
 
 class Downsample(L2pooling):
@@ -54,6 +54,9 @@ class ADISTS(_TrunkModule):
         """``as_loss=False`` -> per-frame scores ``[B]``; ``as_loss=True`` (the reference default) -> the scalar
         ``1 - mean_b D`` (ADISTS.py:192-197).  Asymmetric: probability maps and entropy weights come from ``x``."""
         assert x.shape == y.shape                                  # ADISTS.py:138
+        # the reference's default (as_loss=True) runs the trunk under autograd (ADISTS.py:139-141); this path has no
+        # A-DISTS backward, so a call that expects a gradient raises instead of returning a graph-less scalar
+        _refuse_grad("ADISTS.forward", x, y)
         ctx = self._context(x.device)
         if as_map:
             # ADISTS.py:163,189: D_map_full is [B,H,W] and each level adds a [B,1,H,W] tensor, so for B > 1 the
@@ -64,6 +67,14 @@ class ADISTS(_TrunkModule):
         if as_loss:
             return score.mean()        # 1 - mean(D) == mean(1 - D)
         return score
+
+    def score_host(self, x: torch.Tensor, y: torch.Tensor, device=None) -> torch.Tensor:
+        """Per-frame scores from HOST frames (pinned recommended), as a CPU tensor: what
+        ``adists_model(ref.to(device), render.to(device), as_loss=False).cpu()`` does in prep.py:186-187, with the frames
+        streamed to the GPU in micro-batches overlapped with compute."""
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        ctx = self._context(dev)
+        return ctx.adists_forward_host(x, y, self.window_size, self._prec())
 
     def forward_from_feats(self, feats_x: Sequence[torch.Tensor], feats_y: Sequence[torch.Tensor]) -> torch.Tensor:
         """The statistics half of forward on six NCHW fp32 levels (what ``forward_once`` returns)."""

@@ -817,8 +817,10 @@ int level_window(int window, const LevelPlan& L, const TI* x, const TI* y, int p
 }
 }  // namespace
 
+size_t adists_ps_elems(int H, int W, int window, int level) { return (size_t)make_plan(1, H, W, window).lv[level].on; }
+
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
-                 void* ws, float* score, cudaStream_t st, float* map_out) {
+                 void* ws, float* score, cudaStream_t st, float* map_out, const AdistsParts* parts) {
   // level 0 (the raw frames) is always fp32; levels 1..5 are bf16 planes when feats_bf16
   auto is16 = [&](int k) { return feats_bf16 && k > 0; };
   auto F32 = [](const void* p) { return static_cast<const float*>(p); };
@@ -895,6 +897,16 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
   }
   final_kernel<<<ceil_div(pairs, 128), 128, 0, st>>>(scal, pairs, score);
   ++launches;
+  if (parts) {
+    if (parts->weights)
+      cudaMemcpyAsync(parts->weights, wt, (size_t)pairs * kTotalChannels * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (parts->level_terms)
+      cudaMemcpy2DAsync(parts->level_terms, sizeof(float), &scal[0].d, sizeof(LvlScal), sizeof(float),
+                        (size_t)pairs * kNumLevels, cudaMemcpyDeviceToDevice, st);
+    for (int k = 0; k < kNumLevels; ++k)
+      if (parts->ps[k])
+        cudaMemcpyAsync(parts->ps[k], F(p.lv[k].off_ps), (size_t)pairs * p.lv[k].on * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  }
   if (map_out) {
     DMapLevels dl;
     for (int k = 0; k < kNumLevels; ++k) {

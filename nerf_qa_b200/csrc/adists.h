@@ -15,7 +15,16 @@ size_t adists_workspace_bytes(int pairs, int H, int W, int window);
 // fx[k], fy[k]: planes [pairs, C_k, H_k, W_k]; level 0 (the raw frames) is fp32, levels 1..5 are fp32 or -- when
 // feats_bf16 -- bf16 (the bf16 trunk's activations, half the bytes).  score: [pairs].  Returns the number of kernels
 // launched.  map_out (optional): [pairs, H, W] full-resolution map 1 - sum_k bilinear(D_map_k) (as_map=True).
+// Optional copies of the stage's intermediates (device pointers, any may be null): rows a6 / a7 / a8 of the scope
+// table are checked level by level against the reference with these.
+struct AdistsParts {
+  float* weights = nullptr;       // [pairs][1475] clamped entropy channel weights (ADISTS.py:152-160)
+  float* level_terms = nullptr;   // [pairs][6] D_k = mean_hw sum_c w_c((1-ps) T + ps S) (ADISTS.py:186-191)
+  float* ps[6] = {};              // ps_prod maps [pairs][oh_k*ow_k] (compute_prob, ADISTS.py:71-100)
+};
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
-                 void* ws, float* score, cudaStream_t st, float* map_out = nullptr);
+                 void* ws, float* score, cudaStream_t st, float* map_out = nullptr, const AdistsParts* parts = nullptr);
+// number of elements of the level-k ps map of one frame (1 for a fallback level)
+size_t adists_ps_elems(int H, int W, int window, int level);
 
 }  // namespace nqa

@@ -276,19 +276,6 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int g_sm_count = kNumSMs;
-
-// NQA_CONV_HALO: 0 = plain kernel everywhere; 1..4 = halo-reuse kernel for Cin <= 128 with
-// (halo width, base-offset mode) = (10,0) (10,1) (16,0) (16,1).
-static int halo_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("NQA_CONV_HALO");
-    mode = e ? atoi(e) : NQA_CONV_HALO_DEFAULT;
-    if (mode < 0 || mode > 4) mode = 0;
-  }
-  return mode;
-}
 
 static int choose_tw_log2(int h, int w) {
   // pick the TH x TW = 128 rectangle that wastes the fewest MMA rows on this image size
@@ -336,7 +323,7 @@ static int launch_impl(const ConvTcPlan& plan, cudaStream_t st) {
   p.num_n_tiles = plan.cout / BLOCK_N;
   p.num_tiles = plan.n * plan.tiles_h * plan.tiles_w * p.num_n_tiles;
   p.bias = plan.bias; p.out = plan.out; p.out_lo = plan.out_lo;
-  const int grid = p.num_tiles < g_sm_count ? p.num_tiles : g_sm_count;
+  const int grid = p.num_tiles < plan.sm_count ? p.num_tiles : plan.sm_count;
   conv3x3_tc_kernel<BLOCK_N, SPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(plan.tmap_a, plan.tmap_a_lo, plan.tmap_b,
                                                                              plan.tmap_b_lo, p);
   return 1;
@@ -352,13 +339,27 @@ int conv_tc_make_weight_map(CUtensorMap* map, const bf16* wk, int cout, int k, i
   return tc::encode_w_map(map, wk, cout, k, block_n) ? 0 : 1;
 }
 
-void conv_tc_set_sm_count(int sms) { tc::g_sm_count = sms > 0 ? sms : kNumSMs; }
+// NQA_CONV_HALO: 0 = plain kernel everywhere; 1..4 = halo-reuse kernel with
+// (halo width, base-offset mode) = (10,0) (10,1) (16,0) (16,1).
+ConvTcConfig conv_tc_config_from_env(int sm_count) {
+  ConvTcConfig c;
+  c.sm_count = sm_count > 0 ? sm_count : kNumSMs;
+  c.halo_mode = NQA_CONV_HALO_DEFAULT;
+  if (const char* e = getenv("NQA_CONV_HALO")) c.halo_mode = atoi(e);
+  if (c.halo_mode < 0 || c.halo_mode > 4) c.halo_mode = 0;
+  if (const char* e = getenv("NQA_CONV_HALO_MAXCIN")) c.halo_max_cin = atoi(e);
+  if (const char* e = getenv("NQA_CONV_N64")) c.n64 = atoi(e) != 0;
+  if (const char* e = getenv("NQA_CONV_PAIR")) c.pair = atoi(e) != 0;
+  if (const char* e = getenv("NQA_PAIR_MINCIN")) c.pair_min_cin = atoi(e);
+  return c;
+}
 
-int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
-                      const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout, bool split,
-                      const char** err) {
+int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in, const bf16* in_lo, const bf16* wk,
+                      const bf16* wk_lo, const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout,
+                      bool split, const char** err) {
   if (cin % tc::BLOCK_K != 0 || cout % 64 != 0 || cout > 512) { *err = "conv_tc: cin must be a multiple of 64, cout a multiple of 64 and <= 512"; return 1; }
   plan->n = n; plan->h = h; plan->w = w; plan->cin = cin; plan->cout = cout;
+  plan->sm_count = cfg.sm_count;
   plan->split = split; plan->bias = bias; plan->out = out; plan->out_lo = out_lo;
   plan->tw_log2 = tc::choose_tw_log2(h, w);
   int tw = 1 << plan->tw_log2, th = 128 >> plan->tw_log2;
@@ -373,9 +374,8 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
   plan->pair = false;
   plan->halo_hbw = 10;
   plan->halo_desc_mode = 0;
-  const int halo_mode = tc::halo_mode();
-  static const int halo_max_cin = getenv("NQA_CONV_HALO_MAXCIN") ? atoi(getenv("NQA_CONV_HALO_MAXCIN")) : 512;
-  if (halo_mode > 0 && !split && cin <= halo_max_cin) {
+  const int halo_mode = cfg.halo_mode;
+  if (halo_mode > 0 && !split && cin <= cfg.halo_max_cin) {
     plan->halo = true;
     plan->halo_desc_mode = 0;   // base-offset field 0: validated on hardware (swizzle follows absolute address bits)
     plan->halo_hbw = ((halo_mode - 1) & 2) ? 16 : 10;
@@ -384,12 +384,9 @@ int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const
     th = 16;
     // 128 -> 128 channels: two 64-channel tiles whose weights (147 KB) stay resident in shared memory beat one
     // 128-channel tile whose weights stream from L2 for every pixel tile (NQA_CONV_N64=0 restores the latter)
-    static const bool n64 = getenv("NQA_CONV_N64") ? atoi(getenv("NQA_CONV_N64")) != 0 : true;
-    if (n64 && cin == 128 && cout == 128) plan->block_n = 64;
+    if (cfg.n64 && cin == 128 && cout == 128) plan->block_n = 64;
     // CTA pairs (tcgen05 cta_group::2): 256 pixels x block_n channels per instruction, each CTA holds half the weights
-    static const bool pair = getenv("NQA_CONV_PAIR") ? atoi(getenv("NQA_CONV_PAIR")) != 0 : true;
-    static const int pair_min_cin = getenv("NQA_PAIR_MINCIN") ? atoi(getenv("NQA_PAIR_MINCIN")) : 128;
-    if (pair && cout >= 128 && cin >= pair_min_cin && (tc::g_sm_count & 1) == 0) {
+    if (cfg.pair && cout >= 128 && cin >= cfg.pair_min_cin && (cfg.sm_count & 1) == 0) {
       plan->pair = true;
       plan->block_n = cout >= 256 ? 256 : 128;
     }
@@ -418,13 +415,13 @@ int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st) {
     return 0;
   }
   if (plan.pair) {
-    const int rc = launch_conv3x3_tc_pair(plan, tc::g_sm_count, st);
+    const int rc = launch_conv3x3_tc_pair(plan, plan.sm_count, st);
     if (rc > 0) return rc;
     fprintf(stderr, "nerfqa_b200: CTA-pair conv configuration does not fit (cin %d cout %d)\n", plan.cin, plan.cout);
     return 0;
   }
   if (plan.halo) {
-    const int rc = launch_conv3x3_tc_halo(plan, tc::g_sm_count, st);
+    const int rc = launch_conv3x3_tc_halo(plan, plan.sm_count, st);
     if (rc > 0) return rc;
     fprintf(stderr, "nerfqa_b200: halo conv configuration does not fit (cin %d cout %d)\n", plan.cin, plan.cout);
     return 0;

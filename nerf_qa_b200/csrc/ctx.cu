@@ -105,6 +105,26 @@ struct nqa_ctx {
   bool fuse_stage1 = true;               // NQA_STAGE1_FUSED=0 falls back to conv1_1 + conv1_2 kernels
   int micro_images = 16;                 // full-HD-equivalent images per trunk pass (NQA_MICRO_IMAGES)
   bool fuse_pool_stats = true;           // NQA_POOL_STATS_FUSED=0 falls back to separate pooling / statistics kernels
+  bool pool_stats_tma = true;            // NQA_POOL_STATS_TMA=0: register-fed pooling + moments kernel for bf16 levels too
+  ConvTcConfig conv_cfg;                 // kernel selection of the tensor-pipe convolutions (environment read at creation)
+  // Encoded tensor maps of the convolution launches, keyed on (buffers, shape): the arena hands out the same addresses
+  // for the same shape, so after the first call at a shape no launch goes through cuTensorMapEncodeTiled again.
+  struct PlanKey {
+    const void *in, *in_lo, *wk, *out, *out_lo;
+    int n, h, w, cin, cout, split;
+    bool operator==(const PlanKey& o) const {
+      return in == o.in && in_lo == o.in_lo && wk == o.wk && out == o.out && out_lo == o.out_lo && n == o.n && h == o.h &&
+             w == o.w && cin == o.cin && cout == o.cout && split == o.split;
+    }
+  };
+  std::vector<std::pair<PlanKey, ConvTcPlan>> plan_cache;
+  uint64_t plan_hits = 0, plan_misses = 0;
+  // Cross-stream ordering of the context's shared state (workspace arena, channel weights, staging buffers): every
+  // entry point records ev_last on its stream when it has enqueued its work, and an entry point that runs on a
+  // DIFFERENT stream than the previous one first makes its stream wait for that event.
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool have_last = false;
   Arena arena;
   uint64_t launches = 0;
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
@@ -171,6 +191,7 @@ int ensure_arena(nqa_ctx* ctx, size_t bytes) {
     CUDA_TRY(cudaFree(ctx->arena.base));
     ctx->arena.base = nullptr;
     ctx->arena.cap = 0;
+    ctx->plan_cache.clear();   // the cached tensor maps point into the old arena
   }
   const size_t want = bytes + (bytes >> 4) + (1 << 20);
   void* p = nullptr;
@@ -184,6 +205,46 @@ int ensure_arena(nqa_ctx* ctx, size_t bytes) {
 }
 
 size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// Orders a call on `st` after whatever the previous call enqueued on another stream (see nqa_ctx::ev_last).
+int enter_stream(nqa_ctx* ctx, cudaStream_t st) {
+  if (ctx->have_last && ctx->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_last, 0));
+  return NQA_OK;
+}
+int leave_stream(nqa_ctx* ctx, cudaStream_t st) {
+  CUDA_TRY(cudaEventRecord(ctx->ev_last, st));
+  ctx->last_stream = st;
+  ctx->have_last = true;
+  return NQA_OK;
+}
+// RAII form for the entry points: waits on entry, records on every exit path.
+struct StreamOrder {
+  nqa_ctx* ctx;
+  cudaStream_t st;
+  int rc;
+  StreamOrder(nqa_ctx* c, cudaStream_t s) : ctx(c), st(s), rc(enter_stream(c, s)) {}
+  ~StreamOrder() { leave_stream(ctx, st); }
+};
+
+// conv_tc_make_plan through the context's cache of encoded tensor maps
+int cached_plan(nqa_ctx* ctx, ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
+                const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout, bool split,
+                const char** err) {
+  const nqa_ctx::PlanKey key{in, in_lo, wk, out, out_lo, n, h, w, cin, cout, split ? 1 : 0};
+  for (auto& e : ctx->plan_cache)
+    if (e.first == key) {
+      *plan = e.second;
+      plan->bias = bias;
+      ++ctx->plan_hits;
+      return 0;
+    }
+  const int rc = conv_tc_make_plan(plan, ctx->conv_cfg, in, in_lo, wk, wk_lo, bias, out, out_lo, n, h, w, cin, cout, split, err);
+  if (rc) return rc;
+  ++ctx->plan_misses;
+  if (ctx->plan_cache.size() >= 512) ctx->plan_cache.clear();
+  ctx->plan_cache.emplace_back(key, *plan);
+  return 0;
+}
 
 void level_dims(int H, int W, int (&h)[kNumLevels], int (&w)[kNumLevels]) {
   h[0] = h[1] = H;
@@ -307,11 +368,13 @@ int conv_layer<bf16>(nqa_ctx* ctx, int li, const bf16* in, const bf16* in_lo, bf
   ConvTcPlan plan;
   const char* err = "";
   const bool split = prec == NQA_PREC_BF16X3;
-  if (conv_tc_make_plan(&plan, in, in_lo, ctx->w_hi[li], ctx->w_lo[li], ctx->bias[li], out, out_lo, n, h, w,
-                        kConvCin[li], kConvCout[li], split, &err))
+  if (cached_plan(ctx, &plan, in, in_lo, ctx->w_hi[li], ctx->w_lo[li], ctx->bias[li], out, out_lo, n, h, w,
+                  kConvCin[li], kConvCout[li], split, &err))
     return fail(NQA_ERR_CUDA, "%s (layer %d, %dx%dx%d)", err, li, n, h, w);
   ProfScope ps(ctx, NQA_K_CONV_TC, st);
-  ctx->launches += launch_conv3x3_tc(plan, st);
+  const int nl = launch_conv3x3_tc(plan, st);
+  if (nl <= 0) return fail(NQA_ERR_CUDA, "convolution of layer %d could not be launched (%dx%dx%d)", li, n, h, w);
+  ctx->launches += nl;
   return NQA_OK;
 }
 
@@ -357,8 +420,10 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
     if (stage < 4) {
       if (!pooled_done) {
         ProfScope ps(ctx, NQA_K_L2POOL, st);
-        ctx->launches += launch_l2pool_nhwc<T>(bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, bufs.ping[cur ^ 1],
-                                               split ? bufs.ping_lo[cur ^ 1] : nullptr, n, h, w, kConvCout[li - 1], st);
+        const int nl = launch_l2pool_nhwc<T>(bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, bufs.ping[cur ^ 1],
+                                             split ? bufs.ping_lo[cur ^ 1] : nullptr, n, h, w, kConvCout[li - 1], st);
+        if (nl <= 0) return fail(NQA_ERR_SHAPE, "L2pooling: %d images of %dx%d exceed the launch grid", n, h, w);
+        ctx->launches += nl;
       }
       h = pooled(h);
       w = pooled(w);
@@ -466,7 +531,7 @@ int dists_micro_batch(nqa_ctx* ctx, const float* x, const float* y, int pairs, i
                                   const size_t half_out = (size_t)pairs * pooled(h) * pooled(w) * c;
                                   ProfScope ps(ctx, NQA_K_POOL_STATS, st);
                                   ctx->launches += launch_pool_stats<T>(f, f + half, pooled_dst, pooled_dst + half_out, pairs,
-                                                                        h, w, c, pb.chunks[k], pb.p[k], st);
+                                                                        h, w, c, pb.chunks[k], pb.p[k], st, ctx->pool_stats_tma);
                                   return true;
                                 }
                                 ProfScope ps(ctx, NQA_K_STATS, st);
@@ -537,8 +602,8 @@ int conv_layer_bwd<bf16>(nqa_ctx* ctx, int li, const bf16* gin, bf16* gout, int 
   ConvTcPlan plan;
   const char* err = "";
   // roles of the channel counts are swapped; the bias pointer is only staged (512 floats), never applied
-  if (conv_tc_make_plan(&plan, gin, nullptr, ctx->w_bwd_hi[li], nullptr, ctx->bias[kNumConvs - 1], gout, nullptr, n, h, w,
-                        kConvCout[li], kConvCin[li], false, &err))
+  if (cached_plan(ctx, &plan, gin, nullptr, ctx->w_bwd_hi[li], nullptr, ctx->bias[kNumConvs - 1], gout, nullptr, n, h, w,
+                  kConvCout[li], kConvCin[li], false, &err))
     return fail(NQA_ERR_CUDA, "%s (backward of layer %d, %dx%dx%d)", err, li, n, h, w);
   plan.epi = epi;
   plan.mask = mask;
@@ -566,8 +631,8 @@ int conv1_1_bwd<bf16>(nqa_ctx* ctx, const bf16* gz, bf16* scratch, int pairs, in
   ConvTcPlan plan;
   const char* err = "";
   if (ctx->conv11_bwd_tc &&
-      conv_tc_make_plan(&plan, gz, nullptr, ctx->w11_bwd_hi, nullptr, ctx->bias[kNumConvs - 1], scratch, nullptr, n, H, W, 64, 64,
-                        false, &err) == 0 &&
+      cached_plan(ctx, &plan, gz, nullptr, ctx->w11_bwd_hi, nullptr, ctx->bias[kNumConvs - 1], scratch, nullptr, n, H, W, 64, 64,
+                  false, &err) == 0 &&
       plan.halo && !plan.pair) {
     plan.epi = kEpiFrameGrad;
     plan.fg_x = gx; plan.fg_y = gy; plan.fg_nx = pairs;
@@ -652,7 +717,7 @@ int trunk_forward_keep(nqa_ctx* ctx, Arena& store, const float* x, const float* 
         sv->pool[stage] = pooled_t;
         ProfScope ps(ctx, NQA_K_POOL_STATS, st);
         ctx->launches += launch_pool_stats<T>(cur, cur + half, pooled_t, pooled_t + half_out, pairs, h, w, c, pb.chunks[k], pb.p[k],
-                                              st);
+                                              st, ctx->pool_stats_tma);
         cur = pooled_t;
       } else {
         ProfScope ps(ctx, NQA_K_STATS, st);
@@ -795,6 +860,65 @@ int acquire_tape_buf(nqa_ctx* ctx, size_t bytes) {
   return (int)ctx->tape_bufs.size() - 1;
 }
 
+// Host-buffer entry points: frames are streamed host -> device in micro-batches on the copy stream, double-buffered
+// against the compute stream; `score(dx, dy, pairs, d_out, stream)` enqueues the scoring of one staged micro-batch and
+// writes `pairs` scores to each of d_out[0..n_out).  Returns when the n_out score vectors are in out_host[0..n_out).
+template <typename F>
+int host_stream_run(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W, int mb, int n_out,
+                    float* const* out_host, F&& score) {
+  const size_t frame = (size_t)3 * H * W;
+  const size_t slot_floats = 2 * (size_t)mb * frame + 2 * (size_t)B;  // x frames, y frames (+ the scores in slot 0)
+  if (slot_floats > ctx->stage_cap) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->stage_in[i]) CUDA_TRY(cudaFree(ctx->stage_in[i]));
+      ctx->stage_in[i] = nullptr;
+    }
+    ctx->stage_cap = 0;
+    for (int i = 0; i < 2; ++i)
+      if (cudaMalloc(&ctx->stage_in[i], slot_floats * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(NQA_ERR_NOMEM, "staging allocation of %zu bytes failed", slot_floats * sizeof(float));
+      }
+    ctx->stage_cap = slot_floats;
+  }
+  float* d_scores = ctx->stage_in[0] + 2 * (size_t)mb * frame;
+  // the arena, the staging slots and the channel weights are shared with the device entry points: order this call
+  // after whatever the caller enqueued earlier on its own stream (and later calls after this one)
+  StreamOrder so(ctx, ctx->compute_stream);
+  if (so.rc != NQA_OK) return so.rc;
+  CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->compute_stream));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+  // The first chunk is small so that the copy/compute pipeline fills quickly (its H2D copy is the only one that is
+  // not hidden behind compute); scores do not depend on the chunking (batch-independent reductions).
+  int rc = NQA_OK, it = 0;
+  for (int b0 = 0; b0 < B; ++it) {
+    const int slot = it & 1;
+    const int want = it == 0 ? (mb > 2 ? 2 : mb) : mb;
+    const int pairs = B - b0 < want ? B - b0 : want;
+    float* dx = ctx->stage_in[slot];
+    float* dy = dx + (size_t)mb * frame;
+    if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(dx, x_host + b0 * frame, pairs * frame * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(dy, y_host + b0 * frame, pairs * frame * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->compute_stream, ctx->ev_copied[slot], 0));
+    float* d_out[2] = {d_scores + b0, d_scores + B + b0};
+    if ((rc = score(dx, dy, pairs, d_out, ctx->compute_stream)) != NQA_OK) break;
+    CUDA_TRY(cudaEventRecord(ctx->ev_consumed[slot], ctx->compute_stream));
+    b0 += pairs;
+  }
+  if (rc == NQA_OK)
+    for (int o = 0; o < n_out; ++o)
+      CUDA_TRY(cudaMemcpyAsync(out_host[o], d_scores + (size_t)o * B, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost,
+                               ctx->compute_stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->compute_stream));
+  if (rc != NQA_OK) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
 int check_ready(nqa_ctx* ctx, bool need_ab) {
   if (!ctx) return fail(NQA_ERR_INVALID, "null context");
   if (!ctx->have_weights) return fail(NQA_ERR_STATE, "VGG weights not set (nqa_set_vgg_weights)");
@@ -837,7 +961,9 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   nqa_ctx* ctx = new nqa_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  conv_tc_set_sm_count(ctx->sm_count);
+  ctx->conv_cfg = conv_tc_config_from_env(ctx->sm_count);
+  if (const char* e = getenv("NQA_POOL_STATS_TMA")) ctx->pool_stats_tma = atoi(e) != 0;
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming));
   if (const char* e = getenv("NQA_STAGE1_FUSED")) ctx->fuse_stage1 = atoi(e) != 0;
   if (const char* e = getenv("NQA_POOL_STATS_FUSED")) ctx->fuse_pool_stats = atoi(e) != 0;
   if (const char* e = getenv("NQA_STAGE1_PAIR")) ctx->stage1_pair = atoi(e) != 0;
@@ -911,6 +1037,7 @@ int nqa_ctx_destroy(nqa_ctx* ctx) {
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
   cudaGetLastError();
@@ -960,13 +1087,34 @@ int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const
   return NQA_OK;
 }
 
-int nqa_set_alpha_beta(nqa_ctx* ctx, const float* alpha, const float* beta) {
+int nqa_set_alpha_beta_async(nqa_ctx* ctx, const float* alpha, const float* beta, void* stream) {
   if (!ctx || !alpha || !beta) return fail(NQA_ERR_INVALID, "null argument");
   DeviceGuard guard(ctx->device);
-  CUDA_TRY(cudaMemcpy(ctx->alpha, alpha, kTotalChannels * sizeof(float), cudaMemcpyDefault));
-  CUDA_TRY(cudaMemcpy(ctx->beta, beta, kTotalChannels * sizeof(float), cudaMemcpyDefault));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // ordered after earlier scoring calls that still read the old weights (on whatever stream they ran) and before
+  // later ones: copies on the caller's stream, cross-stream hand-over through the context's ordering event
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
+  CUDA_TRY(cudaMemcpyAsync(ctx->alpha, alpha, kTotalChannels * sizeof(float), cudaMemcpyDefault, st));
+  CUDA_TRY(cudaMemcpyAsync(ctx->beta, beta, kTotalChannels * sizeof(float), cudaMemcpyDefault, st));
   ctx->have_alpha_beta = true;
   ctx->ab_normalize = true;
+  return NQA_OK;
+}
+
+int nqa_set_channel_weights_async(nqa_ctx* ctx, const float* a, const float* b, void* stream) {
+  const int rc = nqa_set_alpha_beta_async(ctx, a, b, stream);
+  if (rc == NQA_OK) ctx->ab_normalize = false;
+  return rc;
+}
+
+// Synchronous forms: the copies run on the legacy default stream (ordered against the context's other streams like
+// every call) and the call returns when they are done, so host buffers may be reused at once.
+int nqa_set_alpha_beta(nqa_ctx* ctx, const float* alpha, const float* beta) {
+  const int rc = nqa_set_alpha_beta_async(ctx, alpha, beta, nullptr);
+  if (rc != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  CUDA_TRY(cudaStreamSynchronize(nullptr));
   return NQA_OK;
 }
 
@@ -984,7 +1132,10 @@ int nqa_dists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H
   if ((rc = check_prec(precision)) != NQA_OK) return rc;
   if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
-  return dists_forward_device(ctx, x, y, B, H, W, precision, score_out, s1s2_out, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
+  return dists_forward_device(ctx, x, y, B, H, W, precision, score_out, s1s2_out, st);
 }
 
 int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W, int precision,
@@ -995,54 +1146,17 @@ int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_hos
   if ((rc = check_prec(precision)) != NQA_OK) return rc;
   if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
-
   const int mb = pick_micro_pairs(ctx, B, H, W);
-  const size_t frame = (size_t)3 * H * W;
-  const size_t slot_floats = 2 * (size_t)mb * frame + (size_t)B;  // x frames, y frames (+ scores in slot 0)
-  if (slot_floats > ctx->stage_cap) {
-    CUDA_TRY(cudaDeviceSynchronize());
-    for (int i = 0; i < 2; ++i) {
-      if (ctx->stage_in[i]) CUDA_TRY(cudaFree(ctx->stage_in[i]));
-      ctx->stage_in[i] = nullptr;
-    }
-    ctx->stage_cap = 0;
-    for (int i = 0; i < 2; ++i)
-      if (cudaMalloc(&ctx->stage_in[i], slot_floats * sizeof(float)) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(NQA_ERR_NOMEM, "staging allocation of %zu bytes failed", slot_floats * sizeof(float));
-      }
-    ctx->stage_cap = slot_floats;
-  }
   const size_t need = precision == NQA_PREC_FP32 ? dists_mb_bytes<float>(ctx, mb, H, W, precision)
                                                  : dists_mb_bytes<bf16>(ctx, mb, H, W, precision);
   if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
-  float* d_scores = ctx->stage_in[0] + 2 * (size_t)mb * frame;
-
-  // The first chunk is small so that the copy/compute pipeline fills quickly (its H2D copy is the only one that is
-  // not hidden behind compute); scores do not depend on the chunking (batch-independent reductions).
-  int it = 0;
-  for (int b0 = 0; b0 < B; ++it) {
-    const int slot = it & 1;
-    const int want = it == 0 ? (mb > 2 ? 2 : mb) : mb;
-    const int pairs = B - b0 < want ? B - b0 : want;
-    float* dx = ctx->stage_in[slot];
-    float* dy = dx + (size_t)mb * frame;
-    if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0));
-    CUDA_TRY(cudaMemcpyAsync(dx, x_host + b0 * frame, pairs * frame * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(dy, y_host + b0 * frame, pairs * frame * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
-    CUDA_TRY(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
-    CUDA_TRY(cudaStreamWaitEvent(ctx->compute_stream, ctx->ev_copied[slot], 0));
-    rc = precision == NQA_PREC_FP32
-             ? dists_micro_batch<float>(ctx, dx, dy, pairs, H, W, precision, d_scores + b0, nullptr, ctx->compute_stream)
-             : dists_micro_batch<bf16>(ctx, dx, dy, pairs, H, W, precision, d_scores + b0, nullptr, ctx->compute_stream);
-    if (rc != NQA_OK) return rc;
-    CUDA_TRY(cudaEventRecord(ctx->ev_consumed[slot], ctx->compute_stream));
-    b0 += pairs;
-  }
-  CUDA_TRY(cudaMemcpyAsync(score_host, d_scores, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, ctx->compute_stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->compute_stream));
-  CUDA_TRY(cudaGetLastError());
-  return NQA_OK;
+  float* outs[1] = {score_host};
+  return host_stream_run(ctx, x_host, y_host, B, H, W, mb, 1, outs,
+                         [&](const float* dx, const float* dy, int pairs, float* const* d_out, cudaStream_t st) {
+                           return precision == NQA_PREC_FP32
+                                      ? dists_micro_batch<float>(ctx, dx, dy, pairs, H, W, precision, d_out[0], nullptr, st)
+                                      : dists_micro_batch<bf16>(ctx, dx, dy, pairs, H, W, precision, d_out[0], nullptr, st);
+                         });
 }
 
 }  // extern "C"
@@ -1084,6 +1198,8 @@ int nqa_dists_features(nqa_ctx* ctx, const float* x, int B, int H, int W, int pr
   if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   rc = precision == NQA_PREC_FP32 ? features_impl<float>(ctx, x, B, H, W, precision, feats_out, st)
                                   : features_impl<bf16>(ctx, x, B, H, W, precision, feats_out, st);
   if (rc != NQA_OK) return rc;
@@ -1103,6 +1219,8 @@ int nqa_dists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS
   if (rc != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   PartialBufs pb;
   const size_t need = partial_bytes(B, H, W, NQA_PREC_FP32, &pb, true);
   if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
@@ -1134,21 +1252,32 @@ static size_t adists_feat_bytes(int pairs, int H, int W, size_t elem = sizeof(fl
   return total + 4096;
 }
 
+static int adists_micro_pairs(const nqa_ctx* ctx, int B, int H, int W) {
+  const int mb = pick_micro_pairs(ctx, B, H, W) / 2;
+  return mb < 1 ? 1 : mb;
+}
+
+template <typename T>
+static size_t adists_need_bytes(const nqa_ctx* ctx, int mb, int H, int W, int window, int prec, bool with_dists) {
+  const bool planes16 = std::is_same<T, bf16>::value && prec == NQA_PREC_BF16;
+  const bool fused_pool = with_dists && prec != NQA_PREC_BF16X3;
+  return trunk_bytes<T>(2 * mb, H, W, prec) + adists_feat_bytes(mb, H, W, planes16 ? sizeof(bf16) : sizeof(float)) +
+         adists_workspace_bytes(mb, H, W, window) + (with_dists ? partial_bytes(mb, H, W, prec, nullptr, false, fused_pool) : 0);
+}
+
 // dists_out != nullptr: the same trunk pass also feeds the DISTS statistics (fused pool + moments kernel), so a
 // scorer that wants both metrics for a batch (prep.py:186-190) runs the VGG trunk once instead of twice.
 template <typename T>
 static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int prec,
-                       float* score_out, float* map_out, cudaStream_t st, float* dists_out = nullptr) {
-  int mb = pick_micro_pairs(ctx, B, H, W) / 2;
-  if (mb < 1) mb = 1;
+                       float* score_out, float* map_out, cudaStream_t st, float* dists_out = nullptr,
+                       const AdistsParts* parts_out = nullptr) {
+  const int mb = adists_micro_pairs(ctx, B, H, W);
   const bool with_dists = dists_out != nullptr;
   const bool fused_pool = with_dists && prec != NQA_PREC_BF16X3;
   // bf16 trunk: the planes the statistics read are bf16 too (exact copies of the activations, half the bytes)
   const bool planes16 = std::is_same<T, bf16>::value && prec == NQA_PREC_BF16;
   const size_t pelem = planes16 ? sizeof(bf16) : sizeof(float);
-  int rc = ensure_arena(ctx, trunk_bytes<T>(2 * mb, H, W, prec) + adists_feat_bytes(mb, H, W, pelem) +
-                                 adists_workspace_bytes(mb, H, W, window) +
-                                 (with_dists ? partial_bytes(mb, H, W, prec, nullptr, false, fused_pool) : 0));
+  int rc = ensure_arena(ctx, adists_need_bytes<T>(ctx, mb, H, W, window, prec, with_dists));
   if (rc != NQA_OK) return rc;
   int lh[kNumLevels], lw[kNumLevels];
   level_dims(H, W, lh, lw);
@@ -1187,7 +1316,7 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
                           const size_t half_out = (size_t)pairs * pooled(h) * pooled(w) * c;
                           ProfScope ps(ctx, NQA_K_POOL_STATS, st);
                           ctx->launches += launch_pool_stats<T>(f, f + half, pooled_dst, pooled_dst + half_out, pairs, h, w, c,
-                                                                pb.chunks[k], pb.p[k], st);
+                                                                pb.chunks[k], pb.p[k], st, ctx->pool_stats_tma);
                           return true;
                         }
                         ProfScope ps(ctx, NQA_K_STATS, st);
@@ -1205,9 +1334,16 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
       fx[k] = planar[k];
       fy[k] = planar[k] + (size_t)pairs * level_channels(k) * lh[k] * lw[k] * pelem;
     }
+    AdistsParts parts;
+    if (parts_out) {   // this micro-batch's slice of the caller's [B, ...] buffers
+      if (parts_out->weights) parts.weights = parts_out->weights + (size_t)b0 * kTotalChannels;
+      if (parts_out->level_terms) parts.level_terms = parts_out->level_terms + (size_t)b0 * kNumLevels;
+      for (int k = 0; k < kNumLevels; ++k)
+        if (parts_out->ps[k]) parts.ps[k] = parts_out->ps[k] + (size_t)b0 * adists_ps_elems(H, W, window, k);
+    }
     ProfScope ps(ctx, NQA_K_ADISTS, st);
     ctx->launches += adists_stage(fx, fy, planes16, pairs, H, W, window, ws, score_out + b0, st,
-                                  map_out ? map_out + (size_t)b0 * H * W : nullptr);
+                                  map_out ? map_out + (size_t)b0 * H * W : nullptr, parts_out ? &parts : nullptr);
   }
   return NQA_OK;
 }
@@ -1237,10 +1373,46 @@ int nqa_adists_map(nqa_ctx* ctx, const float* x, const float* y, int B, int H, i
   if ((rc = check_window(window)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   rc = precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, score_out, map_out, st)
                                   : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, score_out, map_out, st);
   if (rc != NQA_OK) return rc;
   CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_adists_parts(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int precision,
+                     float* score_out, float* weights_out, float* level_terms_out, float* const ps_out[NQA_NUM_LEVELS],
+                     void* stream) {
+  int rc = check_ready(ctx, false);
+  if (rc != NQA_OK) return rc;
+  if (!x || !y || !score_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  if ((rc = check_prec(precision)) != NQA_OK) return rc;
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  if ((rc = check_window(window)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
+  AdistsParts parts;
+  parts.weights = weights_out;
+  parts.level_terms = level_terms_out;
+  for (int k = 0; k < kNumLevels; ++k) parts.ps[k] = ps_out ? ps_out[k] : nullptr;
+  rc = precision == NQA_PREC_FP32
+           ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, score_out, nullptr, st, nullptr, &parts)
+           : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, score_out, nullptr, st, nullptr, &parts);
+  if (rc != NQA_OK) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_adists_ps_elems(int H, int W, int window, int level, size_t* elems) {
+  if (!elems || level < 0 || level >= kNumLevels) return fail(NQA_ERR_INVALID, "bad argument");
+  int rc = check_shape(1, H, W);
+  if (rc != NQA_OK) return rc;
+  if ((rc = check_window(window)) != NQA_OK) return rc;
+  *elems = adists_ps_elems(H, W, window, level);
   return NQA_OK;
 }
 
@@ -1254,11 +1426,53 @@ int nqa_dists_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B
   if ((rc = check_window(window)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   rc = precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, adists_out, nullptr, st, dists_out)
                                   : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, adists_out, nullptr, st, dists_out);
   if (rc != NQA_OK) return rc;
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;
+}
+
+}  // extern "C"
+
+// Host-buffer forms of the two A-DISTS entry points (see nqa_dists_forward_host).
+static int adists_host_impl(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W, int window, int precision,
+                            float* dists_host, float* adists_host) {
+  const bool with_dists = dists_host != nullptr;
+  int rc = check_ready(ctx, with_dists);
+  if (rc != NQA_OK) return rc;
+  if (!x_host || !y_host || !adists_host) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  if ((rc = check_prec(precision)) != NQA_OK) return rc;
+  if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
+  if ((rc = check_window(window)) != NQA_OK) return rc;
+  DeviceGuard guard(ctx->device);
+  const int mb = adists_micro_pairs(ctx, B, H, W);
+  const bool f32 = precision == NQA_PREC_FP32;
+  if ((rc = ensure_arena(ctx, f32 ? adists_need_bytes<float>(ctx, mb, H, W, window, precision, with_dists)
+                                  : adists_need_bytes<bf16>(ctx, mb, H, W, window, precision, with_dists))) != NQA_OK)
+    return rc;
+  float* outs[2] = {adists_host, dists_host};
+  return host_stream_run(ctx, x_host, y_host, B, H, W, mb, with_dists ? 2 : 1, outs,
+                         [&](const float* dx, const float* dy, int pairs, float* const* d_out, cudaStream_t st) {
+                           float* dd = with_dists ? d_out[1] : nullptr;
+                           return f32 ? adists_impl<float>(ctx, dx, dy, pairs, H, W, window, precision, d_out[0], nullptr, st, dd)
+                                      : adists_impl<bf16>(ctx, dx, dy, pairs, H, W, window, precision, d_out[0], nullptr, st, dd);
+                         });
+}
+
+extern "C" {
+
+int nqa_adists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W, int window,
+                            int precision, float* score_host) {
+  return adists_host_impl(ctx, x_host, y_host, B, H, W, window, precision, nullptr, score_host);
+}
+
+int nqa_dists_adists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W, int window,
+                                  int precision, float* dists_host, float* adists_host) {
+  if (!dists_host) return fail(NQA_ERR_INVALID, "null tensor pointer");
+  return adists_host_impl(ctx, x_host, y_host, B, H, W, window, precision, dists_host, adists_host);
 }
 
 int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVELS],
@@ -1273,6 +1487,8 @@ int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVEL
   if ((rc = check_window(window)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   if ((rc = ensure_arena(ctx, adists_workspace_bytes(B, H, W, window) + 4096)) != NQA_OK) return rc;
   ctx->arena.reset();
   void* ws = ctx->arena.take(adists_workspace_bytes(B, H, W, window));
@@ -1297,6 +1513,8 @@ int nqa_dists_backward(nqa_ctx* ctx, const float* x, const float* y, int B, int 
   if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   int mb = pick_micro_pairs(ctx, B, H, W) / 2;
   if (mb < 1) mb = 1;
   const size_t need = precision == NQA_PREC_FP32 ? dists_bwd_bytes<float>(ctx, mb, H, W, precision)
@@ -1326,6 +1544,8 @@ int nqa_dists_forward_saved(nqa_ctx* ctx, const float* x, const float* y, int B,
   if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   *tape_out = 0;
   int mb = pick_micro_pairs(ctx, B, H, W) / 2;
   if (mb < 1) mb = 1;
@@ -1386,6 +1606,8 @@ int nqa_dists_backward_saved(nqa_ctx* ctx, unsigned long long tape_id, const flo
   const Tape tape = *tp;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   const bool f32 = tape.prec == NQA_PREC_FP32;
   const int B = tape.B, H = tape.H, W = tape.W, mb = tape.mb;
   const size_t need = f32 ? bwd_work_bytes<float>(mb, H, W, tape.prec) : bwd_work_bytes<bf16>(mb, H, W, tape.prec);
@@ -1426,6 +1648,8 @@ int nqa_dists_from_feats_backward(nqa_ctx* ctx, const float* const feats_x[NQA_N
   if (rc != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   PartialBufs pb;
   const size_t need = partial_bytes(B, H, W, NQA_PREC_FP32, &pb, true) + align256((size_t)B * kTotalChannels * 5 * sizeof(float)) +
                       align256((size_t)B * 5 * kCoefStride * sizeof(float)) + align256(B * sizeof(float)) + 4096;
@@ -1475,6 +1699,8 @@ int nqa_conv3x3_relu(nqa_ctx* ctx, const float* x, const float* w, const float* 
     return fail(NQA_ERR_SHAPE, "Cin/Cout must be multiples of 64 in [64,512], got %d/%d", Cin, Cout);
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamOrder so(ctx, st);
+  if (so.rc != NQA_OK) return so.rc;
   const size_t nin = (size_t)B * H * W * Cin, nout = (size_t)B * H * W * Cout, nw = (size_t)Cout * Cin * 9;
   const size_t need = 2 * align256(nin * 4) + 2 * align256(nout * 4) + align256(nw * 4) + 2 * align256(nw * 2) + 8192;
   if ((rc = ensure_arena(ctx, need)) != NQA_OK) return rc;
@@ -1499,9 +1725,11 @@ int nqa_conv3x3_relu(nqa_ctx* ctx, const float* x, const float* w, const float* 
     ctx->launches += launch_nchw_to_nhwc<bf16>(x, in_hi, split ? in_lo : nullptr, B, Cin, H, W, st);
     ConvTcPlan plan;
     const char* err = "";
-    if (conv_tc_make_plan(&plan, in_hi, in_lo, w_hi, w_lo, bias, out_hi, out_lo, B, H, W, Cin, Cout, split, &err))
+    if (conv_tc_make_plan(&plan, ctx->conv_cfg, in_hi, in_lo, w_hi, w_lo, bias, out_hi, out_lo, B, H, W, Cin, Cout, split, &err))
       return fail(NQA_ERR_CUDA, "%s", err);
-    ctx->launches += launch_conv3x3_tc(plan, st);
+    const int nl = launch_conv3x3_tc(plan, st);
+    if (nl <= 0) return fail(NQA_ERR_CUDA, "convolution could not be launched (%dx%dx%d, %d -> %d channels)", B, H, W, Cin, Cout);
+    ctx->launches += nl;
     if (split)
       ctx->launches += launch_nhwc_split_to_nchw(out_hi, out_lo, out, B, Cout, H, W, st);
     else

@@ -60,7 +60,7 @@ int launch_pool_stats_tma(const bf16* fx, const bf16* fy, bf16* px_out, bf16* py
                           float* partials, cudaStream_t st);
 template <typename T>
 int launch_pool_stats(const T* fx, const T* fy, T* px_out, T* py_out, int pairs, int h, int w, int c, int chunks,
-                      float* partials, cudaStream_t st);
+                      float* partials, cudaStream_t st, bool allow_tma = true);
 int launch_l2pool_nchw(const float* in, float* out, int n, int c, int h, int w, cudaStream_t st);
 template <typename T>
 int launch_nhwc_to_nchw(const T* in, float* out, int n, int c, int h, int w, cudaStream_t st);
@@ -99,10 +99,23 @@ int launch_conv3x3_f32(const float* in, float* out, const float* wpack, const fl
 
 // tcgen05 implicit-GEMM conv: NHWC bf16 activations, weights [cout][9][cin] bf16 (K-major), fp32 bias.
 // split = bf16x3 mode (hi/lo pairs for activations and weights, three MMAs per k-step).
+// Kernel-selection switches of the tensor-pipe convolutions, read from the environment ONCE per context
+// (nqa_ctx_create) and carried by the context -- nothing about the selection is process-global.
+struct ConvTcConfig {
+  int sm_count = 148;
+  int halo_mode = 1;        // NQA_CONV_HALO: 0 = per-tap kernel everywhere; 1..4 = halo kernel with (halo width, base mode)
+  int halo_max_cin = 512;   // NQA_CONV_HALO_MAXCIN
+  bool n64 = true;          // NQA_CONV_N64: 128 -> 128 channels as two resident 64-channel tiles (halo kernel)
+  bool pair = true;         // NQA_CONV_PAIR: CTA pairs (tcgen05 cta_group::2) for the wide layers
+  int pair_min_cin = 128;   // NQA_PAIR_MINCIN
+};
+ConvTcConfig conv_tc_config_from_env(int sm_count);
+
 struct ConvTcPlan {
   CUtensorMap tmap_a, tmap_a_lo, tmap_b, tmap_b_lo;
   CUtensorMap tmap_out;   // halo kernel: output [n,h,w,cout] with box {64, 8, 16, 1} for the TMA-store epilogue
   int n, h, w, cin, cout;
+  int sm_count;        // persistent-grid size (the context's device)
   int tw_log2;
   int tiles_w, tiles_h;
   int block_n;
@@ -121,13 +134,12 @@ struct ConvTcPlan {
   int fg_nx;
 };
 // Fills the tensor maps; returns 0 on success, nonzero + message on failure.
-int conv_tc_make_plan(ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
-                      const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout, bool split,
-                      const char** err);
+int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in, const bf16* in_lo, const bf16* wk,
+                      const bf16* wk_lo, const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout,
+                      bool split, const char** err);
 int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st);
 int launch_conv3x3_tc_halo(const ConvTcPlan& plan, int sm_count, cudaStream_t st);
 int launch_conv3x3_tc_pair(const ConvTcPlan& plan, int sm_count, cudaStream_t st);
-void conv_tc_set_sm_count(int sms);
 // 4-D SWIZZLE_128B tensor map over NHWC bf16 activations with box {64 channels, box_w, box_h, 1}; 0 on success.
 int conv_tc_make_act_map(CUtensorMap* map, const bf16* ptr, int n, int h, int w, int c, int box_w, int box_h);
 // 2-D SWIZZLE_128B tensor map over K-major weights [cout][k] bf16 with box {64, block_n}; 0 on success.

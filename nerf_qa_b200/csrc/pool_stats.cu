@@ -543,10 +543,9 @@ int pool_stats_chunks(int h, int w, int c, int elem_bytes) {
 
 template <typename T>
 int launch_pool_stats(const T* fx, const T* fy, T* px_out, T* py_out, int pairs, int h, int w, int c, int chunks,
-                      float* partials, cudaStream_t st) {
+                      float* partials, cudaStream_t st, bool allow_tma) {
   if constexpr (std::is_same<T, bf16>::value) {
-    const char* e = getenv("NQA_POOL_STATS_TMA");     // default on; 0 selects the register-fed kernel
-    if (!e || atoi(e) != 0) {
+    if (allow_tma) {   // NQA_POOL_STATS_TMA (per context, default on); off selects the register-fed kernel
       const int rc = launch_pool_stats_tma(fx, fy, px_out, py_out, pairs, h, w, c, chunks, partials, st);
       if (rc > 0) return rc;
     }
@@ -557,8 +556,8 @@ int launch_pool_stats(const T* fx, const T* fy, T* px_out, T* py_out, int pairs,
   pool_stats_kernel<T><<<grid, 256, 0, st>>>(fx, fy, px_out, py_out, h, w, c, pooled(h), pooled(w), r, chunks, partials);
   return 1;
 }
-template int launch_pool_stats<float>(const float*, const float*, float*, float*, int, int, int, int, int, float*, cudaStream_t);
-template int launch_pool_stats<bf16>(const bf16*, const bf16*, bf16*, bf16*, int, int, int, int, int, float*, cudaStream_t);
+template int launch_pool_stats<float>(const float*, const float*, float*, float*, int, int, int, int, int, float*, cudaStream_t, bool);
+template int launch_pool_stats<bf16>(const bf16*, const bf16*, bf16*, bf16*, int, int, int, int, int, float*, cudaStream_t, bool);
 
 // Standalone NCHW fp32 L2pooling (the nn.Module surface): thread = one output element.
 __global__ void __launch_bounds__(256)

@@ -43,10 +43,20 @@ class L2pooling(nn.Module):
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         if not input.is_cuda:
             raise _lib.NerfQAError("L2pooling: CUDA tensor required (no CPU fallback)")
+        _refuse_grad("L2pooling.forward", input)
         idx = input.device.index
         if idx not in self._ctx:
             self._ctx[idx] = _lib.Context(input.device)
         return self._ctx[idx].l2pool(input)
+
+
+def _refuse_grad(what: str, *tensors: torch.Tensor) -> None:
+    """The reference's ops are differentiable everywhere; here only DISTS.forward / forward_from_feats are.  A call
+    that would silently drop out of the autograd graph raises instead."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            f"{what}: gradients are not implemented on this path (nerf_qa_b200 differentiates DISTS.forward and "
+            "DISTS.forward_from_feats); call it under torch.no_grad() or detach the inputs")
 
 
 def build_vgg_stages(module: nn.Module, pool_cls) -> None:
@@ -113,15 +123,36 @@ class _TrunkModule(nn.Module):
             ctx = _lib.Context(torch.device("cuda", idx))
             self._contexts[idx] = ctx
         ws, bs = conv_parameters(self)
-        key = tuple((p.data_ptr(), p._version) for p in ws + bs)
+        # (address, version counter) of the 26 tensors: catches .to(), load_state_dict, optimizer steps and in-place ops on
+        # the parameters.  In-place writes through `.data` (p.data.copy_(...)) bump no counter: call invalidate_weights().
+        key = (self._weights_epoch,) + tuple((p.data_ptr(), p._version) for p in ws + bs)
         if ctx.weights_key != key:
             ctx.set_vgg_weights(ws, bs)
             ctx.weights_key = key
         return ctx
 
+    _weights_epoch = 0
+
+    def invalidate_weights(self) -> None:
+        """Forces the next call to re-upload (and re-pack) the VGG weights.  Needed only after writing conv weights
+        through ``.data`` in place, which torch's version counters do not see; ``load_state_dict``, ``.to()`` and ordinary
+        in-place ops are detected (and call this too)."""
+        self._weights_epoch += 1
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_weights()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_weights()
+        return out
+
     def forward_once(self, x: torch.Tensor) -> List[torch.Tensor]:
         """[x, relu1_2, relu2_2, relu3_3, relu4_3, relu5_3] as NCHW fp32 (DISTS_pt.py:91-103, ADISTS.py:112-125).
         Level 0 is the RAW input, not the normalised tensor."""
+        _refuse_grad("forward_once", x)
         ctx = self._context(x.device)
         return [x] + ctx.features(x, self._prec())
 
@@ -248,11 +279,9 @@ class DISTS(_TrunkModule):
     _squeeze_score = False      # DISTS_pt_original returns score.squeeze() (0-d for B = 1)
 
     def _sync_alpha_beta(self, ctx: _lib.Context) -> None:
-        key = (self.alpha.data_ptr(), self.alpha._version, self.beta.data_ptr(), self.beta._version)
-        if ctx.ab_key != key:
-            ctx.set_alpha_beta(self.alpha, self.beta)
-            ctx.ab_key = key
-
+        # every call, like the reference reads the live parameters (2 x 5.9 KB, stream-ordered): `.data` edits such as
+        # project_weights() or a checkpoint copy are never missed
+        ctx.set_alpha_beta(self.alpha, self.beta)
 
     # -- scoring ---------------------------------------------------------------------------------
     def forward(self, x, y, require_grad: bool = False, batch_average: bool = False, warp=None, certainty=None):
@@ -316,6 +345,15 @@ class DISTS(_TrunkModule):
         ctx = self._context(dev)
         self._sync_weights_nograd(ctx)
         return ctx.dists_forward_host(x, y, self._prec())
+
+    def score_with_adists_host(self, x: torch.Tensor, y: torch.Tensor, window_size: int = 21,
+                               device: Optional[torch.device] = None):
+        """``score_with_adists`` from HOST frames: (DISTS [B], A-DISTS [B]) as CPU tensors, frames streamed to the GPU
+        in micro-batches overlapped with compute (the whole per-batch body of prep.py:181-190)."""
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        ctx = self._context(dev)
+        self._sync_weights_nograd(ctx)
+        return ctx.dists_adists_forward_host(x, y, window_size, self._prec())
 
 
 class _FlavourConfig:

@@ -83,3 +83,26 @@ def test_pooling_and_correlations():
     a = r.rand(20); b = a + 0.1 * r.rand(20)
     c = O.correlations(a, b)
     assert 0.5 < c["srcc"] <= 1 and 0.5 < c["plcc"] <= 1 and 0.3 < c["ktcc"] <= 1
+
+
+def test_oracle_matches_reference_at_1080p(golden, vgg_weights, alpha_beta):
+    """The benchmarked shape (BASELINE configs[1] / [2]): one 1920x1080 pair, every A-DISTS level windowed.  The fixture
+    is what the unmodified reference DISTS / ADISTS modules return (tests/golden/make_golden_1080p.py)."""
+    g = golden("pair_1080p")
+    x, y = _inputs(g)
+    np.testing.assert_allclose([float(x.double().sum()), float(y.double().sum())], g["input_checksum"], rtol=1e-9)
+    ws, bs = vgg_weights
+    a, b = alpha_beta
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        fx, fy = O.trunk(x, ws, bs), O.trunk(y, ws, bs)
+        sd = O.dists_from_feats(fx, fy, a, b)
+        sa, ps, wts, terms = O.adists_from_feats(fx, fy, return_parts=True)
+    np.testing.assert_allclose(sd.numpy(), g["dists_f32"], rtol=5e-5, atol=2e-7)
+    np.testing.assert_allclose(sa.numpy(), g["adists_f32"], rtol=1e-4, atol=5e-7)
+    np.testing.assert_allclose(torch.stack(terms, 1).numpy(), g["adists_level_terms"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(wts.squeeze(-1).numpy(), g["adists_weights"], rtol=1e-5, atol=1e-9)
+    assert [list(p.shape) for p in ps] == g["ps_shapes"].tolist()
+    np.testing.assert_allclose(ps[5].numpy(), g["ps_level5"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(ps[3].numpy(), g["ps_level3"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(ps[1][..., ::8, ::8].numpy(), g["ps_level1_dec8"], rtol=1e-4, atol=1e-5)
