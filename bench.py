@@ -1,24 +1,36 @@
 #!/usr/bin/env python
 """Benchmark of the DISTS / A-DISTS frame-pair hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dists|adists] [--precision bf16|bf16x3|fp32]
-    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # headline line (driver contract)
+    python bench.py --workload dists|adists|train|both|video|latency    # one workload
+    python bench.py --impl reference ...                                 # the reference's CPU path (oracle port)
 
 A "step" is one pass of the hot path over one batch of synthetic frame pairs:
-  dists  (default, BASELINE configs[1]): DISTS on 64 synthetic 1920x1080 frame pairs per GPU;
-  adists (configs[2]):                   A-DISTS on 32 synthetic 1920x1080 frame pairs per GPU.
-With N > 1 (torchrun) every rank scores its own batch (weak scaling, frames are independent) and the
-per-frame scores are all-gathered once per step -- the only collective on this path.
+  dists   (BASELINE configs[1]): DISTS on 64 synthetic 1920x1080 frame pairs per GPU;
+  adists  (configs[2]):          A-DISTS on 32 synthetic 1920x1080 frame pairs per GPU;
+  train   (configs[4]):          DISTS forward + backward (require_grad=True) on 32 512x512 crop pairs per GPU;
+  both:                          DISTS and A-DISTS of 32 1080p pairs from ONE trunk pass (prep.py:186-190);
+  video   (configs[3]):          8 scenes x 300 frames at 1080p, both metrics, frames sharded round-robin over the ranks
+                                 (STRONG scaling), one score gather, per-video temporal pooling;
+  latency:                       the reference's own call pattern, 256x256 frames at batch 1 / 4 / 32 (settings.py:1,
+                                 prep.py:163), microseconds per call.
+The default (no --workload) is the headline: the line is the `dists` workload -- the configuration the metric is quoted
+on that fits one GPU -- and carries the second half of the metric and the training configuration as extra keys
+(`adists`, `train`), each with its own value / ms_per_step / roofline / e2e / cpu_baseline.
 
-One JSON line is printed by rank 0.  `value` is whole-job frame-pairs/s with inputs resident in HBM
-(CUDA events, max over ranks); `e2e` is the same metric through the host-buffer C-ABI call with the
-H2D copies of the frames and the D2H read of the scores inside the timed region; `roofline` is the
-dominant kernel family (the tcgen05 convolutions) from CUDA events recorded around every launch during
-the timed region; `cpu_baseline` is the oracle port of the reference timed on the host cores.
+With N > 1 (torchrun) every rank scores its own batch (weak scaling, frames are independent) and the per-frame scores
+are all-gathered once per step -- the only collective on this path.
+
+`value` is whole-job frame-pairs/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` is the same metric
+through the host-buffer C-ABI call with the H2D copies of the frames and the D2H read of the scores inside the timed
+region; `roofline` describes the kernel family with the LARGEST share of the step, from CUDA events recorded around
+every launch during the timed region (the other families sit under `roofline_other`); `cpu_baseline` is the oracle port
+of the reference timed on the host cores.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,40 +46,122 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-H, W = 1080, 1920
 WORKLOADS = {
-    "dists": dict(pairs=64, metric="dists_1080p_frame_pairs_per_sec",
+    "dists": dict(pairs=64, metric="dists_1080p_frame_pairs_per_sec", hw=(1080, 1920), model="dists",
                   desc="DISTS batch of 64 synthetic 1920x1080 frame pairs per GPU (BASELINE configs[1])"),
-    "adists": dict(pairs=32, metric="adists_1080p_frame_pairs_per_sec",
+    "adists": dict(pairs=32, metric="adists_1080p_frame_pairs_per_sec", hw=(1080, 1920), model="adists",
                    desc="A-DISTS batch of 32 synthetic 1920x1080 frame pairs per GPU (BASELINE configs[2])"),
-    "train": dict(pairs=32, metric="dists_512_fwd_bwd_frame_pairs_per_sec", hw=(512, 512),
+    "both": dict(pairs=32, metric="dists_and_adists_1080p_frame_pairs_per_sec", hw=(1080, 1920), model="dists",
+                 desc="DISTS + A-DISTS of 32 synthetic 1920x1080 frame pairs per GPU from one trunk pass "
+                      "(the per-batch body of prep.py:186-190)"),
+    "train": dict(pairs=32, metric="dists_512_fwd_bwd_frame_pairs_per_sec", hw=(512, 512), model="dists",
                   desc="DISTS forward+backward (require_grad=True) on 32 synthetic 512x512 crop pairs per GPU "
                        "(BASELINE configs[4]); a step = scores + d(mean score)/d frames"),
 }
-# algorithmic work per 1080p frame PAIR
-TRUNK_FLOP_PER_PAIR = 2.5386e12
+CHNS = (3, 64, 128, 256, 512, 512)
+WINDOW = 21
 
 
-def load_conv_traffic():
-    """DRAM bytes per launch of the trunk-convolution family from the committed `ncu --set full` capture of the same
-    bench command (profiles/r1z_ncu_full_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of every
-    stage1 / pair / halo kernel of one 16-frame micro-batch, averaged over those launches)."""
-    path = os.path.join(ROOT, "profiles", "r1z_ncu_full_summary.json")
+# ---------------------------------------------------------------------------------------------------
+# algorithmic work per frame pair (DESIGN.md section 4 states the same figures)
+# ---------------------------------------------------------------------------------------------------
+def level_dims(h, w):
+    dims = [(h, w), (h, w)]
+    for _ in range(4):
+        h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        dims.append((h, w))
+    return dims
+
+
+def trunk_flop_per_pair(h, w):
+    """2 * 9 * Cin * Cout * H_l * W_l over the 13 convolutions, two images (2.5386 TFLOP at 1080p)."""
+    convs = [(3, 64, 1), (64, 64, 1), (64, 128, 2), (128, 128, 2), (128, 256, 3), (256, 256, 3), (256, 256, 3),
+             (256, 512, 4), (512, 512, 4), (512, 512, 4), (512, 512, 5), (512, 512, 5), (512, 512, 5)]
+    d = level_dims(h, w)
+    return 2.0 * sum(2.0 * 9 * ci * co * d[l][0] * d[l][1] for ci, co, l in convs)
+
+
+def level_elems(h, w, levels=range(1, 6)):
+    d = level_dims(h, w)
+    return sum(CHNS[k] * d[k][0] * d[k][1] for k in levels)
+
+
+def window_fma_per_pair(h, w, window=WINDOW):
+    """Separable local-window statistics: five filtered maps (x, y, x^2, y^2, xy) per channel, window taps per pass,
+    two passes, per OUTPUT pixel of every windowed level (ADISTS.py:165-175; the two extra maps of compute_prob,
+    ADISTS.py:75-80, follow from the same five)."""
+    d = level_dims(h, w)
+    out = sum(CHNS[k] * (d[k][0] - window + 1) * (d[k][1] - window + 1) for k in range(6)
+              if d[k][0] >= window and d[k][1] >= window)
+    return 5.0 * 2 * window * out
+
+
+def family_models(workload, h, w, precision, train_recompute=False):
+    """family -> (bound, algorithmic work per frame pair, unit of the work).  bf16 activations are 2 bytes."""
+    eb = 4 if precision == "fp32" else 2
+    hw = h * w
+    fl = trunk_flop_per_pair(h, w)
+    pooled_in = 2 * level_elems(h, w, range(1, 5)) * eb
+    d = level_dims(h, w)
+    pooled_out = 2 * sum(CHNS[k] * d[k + 1][0] * d[k + 1][1] for k in range(1, 5)) * eb   # C_k channels at level k+1's size
+    m = {
+        # fused stage 1 + the 11 other convolutions (+ the 13 data-gradient convolutions of a training step; + a second
+        # forward when the backward recomputes activations instead of using the tape)
+        "conv": ("tensor", fl * ((3.0 if train_recompute else 2.0) if workload == "train" else 1.0), "flop"),
+        "pool_stats": ("hbm", pooled_in + pooled_out, "bytes"),          # levels 1-4 read once, pooled tensors written
+        "l2pool": ("hbm", pooled_in + pooled_out, "bytes"),
+        "stats": ("hbm", 2 * 3 * hw * 4 + 2 * CHNS[5] * level_dims(h, w)[5][0] * level_dims(h, w)[5][1] * eb, "bytes"),
+        "layout": ("hbm", 2 * 2 * level_elems(h, w) * eb, "bytes"),       # NHWC -> planes: read + write of levels 1-5
+        # channel sums read x and y, the entropy pass reads x again (levels 1-5 at eb bytes, level 0 fp32)
+        "adists": ("hbm", 3 * level_elems(h, w) * eb + 3 * 3 * hw * 4, "bytes"),
+        "adists_window": ("fma", window_fma_per_pair(h, w), "fma"),
+    }
+    return m
+
+
+def window_bytes_per_pair(h, w, precision):
+    eb = 4 if precision == "fp32" else 2
+    return 2 * level_elems(h, w) * eb + 2 * 3 * h * w * 4
+
+
+def csrc_sha16():
+    """Fingerprint of the kernel sources; ncu captures under profiles/ record it so that a stale capture is not quoted."""
+    hsh = hashlib.sha256()
+    d = os.path.join(ROOT, "nerf_qa_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, name), "rb") as f:
+                hsh.update(name.encode())
+                hsh.update(f.read())
+    return hsh.hexdigest()[:16]
+
+
+def load_traffic(kernel_substrings):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the named kernels from the newest
+    committed `ncu --set full` summary WHOSE SOURCE FINGERPRINT MATCHES this checkout; None otherwise."""
+    pdir = os.path.join(ROOT, "profiles")
+    sha = csrc_sha16()
+    best = None
     try:
-        with open(path) as f:
-            d = json.load(f)
-        cols = d["columns"]
-        kn, rd, wr = cols.index("Kernel Name"), cols.index("dram__bytes_read.sum"), cols.index("dram__bytes_write.sum")
-        rows = [r for r in d["rows"] if any(t in r[kn] for t in ("stage1_fused", "conv3x3_tc_pair", "conv3x3_tc_halo"))]
-        # the capture covers a little more than one micro-batch: keep the first 12 conv launches (1 fused + 11)
-        rows = rows[:12]
-        if len(rows) < 12:
-            return None
-        total_gb = sum(float(r[rd]) + float(r[wr]) for r in rows)
-        return {"bytes_per_launch": total_gb * 1e9 / len(rows), "launches_in_capture": len(rows),
-                "source": "profiles/r1z_ncu_full_summary.json (ncu --set full, bench.py --pairs 8, 16 frames per launch)"}
-    except Exception:
+        names = sorted(n for n in os.listdir(pdir) if n.endswith("_ncu_full_summary.json"))
+    except OSError:
         return None
+    for name in names:
+        try:
+            with open(os.path.join(pdir, name)) as f:
+                d = json.load(f)
+            if d.get("csrc_sha16") != sha:
+                continue
+            cols = d["columns"]
+            kn, rd, wr = cols.index("Kernel Name"), cols.index("dram__bytes_read.sum"), cols.index("dram__bytes_write.sum")
+            rows = [r for r in d["rows"] if any(t in r[kn] for t in kernel_substrings)]
+            if rows:
+                scale = 1e9 if d.get("dram_unit", "Gbyte") == "Gbyte" else 1.0
+                best = {"bytes_per_launch": sum(float(r[rd]) + float(r[wr]) for r in rows) * scale / len(rows),
+                        "launches_in_capture": len(rows), "source": f"profiles/{name}"}
+        except Exception:
+            continue
+    return best
 
 
 def load_peaks():
@@ -123,36 +217,48 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_frames_device(pairs: int, device, seed: int = 0, H: int = H, W: int = W):
+def _smooth(n, h, w, g, device):
+    import torch.nn.functional as F
+    r = torch.rand(n, 3, h, w, generator=g, device=device)
+    r = F.avg_pool2d(F.pad(r, (4, 4, 4, 4), mode="reflect"), 9, stride=1)
+    lo, hi = r.amin(dim=(1, 2, 3), keepdim=True), r.amax(dim=(1, 2, 3), keepdim=True)
+    return (r - lo) / (hi - lo)
+
+
+def _distort(ref, kind, g, device):
+    import torch.nn.functional as F
+    if kind == 0:
+        d = ref + 0.05 * torch.randn(ref.shape, generator=g, device=device)
+    elif kind == 1:
+        d = ref + 0.2 * torch.randn(ref.shape, generator=g, device=device)
+    elif kind == 2:
+        d = F.avg_pool2d(F.pad(ref[None], (3, 3, 3, 3), mode="reflect"), 7, stride=1)[0]
+    elif kind == 3:
+        d = torch.roll(ref, 5, dims=2)
+    else:
+        d = _smooth(1, ref.shape[1], ref.shape[2], g, device)[0]
+    return d.clamp(0, 1)
+
+
+def make_frames_device(pairs: int, device, seed: int = 0, H: int = 1080, W: int = 1920):
     """Synthetic "NeRF-like" frames generated on the device: box-blurred noise + the five distortion
     types of nerf_qa_b200.synth, 8 distinct pairs tiled to the batch."""
-    import torch.nn.functional as F
     g = torch.Generator(device=device).manual_seed(seed)
     distinct = min(8, pairs)
-
-    def smooth(n):
-        r = torch.rand(n, 3, H, W, generator=g, device=device)
-        r = F.avg_pool2d(F.pad(r, (4, 4, 4, 4), mode="reflect"), 9, stride=1)
-        lo, hi = r.amin(dim=(1, 2, 3), keepdim=True), r.amax(dim=(1, 2, 3), keepdim=True)
-        return (r - lo) / (hi - lo)
-
-    ref = smooth(distinct)
+    ref = _smooth(distinct, H, W, g, device)
     dist = torch.empty_like(ref)
     for i in range(distinct):
-        k = i % 5
-        if k == 0:
-            d = ref[i] + 0.05 * torch.randn(ref[i].shape, generator=g, device=device)
-        elif k == 1:
-            d = ref[i] + 0.2 * torch.randn(ref[i].shape, generator=g, device=device)
-        elif k == 2:
-            d = F.avg_pool2d(F.pad(ref[i:i + 1], (3, 3, 3, 3), mode="reflect"), 7, stride=1)[0]
-        elif k == 3:
-            d = torch.roll(ref[i], 5, dims=2)
-        else:
-            d = smooth(1)[0]
-        dist[i] = d.clamp(0, 1)
+        dist[i] = _distort(ref[i], i % 5, g, device)
     reps = (pairs + distinct - 1) // distinct
     return ref.repeat(reps, 1, 1, 1)[:pairs].contiguous(), dist.repeat(reps, 1, 1, 1)[:pairs].contiguous()
+
+
+def make_video_frame(scene: int, frame: int, device, H: int = 1080, W: int = 1920):
+    """One (reference, render) pair of the synthetic video set, a pure function of (scene, frame): any rank can
+    regenerate any frame, which is how the gathered scores are cross-checked."""
+    g = torch.Generator(device=device).manual_seed(scene * 1000 + frame)
+    ref = _smooth(1, H, W, g, device)[0]
+    return ref, _distort(ref, (scene + frame) % 5, g, device)
 
 
 def build_model(kind: str, precision: str, device):
@@ -170,9 +276,12 @@ def build_model(kind: str, precision: str, device):
     return m.to(device).eval()
 
 
-def cpu_reference_pairs_per_sec(kind: str, steps: int, warmup: int):
+# ---------------------------------------------------------------------------------------------------
+# the reference's CPU path (the one place besides tests/ and smoke() that executes oracle/)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_pairs_per_sec(kind: str, steps: int, warmup: int, hw=(1080, 1920)):
     """The reference's CPU path (oracle port: same ATen ops, all host threads) on a bounded sample:
-    one 1080p frame pair per step."""
+    one frame pair per step."""
     from nerf_qa_b200 import synth
     from oracle import reference_oracle as O
     cores = os.cpu_count() or 1
@@ -180,9 +289,13 @@ def cpu_reference_pairs_per_sec(kind: str, steps: int, warmup: int):
     ws, bs = synth.make_vgg_weights(1234)
     ab = np.load(os.path.join(ROOT, "nerf_qa_b200", "data", "dists_alpha_beta.npy"))
     a, b = torch.from_numpy(ab[0].copy()), torch.from_numpy(ab[1].copy())
-    x, y = synth.make_frame_pairs(1, H, W, seed=0)
+    x, y = synth.make_frame_pairs(1, hw[0], hw[1], seed=0)
 
     def step():
+        if kind == "train":
+            xg, yg = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+            O.dists_score(xg, yg, ws, bs, a, b).mean().backward()
+            return xg.grad
         with torch.no_grad():
             return O.dists_score(x, y, ws, bs, a, b) if kind == "dists" else O.adists_score(x, y, ws, bs)
 
@@ -195,21 +308,32 @@ def cpu_reference_pairs_per_sec(kind: str, steps: int, warmup: int):
     return 1.0 / dt, dt, cores
 
 
+def cpu_baseline_block(kind, hw):
+    n, wu = (2, 1) if kind == "dists" else (1, 0) if kind == "adists" else (2, 1)
+    pps, _, cores = cpu_reference_pairs_per_sec(kind, n, wu, hw)
+    what = {"dists": "DISTS", "adists": "A-DISTS", "train": "DISTS forward + autograd backward"}[kind]
+    return {"value": pps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{n} timed {hw[1]}x{hw[0]} frame pair(s) of {what}, one per step, oracle port of the reference "
+                      f"(torch CPU fp32, {cores} threads)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload]
-    # a 1080p pair costs ~5-30 s of CPU: bound the run to a few minutes whatever K/W the driver passes
-    steps = max(1, min(args.steps, 6 if args.workload == "dists" else 2))
+    name = args.workload or "dists"
+    kind = "adists" if name == "adists" else "train" if name == "train" else "dists"
+    wl = WORKLOADS.get(name, WORKLOADS["dists"])
+    # a 1080p pair costs ~3-30 s of CPU: bound the run to a few minutes whatever K/W the driver passes
+    steps = max(1, min(args.steps, 6 if kind != "adists" else 2))
     warmup = max(0, min(args.warmup, 1))
-    pps, dt, cores = cpu_reference_pairs_per_sec(args.workload, steps, warmup)
-    sample = f"1 synthetic 1920x1080 frame pair per step, {steps} timed steps, {warmup} warm-up, torch CPU fp32"
+    pps, dt, cores = cpu_reference_pairs_per_sec(kind, steps, warmup, wl["hw"])
+    sample = f"1 synthetic {wl['hw'][1]}x{wl['hw'][0]} frame pair per step, {steps} timed steps, {warmup} warm-up, torch CPU fp32"
     line = {
         "impl": "reference", "metric": wl["metric"], "value": pps, "unit": "frame-pairs/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "resolution": "1920x1080", "pairs_per_step": 1,
+        "config": {"workload": wl["desc"], "resolution": f"{wl['hw'][1]}x{wl['hw'][0]}", "pairs_per_step": 1,
                    "note": "reference CPU path = oracle/reference_oracle.py (torch-CPU port pinned to the reference "
                            "modules by tests/golden); the reference itself is pure Python and cannot be pip-installed "
                            "offline (needs torchvision ImageNet weights download)"},
@@ -217,54 +341,152 @@ def run_reference_arm(args):
         "e2e": {"value": pps, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.workload is None:      # headline: the second half of the metric beside it, like the b200 arm
+        apps, adt, _ = cpu_reference_pairs_per_sec("adists", 1, 0, WORKLOADS["adists"]["hw"])
+        line["adists"] = {"metric": WORKLOADS["adists"]["metric"], "value": apps, "unit": "frame-pairs/s",
+                          "ms_per_step": adt * 1e3,
+                          "cpu_baseline": {"value": apps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+                                           "sample": "1 timed 1920x1080 frame pair of A-DISTS, torch CPU fp32"},
+                          "e2e": {"value": apps, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dists", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
-    ap.add_argument("--pairs", type=int, default=0, help="override frame pairs per GPU per step")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
+# ---------------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------------
+class Env:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (nerf_qa_b200 has no CPU fallback)")
+        self.device = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(self.device)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.device)
+        self.peaks = load_peaks()
+        self.rates = {}
+        self.models = {}
+        self.args = args
 
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
 
-    import torch.distributed as dist
-    from nerf_qa_b200 import _lib
+    def model(self, kind, precision):
+        key = (kind, precision)
+        if key not in self.models:
+            self.models[key] = build_model(kind, precision, self.device)
+        return self.models[key]
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (nerf_qa_b200 has no CPU fallback)")
-    device = torch.device("cuda", local_rank)
-    torch.cuda.set_device(device)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+    def rate(self, ctx, which):
+        if which not in self.rates:
+            self.rates[which] = ctx.measure_rate(which)
+        return self.rates[which]
 
-    wl = WORKLOADS[args.workload]
+    def max_over_ranks(self, v: float) -> float:
+        t = torch.tensor([v], device=self.device, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v: float) -> float:
+        t = torch.tensor([v], device=self.device, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def rooflines(env, ctx, name, prof, steps, pairs, h, w, precision):
+    """One roofline entry per kernel family that ran, from the live per-family CUDA-event times; the family with the
+    largest share of the step first."""
+    fams = {}
+    conv_ms = sum(prof[k][0] for k in ("conv_tc", "stage1", "conv1_1", "conv_f32") if k in prof)
+    conv_n = sum(prof[k][1] for k in ("conv_tc", "stage1", "conv1_1", "conv_f32") if k in prof)
+    merged = {"conv": (conv_ms, conv_n)}
+    for k in ("pool_stats", "l2pool", "stats", "layout", "adists", "adists_window", "backward", "finalize"):
+        if k in prof and prof[k][1]:
+            merged[k] = prof[k]
+    total_ms = sum(v[0] for v in merged.values())
+    recompute = os.environ.get("NQA_TAPE_MAX_MB") == "0"
+    models = family_models(name, h, w, precision, recompute)
+    hbm = env.peaks["hbm_gbs"]
+    for fam, (ms, n) in merged.items():
+        if not n or ms <= 0 or fam not in models:
+            continue
+        bound, work, unit = models[fam]
+        per_s = work * pairs * steps / (ms / 1e3)
+        e = {"family": fam, "bound": bound, "avg_launch_ms": ms / n, "launches": int(n),
+             "share_of_step": ms / total_ms if total_ms > 0 else None}
+        if bound == "tensor":
+            peak = env.peaks["bf16_tflops_sustained"] if precision != "fp32" else None
+            e.update(kernel="VGG16 trunk convolutions on tcgen05: stage1_fused_kernel (normalise + conv1_1 + conv1_2) + "
+                            "conv3x3_tc_pair / conv3x3_tc_halo kernels, bias + ReLU fused"
+                            + ("; forward + 13 data-gradient convolutions" if name == "train" else ""),
+                     achieved=per_s / 1e12, peak=peak, unit="TFLOP/s", frac=(per_s / 1e12 / peak) if peak else None,
+                     peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({env.peaks['source']}); kernel timed inside a long step",
+                     algorithmic_flop_per_launch=work * pairs * steps / n,
+                     issued_mma_flop_factor=3.0 if precision == "bf16x3" else 1.0)
+            if name == "train":
+                e["flop_note"] = ("forward + recomputed forward + data gradients (3x)" if recompute
+                                  else "forward + data gradients of the 13 convolutions (2x forward); no weight gradients (frozen trunk)")
+        elif bound == "hbm":
+            e.update(kernel={"pool_stats": "pool_stats_tma_kernel: L2pooling + DISTS moments of levels 1-4 in one read",
+                             "l2pool": "l2pool_nhwc_kernel", "stats": "stats_planar / stats_nhwc (levels 0 and 5)",
+                             "layout": "nhwc_to_planes_bf16_kernel (A-DISTS feature planes)",
+                             "adists": "A-DISTS channel sums + entropy weights + ps chain"}.get(fam, fam),
+                     achieved=per_s / 1e9, peak=hbm, unit="GB/s", frac=per_s / 1e9 / hbm,
+                     peak_source=f"MEASURED_PEAKS.json hbm_gbs ({env.peaks['source']})",
+                     algorithmic_bytes_per_launch=work * pairs * steps / n)
+        else:   # the A-DISTS window kernels: CUDA-core FMAs (fp32 planes) or warp-level MMAs (bf16 planes)
+            fma_peak = env.rate(ctx, "fp32_fma")
+            gbs = window_bytes_per_pair(h, w, precision) * pairs * steps / (ms / 1e3) / 1e9
+            e.update(kernel="A-DISTS local-window statistics (adists.cu window_kernel / adists_tc.cu window_mma_kernel): "
+                            "five 21x21 gaussian-filtered maps per channel + T/S/gamma, reduced over channels on the fly",
+                     achieved=per_s / 1e12, peak=fma_peak / 1e12, unit="TFMA/s", frac=per_s / fma_peak,
+                     peak_source="nqa_measure_rate(NQA_RATE_FP32_FMA): packed fp32 FMAs measured on this GPU in this run; "
+                                 "a value above 1 means the filters run on the tensor pipe (see mma_sync_peak)",
+                     algorithmic_fma_per_launch=work * pairs * steps / n,
+                     hbm={"achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                          "algorithmic_bytes_per_launch": window_bytes_per_pair(h, w, precision) * pairs * steps / n},
+                     mma_sync_peak={"value": env.rate(ctx, "mma_sync_bf16") / 1e12, "unit": "TFMA/s",
+                                    "source": "nqa_measure_rate(NQA_RATE_MMA_SYNC_BF16), this run"})
+        e["traffic"] = None
+        fams[fam] = e
+    order = sorted(fams.values(), key=lambda e: -(e["share_of_step"] or 0))
+    if order:
+        top = order[0]
+        subs = {"conv": ("stage1_fused", "conv3x3_tc_pair", "conv3x3_tc_halo"), "pool_stats": ("pool_stats",),
+                "adists_window": ("window_",), "layout": ("nhwc_to_planes",)}.get(top["family"])
+        tr = load_traffic(subs) if (subs and precision == "bf16" and h == 1080) else None
+        if tr:
+            top["traffic"] = tr["bytes_per_launch"]
+            top["traffic_source"] = tr["source"] + " (ncu --set full of this checkout's kernels: csrc_sha16 matches)"
+    return order
+
+
+def run_batch_workload(env, name, args, steps, warmup):
+    """dists / adists / both / train: `pairs` frame pairs per GPU per step."""
+    from nerf_qa_b200 import _lib  # noqa: F401
+    wl = WORKLOADS[name]
+    precision = args.precision
     pairs = args.pairs or wl["pairs"]
-    steps, warmup = args.steps, max(args.warmup, 3)
-    peaks = load_peaks()
-    H, W = wl.get("hw", (1080, 1920))
-    train = args.workload == "train"
-
-    model = build_model("adists" if args.workload == "adists" else "dists", args.precision, device)
+    H, W = wl["hw"]
+    train = name == "train"
+    world, rank, device, dist = env.world, env.rank, env.device, env.dist
+    model = env.model("adists" if name == "adists" else "dists", precision)
     x, y = make_frames_device(pairs, device, seed=rank, H=H, W=W)
     if train:
         x.requires_grad_(True)
         y.requires_grad_(True)
     ctx = model._context(device)
-    gathered = torch.empty(world * pairs, device=device, dtype=torch.float32) if world > 1 else None
+    n_out = 2 if name == "both" else 1
+    gathered = torch.empty(world * n_out * pairs, device=device, dtype=torch.float32) if world > 1 else None
 
     def step():
         if train:
@@ -274,24 +496,24 @@ def main():
             s = s.detach()
         else:
             with torch.no_grad():
-                s = model(x, y) if args.workload == "dists" else model(x, y, as_loss=False)
+                if name == "dists":
+                    s = model(x, y)
+                elif name == "adists":
+                    s = model(x, y, as_loss=False)
+                else:
+                    s = torch.cat(model.score_with_adists(x, y))
         if world > 1:
             dist.all_gather_into_tensor(gathered, s)     # the path's one collective: per-frame score gather
             return gathered
         return s
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(warmup):
         scores = step()
-    barrier()
+    env.barrier()
     if not bool(torch.isfinite(scores).all()):
-        raise SystemExit("bench.py: non-finite scores")
+        raise SystemExit(f"bench.py: non-finite scores in workload {name}")
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(env.local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
@@ -299,102 +521,245 @@ def main():
     ctx.profile_read()
     ctx.profile_enable(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    env.barrier()
     ev0.record()
     for _ in range(steps):
         scores = step()
     ev1.record()
-    barrier()
+    env.barrier()
     ctx.profile_enable(False)
     prof = ctx.profile_read()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
-    lsum = torch.tensor([float(launches)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
-    ms_step = float(ms_total.item()) / steps
+    ms_step = env.max_over_ranks(ev0.elapsed_time(ev1)) / steps
+    lsum = env.sum_over_ranks(float(launches))
     value = world * pairs / (ms_step / 1e3)
 
     # ---- end to end through the host-buffer C-ABI call (H2D of the frames + D2H of the scores inside) ----
     e2e = None
-    if args.workload == "dists" and not args.no_e2e:
+    if not train and not args.no_e2e:
         xh, yh = x.detach().cpu().pin_memory(), y.detach().cpu().pin_memory()
-        out = torch.empty(pairs, dtype=torch.float32).pin_memory()
-        model.score_host(xh, yh, device)                     # warm-up (staging buffers)
-        barrier()
+        outs = [torch.empty(pairs, dtype=torch.float32).pin_memory() for _ in range(n_out)]
+        if name == "dists":
+            call, api = (lambda: ctx.dists_forward_host(xh, yh, model._prec(), out=outs[0])), \
+                "DISTS.score_host -> nqa_dists_forward_host"
+        elif name == "adists":
+            call, api = (lambda: ctx.adists_forward_host(xh, yh, WINDOW, model._prec(), out=outs[0])), \
+                "ADISTS.score_host -> nqa_adists_forward_host"
+        else:
+            call, api = (lambda: ctx.dists_adists_forward_host(xh, yh, WINDOW, model._prec(), out=outs)), \
+                "DISTS.score_with_adists_host -> nqa_dists_adists_forward_host"
+        if name != "adists":
+            model._sync_weights_nograd(ctx)
+        call()                                               # warm-up (staging buffers)
+        env.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            ctx.dists_forward_host(xh, yh, model._prec(), out=out)
+            call()
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * pairs * steps / float(dt.item()), "unit": "frame-pairs/s",
-               "h2d_bytes_per_step": int(2 * pairs * 3 * H * W * 4), "d2h_bytes_per_step": int(pairs * 4),
-               "api": "DISTS.score_host -> nqa_dists_forward_host (pinned host frames, copy stream overlapped with compute)",
-               "matches_device_path": bool(torch.equal(out, scores[rank * pairs:(rank + 1) * pairs].cpu()
-                                                       if world > 1 else scores.cpu()))}
+        dt = env.max_over_ranks(time.perf_counter() - t0)
+        mine = scores.view(world, -1)[rank] if world > 1 else scores
+        e2e = {"value": world * pairs * steps / dt, "unit": "frame-pairs/s",
+               "h2d_bytes_per_step": int(2 * pairs * 3 * H * W * 4), "d2h_bytes_per_step": int(n_out * pairs * 4),
+               "api": api + " (pinned host frames, copy stream overlapped with compute)",
+               "matches_device_path": bool(torch.equal(torch.cat(outs), mine.cpu()))}
 
+    if rank != 0:
+        return None
+    order = rooflines(env, ctx, name, prof, steps, pairs, H, W, precision)
+    families = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in prof.items() if v[1]}
+    res = {
+        "metric": wl["metric"], "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": precision, "data": "synthetic",
+        "config": {"workload": wl["desc"], "pairs_per_gpu": pairs, "resolution": f"{W}x{H}",
+                   "trunk_precision": precision, "vgg16": "random-init (seed 1234), shipped alpha/beta",
+                   "micro_batch_pairs": ctx.micro_batch(pairs, H, W, model._prec()),
+                   "l2": f"inputs are {2 * pairs * 3 * H * W * 4 / 1e9:.2f} GB per step, larger than the 126 MB L2",
+                   "parallelism": f"frame-sharded dp{world}, one all_gather of scores per step" if world > 1 else "single GPU"},
+        "e2e": e2e, "gpu_launches": int(lsum), "clocks": clocks,
+        "roofline": order[0] if order else None, "roofline_other": order[1:],
+        "kernel_families": families,
+    }
+    if world == 1 and not args.no_cpu_baseline and name != "both":
+        res["cpu_baseline"] = cpu_baseline_block("adists" if name == "adists" else "train" if train else "dists", (H, W))
+    else:
+        res["cpu_baseline"] = None
+    return res
+
+
+def run_video_workload(env, args):
+    """BASELINE configs[3]: 8 synthetic scenes x 300 frames at 1080p, DISTS and A-DISTS of every (reference, render) pair
+    from one trunk pass, frames sharded round-robin over the ranks (strong scaling), ONE gather of the per-frame scores,
+    per-video mean / std / min / max and the correlation of the pooled scores (prep.py:171-216, logger.py:93-141)."""
+    from nerf_qa_b200 import video
+    scenes, frames, H, W = args.scenes, args.frames, 1080, 1920
+    batch = args.pairs or 32
+    world, rank, device = env.world, env.rank, env.device
+    model = env.model("dists", args.precision)
+    ctx = model._context(device)
+    lengths = [frames] * scenes
+    total = scenes * frames
+    mine = video.shard_indices(total, rank, world)
+    vid, fr = video.frame_to_video(lengths)
+
+    free, _ = torch.cuda.mem_get_info(device)
+    shard_bytes = len(mine) * 2 * 3 * H * W * 4
+    resident = shard_bytes + (28 << 30) < free
+    if resident:
+        xs = torch.empty(len(mine), 3, H, W, device=device)
+        ys = torch.empty(len(mine), 3, H, W, device=device)
+        for j, gidx in enumerate(mine):
+            xs[j], ys[j] = make_video_frame(int(vid[gidx]), int(fr[gidx]), device, H, W)
+
+    def source(gidx):
+        if resident:
+            lo = int(np.searchsorted(mine, gidx[0]))
+            return xs[lo: lo + len(gidx)], ys[lo: lo + len(gidx)]
+        pairs_ = [make_video_frame(int(vid[g]), int(fr[g]), device, H, W) for g in gidx]
+        return torch.stack([p[0] for p in pairs_]), torch.stack([p[1] for p in pairs_])
+
+    def score_both(a, b):     # [2, b]: DISTS then A-DISTS
+        return torch.stack(model.score_with_adists(a, b))
+
+    with torch.no_grad():
+        for i in range(3):                      # warm-up: three batches of this rank's shard
+            score_both(*source(mine[: min(batch, len(mine))]))
+    env.barrier()
+    sampler = ClockSampler(env.local_rank)
     if rank == 0:
-        # the trunk's 13 convolutions: fused stage 1 (normalise + conv1_1 + conv1_2) + the 11 other tcgen05 convs
-        # (+ the stand-alone conv1_1 kernel when the fused stage-1 kernel is switched off)
-        conv_fams = [prof[k] for k in ("conv_tc", "stage1", "conv1_1") if k in prof]
-        tc_ms, tc_launches = sum(v[0] for v in conv_fams), sum(v[1] for v in conv_fams)
-        # train: forward, recomputed forward inside the backward call, and 12 of 13 data-gradient convolutions
-        flop_pair = TRUNK_FLOP_PER_PAIR * (H * W) / (1080 * 1920) * (3.0 if train else 1.0)
-        tc_flop = flop_pair * pairs * steps
-        tc_peak = peaks["bf16_tflops_sustained"] * (1.0 if args.precision == "bf16" else 1.0)
-        achieved = tc_flop / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None
-        mma_factor = 3.0 if args.precision == "bf16x3" else 1.0
-        total_prof_ms = sum(v[0] for v in prof.values())
-        roofline = {
-            "kernel": "VGG16 trunk convolutions on tcgen05: stage1_fused_kernel (normalise + conv1_1 + conv1_2) + "
-                      "conv3x3_tc[_halo]_kernel (11 layers), bias + ReLU fused",
-            "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-            "frac": (achieved / tc_peak) if achieved else None,
-            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
-            "algorithmic_flop_per_launch": tc_flop / max(tc_launches, 1),
-            "issued_mma_flop_factor": mma_factor,
-            "avg_launch_ms": tc_ms / max(tc_launches, 1), "launches": tc_launches,
-            "share_of_step": tc_ms / total_prof_ms if total_prof_ms > 0 else None,
-            "traffic": None,
-        }
-        tr = load_conv_traffic() if (args.workload == "dists" and args.precision == "bf16") else None
-        if tr is not None:
-            roofline["traffic"] = tr["bytes_per_launch"]
-            roofline["traffic_source"] = tr["source"]
-            # algorithmic HBM bytes of the same 12 launches: frames in (fp32), every conv output written once (bf16),
-            # every conv input except the fused stage's read once
-            roofline["traffic_note"] = "DRAM bytes per conv launch (avg of the 12 trunk launches of one 8-pair micro-batch)"
-        families = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in prof.items() if v[1]}
-        line = {
-            "metric": wl["metric"], "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": wl["desc"], "pairs_per_gpu": pairs, "resolution": f"{W}x{H}",
-                       "trunk_precision": args.precision, "vgg16": "random-init (seed 1234), shipped alpha/beta",
-                       "micro_batch_pairs": ctx.micro_batch(pairs, H, W, model._prec()),
-                       "l2": f"inputs are {2 * pairs * 3 * H * W * 4 / 1e9:.2f} GB per step, larger than the 126 MB L2",
-                       "parallelism": f"frame-sharded dp{world}, one all_gather of scores per step" if world > 1 else "single GPU"},
-            "e2e": e2e, "gpu_launches": int(lsum.item()), "clocks": clocks, "roofline": roofline,
-            "kernel_families": families,
-        }
-        if world == 1 and not args.no_cpu_baseline and not train:
-            n = 2 if args.workload == "dists" else 1
-            pps, dt_cpu, cores = cpu_reference_pairs_per_sec(args.workload, n, 1 if args.workload == "dists" else 0)
-            line["cpu_baseline"] = {"value": pps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n} timed 1920x1080 frame pair(s), one per step, oracle port of the "
-                                              f"reference (torch CPU fp32, {cores} threads)"}
-        else:
-            line["cpu_baseline"] = None
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.barrier()
+    ev0.record()
+    chunks = []
+    with torch.no_grad():
+        for i in range(0, len(mine), batch):
+            chunks.append(score_both(*source(mine[i: i + batch])))
+    local = torch.cat(chunks, dim=1) if chunks else torch.empty(2, 0, device=device)
+    d_all = video.gather_scores(local[0], total, rank, world)     # the gather is inside the timed region
+    a_all = video.gather_scores(local[1], total, rank, world)
+    ev1.record()
+    env.barrier()
+    ms = env.max_over_ranks(ev0.elapsed_time(ev1))
+    launches = env.sum_over_ranks(float(ctx.launch_count() - launches0))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # cross-check: frames are a pure function of (scene, frame), so rank 0 re-scores a sample of OTHER ranks' frames and
+    # must reproduce the gathered values bit for bit (batch-independent reductions)
+    ok = True
+    if rank == 0:
+        r = np.random.RandomState(0)
+        sample = np.sort(r.choice(total, size=min(16, total), replace=False))
+        pairs_ = [make_video_frame(int(vid[g]), int(fr[g]), device, H, W) for g in sample]
+        with torch.no_grad():
+            chk = score_both(torch.stack([p[0] for p in pairs_]), torch.stack([p[1] for p in pairs_]))
+        ok = bool(torch.equal(chk[0], d_all[sample]) and torch.equal(chk[1], a_all[sample]))
+    if rank != 0:
+        return None
+    d_np, a_np = d_all.cpu().numpy(), a_all.cpu().numpy()
+    pooled_d, pooled_a = video.pool_videos(d_np, lengths), video.pool_videos(a_np, lengths)
+    corr = video.correlations(pooled_d["mean"], pooled_a["mean"]) if scenes > 2 else None
+    return {
+        "metric": "video_level_1080p_frame_pairs_per_sec", "value": total / (ms / 1e3), "unit": "frame-pairs/s",
+        "n_gpus": world, "steps": 1, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"video-level FR scoring: {scenes} synthetic scenes x {frames} frames at 1920x1080, DISTS + A-DISTS "
+                               "from one trunk pass, score gather + temporal pooling (BASELINE configs[3])",
+                   "frames_total": total, "frames_per_rank": int(len(mine)), "batch_pairs": batch,
+                   "frames": "resident in HBM before the timed region" if resident else "generated per batch inside the timed region",
+                   "parallelism": f"round-robin frame sharding over {world} rank(s), one all_gather per metric"},
+        "gathered_matches_rescored_sample": ok, "gpu_launches": int(launches), "clocks": clocks,
+        "per_video": {"dists_mean": pooled_d["mean"].tolist(), "dists_std": pooled_d["std"].tolist(),
+                      "adists_mean": pooled_a["mean"].tolist(), "adists_std": pooled_a["std"].tolist()},
+        "dists_vs_adists_over_videos": corr,
+        "score_checksum": {"dists_sum": float(d_np.astype(np.float64).sum()), "adists_sum": float(a_np.astype(np.float64).sum())},
+        "e2e": None, "cpu_baseline": None,
+    }
+
+
+def run_latency_workload(env, args):
+    """The reference's own call pattern (nerf_qa/settings.py:1 -> 256x256 frames; prep.py:163 batches of 4):
+    microseconds per call at batch 1 / 4 / 32, device-resident inputs, synchronised per call (latency) and back to back
+    (throughput)."""
+    out = {}
+    for kind in ("dists", "adists"):
+        model = env.model(kind, args.precision)
+        for b in (1, 4, 32):
+            x, y = make_frames_device(b, env.device, seed=b, H=256, W=256)
+            call = (lambda: model(x, y)) if kind == "dists" else (lambda: model(x, y, as_loss=False))
+            with torch.no_grad():
+                for _ in range(5):
+                    call()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                n = 50
+                for _ in range(n):
+                    call()
+                    torch.cuda.synchronize()
+                lat = (time.perf_counter() - t0) / n
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for _ in range(n):
+                    call()
+                ev1.record()
+                torch.cuda.synchronize()
+                thr = ev0.elapsed_time(ev1) / n * 1e-3
+            out[f"{kind}_b{b}"] = {"us_per_call_synchronised": lat * 1e6, "us_per_call_back_to_back": thr * 1e6,
+                                   "pairs_per_s_back_to_back": b / thr}
+    return {"metric": "latency_256x256", "unit": "us per call", "n_gpus": 1, "dtype": args.precision,
+            "config": {"workload": "256x256 frames (nerf_qa/settings.py:1), batch 1 / 4 / 32, device-resident inputs"},
+            "calls": out}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["video", "latency"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
+    ap.add_argument("--pairs", type=int, default=0, help="override frame pairs per GPU per step")
+    ap.add_argument("--scenes", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the adists / train extra keys of the default line")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    env = Env(args)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    if args.workload == "video":
+        line = run_video_workload(env, args)
+    elif args.workload == "latency":
+        line = run_latency_workload(env, args) if env.rank == 0 else None
+    elif args.workload is not None:
+        line = run_batch_workload(env, args.workload, args, steps, warmup)
+    else:
+        line = run_batch_workload(env, "dists", args, steps, warmup)
+        if not args.headline_only:
+            extra_a = run_batch_workload(env, "adists", args, steps, warmup)
+            sub = argparse.Namespace(**vars(args))
+            sub.no_cpu_baseline = True            # the autograd CPU port of a 512x512 pair: keep the default run short
+            extra_t = run_batch_workload(env, "train", sub, steps, warmup)
+            if line is not None:
+                keep = ("metric", "value", "unit", "ms_per_step", "config", "e2e", "gpu_launches", "clocks", "roofline",
+                        "roofline_other", "kernel_families", "cpu_baseline", "dtype", "steps", "warmup")
+                line["adists"] = {k: extra_a[k] for k in keep}
+                line["train"] = {k: extra_t[k] for k in keep}
+    if env.rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if env.world > 1:
         # Every rank is done and rank 0 has printed its line.  Leave without the NCCL communicator teardown:
         # destroy_process_group() was observed to block for minutes under torchrun on the B200 box after the line
         # had been printed, and the driver times the whole process.
-        dist.barrier()
+        env.dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()

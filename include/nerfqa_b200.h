@@ -234,7 +234,7 @@ NQA_API int nqa_launch_count(nqa_ctx* ctx, uint64_t* launches);
 /* Per-kernel-family device timing with CUDA events recorded on the launching stream around every
  * launch (bench.py's live roofline numbers).  nqa_profile_read synchronises the device, returns the
  * milliseconds and launch counts accumulated since the previous read, and resets them. */
-#define NQA_NUM_KERNEL_FAMILIES 11
+#define NQA_NUM_KERNEL_FAMILIES 12
 enum nqa_kernel_family {
   NQA_K_CONV_TC = 0,  /* tcgen05 implicit-GEMM 3x3 conv + bias + ReLU          */
   NQA_K_CONV1_1 = 1,  /* normalise + conv1_1 (CUDA cores)                      */
@@ -243,13 +243,23 @@ enum nqa_kernel_family {
   NQA_K_STATS = 4,    /* DISTS per-level statistics (NHWC + planar level 0)    */
   NQA_K_FINALIZE = 5, /* S1/S2 + alpha/beta combination                        */
   NQA_K_LAYOUT = 6,   /* NHWC <-> NCHW conversions                             */
-  NQA_K_ADISTS = 7,   /* the whole A-DISTS statistics stage                    */
+  NQA_K_ADISTS = 7,   /* A-DISTS: channel sums, entropy weights, ps chain      */
   NQA_K_POOL_STATS = 8, /* fused L2pooling + DISTS statistics (levels 1..4)    */
   NQA_K_STAGE1 = 9,   /* fused normalise + conv1_1 + conv1_2 (tcgen05)         */
-  NQA_K_BACKWARD = 10 /* statistics / pooling / conv1_1 gradient kernels       */
+  NQA_K_BACKWARD = 10, /* statistics / pooling / conv1_1 gradient kernels      */
+  NQA_K_ADISTS_WINDOW = 11 /* A-DISTS: the local-window statistics kernels     */
 };
 NQA_API int nqa_profile_enable(nqa_ctx* ctx, int on);
 NQA_API int nqa_profile_read(nqa_ctx* ctx, double ms[NQA_NUM_KERNEL_FAMILIES], uint64_t launches[NQA_NUM_KERNEL_FAMILIES]);
+
+/* Measured arithmetic rates of this GPU for the roofline denominators MEASURED_PEAKS.json does not carry (it has the
+ * HBM copy and the cuBLAS bf16 figures): a short register-resident micro-benchmark on every SM, best of three, in
+ * multiply-adds per second.  Synchronises the device. */
+enum nqa_rate {
+  NQA_RATE_FP32_FMA = 0,       /* packed fp32 FMAs on the CUDA cores (what the fp32 window kernel issues) */
+  NQA_RATE_MMA_SYNC_BF16 = 1   /* warp-level mma.sync m16n8k16 bf16 -> fp32 (the banded-Toeplitz window kernel) */
+};
+NQA_API int nqa_measure_rate(nqa_ctx* ctx, int which, double* fma_per_s);
 
 /* Micro-batch (frame pairs per trunk pass) the scheduler would use for this shape. */
 NQA_API int nqa_micro_batch(nqa_ctx* ctx, int B, int H, int W, int precision, int* pairs);

@@ -28,9 +28,10 @@ EXPORTS = (
     "nqa_set_channel_weights", "nqa_adists_map", "nqa_dists_adists_forward", "nqa_dists_forward_saved",
     "nqa_dists_backward_saved", "nqa_tape_release", "nqa_set_alpha_beta_async", "nqa_set_channel_weights_async",
     "nqa_adists_forward_host", "nqa_dists_adists_forward_host", "nqa_adists_parts", "nqa_adists_ps_elems",
+    "nqa_measure_rate",
 )
 KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists", "pool_stats",
-                   "stage1", "backward")
+                   "stage1", "backward", "adists_window")
 
 
 class NerfQAError(RuntimeError):
@@ -85,6 +86,7 @@ def load_library() -> ctypes.CDLL:
     lib.nqa_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
     lib.nqa_profile_enable.argtypes = [vp, ci]
     lib.nqa_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+    lib.nqa_measure_rate.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double)]
     lib.nqa_micro_batch.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(ci)]
     for name in EXPORTS:
         if name not in ("nqa_last_error",):
@@ -427,6 +429,12 @@ class Context:
         n = (ctypes.c_uint64 * len(KERNEL_FAMILIES))()
         _check(self.lib.nqa_profile_read(self.handle, ms, n))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_FAMILIES)}
+
+    def measure_rate(self, which: str) -> float:
+        """Measured multiply-adds per second: "fp32_fma" (packed FFMA2 on the CUDA cores) or "mma_sync_bf16"."""
+        v = ctypes.c_double()
+        _check(self.lib.nqa_measure_rate(self.handle, {"fp32_fma": 0, "mma_sync_bf16": 1}[which], ctypes.byref(v)))
+        return float(v.value)
 
     def workspace_bytes(self) -> int:
         n = ctypes.c_size_t()

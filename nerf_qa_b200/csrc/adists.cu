@@ -820,7 +820,15 @@ int level_window(int window, const LevelPlan& L, const TI* x, const TI* y, int p
 size_t adists_ps_elems(int H, int W, int window, int level) { return (size_t)make_plan(1, H, W, window).lv[level].on; }
 
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
-                 void* ws, float* score, cudaStream_t st, float* map_out, const AdistsParts* parts) {
+                 void* ws, float* score, cudaStream_t st, float* map_out, const AdistsParts* parts, const AdistsProf* prof) {
+  int launches = 0;
+  struct Part {
+    const AdistsProf* p;
+    const int* n;
+    int n0;
+    Part(const AdistsProf* pr, int part, const int* counter) : p(pr), n(counter), n0(*counter) { if (p && p->begin) p->begin(p->user, part); }
+    ~Part() { if (p && p->end) p->end(p->user, *n - n0); }
+  };
   // level 0 (the raw frames) is always fp32; levels 1..5 are bf16 planes when feats_bf16
   auto is16 = [&](int k) { return feats_bf16 && k > 0; };
   auto F32 = [](const void* p) { return static_cast<const float*>(p); };
@@ -834,12 +842,13 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
   double* red = reinterpret_cast<double*>(base + p.off_red);
   unsigned int* cnt = reinterpret_cast<unsigned int*>(base + p.off_cnt);
   const Taps taps = make_taps(window);
-  int launches = 0;
 
   cudaMemsetAsync(cnt, 0, (size_t)pairs * sizeof(unsigned int), st);
 
   SumLevels sl;
   EntLevels el;
+  {
+  Part part(prof, 0, &launches);
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
     launches += is16(k) ? level_front<bf16>(L, B16(fx[k]), B16(fy[k]), pairs, F(L.off_sum), st)
@@ -856,7 +865,10 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
   }
   weights_kernel<<<pairs, 256, 0, st>>>(el, wt);
   ++launches;
+  }
 
+  {
+  Part part(prof, 1, &launches);
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
     if (L.windowed) {
@@ -869,7 +881,9 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
       ++launches;
     }
   }
+  }
 
+  Part part(prof, 0, &launches);
   const float* prev = nullptr;
   int ph = 1, pw = 1;
   for (int k = kNumLevels - 1; k >= 0; --k) {

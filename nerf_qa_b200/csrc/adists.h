@@ -22,8 +22,16 @@ struct AdistsParts {
   float* level_terms = nullptr;   // [pairs][6] D_k = mean_hw sum_c w_c((1-ps) T + ps S) (ADISTS.py:186-191)
   float* ps[6] = {};              // ps_prod maps [pairs][oh_k*ow_k] (compute_prob, ADISTS.py:71-100)
 };
+// Optional timing hook of the caller (per-family CUDA events): begin(user, part) / end(user, launches) bracket the launches of
+// part 0 = reductions, entropy weights and the ps chain, part 1 = the window kernels.
+struct AdistsProf {
+  void* user = nullptr;
+  void (*begin)(void* user, int part) = nullptr;
+  void (*end)(void* user, int launches) = nullptr;   // launches made since begin
+};
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
-                 void* ws, float* score, cudaStream_t st, float* map_out = nullptr, const AdistsParts* parts = nullptr);
+                 void* ws, float* score, cudaStream_t st, float* map_out = nullptr, const AdistsParts* parts = nullptr,
+                 const AdistsProf* prof = nullptr);
 // number of elements of the level-k ps map of one frame (1 for a fallback level)
 size_t adists_ps_elems(int H, int W, int window, int level);
 

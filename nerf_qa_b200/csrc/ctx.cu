@@ -1252,6 +1252,28 @@ static size_t adists_feat_bytes(int pairs, int H, int W, size_t elem = sizeof(fl
   return total + 4096;
 }
 
+// per-family timing of the A-DISTS stage: adists.cu brackets its two parts through this hook
+struct AdistsProfState {
+  nqa_ctx* ctx;
+  cudaStream_t st;
+  ProfScope* open;
+};
+static AdistsProf adists_prof_hook(AdistsProfState* s) {
+  AdistsProf p;
+  p.user = s;
+  p.begin = [](void* u, int part) {
+    auto* ps = static_cast<AdistsProfState*>(u);
+    ps->open = new ProfScope(ps->ctx, part == 1 ? NQA_K_ADISTS_WINDOW : NQA_K_ADISTS, ps->st);
+  };
+  p.end = [](void* u, int launches) {
+    auto* ps = static_cast<AdistsProfState*>(u);
+    ps->ctx->launches += launches;   // inside the scope, so that the family's launch count is right
+    delete ps->open;
+    ps->open = nullptr;
+  };
+  return p;
+}
+
 static int adists_micro_pairs(const nqa_ctx* ctx, int B, int H, int W) {
   const int mb = pick_micro_pairs(ctx, B, H, W) / 2;
   return mb < 1 ? 1 : mb;
@@ -1341,9 +1363,10 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
       for (int k = 0; k < kNumLevels; ++k)
         if (parts_out->ps[k]) parts.ps[k] = parts_out->ps[k] + (size_t)b0 * adists_ps_elems(H, W, window, k);
     }
-    ProfScope ps(ctx, NQA_K_ADISTS, st);
-    ctx->launches += adists_stage(fx, fy, planes16, pairs, H, W, window, ws, score_out + b0, st,
-                                  map_out ? map_out + (size_t)b0 * H * W : nullptr, parts_out ? &parts : nullptr);
+    AdistsProfState prof_state{ctx, st, nullptr};
+    const AdistsProf prof = adists_prof_hook(&prof_state);
+    adists_stage(fx, fy, planes16, pairs, H, W, window, ws, score_out + b0, st,
+                 map_out ? map_out + (size_t)b0 * H * W : nullptr, parts_out ? &parts : nullptr, &prof);   // launches counted by the hook
   }
   return NQA_OK;
 }
@@ -1493,11 +1516,12 @@ int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVEL
   ctx->arena.reset();
   void* ws = ctx->arena.take(adists_workspace_bytes(B, H, W, window));
   {
-    ProfScope ps(ctx, NQA_K_ADISTS, st);
+    AdistsProfState prof_state{ctx, st, nullptr};
+    const AdistsProf prof = adists_prof_hook(&prof_state);
     const void* vx[kNumLevels];
     const void* vy[kNumLevels];
     for (int k = 0; k < kNumLevels; ++k) { vx[k] = feats_x[k]; vy[k] = feats_y[k]; }
-    ctx->launches += adists_stage(vx, vy, false, B, H, W, window, ws, score_out, st);
+    adists_stage(vx, vy, false, B, H, W, window, ws, score_out, st, nullptr, nullptr, &prof);   // launches counted by the hook
   }
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;
@@ -1773,6 +1797,17 @@ int nqa_profile_read(nqa_ctx* ctx, double ms[NQA_NUM_KERNEL_FAMILIES], uint64_t 
   }
   ctx->prof_recs.clear();
   cudaGetLastError();
+  return NQA_OK;
+}
+
+int nqa_measure_rate(nqa_ctx* ctx, int which, double* fma_per_s) {
+  if (!ctx || !fma_per_s) return fail(NQA_ERR_INVALID, "null argument");
+  if (which != NQA_RATE_FP32_FMA && which != NQA_RATE_MMA_SYNC_BF16) return fail(NQA_ERR_INVALID, "unknown rate %d", which);
+  DeviceGuard guard(ctx->device);
+  if (microbench_rate(which, ctx->sm_count, ctx->alpha /* never written */, nullptr, fma_per_s) != 0) {
+    cudaGetLastError();
+    return fail(NQA_ERR_CUDA, "micro-benchmark failed");
+  }
   return NQA_OK;
 }
 
