@@ -71,6 +71,70 @@ def correlations(pred: np.ndarray, target: np.ndarray) -> Dict[str, float]:
             "ktcc": float(st.kendalltau(pred, target)[0])}
 
 
+REAL_SCENES = ("train", "m60", "playground", "truck", "fortress", "horns", "trex", "room")          # logger.py:217
+SYNTH_SCENES = ("ship", "lego", "drums", "ficus", "hotdog", "materials", "mic", "chair")            # logger.py:218
+
+
+def summarize(frame_scores: np.ndarray, video_ids: Sequence, scene_ids: Sequence, mos: Optional[np.ndarray] = None,
+              name: str = "score") -> Dict[str, object]:
+    """The wandb-free content of ``MetricCollectionLogger.log_summary`` (logger.py:144-282) for one metric:
+
+    * per-video mean of the frame scores (logger.py:157-160) and per-scene mean of those video means (logger.py:173-178);
+    * their averages over videos / over scenes (logger.py:182-186);
+    * with ``mos`` (one value per FRAME, constant inside a video, exactly how the reference logs it): PLCC / SRCC / KTCC
+      over all videos (logger.py:264-269), per scene with at least two videos (logger.py:230-231), over the videos of
+      the real and of the synthetic scenes (logger.py:239-249), and min / mean over scenes of the absolute per-scene
+      correlations (logger.py:252-266).
+
+    ``video_ids`` / ``scene_ids`` have one entry per frame; videos and scenes are reported in ``np.unique`` order."""
+    s = np.asarray(frame_scores, dtype=np.float64)
+    vids, sids = np.asarray(video_ids), np.asarray(scene_ids)
+    uv, us = np.unique(vids), np.unique(sids)
+    vmean, vscene, vmos = {}, {}, {}
+    for v in uv:
+        m = vids == v
+        vmean[v] = float(np.mean(s[m]))
+        vscene[v] = sids[m][0]
+        if mos is not None:
+            vmos[v] = float(np.mean(np.asarray(mos, dtype=np.float64)[m]))
+    scene_videos = {sc: [v for v in uv if vscene[v] == sc] for sc in us}
+    smean = {sc: float(np.mean([vmean[v] for v in scene_videos[sc]])) for sc in us}
+    out: Dict[str, object] = {
+        "name": name, "videos": list(uv), "scenes": list(us),
+        "video_mean": np.array([vmean[v] for v in uv]), "scene_mean": np.array([smean[sc] for sc in us]),
+        "average_over_videos": float(np.mean([vmean[v] for v in uv])),
+        "average_over_scenes": float(np.mean([smean[sc] for sc in us])),
+    }
+    if mos is None:
+        return out
+    pred = np.array([vmean[v] for v in uv])
+    gt = np.array([vmos[v] for v in uv])
+    out["video_mos"] = gt
+    if len(uv) > 1:
+        out["correlations"] = correlations(pred, gt)
+    per_scene = {}
+    groups = {"real": ([], []), "synthetic": ([], [])}
+    for sc in us:
+        p = np.array([vmean[v] for v in scene_videos[sc]])
+        g = np.array([vmos[v] for v in scene_videos[sc]])
+        if len(p) > 1:
+            per_scene[sc] = correlations(p, g)
+        grp = "real" if str(sc) in REAL_SCENES else "synthetic" if str(sc) in SYNTH_SCENES else None
+        if grp:
+            groups[grp][0].append(p)
+            groups[grp][1].append(g)
+    out["scene_correlations"] = per_scene
+    for grp, (ps, gs) in groups.items():
+        if len(ps) > 1:
+            out[f"{grp}_correlations"] = correlations(np.concatenate(ps), np.concatenate(gs))
+    if per_scene:
+        for k in ("plcc", "srcc", "ktcc"):
+            vals = np.abs([c[k] for c in per_scene.values()])
+            out[f"scene_min_{k}"] = float(np.min(vals))
+            out[f"scene_mean_{k}"] = float(np.mean(vals))
+    return out
+
+
 @dataclass
 class VideoScores:
     per_frame: np.ndarray            # [total] in global frame order
