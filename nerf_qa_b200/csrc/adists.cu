@@ -15,8 +15,10 @@
 // Pass structure per micro-batch: (1) per-channel sums, (2) entropy, (3) channel weights,
 // (4) window / global statistics per level, (5) ps chain + D per level (k = 5..0), (6) score.
 #include <math.h>
+#include <stdlib.h>
 
 #include "adists.h"
+#include "adists_tc.h"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -81,6 +83,7 @@ struct LevelPlan {
   int oh, ow, on;          // window map (1x1 in the global-statistics fallback)
   int chunks;              // planar-sum chunks
   int tiles_x, tiles_y, csplit;
+  int csplit_mma;          // channel split of the tensor-pipe window kernel (64 x 72 tiles: fewer blocks per map)
   size_t off_sum, off_ent, off_a, off_b, off_g, off_ps;  // byte offsets into the workspace
 };
 
@@ -118,11 +121,21 @@ Plan make_plan(int pairs, int H, int W, int window) {
       if (cs < 1) cs = 1;
       L.csplit = cs;
     }
+    L.csplit_mma = 1;
+    if (L.windowed) {
+      int tx, ty;
+      window_mma_tiles(L.oh, L.ow, &tx, &ty);
+      int cs = ceil_div(2 * kNumSMs, tx * ty);   // one 12-warp block per SM
+      if (cs > L.c / 8) cs = L.c / 8;
+      if (cs < 1) cs = 1;
+      L.csplit_mma = cs;
+    }
+    const int cs_max = L.csplit > L.csplit_mma ? L.csplit : L.csplit_mma;
     L.off_sum = take((size_t)pairs * L.chunks * 7 * L.c * sizeof(float));
     L.off_ent = take((size_t)pairs * L.chunks * L.c * sizeof(float));
-    L.off_a = take((size_t)pairs * L.csplit * L.on * sizeof(float));
-    L.off_b = take((size_t)pairs * L.csplit * L.on * sizeof(float));
-    L.off_g = take((size_t)pairs * L.csplit * L.on * sizeof(float));
+    L.off_a = take((size_t)pairs * cs_max * L.on * sizeof(float));
+    L.off_b = take((size_t)pairs * cs_max * L.on * sizeof(float));
+    L.off_g = take((size_t)pairs * cs_max * L.on * sizeof(float));
     L.off_ps = take((size_t)pairs * L.on * sizeof(float));
   }
   p.off_chan = take((size_t)pairs * kTotalChannels * kChan * sizeof(double));
@@ -544,7 +557,7 @@ global_level_kernel(int c, int choff, const double* __restrict__ chan, const flo
 // ================================================================================================
 struct MapArgs {
   const float* amap; const float* bmap; float* gmap;   // [pairs][csplit][on]
-  int csplit, on, oh, ow, c;
+  int csplit, stride, on, oh, ow, c;   // slices summed per pixel (1 after reduce_splits_kernel), slices per pair
   const float* prev;     // coarser ps_prod [pairs][ph*pw], or nullptr = ones
   int ph, pw;
   float* ps_out;         // [pairs][on]
@@ -555,18 +568,14 @@ struct MapArgs {
   int store_d;           // as_map: keep the per-pixel D value in slot 0 of gmap
 };
 
-__device__ inline float map_sum(const float* m, int csplit, int on, int b, int i) {
-  float s = 0.f;
-  for (int q = 0; q < csplit; ++q) s += m[((size_t)b * csplit + q) * on + i];
-  return s;
-}
+__device__ inline float map_sum(const float* m, int stride, int on, int b, int i) { return m[(size_t)b * stride * on + i]; }
 
-// bilinear, align_corners=True (torch upsample_bilinear2d semantics)
-__device__ inline float interp_prev(const float* prev, int ph, int pw, int b, int oy, int ox, int oh, int ow) {
+// bilinear, align_corners=True (torch upsample_bilinear2d semantics); sy / sx are the per-map scale factors
+// (in - 1) / (out - 1), computed once per thread
+__device__ inline float interp_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+__device__ inline float interp_prev(const float* prev, int ph, int pw, int b, int oy, int ox, float sy, float sx) {
   if (!prev) return 1.f;
   const float* p = prev + (size_t)b * ph * pw;
-  const float sy = oh > 1 ? (float)(ph - 1) / (float)(oh - 1) : 0.f;
-  const float sx = ow > 1 ? (float)(pw - 1) / (float)(ow - 1) : 0.f;
   const float fy = sy * oy, fxx = sx * ox;
   const int y0 = (int)fy, x0 = (int)fxx;
   const int y1 = y0 + (y0 < ph - 1 ? 1 : 0), x1 = x0 + (x0 < pw - 1 ? 1 : 0);
@@ -593,6 +602,19 @@ __device__ inline bool publish_partials(double* red, unsigned int* cnt, int b, c
   return is_last;
 }
 
+// Sum of the channel-split slices of the three maps into slice 0, in slice order (deterministic); afterwards the ps
+// chain reads one slice per map instead of csplit strided ones in each of its three kernels.
+__global__ void __launch_bounds__(256)
+reduce_splits_kernel(float* __restrict__ amap, float* __restrict__ bmap, float* __restrict__ gmap, int csplit, int on) {
+  const int b = blockIdx.z;
+  float* m = (blockIdx.y == 0 ? amap : blockIdx.y == 1 ? bmap : gmap) + (size_t)b * csplit * on;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < on; i += gridDim.x * 256) {
+    float s = 0.f;
+    for (int q = 0; q < csplit; ++q) s += m[(size_t)q * on + i];
+    m[i] = s;
+  }
+}
+
 // R1: mean / unbiased std / min / max of gamma
 __global__ void __launch_bounds__(256)
 gamma_stats_kernel(MapArgs a) {
@@ -602,7 +624,7 @@ gamma_stats_kernel(MapArgs a) {
   double s = 0, ss = 0;
   float mn = INFINITY, mx = -INFINITY;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < a.on; i += gridDim.x * 256) {
-    const float gmm = map_sum(a.gmap, a.csplit, a.on, b, i) / (float)a.c;
+    const float gmm = map_sum(a.gmap, a.stride, a.on, b, i) / (float)a.c;
     s += gmm; ss += (double)gmm * gmm;
     mn = fminf(mn, gmm); mx = fmaxf(mx, gmm);
   }
@@ -636,12 +658,20 @@ gamma_stats_kernel(MapArgs a) {
   }
 }
 
-__device__ inline float ps_norm(const MapArgs& a, const LvlScal& sc, int b, int i) {
-  const float gmm = map_sum(a.gmap, a.csplit, a.on, b, i) / (float)a.c;
-  const float den = sc.stdv + 1e-12f;
-  const float ps = sigmoidf_ref((gmm - sc.mean) / den);
-  const float smin = sigmoidf_ref((sc.gmin - sc.mean) / den), smax = sigmoidf_ref((sc.gmax - sc.mean) / den);
-  return (ps - smin) / (smax - smin + 1e-12f);
+// per-(pair, level) constants of the min-max normalised sigmoid, formed once per thread
+struct PsNorm {
+  float mean, den, smin, range;
+  __device__ explicit PsNorm(const LvlScal& sc) {
+    mean = sc.mean;
+    den = sc.stdv + 1e-12f;
+    smin = sigmoidf_ref((sc.gmin - sc.mean) / den);
+    range = sigmoidf_ref((sc.gmax - sc.mean) / den) - smin + 1e-12f;
+  }
+};
+__device__ inline float ps_norm(const MapArgs& a, const PsNorm& n, int b, int i) {
+  const float gmm = map_sum(a.gmap, a.stride, a.on, b, i) / (float)a.c;
+  const float ps = sigmoidf_ref((gmm - n.mean) / n.den);
+  return (ps - n.smin) / n.range;
 }
 
 // R2: min / max of ps_n * interp(prev)
@@ -649,11 +679,12 @@ __global__ void __launch_bounds__(256)
 prod_minmax_kernel(MapArgs a) {
   __shared__ float redf[33];
   const int b = blockIdx.y;
-  const LvlScal sc = a.scal[(size_t)b * kNumLevels + a.level];
+  const PsNorm sc(a.scal[(size_t)b * kNumLevels + a.level]);
+  const float isy = interp_scale(a.ph, a.oh), isx = interp_scale(a.pw, a.ow);
   float mn = INFINITY, mx = -INFINITY;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < a.on; i += gridDim.x * 256) {
     const int oy = i / a.ow, ox = i - oy * a.ow;
-    const float pr = ps_norm(a, sc, b, i) * interp_prev(a.prev, a.ph, a.pw, b, oy, ox, a.oh, a.ow);
+    const float pr = ps_norm(a, sc, b, i) * interp_prev(a.prev, a.ph, a.pw, b, oy, ox, isy, isx);
     mn = fminf(mn, pr); mx = fmaxf(mx, pr);
   }
   mn = warp_min(mn); mx = warp_max(mx);
@@ -684,16 +715,19 @@ __global__ void __launch_bounds__(256)
 prod_store_kernel(MapArgs a) {
   __shared__ double redd[33];
   const int b = blockIdx.y;
-  const LvlScal sc = a.scal[(size_t)b * kNumLevels + a.level];
+  const LvlScal raw = a.scal[(size_t)b * kNumLevels + a.level];
+  const PsNorm sc(raw);
+  const float isy = interp_scale(a.ph, a.oh), isx = interp_scale(a.pw, a.ow);
+  const float pmin = raw.pmin, prange = raw.pmax - raw.pmin + 1e-12f;
   double s = 0;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < a.on; i += gridDim.x * 256) {
     const int oy = i / a.ow, ox = i - oy * a.ow;
-    const float pr = ps_norm(a, sc, b, i) * interp_prev(a.prev, a.ph, a.pw, b, oy, ox, a.oh, a.ow);
-    const float p = (pr - sc.pmin) / (sc.pmax - sc.pmin + 1e-12f);
+    const float pr = ps_norm(a, sc, b, i) * interp_prev(a.prev, a.ph, a.pw, b, oy, ox, isy, isx);
+    const float p = (pr - pmin) / prange;
     a.ps_out[(size_t)b * a.on + i] = p;
-    const float av = map_sum(a.amap, a.csplit, a.on, b, i), bv = map_sum(a.bmap, a.csplit, a.on, b, i);
+    const float av = map_sum(a.amap, a.stride, a.on, b, i), bv = map_sum(a.bmap, a.stride, a.on, b, i);
     const float dv = (1.f - p) * av + p * bv;
-    if (a.store_d) a.gmap[(size_t)b * a.csplit * a.on + i] = dv;   // gamma of pixel i is no longer needed (same thread read it)
+    if (a.store_d) a.gmap[(size_t)b * a.stride * a.on + i] = dv;   // gamma of pixel i is no longer needed (same thread read it)
     s += (double)dv;
   }
   const double ts = block_sum<double>(s, redd);
@@ -711,7 +745,7 @@ __global__ void fallback_ps_kernel(MapArgs a, int pairs) {
   if (b >= pairs) return;
   const float gmm = a.gmap[b] / (float)a.c;
   const float ps = sigmoidf_ref(gmm);
-  const float pr = ps * interp_prev(a.prev, a.ph, a.pw, b, 0, 0, 1, 1);
+  const float pr = ps * interp_prev(a.prev, a.ph, a.pw, b, 0, 0, 0.f, 0.f);
   a.ps_out[b] = pr;
   a.scal[(size_t)b * kNumLevels + a.level].d = (1.f - pr) * a.amap[b] + pr * a.bmap[b];
 }
@@ -842,6 +876,7 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
   double* red = reinterpret_cast<double*>(base + p.off_red);
   unsigned int* cnt = reinterpret_cast<unsigned int*>(base + p.off_cnt);
   const Taps taps = make_taps(window);
+  static const bool use_mma = !(getenv("NQA_ADISTS_MMA") && atoi(getenv("NQA_ADISTS_MMA")) == 0);
 
   cudaMemsetAsync(cnt, 0, (size_t)pairs * sizeof(unsigned int), st);
 
@@ -867,11 +902,18 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
   ++launches;
   }
 
+  int csplit_used[kNumLevels];
   {
   Part part(prof, 1, &launches);
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
-    if (L.windowed) {
+    csplit_used[k] = L.csplit;
+    if (L.windowed && is16(k) && use_mma && window_mma_supported(window, L.h, L.w, fx[k], fy[k])) {
+      // bf16 planes: the two gaussian passes as banded-Toeplitz products on the tensor pipe (adists_tc.cu)
+      csplit_used[k] = L.csplit_mma;
+      launches += launch_window_mma(B16(fx[k]), B16(fy[k]), pairs, L.c, L.h, L.w, window, L.csplit_mma, L.choff, chan, wt,
+                                    taps.g, F(L.off_a), F(L.off_b), F(L.off_g), st);
+    } else if (L.windowed) {
       launches += is16(k) ? level_window<bf16>(window, L, B16(fx[k]), B16(fy[k]), pairs, chan, wt, taps, F(L.off_a), F(L.off_b),
                                                F(L.off_g), st)
                           : level_window<float>(window, L, F32(fx[k]), F32(fy[k]), pairs, chan, wt, taps, F(L.off_a), F(L.off_b),
@@ -890,7 +932,13 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
     const LevelPlan& L = p.lv[k];
     MapArgs a;
     a.amap = F(L.off_a); a.bmap = F(L.off_b); a.gmap = F(L.off_g);
-    a.csplit = L.csplit; a.on = L.on; a.oh = L.oh; a.ow = L.ow; a.c = L.c;
+    if (L.windowed && csplit_used[k] > 1) {
+      int nb = ceil_div(L.on, 256);
+      if (nb > 1024) nb = 1024;
+      reduce_splits_kernel<<<dim3(nb, 3, pairs), 256, 0, st>>>(F(L.off_a), F(L.off_b), F(L.off_g), csplit_used[k], L.on);
+      ++launches;
+    }
+    a.csplit = 1; a.stride = csplit_used[k]; a.on = L.on; a.oh = L.oh; a.ow = L.ow; a.c = L.c;
     a.prev = prev; a.ph = ph; a.pw = pw;
     a.ps_out = F(L.off_ps); a.scal = scal; a.level = k; a.red = red; a.cnt = cnt;
     a.store_d = map_out ? 1 : 0;
@@ -925,7 +973,7 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
     DMapLevels dl;
     for (int k = 0; k < kNumLevels; ++k) {
       const LevelPlan& L = p.lv[k];
-      dl.dmap[k] = F(L.off_g); dl.oh[k] = L.oh; dl.ow[k] = L.ow; dl.csplit[k] = L.csplit; dl.windowed[k] = L.windowed ? 1 : 0;
+      dl.dmap[k] = F(L.off_g); dl.oh[k] = L.oh; dl.ow[k] = L.ow; dl.csplit[k] = csplit_used[k]; dl.windowed[k] = L.windowed ? 1 : 0;
     }
     int nblk = ceil_div(H * W, 256 * 4);
     if (nblk > 2048) nblk = 2048;

@@ -1,0 +1,347 @@
+// A-DISTS local-window statistics on the tensor pipe (bf16 feature planes of the bf16 trunk): the two 21-tap gaussian
+// passes of ADISTS.forward / compute_prob (nerf_qa/ADISTS/ADISTS.py:75-80, 165-175) as banded-Toeplitz matrix products.
+//
+// Why warp-level mma.sync (HMMA m16n8k16) and not tcgen05 here: the filter matrix is a 21-wide band.  With an M = 16
+// output block the band fills 21 of 48 K columns (44%) in the horizontal pass and 21 of 32 (66%) in the vertical one; a
+// tcgen05 tile (M = 128 outputs, K = 148 -> 160 inputs) fills 13%, so its 4x higher peak (measured on this pool:
+// mma.sync 279 TFMA/s, cuBLAS tcgen05 ~800 TFMA/s) buys nothing, while the accumulator would have to leave TMEM for the
+// bf16 hi/lo conversion between the passes.  With mma.sync the first pass' accumulator fragment IS the second pass' A
+// fragment (same register layout), so the two passes chain in registers.
+//
+// Precision.  The features are exact bf16 values, so x^2, y^2 and x*y have <= 16 significant bits and split EXACTLY into
+// bf16 hi + lo; the fp32 results of the first pass are split into hi + lo as well (2^-17 relative); the gaussian taps are
+// rounded to bf16 once (the same perturbed window for all five maps) and the exact sum of the rounded taps renormalises
+// the results.  Variances therefore cancel at ~1e-5 of E[x^2] (fp32 CUDA-core kernel: 1e-7), far inside the 2e-3
+// tolerance of the bf16 path; the fp32 / bf16x3 trunks keep the CUDA-core kernel (adists.cu).
+//
+// Block = 12 warps = 4 (columns) x 3 (rows); warp tile = 16 output columns x 24 output rows; block tile 64 x 72 outputs
+// from a 96 x 96 input tile.  Per channel: the raw x / y tiles arrive by cp.async (double-buffered), all threads write
+// the six product tiles (x^2, y^2, xy as hi / lo) once, then every warp runs, per map q in (x, y, x^2, y^2, xy):
+//   pass 1:  D1[16 out cols][8 rows] += T[16 x 16] * tile[16 cols x 8 rows]      3 k-steps x 6 row blocks x terms
+//   split :  D1 -> bf16 hi / lo A fragments (in registers)
+//   pass 2:  D2[16 out cols][8 out rows] += D1[16 x 16 rows] * T2[16 rows x 8]   2 k-steps x 3 row blocks x 2 terms
+// and folds the five maps into T, S and gamma per pixel, accumulated over the channel loop in registers.
+#include <math.h>
+
+#include "adists.h"
+#include "adists_tc.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nqa {
+namespace {
+
+constexpr int kWarpsX = 4, kWarpsY = 3, kOB = 3;                 // warp grid, output row blocks (of 8) per warp
+constexpr int kThreads = 32 * kWarpsX * kWarpsY;                  // 384
+constexpr int kTileOW = 16 * kWarpsX, kTileOH = 8 * kOB * kWarpsY;  // 64 x 72 outputs per block
+constexpr int kInW = kTileOW + 32, kInH = kTileOH + 24;           // 96 x 96 inputs (halo of 20 rounded up to blocks)
+constexpr int kLD = 104;                                          // padded row stride (208 B): conflict-free ldmatrix
+constexpr int kTileElems = kInH * kLD;
+constexpr int kTileBytes = kTileElems * 2;                        // 19968
+constexpr int kRB = kOB + 3;                                      // input row blocks (of 8) per warp
+constexpr int kChunksPerRow = kInW / 8;                           // 16-byte chunks
+constexpr int kSmemBytes = (4 + 6) * kTileBytes;                  // raw x/y double-buffered + six product tiles
+
+struct TcTaps {
+  float g[32];      // bf16-representable taps, zero beyond the window
+  float inv_sum2;   // 1 / (sum of the rounded taps)^2
+};
+
+__device__ inline uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ inline float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ inline float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ inline uint32_t pack_bf16x2(float2 v) { return pack_bf16x2(v.x, v.y); }
+// p = hi + lo with hi = bf16(p), lo = bf16(p - hi), two values at a time: the residual is one packed FMA, p - 1 * hi
+// (exact whenever p - hi is representable, which it is for the products of two bf16 values)
+__device__ inline void split_bf16x2(float2 p, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(p);
+  lo = pack_bf16x2(__ffma2_rn(make_float2(bf16_lo(hi), bf16_hi(hi)), make_float2(-1.f, -1.f), p));
+}
+
+__device__ inline void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ inline void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ inline void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ inline void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ inline void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One filtered map of the warp tile: pass 1 over the NT term tiles, hi/lo split, pass 2.  out[ob][4] (raw sums, to be
+// scaled by 1/sum(g')^2): thread (lane) holds columns lane/4 (+8), rows 8*ob + 2*(lane%4) + {0,1}.
+template <int NT>
+__device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t lane_off, const uint32_t (&ta)[3][4],
+                                    const uint32_t (&tb)[2][2], float (&out)[kOB][4]) {
+  uint32_t fh[kRB][2], fl[kRB][2];
+#pragma unroll
+  for (int rb = 0; rb < kRB; ++rb) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const uint32_t base = tile_addr[t] + lane_off + rb * 8 * kLD * 2;
+      uint32_t b01[4], b2[2];
+      ldmatrix_x4(b01, base);            // k-blocks 0 and 1 (columns +0, +8, +16, +24)
+      ldmatrix_x2(b2, base + 32 * 2);    // k-block 2 (columns +32, +40)
+      mma16816(c, ta[0][0], ta[0][1], ta[0][2], ta[0][3], b01[0], b01[1]);
+      mma16816(c, ta[1][0], ta[1][1], ta[1][2], ta[1][3], b01[2], b01[3]);
+      mma16816(c, ta[2][0], ta[2][1], ta[2][2], ta[2][3], b2[0], b2[1]);
+    }
+    // fp32 -> bf16 hi + lo (round to nearest both; hi + lo carries 16 significant bits)
+    split_bf16x2(make_float2(c[0], c[1]), fh[rb][0], fl[rb][0]);
+    split_bf16x2(make_float2(c[2], c[3]), fh[rb][1], fl[rb][1]);
+  }
+#pragma unroll
+  for (int ob = 0; ob < kOB; ++ob) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int rb = ob + 2 * s;
+      mma16816(d, fh[rb][0], fh[rb][1], fh[rb + 1][0], fh[rb + 1][1], tb[s][0], tb[s][1]);
+      mma16816(d, fl[rb][0], fl[rb][1], fl[rb + 1][0], fl[rb + 1][1], tb[s][0], tb[s][1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[ob][i] = d[i];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int c, int h, int w, int oh, int ow, int tiles_x,
+                  int csplit, int choff, const double* __restrict__ chan, const float* __restrict__ wt, TcTaps taps,
+                  float* __restrict__ amap, float* __restrict__ bmap, float* __restrict__ gmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  // tiles: raw[buf][x|y] at (buf*2 + i), products xx_h, xx_l, yy_h, yy_l, xy_h, xy_l at 4..9
+  auto tile = [&](int i) { return smem + (uint32_t)i * kTileBytes; };
+
+  const int tile_id = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
+  const int oy0 = (tile_id / tiles_x) * kTileOH, ox0 = (tile_id % tiles_x) * kTileOW;
+  const int c_per = ceil_div(c, csplit);
+  const int c_begin = split * c_per, c_end = min(c, c_begin + c_per);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wx = warp % kWarpsX, wy = warp / kWarpsX;
+
+  // Toeplitz fragments (constant over the kernel).  Pass 1, A operand (16 output columns x 16 input columns of k-block
+  // d): element (j, k) = g'[16 d + k - j]; pass 2, B operand (16 input rows of k-step s x 8 output rows): g'[16 s + k - i].
+  auto tap = [&](int i) { return (i >= 0 && i < 32) ? taps.g[i] : 0.f; };
+  uint32_t ta[3][4], tb[2][2];
+  {
+    const int j0 = lane >> 2, k0 = 2 * (lane & 3);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      ta[d][0] = pack_bf16x2(tap(16 * d + k0 - j0), tap(16 * d + k0 + 1 - j0));
+      ta[d][1] = pack_bf16x2(tap(16 * d + k0 - j0 - 8), tap(16 * d + k0 + 1 - j0 - 8));
+      ta[d][2] = pack_bf16x2(tap(16 * d + k0 + 8 - j0), tap(16 * d + k0 + 9 - j0));
+      ta[d][3] = pack_bf16x2(tap(16 * d + k0 - j0), tap(16 * d + k0 + 1 - j0));   // (k + 8) - (j + 8)
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      tb[s][0] = pack_bf16x2(tap(16 * s + k0 - j0), tap(16 * s + k0 + 1 - j0));
+      tb[s][1] = pack_bf16x2(tap(16 * s + k0 + 8 - j0), tap(16 * s + k0 + 9 - j0));
+    }
+  }
+
+  // raw tile loader: 96 rows x 12 chunks per image; out-of-image chunks are zero-filled (w % 8 == 0: a chunk is either
+  // inside or outside)
+  const size_t plane = (size_t)h * w;
+  auto load_raw = [&](int ch, int buf) {
+    const bf16* px = fx + ((size_t)b * c + ch) * plane;
+    const bf16* py = fy + ((size_t)b * c + ch) * plane;
+    for (int i = threadIdx.x; i < kInH * kChunksPerRow; i += kThreads) {
+      const int r = i / kChunksPerRow, q = i - r * kChunksPerRow;
+      const int gy = oy0 + r, gx = ox0 + 8 * q;
+      const bool ok = gy < h && gx < w;
+      const size_t off = ok ? (size_t)gy * w + gx : 0;
+      const uint32_t dst = (uint32_t)(r * kLD + 8 * q) * 2;
+      cp_async16(tile(buf * 2 + 0) + dst, px + off, ok ? 16 : 0);
+      cp_async16(tile(buf * 2 + 1) + dst, py + off, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  // per-lane part of the ldmatrix address inside the warp's 48 x 48 input window: row (lane % 8), column 8 * (lane / 8)
+  const uint32_t lane_off = (uint32_t)(((wy * 8 * kOB + (lane & 7)) * kLD) + wx * 16 + 8 * (lane >> 3)) * 2;
+  const bool warp_live = (oy0 + wy * 8 * kOB) < oh && (ox0 + wx * 16) < ow;
+  const bool producer = wy != 0;
+  // named barrier 1: every thread arrives once per channel, the producers after writing the product tiles, the row-0
+  // warps before they read them
+  auto products_ready = [] { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); };
+
+  float2 acc_a[kOB][2], acc_b[kOB][2], acc_g[kOB][2];   // element i: pixels (row pair) of columns lane/4 + 8 i
+#pragma unroll
+  for (int ob = 0; ob < kOB; ++ob)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) acc_a[ob][i] = acc_b[ob][i] = acc_g[ob][i] = make_float2(0.f, 0.f);
+
+  int buf = 0;
+  if (c_begin < c_end) load_raw(c_begin, 0);
+  for (int ch = c_begin; ch < c_end; ++ch, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();   // raw[buf] has landed for every thread; every warp is done with the previous channel's tiles
+    if (ch + 1 < c_end) load_raw(ch + 1, buf ^ 1);
+
+    // ---- products: x^2, y^2, xy as exact bf16 hi + lo, written once per block by the warps of rows 1 and 2, while the
+    // warps of row 0 already filter the two maps that only need the raw tiles.  The three warps of a scheduler (same
+    // wx) thereby run out of phase: one issues its MMA bursts while the others do the scalar work between theirs. ----
+    if (producer)
+    for (int i = threadIdx.x - 32 * kWarpsX; i < kInH * kChunksPerRow; i += kThreads - 32 * kWarpsX) {
+      const int r = i / kChunksPerRow, q = i - r * kChunksPerRow;
+      const uint32_t off = (uint32_t)(r * kLD + 8 * q) * 2;
+      const uint4 vx = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 0) * kTileBytes + off);
+      const uint4 vy = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 1) * kTileBytes + off);
+      const uint32_t xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w};
+      uint32_t o[6][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = make_float2(bf16_lo(xs[e]), bf16_hi(xs[e])), y = make_float2(bf16_lo(ys[e]), bf16_hi(ys[e]));
+        split_bf16x2(__fmul2_rn(x, x), o[0][e], o[1][e]);   // products of bf16 values: the residuals are exact
+        split_bf16x2(__fmul2_rn(y, y), o[2][e], o[3][e]);
+        split_bf16x2(__fmul2_rn(x, y), o[4][e], o[5][e]);
+      }
+#pragma unroll
+      for (int m = 0; m < 6; ++m)
+        *reinterpret_cast<uint4*>(smem_raw + (4 + m) * kTileBytes + off) = make_uint4(o[m][0], o[m][1], o[m][2], o[m][3]);
+    }
+    if (producer) products_ready();
+    if (!warp_live) {
+      if (!producer) products_ready();
+      continue;
+    }
+    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * 10;
+    const float ax = (float)cs[0], ay = (float)cs[1];
+    const float wc = wt[(size_t)b * kTotalChannels + choff + ch];
+    // maps arrive as raw sums D; the 1 / sum(g')^2 renormalisation and the per-channel 1/||f|| scales are folded
+    const float inv = taps.inv_sum2;
+    const float2 kx = make_float2(ax * inv, ax * inv), ky = make_float2(ay * inv, ay * inv);
+    const float2 kxx = make_float2(ax * ax * inv, ax * ax * inv), kyy = make_float2(ay * ay * inv, ay * ay * inv);
+    const float2 kxy = make_float2(ax * ay * inv, ax * ay * inv);
+    const float2 c6 = make_float2(1e-6f, 1e-6f), two = make_float2(2.f, 2.f), wc2 = make_float2(wc, wc);
+    // gamma = (E[x^2] - m^2) / (m + 1e-12) on the RAW features (ADISTS.py:81-84) = vx / (ax mx + ax^2 1e-12) in
+    // normalised units
+    const float2 gk = make_float2(ax, ax), ge = make_float2(ax * ax * 1e-12f, ax * ax * 1e-12f);
+
+    float2 mx[kOB][2], my[kOB][2], vs[kOB][2];
+    float d[kOB][4];
+    {
+      const uint32_t t0[1] = {tile(buf * 2 + 0)};
+      filtered_map<1>(t0, lane_off, ta, tb, d);
+#pragma unroll
+      for (int ob = 0; ob < kOB; ++ob)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) mx[ob][i] = __fmul2_rn(kx, make_float2(d[ob][2 * i], d[ob][2 * i + 1]));
+      const uint32_t t1[1] = {tile(buf * 2 + 1)};
+      filtered_map<1>(t1, lane_off, ta, tb, d);
+    }
+#pragma unroll
+    for (int ob = 0; ob < kOB; ++ob)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        my[ob][i] = __fmul2_rn(ky, make_float2(d[ob][2 * i], d[ob][2 * i + 1]));
+        const float2 num = __ffma2_rn(two, __fmul2_rn(mx[ob][i], my[ob][i]), c6);
+        const float2 den = __ffma2_rn(mx[ob][i], mx[ob][i], __ffma2_rn(my[ob][i], my[ob][i], c6));
+        const float2 t = make_float2(__fdividef(num.x, den.x), __fdividef(num.y, den.y));
+        acc_a[ob][i] = __ffma2_rn(wc2, t, acc_a[ob][i]);
+      }
+    if (!producer) products_ready();
+    {
+      const uint32_t t2[2] = {tile(4), tile(5)};
+      filtered_map<2>(t2, lane_off, ta, tb, d);
+    }
+#pragma unroll
+    for (int ob = 0; ob < kOB; ++ob)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float2 m2 = __fmul2_rn(mx[ob][i], mx[ob][i]);
+        const float2 vx = __ffma2_rn(kxx, make_float2(d[ob][2 * i], d[ob][2 * i + 1]), make_float2(-m2.x, -m2.y));
+        vs[ob][i] = vx;
+        const float2 gd = __ffma2_rn(gk, mx[ob][i], ge);
+        acc_g[ob][i] = __fadd2_rn(acc_g[ob][i], make_float2(__fdividef(vx.x, gd.x), __fdividef(vx.y, gd.y)));
+      }
+    {
+      const uint32_t t3[2] = {tile(6), tile(7)};
+      filtered_map<2>(t3, lane_off, ta, tb, d);
+    }
+#pragma unroll
+    for (int ob = 0; ob < kOB; ++ob)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float2 m2 = __fmul2_rn(my[ob][i], my[ob][i]);
+        const float2 vy = __ffma2_rn(kyy, make_float2(d[ob][2 * i], d[ob][2 * i + 1]), make_float2(-m2.x, -m2.y));
+        vs[ob][i] = __fadd2_rn(vs[ob][i], __fadd2_rn(vy, c6));
+      }
+    {
+      const uint32_t t4[2] = {tile(8), tile(9)};
+      filtered_map<2>(t4, lane_off, ta, tb, d);
+    }
+#pragma unroll
+    for (int ob = 0; ob < kOB; ++ob)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float2 mm = __fmul2_rn(mx[ob][i], my[ob][i]);
+        const float2 cov = __ffma2_rn(kxy, make_float2(d[ob][2 * i], d[ob][2 * i + 1]), make_float2(-mm.x, -mm.y));
+        const float2 num = __ffma2_rn(two, cov, c6);
+        const float2 sv = make_float2(__fdividef(num.x, vs[ob][i].x), __fdividef(num.y, vs[ob][i].y));
+        acc_b[ob][i] = __ffma2_rn(wc2, sv, acc_b[ob][i]);
+      }
+  }
+
+  if (!warp_live) return;
+  const size_t mbase = ((size_t)b * csplit + split) * oh * ow;
+#pragma unroll
+  for (int ob = 0; ob < kOB; ++ob)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ox = ox0 + wx * 16 + (lane >> 2) + ((i & 2) ? 8 : 0);
+      const int oy = oy0 + wy * 8 * kOB + ob * 8 + 2 * (lane & 3) + (i & 1);
+      if (oy < oh && ox < ow) {
+        const size_t o = mbase + (size_t)oy * ow + ox;
+        amap[o] = (i & 1) ? acc_a[ob][i >> 1].y : acc_a[ob][i >> 1].x;
+        bmap[o] = (i & 1) ? acc_b[ob][i >> 1].y : acc_b[ob][i >> 1].x;
+        gmap[o] = (i & 1) ? acc_g[ob][i >> 1].y : acc_g[ob][i >> 1].x;
+      }
+    }
+}
+
+}  // namespace
+
+bool window_mma_supported(int window, int h, int w, const void* fx, const void* fy) {
+  return window >= 3 && window <= 21 && (window & 1) && h >= window && w >= window && (w % 8) == 0 &&
+         (reinterpret_cast<uintptr_t>(fx) & 15) == 0 && (reinterpret_cast<uintptr_t>(fy) & 15) == 0;
+}
+
+void window_mma_tiles(int oh, int ow, int* tiles_x, int* tiles_y) {
+  *tiles_x = ceil_div(ow, kTileOW);
+  *tiles_y = ceil_div(oh, kTileOH);
+}
+
+int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, int w, int window, int csplit, int choff,
+                      const double* chan, const float* wt, const float* taps_f32, float* amap, float* bmap, float* gmap,
+                      cudaStream_t st) {
+  TcTaps t;
+  double sum = 0.0;
+  for (int i = 0; i < 32; ++i) {
+    t.g[i] = i < window ? __bfloat162float(__float2bfloat16_rn(taps_f32[i])) : 0.f;
+    sum += (double)t.g[i];
+  }
+  t.inv_sum2 = (float)(1.0 / (sum * sum));
+  const int oh = h - window + 1, ow = w - window + 1;
+  int tx, ty;
+  window_mma_tiles(oh, ow, &tx, &ty);
+  ensure_dynamic_smem(window_mma_kernel, kSmemBytes);
+  dim3 grid(tx * ty, csplit, pairs);
+  window_mma_kernel<<<grid, kThreads, kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap);
+  return 1;
+}
+
+}  // namespace nqa

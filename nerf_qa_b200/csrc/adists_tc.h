@@ -1,0 +1,20 @@
+// Tensor-pipe (mma.sync, banded Toeplitz) version of the A-DISTS window statistics for bf16 feature planes; see
+// adists_tc.cu.  Same outputs as window_kernel in adists.cu: per frame pair and channel split the three maps
+// sum_c w_c T_c, sum_c w_c S_c and sum_c gamma_c of shape (h - window + 1) x (w - window + 1).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace nqa {
+
+// bf16 planes with 16-byte aligned rows (w % 8 == 0) and an odd window <= 21
+bool window_mma_supported(int window, int h, int w, const void* fx, const void* fy);
+// block tiling of the output map (64 x 72 outputs per block)
+void window_mma_tiles(int oh, int ow, int* tiles_x, int* tiles_y);
+// taps_f32: the `window` fp32 gaussian taps (rounded to bf16 inside; the result is renormalised by their exact sum)
+int launch_window_mma(const __nv_bfloat16* fx, const __nv_bfloat16* fy, int pairs, int c, int h, int w, int window, int csplit,
+                      int choff, const double* chan, const float* wt, const float* taps_f32, float* amap, float* bmap,
+                      float* gmap, cudaStream_t st);
+
+}  // namespace nqa
