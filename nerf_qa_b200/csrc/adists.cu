@@ -62,7 +62,8 @@ __device__ inline void ld4(const bf16* p, float (&v)[4]) {
 }
 
 constexpr int WT = 32;           // window kernel: 32x32 output pixels per block
-constexpr int kChan = 10;        // doubles per (pair, channel) in the chan table
+constexpr int kChan = 10;        // doubles per (pair, channel) in the chan table (slot 9: closed-form entropy)
+constexpr int kPlaneTile = 256;  // pixels per tile of the fused NHWC -> planes + channel-sums kernel
 constexpr int kRedBlocks = 512;  // blocks per frame pair in the map reductions (latency-bound gathers: fill the machine)
 
 struct Taps {
@@ -84,6 +85,8 @@ struct LevelPlan {
   int chunks;              // planar-sum chunks
   int tiles_x, tiles_y, csplit;
   int csplit_mma;          // channel split of the tensor-pipe window kernel (64 x 72 tiles: fewer blocks per map)
+  int chunks8;             // pixel chunks of the fused NHWC -> planes + channel-sums kernel (levels with c % 64 == 0)
+  size_t off_sum8;         // its partials [pairs][chunks8][8][c]
   size_t off_sum, off_ent, off_a, off_b, off_g, off_ps;  // byte offsets into the workspace
 };
 
@@ -129,6 +132,18 @@ Plan make_plan(int pairs, int H, int W, int window) {
       if (cs > L.c / 8) cs = L.c / 8;
       if (cs < 1) cs = 1;
       L.csplit_mma = cs;
+    }
+    L.chunks8 = 0;
+    L.off_sum8 = 0;
+    // (maps of fewer than 256 pixels keep the separate kernels: their entropies are tiny or exactly zero -- 1x1 maps --
+    // and the per-level normalisation of ADISTS.py:134 would amplify the rounding of the closed form)
+    if (L.c % 64 == 0 && L.hw >= kPlaneTile) {
+      // ~512 blocks per frame pair whatever the level (batch-independent: the chunking fixes the summation order)
+      const int ntiles = ceil_div(L.hw, kPlaneTile);
+      int ch8 = 512 / (L.c / 64);
+      if (ch8 > ntiles) ch8 = ntiles;
+      L.chunks8 = ch8 < 1 ? 1 : ch8;
+      L.off_sum8 = take((size_t)pairs * L.chunks8 * 8 * L.c * sizeof(float));
     }
     const int cs_max = L.csplit > L.csplit_mma ? L.csplit : L.csplit_mma;
     L.off_sum = take((size_t)pairs * L.chunks * 7 * L.c * sizeof(float));
@@ -200,38 +215,161 @@ sums7_kernel(const TI* __restrict__ x, const TI* __restrict__ y, int c, int hw, 
   }
 }
 
+// ================================================================================================
+// (1') bf16 trunk: the NHWC level -> bf16 planes transposition fused with the channel sums, so that the
+// planes are not read again for sums and entropy.  Eight sums per (pair, channel): x, y, x^2, y^2, xy, relu(x),
+// relu(x)^2 and relu(x) log2 relu(x) -- the last gives the entropy of ADISTS.py:127-135 in closed form:
+//   p = r / Z,  Z = sum r + ||r|| 1e-12,   E = -sum p log2 p = (log2(Z) sum r - sum r log2 r) / Z
+// (the reference's log2(p + 1e-12) differs only where p <~ 1e-12, i.e. by < 1e-10 of an entropy of ~20 bits).
+// Block = 256 pixels x 64 channels of the x AND the y image of one pair per tile, `per` tiles per block;
+// sums accumulate per thread in the load-phase registers (a thread owns 8 channels of 8 pixels per tile) and are
+// combined at the end in a fixed order.  grid = (chunks8, c/64, pairs), block = 256, dynamic smem 2 x 33 KB.
+// partial[((b*chunks8 + chunk)*8 + s)*C + ch]
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+planes_sums_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int pairs, int c, int hw, int chunks8,
+                   float* __restrict__ partials) {
+  extern __shared__ uint32_t ps_smem[];
+  uint32_t (*tx)[33] = reinterpret_cast<uint32_t (*)[33]>(ps_smem);                      // [pixel][channel pair]
+  uint32_t (*ty)[33] = reinterpret_cast<uint32_t (*)[33]>(ps_smem + kPlaneTile * 33);
+  const int chunk = blockIdx.x, c0 = blockIdx.y * 64, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lp = lane >> 3, lc = lane & 7;
+  const int ntiles = ceil_div(hw, kPlaneTile), per = ceil_div(ntiles, chunks8);
+  const int t0 = chunk * per, t1 = min(ntiles, t0 + per);
+  const bf16* srcx = in + (size_t)b * hw * c + c0;
+  const bf16* srcy = in + (size_t)(pairs + b) * hw * c + c0;
+  bf16* dstx = out + (size_t)b * c * hw;
+  bf16* dsty = out + (size_t)(pairs + b) * c * hw;
+  const bool even = (hw & 1) == 0;     // 4-byte stores need even plane sizes (plane starts stay 4-byte aligned)
+
+  float acc[8][8];   // [channel lc*8 + j][sum]
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[j][q] = 0.f;
+
+  for (int t = t0; t < t1; ++t) {
+    const int p0 = t * kPlaneTile;
+#pragma unroll 2
+    for (int k = 0; k < 8; ++k) {
+      const int pix = (k * 8 + warp) * 4 + lp, p = p0 + pix;
+      const size_t off = (size_t)min(p, hw - 1) * c;   // clamped, unconditional (masked below)
+      const uint4 vx = __ldg(reinterpret_cast<const uint4*>(srcx + off) + lc);
+      const uint4 vy = __ldg(reinterpret_cast<const uint4*>(srcy + off) + lc);
+      uint32_t* rx = &tx[pix][lc * 4];
+      uint32_t* ry = &ty[pix][lc * 4];
+      rx[0] = vx.x; rx[1] = vx.y; rx[2] = vx.z; rx[3] = vx.w;
+      ry[0] = vy.x; ry[1] = vy.y; ry[2] = vy.z; ry[3] = vy.w;
+      if (p < hw) {
+        const uint32_t wx[4] = {vx.x, vx.y, vx.z, vx.w}, wy[4] = {vy.x, vy.y, vy.z, vy.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const float a = __uint_as_float(hlf ? (wx[e] & 0xffff0000u) : (wx[e] << 16));
+            const float d = __uint_as_float(hlf ? (wy[e] & 0xffff0000u) : (wy[e] << 16));
+            const float r = fmaxf(a, 0.f);
+            float* s = acc[2 * e + hlf];
+            s[0] += a; s[1] += d;
+            s[2] = fmaf(a, a, s[2]); s[3] = fmaf(d, d, s[3]); s[4] = fmaf(a, d, s[4]);
+            s[5] += r; s[6] = fmaf(r, r, s[6]);
+            s[7] += r > 0.f ? r * __log2f(r) : 0.f;
+          }
+      }
+    }
+    __syncthreads();
+    for (int ch = warp; ch < 64; ch += 8) {
+      unsigned short* rowx = reinterpret_cast<unsigned short*>(dstx + (size_t)(c0 + ch) * hw);
+      unsigned short* rowy = reinterpret_cast<unsigned short*>(dsty + (size_t)(c0 + ch) * hw);
+#pragma unroll
+      for (int q = 0; q < kPlaneTile / 64; ++q) {
+        const int pp = q * 32 + lane, p = p0 + 2 * pp;
+        const uint32_t ax = tx[2 * pp][ch >> 1], bx = tx[2 * pp + 1][ch >> 1];
+        const uint32_t ay = ty[2 * pp][ch >> 1], by = ty[2 * pp + 1][ch >> 1];
+        const uint32_t lox = (ch & 1) ? (ax >> 16) : (ax & 0xffffu), hix = (ch & 1) ? (bx >> 16) : (bx & 0xffffu);
+        const uint32_t loy = (ch & 1) ? (ay >> 16) : (ay & 0xffffu), hiy = (ch & 1) ? (by >> 16) : (by & 0xffffu);
+        if (even && p + 1 < hw) {
+          *reinterpret_cast<uint32_t*>(rowx + p) = lox | (hix << 16);
+          *reinterpret_cast<uint32_t*>(rowy + p) = loy | (hiy << 16);
+        } else {
+          if (p < hw) { rowx[p] = (unsigned short)lox; rowy[p] = (unsigned short)loy; }
+          if (p + 1 < hw) { rowx[p + 1] = (unsigned short)hix; rowy[p + 1] = (unsigned short)hiy; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // combine: the four pixel lanes (lp) of a channel group by shuffles, the eight warps through shared memory, in order
+  float* red = reinterpret_cast<float*>(ps_smem);   // [warp][lc][j][s] = 8 * 8 * 64 floats
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v = acc[j][q];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lp == 0) red[((warp * 8 + lc) * 8 + j) * 8 + q] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += 256) {   // i = (channel within the group) * 8 + sum
+    const int chl = i >> 3, q = i & 7;             // chl = lc * 8 + j
+    float v = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) v += red[(wq * 64 + chl) * 8 + q];
+    partials[(((size_t)b * chunks8 + chunk) * 8 + q) * c + c0 + chl] = v;
+  }
+}
+
 // chan[b][1475][kChan] (double): 1/max(||x||,eps), 1/max(||y||,eps), max(||relu x||,eps), mean x, mean y, E[x^2], E[y^2],
 // E[xy], sum_hw(relu x / max(||relu x||,eps))
 struct SumLevels {
   const float* partials[kNumLevels];
   int chunks[kNumLevels];
   int hw[kNumLevels];
+  int fused[kNumLevels];   // 1: eight sums per chunk from planes_sums_kernel (entropy in closed form), 0: seven
 };
 
+// grid = (ceil(1475 / 32), pairs), block = 256: eight threads per channel split the chunks (thread t takes chunks t,
+// t + 8, ...), combined in lane order -- a fixed summation order.
 __global__ void __launch_bounds__(256)
 chan_kernel(SumLevels sl, double* __restrict__ chan) {
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < kTotalChannels; c += 256) {
-    const int k = c < 3 ? 0 : c < 67 ? 1 : c < 195 ? 2 : c < 451 ? 3 : c < 963 ? 4 : 5;
-    const int C = level_channels(k), cc = c - level_offset(k), chunks = sl.chunks[k];
-    const float* base = sl.partials[k] + (size_t)b * chunks * 7 * C + cc;
-    double s[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int ch = 0; ch < chunks; ++ch)
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x >> 3), part = threadIdx.x & 7;
+  const bool live = c < kTotalChannels;
+  const int cl = live ? c : kTotalChannels - 1;
+  const int k = cl < 3 ? 0 : cl < 67 ? 1 : cl < 195 ? 2 : cl < 451 ? 3 : cl < 963 ? 4 : 5;
+  const int C = level_channels(k), cc = cl - level_offset(k), chunks = sl.chunks[k];
+  const int ns = sl.fused[k] ? 8 : 7;
+  const float* base = sl.partials[k] + (size_t)b * chunks * ns * C + cc;
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int ch = part; ch < chunks; ch += 8)
+    for (int i = 0; i < ns; ++i) s[i] += (double)base[((size_t)ch * ns + i) * C];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) s[i] += (double)base[((size_t)ch * 7 + i) * C];
-    const double n = (double)sl.hw[k];
-    const double eps = 1e-12;
-    const double nx = fmax(sqrt(s[2]), eps), ny = fmax(sqrt(s[3]), eps), nr = fmax(sqrt(s[6]), eps);
-    double* o = chan + ((size_t)b * kTotalChannels + c) * kChan;
-    o[0] = 1.0 / nx;
-    o[1] = 1.0 / ny;
-    o[2] = nr;                     // p = (relu(x) / o[2]) / (o[8] + 1e-12)  (ADISTS.py:130-132), formed in fp32 like
-    o[8] = s[5] / nr;              // the reference so that degenerate 1x1 maps give exactly p = 1 and zero entropy
-    o[3] = s[0] / n;
-    o[4] = s[1] / n;
-    o[5] = s[2] / n;
-    o[6] = s[3] / n;
-    o[7] = s[4] / n;
+  for (int i = 0; i < 8; ++i) {
+    s[i] += __shfl_xor_sync(0xffffffffu, s[i], 1);
+    s[i] += __shfl_xor_sync(0xffffffffu, s[i], 2);
+    s[i] += __shfl_xor_sync(0xffffffffu, s[i], 4);
+  }
+  if (!live || part != 0) return;
+  const double n = (double)sl.hw[k];
+  const double eps = 1e-12;
+  const double nx = fmax(sqrt(s[2]), eps), ny = fmax(sqrt(s[3]), eps), nr = fmax(sqrt(s[6]), eps);
+  double* o = chan + ((size_t)b * kTotalChannels + c) * kChan;
+  o[0] = 1.0 / nx;
+  o[1] = 1.0 / ny;
+  o[2] = nr;                     // p = (relu(x) / o[2]) / (o[8] + 1e-12)  (ADISTS.py:130-132), formed in fp32 like
+  o[8] = s[5] / nr;              // the reference so that degenerate 1x1 maps give exactly p = 1 and zero entropy
+  o[3] = s[0] / n;
+  o[4] = s[1] / n;
+  o[5] = s[2] / n;
+  o[6] = s[3] / n;
+  o[7] = s[4] / n;
+  if (sl.fused[k]) {             // entropy in closed form (see planes_sums_kernel)
+    const double z = s[5] + nr * 1e-12;
+    o[9] = s[5] > 0.0 ? (log2(z) * s[5] - s[7]) / z : 0.0;
+  } else {
+    o[9] = 0.0;
   }
 }
 
@@ -284,20 +422,24 @@ entropy_kernel(const TI* __restrict__ x, int c, int hw, int chunks, int choff, c
 // ================================================================================================
 struct EntLevels {
   const float* partials[kNumLevels];
-  int chunks[kNumLevels];
+  int chunks[kNumLevels];   // 0: the level's entropies are already in chan[..][9] (closed form)
 };
 
 __global__ void __launch_bounds__(256)
-weights_kernel(EntLevels el, float* __restrict__ wt) {
+weights_kernel(EntLevels el, const double* __restrict__ chan, float* __restrict__ wt) {
   __shared__ double e[kTotalChannels];
   __shared__ double red[33];
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < kTotalChannels; c += 256) {
     const int k = c < 3 ? 0 : c < 67 ? 1 : c < 195 ? 2 : c < 451 ? 3 : c < 963 ? 4 : 5;
     const int C = level_channels(k), cc = c - level_offset(k), chunks = el.chunks[k];
-    const float* base = el.partials[k] + (size_t)b * chunks * C + cc;
     double s = 0;
-    for (int ch = 0; ch < chunks; ++ch) s += (double)base[(size_t)ch * C];
+    if (chunks == 0) {
+      s = chan[((size_t)b * kTotalChannels + c) * kChan + 9];
+    } else {
+      const float* base = el.partials[k] + (size_t)b * chunks * C + cc;
+      for (int ch = 0; ch < chunks; ++ch) s += (double)base[(size_t)ch * C];
+    }
     e[c] = s;
   }
   __syncthreads();
@@ -851,10 +993,30 @@ int level_window(int window, const LevelPlan& L, const TI* x, const TI* y, int p
 }
 }  // namespace
 
+bool adists_planes_sums_supported(int level, int H, int W) {
+  int h = H, w = W;
+  for (int k = 2; k <= level; ++k) { h = pooled(h); w = pooled(w); }
+  return level >= 1 && level_channels(level) % 64 == 0 && h * w >= kPlaneTile;
+}
+
+int adists_planes_and_sums(const bf16* nhwc, bf16* planes, int pairs, int level, int H, int W, int window, void* ws,
+                           cudaStream_t st) {
+  const Plan p = make_plan(pairs, H, W, window);
+  const LevelPlan& L = p.lv[level];
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  constexpr int smem = 2 * kPlaneTile * 33 * (int)sizeof(uint32_t);
+  ensure_dynamic_smem(planes_sums_kernel, smem);
+  dim3 grid(L.chunks8, L.c / 64, pairs);
+  planes_sums_kernel<<<grid, 256, smem, st>>>(nhwc, planes, pairs, L.c, L.hw, L.chunks8,
+                                             reinterpret_cast<float*>(base + L.off_sum8));
+  return 1;
+}
+
 size_t adists_ps_elems(int H, int W, int window, int level) { return (size_t)make_plan(1, H, W, window).lv[level].on; }
 
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
-                 void* ws, float* score, cudaStream_t st, float* map_out, const AdistsParts* parts, const AdistsProf* prof) {
+                 void* ws, float* score, cudaStream_t st, float* map_out, const AdistsParts* parts, const AdistsProf* prof,
+                 unsigned sums_done_mask) {
   int launches = 0;
   struct Part {
     const AdistsProf* p;
@@ -886,19 +1048,28 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
   Part part(prof, 0, &launches);
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
+    const bool fused = ((sums_done_mask >> k) & 1) != 0 && L.chunks8 > 0;   // planes_sums_kernel has run for this level
+    sl.hw[k] = L.hw;
+    sl.fused[k] = fused ? 1 : 0;
+    if (fused) {
+      sl.partials[k] = F(L.off_sum8); sl.chunks[k] = L.chunks8;
+      el.partials[k] = nullptr; el.chunks[k] = 0;
+      continue;
+    }
     launches += is16(k) ? level_front<bf16>(L, B16(fx[k]), B16(fy[k]), pairs, F(L.off_sum), st)
                         : level_front<float>(L, F32(fx[k]), F32(fy[k]), pairs, F(L.off_sum), st);
-    sl.partials[k] = F(L.off_sum); sl.chunks[k] = L.chunks; sl.hw[k] = L.hw;
+    sl.partials[k] = F(L.off_sum); sl.chunks[k] = L.chunks;
     el.partials[k] = F(L.off_ent); el.chunks[k] = L.chunks;
   }
-  chan_kernel<<<pairs, 256, 0, st>>>(sl, chan);
+  chan_kernel<<<dim3(ceil_div(kTotalChannels, 32), pairs), 256, 0, st>>>(sl, chan);
   ++launches;
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
+    if (sl.fused[k]) continue;
     launches += is16(k) ? level_entropy<bf16>(L, B16(fx[k]), pairs, chan, F(L.off_ent), st)
                         : level_entropy<float>(L, F32(fx[k]), pairs, chan, F(L.off_ent), st);
   }
-  weights_kernel<<<pairs, 256, 0, st>>>(el, wt);
+  weights_kernel<<<pairs, 256, 0, st>>>(el, chan, wt);
   ++launches;
   }
 

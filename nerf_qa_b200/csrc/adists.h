@@ -2,6 +2,7 @@
 // (nerf_qa/ADISTS/ADISTS.py:147-197) on planar (NCHW) fp32 feature levels.
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 
@@ -31,7 +32,13 @@ struct AdistsProf {
 };
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
                  void* ws, float* score, cudaStream_t st, float* map_out = nullptr, const AdistsParts* parts = nullptr,
-                 const AdistsProf* prof = nullptr);
+                 const AdistsProf* prof = nullptr, unsigned sums_done_mask = 0);
+// bf16 trunk: level `level`'s NHWC activations [2*pairs][h][w][c] (x images first) -> bf16 planes [2*pairs][c][h*w],
+// with the level's per-channel sums written into the workspace `ws` on the way (one read of the level instead of
+// three).  Pass bit `level` in adists_stage's sums_done_mask afterwards.  Levels 1..5 (c % 64 == 0) with at least 256 pixels.
+bool adists_planes_sums_supported(int level, int H, int W);
+int adists_planes_and_sums(const __nv_bfloat16* nhwc, __nv_bfloat16* planes, int pairs, int level, int H, int W, int window,
+                           void* ws, cudaStream_t st);
 // number of elements of the level-k ps map of one frame (1 for a fallback level)
 size_t adists_ps_elems(int H, int W, int window, int level);
 

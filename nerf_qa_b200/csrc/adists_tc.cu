@@ -22,6 +22,7 @@
 //   pass 2:  D2[16 out cols][8 out rows] += D1[16 x 16 rows] * T2[16 rows x 8]   2 k-steps x 3 row blocks x 2 terms
 // and folds the five maps into T, S and gamma per pixel, accumulated over the channel loop in registers.
 #include <math.h>
+#include <stdlib.h>
 
 #include "adists.h"
 #include "adists_tc.h"
@@ -81,10 +82,12 @@ __device__ inline void cp_async_wait_all() { asm volatile("cp.async.wait_group 0
 
 // One filtered map of the warp tile: pass 1 over the NT term tiles, hi/lo split, pass 2.  out[ob][4] (raw sums, to be
 // scaled by 1/sum(g')^2): thread (lane) holds columns lane/4 (+8), rows 8*ob + 2*(lane%4) + {0,1}.
-template <int NT>
+// kTwo = false: the first-pass results go into the second pass as ONE bf16 term (levels whose maps are large enough
+// that the 1e-6 stabilisers of T and S dwarf the rounding, see launch_window_mma).
+template <int NT, bool kTwo>
 __device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t lane_off, const uint32_t (&ta)[3][4],
                                     const uint32_t (&tb)[2][2], float (&out)[kOB][4]) {
-  uint32_t fh[kRB][2], fl[kRB][2];
+  uint32_t fh[kRB][2], fl[kTwo ? kRB : 1][2];
 #pragma unroll
   for (int rb = 0; rb < kRB; ++rb) {
     float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -99,8 +102,13 @@ __device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t la
       mma16816(c, ta[2][0], ta[2][1], ta[2][2], ta[2][3], b2[0], b2[1]);
     }
     // fp32 -> bf16 hi + lo (round to nearest both; hi + lo carries 16 significant bits)
-    split_bf16x2(make_float2(c[0], c[1]), fh[rb][0], fl[rb][0]);
-    split_bf16x2(make_float2(c[2], c[3]), fh[rb][1], fl[rb][1]);
+    if (kTwo) {
+      split_bf16x2(make_float2(c[0], c[1]), fh[rb][0], fl[rb][0]);
+      split_bf16x2(make_float2(c[2], c[3]), fh[rb][1], fl[rb][1]);
+    } else {
+      fh[rb][0] = pack_bf16x2(c[0], c[1]);
+      fh[rb][1] = pack_bf16x2(c[2], c[3]);
+    }
   }
 #pragma unroll
   for (int ob = 0; ob < kOB; ++ob) {
@@ -109,20 +117,22 @@ __device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t la
     for (int s = 0; s < 2; ++s) {
       const int rb = ob + 2 * s;
       mma16816(d, fh[rb][0], fh[rb][1], fh[rb + 1][0], fh[rb + 1][1], tb[s][0], tb[s][1]);
-      mma16816(d, fl[rb][0], fl[rb][1], fl[rb + 1][0], fl[rb + 1][1], tb[s][0], tb[s][1]);
+      if (kTwo) mma16816(d, fl[rb][0], fl[rb][1], fl[rb + 1][0], fl[rb + 1][1], tb[s][0], tb[s][1]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[ob][i] = d[i];
   }
 }
 
+template <bool kTwo>
 __global__ void __launch_bounds__(kThreads, 1)
 window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int c, int h, int w, int oh, int ow, int tiles_x,
                   int csplit, int choff, const double* __restrict__ chan, const float* __restrict__ wt, TcTaps taps,
                   float* __restrict__ amap, float* __restrict__ bmap, float* __restrict__ gmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  // tiles: raw[buf][x|y] at (buf*2 + i), products xx_h, xx_l, yy_h, yy_l, xy_h, xy_l at 4..9
+  // tiles: raw[buf][x|y] at (buf*2 + i), products xx_h, xx_l, yy_h, yy_l, xy_h, xy_l at 4..9 (kTwo) or xx, yy, xy
+  // rounded to bf16 at 4, 6, 8
   auto tile = [&](int i) { return smem + (uint32_t)i * kTileBytes; };
 
   const int tile_id = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
@@ -190,37 +200,67 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
     cp_async_wait_all();
     __syncthreads();   // raw[buf] has landed for every thread; every warp is done with the previous channel's tiles
     if (ch + 1 < c_end) load_raw(ch + 1, buf ^ 1);
+    // per-channel scalars: requested here, first used after a map has been filtered (L2 latency off the critical path)
+    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * 10;
+    const double sc_ax = __ldg(cs), sc_ay = __ldg(cs + 1);
+    const float sc_wc = __ldg(wt + (size_t)b * kTotalChannels + choff + ch);
 
     // ---- products: x^2, y^2, xy as exact bf16 hi + lo, written once per block by the warps of rows 1 and 2, while the
     // warps of row 0 already filter the two maps that only need the raw tiles.  The three warps of a scheduler (same
     // wx) thereby run out of phase: one issues its MMA bursts while the others do the scalar work between theirs. ----
-    if (producer)
-    for (int i = threadIdx.x - 32 * kWarpsX; i < kInH * kChunksPerRow; i += kThreads - 32 * kWarpsX) {
-      const int r = i / kChunksPerRow, q = i - r * kChunksPerRow;
-      const uint32_t off = (uint32_t)(r * kLD + 8 * q) * 2;
-      const uint4 vx = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 0) * kTileBytes + off);
-      const uint4 vy = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 1) * kTileBytes + off);
-      const uint32_t xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w};
-      uint32_t o[6][4];
+    if (producer) {
+      // chunk i = tid + 256 k of the 96 x 12 grid; (row, column chunk) advance by (21, 4) per step (256 = 21 * 12 + 4).
+      // All loads of the thread are issued before the arithmetic (the shared-memory latency is paid once).
+      constexpr int kProducers = kThreads - 32 * kWarpsX;                           // 256
+      constexpr int kIters = (kInH * kChunksPerRow + kProducers - 1) / kProducers;  // 5
+      const int tid = threadIdx.x - 32 * kWarpsX;
+      uint4 vx[kIters], vy[kIters];
+      uint32_t off[kIters];
+      {
+        int r = tid / kChunksPerRow, q = tid - r * kChunksPerRow;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 x = make_float2(bf16_lo(xs[e]), bf16_hi(xs[e])), y = make_float2(bf16_lo(ys[e]), bf16_hi(ys[e]));
-        split_bf16x2(__fmul2_rn(x, x), o[0][e], o[1][e]);   // products of bf16 values: the residuals are exact
-        split_bf16x2(__fmul2_rn(y, y), o[2][e], o[3][e]);
-        split_bf16x2(__fmul2_rn(x, y), o[4][e], o[5][e]);
+        for (int k = 0; k < kIters; ++k) {
+          off[k] = (uint32_t)(r * kLD + 8 * q) * 2;
+          if (r < kInH) {
+            vx[k] = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 0) * kTileBytes + off[k]);
+            vy[k] = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 1) * kTileBytes + off[k]);
+          } else {
+            off[k] = 0xffffffffu;
+          }
+          r += kProducers / kChunksPerRow;
+          q += kProducers % kChunksPerRow;
+          if (q >= kChunksPerRow) { q -= kChunksPerRow; ++r; }
+        }
       }
 #pragma unroll
-      for (int m = 0; m < 6; ++m)
-        *reinterpret_cast<uint4*>(smem_raw + (4 + m) * kTileBytes + off) = make_uint4(o[m][0], o[m][1], o[m][2], o[m][3]);
+      for (int k = 0; k < kIters; ++k) {
+        if (off[k] == 0xffffffffu) continue;
+        const uint32_t xs[4] = {vx[k].x, vx[k].y, vx[k].z, vx[k].w}, ys[4] = {vy[k].x, vy[k].y, vy[k].z, vy[k].w};
+        uint32_t o[6][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 x = make_float2(bf16_lo(xs[e]), bf16_hi(xs[e])), y = make_float2(bf16_lo(ys[e]), bf16_hi(ys[e]));
+          if (kTwo) {
+            split_bf16x2(__fmul2_rn(x, x), o[0][e], o[1][e]);   // products of bf16 values: the residuals are exact
+            split_bf16x2(__fmul2_rn(y, y), o[2][e], o[3][e]);
+            split_bf16x2(__fmul2_rn(x, y), o[4][e], o[5][e]);
+          } else {
+            o[0][e] = pack_bf16x2(__fmul2_rn(x, x));
+            o[2][e] = pack_bf16x2(__fmul2_rn(y, y));
+            o[4][e] = pack_bf16x2(__fmul2_rn(x, y));
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 6; m += (kTwo ? 1 : 2))
+          *reinterpret_cast<uint4*>(smem_raw + (4 + m) * kTileBytes + off[k]) = make_uint4(o[m][0], o[m][1], o[m][2], o[m][3]);
+      }
     }
     if (producer) products_ready();
     if (!warp_live) {
       if (!producer) products_ready();
       continue;
     }
-    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * 10;
-    const float ax = (float)cs[0], ay = (float)cs[1];
-    const float wc = wt[(size_t)b * kTotalChannels + choff + ch];
+    const float ax = (float)sc_ax, ay = (float)sc_ay, wc = sc_wc;
     // maps arrive as raw sums D; the 1 / sum(g')^2 renormalisation and the per-channel 1/||f|| scales are folded
     const float inv = taps.inv_sum2;
     const float2 kx = make_float2(ax * inv, ax * inv), ky = make_float2(ay * inv, ay * inv);
@@ -235,13 +275,13 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
     float d[kOB][4];
     {
       const uint32_t t0[1] = {tile(buf * 2 + 0)};
-      filtered_map<1>(t0, lane_off, ta, tb, d);
+      filtered_map<1, kTwo>(t0, lane_off, ta, tb, d);
 #pragma unroll
       for (int ob = 0; ob < kOB; ++ob)
 #pragma unroll
         for (int i = 0; i < 2; ++i) mx[ob][i] = __fmul2_rn(kx, make_float2(d[ob][2 * i], d[ob][2 * i + 1]));
       const uint32_t t1[1] = {tile(buf * 2 + 1)};
-      filtered_map<1>(t1, lane_off, ta, tb, d);
+      filtered_map<1, kTwo>(t1, lane_off, ta, tb, d);
     }
 #pragma unroll
     for (int ob = 0; ob < kOB; ++ob)
@@ -255,8 +295,13 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
       }
     if (!producer) products_ready();
     {
-      const uint32_t t2[2] = {tile(4), tile(5)};
-      filtered_map<2>(t2, lane_off, ta, tb, d);
+      if (kTwo) {
+        const uint32_t t2[2] = {tile(4), tile(5)};
+        filtered_map<2, true>(t2, lane_off, ta, tb, d);
+      } else {
+        const uint32_t t2[1] = {tile(4)};
+        filtered_map<1, false>(t2, lane_off, ta, tb, d);
+      }
     }
 #pragma unroll
     for (int ob = 0; ob < kOB; ++ob)
@@ -269,8 +314,13 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         acc_g[ob][i] = __fadd2_rn(acc_g[ob][i], make_float2(__fdividef(vx.x, gd.x), __fdividef(vx.y, gd.y)));
       }
     {
-      const uint32_t t3[2] = {tile(6), tile(7)};
-      filtered_map<2>(t3, lane_off, ta, tb, d);
+      if (kTwo) {
+        const uint32_t t3[2] = {tile(6), tile(7)};
+        filtered_map<2, true>(t3, lane_off, ta, tb, d);
+      } else {
+        const uint32_t t3[1] = {tile(6)};
+        filtered_map<1, false>(t3, lane_off, ta, tb, d);
+      }
     }
 #pragma unroll
     for (int ob = 0; ob < kOB; ++ob)
@@ -281,8 +331,13 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         vs[ob][i] = __fadd2_rn(vs[ob][i], __fadd2_rn(vy, c6));
       }
     {
-      const uint32_t t4[2] = {tile(8), tile(9)};
-      filtered_map<2>(t4, lane_off, ta, tb, d);
+      if (kTwo) {
+        const uint32_t t4[2] = {tile(8), tile(9)};
+        filtered_map<2, true>(t4, lane_off, ta, tb, d);
+      } else {
+        const uint32_t t4[1] = {tile(8)};
+        filtered_map<1, false>(t4, lane_off, ta, tb, d);
+      }
     }
 #pragma unroll
     for (int ob = 0; ob < kOB; ++ob)
@@ -338,9 +393,20 @@ int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, i
   const int oh = h - window + 1, ow = w - window + 1;
   int tx, ty;
   window_mma_tiles(oh, ow, &tx, &ty);
-  ensure_dynamic_smem(window_mma_kernel, kSmemBytes);
+  // One bf16 term per operand or two.  The rounding of a one-term operand (2^-9 per element, ~4e-4 after the window
+  // average) is an error of that fraction of E[f^2] in a variance; in the L2-normalised units of ADISTS.py:166-167 E[f^2]
+  // is 1 / (h w) on average, so for maps of >= 400k pixels even a 10x locally concentrated channel errs by ~1e-8, one
+  // hundredth of the 1e-6 stabilisers c1 / c2 -- the 1080p levels 1 and 2, 77% of the work.  Smaller maps (deeper
+  // levels, small frames) keep the exact two-term products and the hi + lo split between the passes.
+  const bool two = (long long)h * w < 400000 || (getenv("NQA_ADISTS_MMA_TERMS") && atoi(getenv("NQA_ADISTS_MMA_TERMS")) == 2);
   dim3 grid(tx * ty, csplit, pairs);
-  window_mma_kernel<<<grid, kThreads, kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap);
+  if (two) {
+    ensure_dynamic_smem(window_mma_kernel<true>, kSmemBytes);
+    window_mma_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap);
+  } else {
+    ensure_dynamic_smem(window_mma_kernel<false>, kSmemBytes);
+    window_mma_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap);
+  }
   return 1;
 }
 

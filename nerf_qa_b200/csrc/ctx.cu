@@ -106,6 +106,7 @@ struct nqa_ctx {
   int micro_images = 16;                 // full-HD-equivalent images per trunk pass (NQA_MICRO_IMAGES)
   bool fuse_pool_stats = true;           // NQA_POOL_STATS_FUSED=0 falls back to separate pooling / statistics kernels
   bool pool_stats_tma = true;            // NQA_POOL_STATS_TMA=0: register-fed pooling + moments kernel for bf16 levels too
+  bool adists_fused_sums = true;         // NQA_ADISTS_FUSED_SUMS=0: separate planes / sums / entropy kernels (bf16 trunk)
   ConvTcConfig conv_cfg;                 // kernel selection of the tensor-pipe convolutions (environment read at creation)
   // Encoded tensor maps of the convolution launches, keyed on (buffers, shape): the arena hands out the same addresses
   // for the same shape, so after the first call at a shape no launch goes through cuTensorMapEncodeTiled again.
@@ -963,6 +964,7 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->conv_cfg = conv_tc_config_from_env(ctx->sm_count);
   if (const char* e = getenv("NQA_POOL_STATS_TMA")) ctx->pool_stats_tma = atoi(e) != 0;
+  if (const char* e = getenv("NQA_ADISTS_FUSED_SUMS")) ctx->adists_fused_sums = atoi(e) != 0;
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming));
   if (const char* e = getenv("NQA_STAGE1_FUSED")) ctx->fuse_stage1 = atoi(e) != 0;
   if (const char* e = getenv("NQA_POOL_STATS_FUSED")) ctx->fuse_pool_stats = atoi(e) != 0;
@@ -1274,8 +1276,10 @@ static AdistsProf adists_prof_hook(AdistsProfState* s) {
   return p;
 }
 
-static int adists_micro_pairs(const nqa_ctx* ctx, int B, int H, int W) {
-  const int mb = pick_micro_pairs(ctx, B, H, W) / 2;
+// bf16 trunk: bf16 planes (2 bytes per feature) leave room for the DISTS micro-batch (8 pairs at 1080p: 17 GB of
+// workspace); the fp32 / bf16x3 paths carry fp32 planes and take half of it.
+static int adists_micro_pairs(const nqa_ctx* ctx, int B, int H, int W, int prec) {
+  const int mb = prec == NQA_PREC_BF16 ? pick_micro_pairs(ctx, B, H, W) : pick_micro_pairs(ctx, B, H, W) / 2;
   return mb < 1 ? 1 : mb;
 }
 
@@ -1293,7 +1297,7 @@ template <typename T>
 static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window, int prec,
                        float* score_out, float* map_out, cudaStream_t st, float* dists_out = nullptr,
                        const AdistsParts* parts_out = nullptr) {
-  const int mb = adists_micro_pairs(ctx, B, H, W);
+  const int mb = adists_micro_pairs(ctx, B, H, W, prec);
   const bool with_dists = dists_out != nullptr;
   const bool fused_pool = with_dists && prec != NQA_PREC_BF16X3;
   // bf16 trunk: the planes the statistics read are bf16 too (exact copies of the activations, half the bytes)
@@ -1313,6 +1317,7 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     for (int k = 1; k < kNumLevels; ++k)
       planar[k] = static_cast<char*>(ctx->arena.take((size_t)2 * pairs * level_channels(k) * lh[k] * lw[k] * pelem));
     void* ws = ctx->arena.take(adists_workspace_bytes(pairs, H, W, window));
+    unsigned sums_done = 0;   // levels whose channel sums were produced together with the planes
     const float* xb = x + b0 * frame;
     const float* yb = y + b0 * frame;
     PartialBufs pb;
@@ -1325,7 +1330,13 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     rc = run_trunk<T>(ctx, xb, yb, pairs, 2 * pairs, H, W, prec, bufs, st,
                       [&](int k, const T* f, const T* f_lo, int h, int w, T* pooled_dst) {
                         const int c = level_channels(k);
-                        if (planes16) {
+                        if (planes16 && ctx->adists_fused_sums && adists_planes_sums_supported(k, H, W)) {
+                          // transposition + the level's channel sums in one read (adists.cu planes_sums_kernel)
+                          ProfScope ps(ctx, NQA_K_LAYOUT, st);
+                          ctx->launches += adists_planes_and_sums(reinterpret_cast<const bf16*>(f), reinterpret_cast<bf16*>(planar[k]),
+                                                                  pairs, k, H, W, window, ws, st);
+                          sums_done |= 1u << k;
+                        } else if (planes16) {
                           ProfScope ps(ctx, NQA_K_LAYOUT, st);
                           ctx->launches += launch_nhwc_to_nchw_bf16(reinterpret_cast<const bf16*>(f), reinterpret_cast<bf16*>(planar[k]),
                                                                     2 * pairs, c, h, w, st);
@@ -1366,7 +1377,8 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     AdistsProfState prof_state{ctx, st, nullptr};
     const AdistsProf prof = adists_prof_hook(&prof_state);
     adists_stage(fx, fy, planes16, pairs, H, W, window, ws, score_out + b0, st,
-                 map_out ? map_out + (size_t)b0 * H * W : nullptr, parts_out ? &parts : nullptr, &prof);   // launches counted by the hook
+                 map_out ? map_out + (size_t)b0 * H * W : nullptr, parts_out ? &parts : nullptr, &prof,
+                 sums_done);   // launches counted by the hook
   }
   return NQA_OK;
 }
@@ -1471,7 +1483,7 @@ static int adists_host_impl(nqa_ctx* ctx, const float* x_host, const float* y_ho
   if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
   if ((rc = check_window(window)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
-  const int mb = adists_micro_pairs(ctx, B, H, W);
+  const int mb = adists_micro_pairs(ctx, B, H, W, precision);
   const bool f32 = precision == NQA_PREC_FP32;
   if ((rc = ensure_arena(ctx, f32 ? adists_need_bytes<float>(ctx, mb, H, W, window, precision, with_dists)
                                   : adists_need_bytes<bf16>(ctx, mb, H, W, window, precision, with_dists))) != NQA_OK)

@@ -14,3 +14,9 @@ for f in ('${TAG}_bench_adists','${TAG}_bench_adists_nomma'):
     d=json.loads(l[-1]); print(f, round(d['value'],1), 'e2e', (round(d['e2e']['value'],1) if d.get('e2e') else None), {k:round(v['ms_per_step'],1) for k,v in d['kernel_families'].items()})
     r=d['roofline']; print('  top', r['family'], 'frac', r['frac'], r.get('hbm',{}).get('frac'))
 PY
+NQA_MICRO_IMAGES=32 timeout 600 python bench.py --workload adists --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_adists_mi32.json 2>&1
+python - <<PY
+import json
+l=[x for x in open('gpurun_out/${TAG}_bench_adists_mi32.json').read().splitlines() if x.startswith('{')]
+d=json.loads(l[-1]); print('micro_images=32', round(d['value'],1), {k:round(v['ms_per_step'],1) for k,v in d['kernel_families'].items()})
+PY
