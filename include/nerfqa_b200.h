@@ -218,6 +218,14 @@ NQA_API int nqa_dists_from_feats_backward(nqa_ctx* ctx, const float* const feats
  * ADISTS.py:16-31): out[B,C,(H-1)/2+1,(W-1)/2+1] = sqrt(hanning3x3(x^2, stride 2, pad 1) + 1e-12). */
 NQA_API int nqa_l2pool(nqa_ctx* ctx, const float* x, int B, int C, int H, int W, float* out, void* stream);
 
+/* Frame resizing in front of the scorers, on the device: x [B,C,H,W] fp32 -> out [B,C,OH,OW] fp32, bilinear with
+ * align_corners=False.  antialias = 0 is F.interpolate(mode='bilinear', align_corners=False) as prep.py:91-96 and
+ * the "pixel count" variant test2_prep.py:424-439 call it; antialias = 1 is the antialiased (triangle filter, support
+ * = downscale factor) resize that torchvision's transforms.functional.resize performs on PIL images in
+ * test2_prep.py:109-114 (short side 256) and :221-227 (256 x 256) -- equal to PIL up to its uint8 rounding. */
+NQA_API int nqa_resize_bilinear(nqa_ctx* ctx, const float* x, int B, int C, int H, int W, int OH, int OW, int antialias,
+                                float* out, void* stream);
+
 /* Op-level 3x3 convolution + bias + ReLU (stride 1, zero pad 1) through the selected implementation,
  * for kernel parity tests: x [B,Cin,H,W], w [Cout,Cin,3,3], bias [Cout], out [B,Cout,H,W], all NCHW /
  * OIHW fp32 device tensors; Cin and Cout multiples of 64, Cout <= 512.  Equivalent of one

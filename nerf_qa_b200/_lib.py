@@ -28,7 +28,7 @@ EXPORTS = (
     "nqa_set_channel_weights", "nqa_adists_map", "nqa_dists_adists_forward", "nqa_dists_forward_saved",
     "nqa_dists_backward_saved", "nqa_tape_release", "nqa_set_alpha_beta_async", "nqa_set_channel_weights_async",
     "nqa_adists_forward_host", "nqa_dists_adists_forward_host", "nqa_adists_parts", "nqa_adists_ps_elems",
-    "nqa_measure_rate",
+    "nqa_measure_rate", "nqa_resize_bilinear",
 )
 KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists", "pool_stats",
                    "stage1", "backward", "adists_window")
@@ -86,6 +86,7 @@ def load_library() -> ctypes.CDLL:
     lib.nqa_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
     lib.nqa_profile_enable.argtypes = [vp, ci]
     lib.nqa_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+    lib.nqa_resize_bilinear.argtypes = [vp, fp, ci, ci, ci, ci, ci, ci, ci, fp, vp]
     lib.nqa_measure_rate.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double)]
     lib.nqa_micro_batch.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(ci)]
     for name in EXPORTS:
@@ -402,6 +403,16 @@ class Context:
         b, c, h, w = x.shape
         out = torch.empty(b, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, device=x.device, dtype=torch.float32)
         _check(self.lib.nqa_l2pool(self.handle, _ptr(x), b, c, h, w, _ptr(out), _stream(x.device)))
+        return out
+
+    def resize_bilinear(self, x: torch.Tensor, size, antialias: bool = False) -> torch.Tensor:
+        """[B,C,H,W] -> [B,C,OH,OW], bilinear, align_corners=False (optionally antialiased like PIL / torchvision)."""
+        x = _as_input(x, "x")
+        b, c, h, w = x.shape
+        oh, ow = int(size[0]), int(size[1])
+        out = torch.empty(b, c, oh, ow, device=x.device, dtype=torch.float32)
+        _check(self.lib.nqa_resize_bilinear(self.handle, _ptr(x), b, c, h, w, oh, ow, 1 if antialias else 0, _ptr(out),
+                                            _stream(x.device)))
         return out
 
     def conv3x3_relu(self, x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, precision: int) -> torch.Tensor:

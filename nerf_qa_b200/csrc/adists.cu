@@ -243,11 +243,13 @@ planes_sums_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int pair
   bf16* dsty = out + (size_t)(pairs + b) * c * hw;
   const bool even = (hw & 1) == 0;     // 4-byte stores need even plane sizes (plane starts stay 4-byte aligned)
 
-  float acc[8][8];   // [channel lc*8 + j][sum]
+  // acc[e][s]: sums of the channel pair (lc*8 + 2e, lc*8 + 2e + 1) -- the two bf16 halves of a loaded word -- on the
+  // packed fp32 pipe
+  float2 acc[4][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int e = 0; e < 4; ++e)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[j][q] = 0.f;
+    for (int q = 0; q < 8; ++q) acc[e][q] = make_float2(0.f, 0.f);
 
   for (int t = t0; t < t1; ++t) {
     const int p0 = t * kPlaneTile;
@@ -264,18 +266,18 @@ planes_sums_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int pair
       if (p < hw) {
         const uint32_t wx[4] = {vx.x, vx.y, vx.z, vx.w}, wy[4] = {vy.x, vy.y, vy.z, vy.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-#pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            const float a = __uint_as_float(hlf ? (wx[e] & 0xffff0000u) : (wx[e] << 16));
-            const float d = __uint_as_float(hlf ? (wy[e] & 0xffff0000u) : (wy[e] << 16));
-            const float r = fmaxf(a, 0.f);
-            float* s = acc[2 * e + hlf];
-            s[0] += a; s[1] += d;
-            s[2] = fmaf(a, a, s[2]); s[3] = fmaf(d, d, s[3]); s[4] = fmaf(a, d, s[4]);
-            s[5] += r; s[6] = fmaf(r, r, s[6]);
-            s[7] += r > 0.f ? r * __log2f(r) : 0.f;
-          }
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = make_float2(__uint_as_float(wx[e] << 16), __uint_as_float(wx[e] & 0xffff0000u));
+          const float2 d = make_float2(__uint_as_float(wy[e] << 16), __uint_as_float(wy[e] & 0xffff0000u));
+          const float2 r = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
+          // r log2 r with the logarithm of max(r, 1e-30): 0 * (-99.7) = 0 for the rectified zeros, no select
+          const float2 lg = make_float2(__log2f(fmaxf(a.x, 1e-30f)), __log2f(fmaxf(a.y, 1e-30f)));
+          float2* s = acc[e];
+          s[0] = __fadd2_rn(s[0], a); s[1] = __fadd2_rn(s[1], d);
+          s[2] = __ffma2_rn(a, a, s[2]); s[3] = __ffma2_rn(d, d, s[3]); s[4] = __ffma2_rn(a, d, s[4]);
+          s[5] = __fadd2_rn(s[5], r); s[6] = __ffma2_rn(r, r, s[6]);
+          s[7] = __ffma2_rn(r, lg, s[7]);
+        }
       }
     }
     __syncthreads();
@@ -306,7 +308,7 @@ planes_sums_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int pair
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      float v = acc[j][q];
+      float v = (j & 1) ? acc[j >> 1][q].y : acc[j >> 1][q].x;
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
       if (lp == 0) red[((warp * 8 + lc) * 8 + j) * 8 + q] = v;
@@ -1016,7 +1018,9 @@ size_t adists_ps_elems(int H, int W, int window, int level) { return (size_t)mak
 
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
                  void* ws, float* score, cudaStream_t st, float* map_out, const AdistsParts* parts, const AdistsProf* prof,
-                 unsigned sums_done_mask) {
+                 unsigned sums_done_mask, const AdistsOptions* opt) {
+  const AdistsOptions options = opt ? *opt : AdistsOptions();
+  const bool use_mma = options.use_mma;
   int launches = 0;
   struct Part {
     const AdistsProf* p;
@@ -1038,7 +1042,6 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
   double* red = reinterpret_cast<double*>(base + p.off_red);
   unsigned int* cnt = reinterpret_cast<unsigned int*>(base + p.off_cnt);
   const Taps taps = make_taps(window);
-  static const bool use_mma = !(getenv("NQA_ADISTS_MMA") && atoi(getenv("NQA_ADISTS_MMA")) == 0);
 
   cudaMemsetAsync(cnt, 0, (size_t)pairs * sizeof(unsigned int), st);
 
@@ -1083,7 +1086,7 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
       // bf16 planes: the two gaussian passes as banded-Toeplitz products on the tensor pipe (adists_tc.cu)
       csplit_used[k] = L.csplit_mma;
       launches += launch_window_mma(B16(fx[k]), B16(fy[k]), pairs, L.c, L.h, L.w, window, L.csplit_mma, L.choff, chan, wt,
-                                    taps.g, F(L.off_a), F(L.off_b), F(L.off_g), st);
+                                    taps.g, options.mma_terms == 2, F(L.off_a), F(L.off_b), F(L.off_g), st);
     } else if (L.windowed) {
       launches += is16(k) ? level_window<bf16>(window, L, B16(fx[k]), B16(fy[k]), pairs, chan, wt, taps, F(L.off_a), F(L.off_b),
                                                F(L.off_g), st)

@@ -25,6 +25,11 @@ struct AdistsParts {
 };
 // Optional timing hook of the caller (per-family CUDA events): begin(user, part) / end(user, launches) bracket the launches of
 // part 0 = reductions, entropy weights and the ps chain, part 1 = the window kernels.
+// Kernel selection of the stage, owned by the context (read from the environment once, at nqa_ctx_create).
+struct AdistsOptions {
+  bool use_mma = true;   // NQA_ADISTS_MMA=0: CUDA-core window kernel for bf16 planes too
+  int mma_terms = 0;     // NQA_ADISTS_MMA_TERMS: 0 = one bf16 term per operand for maps >= 400k pixels, else two; 2 = always two
+};
 struct AdistsProf {
   void* user = nullptr;
   void (*begin)(void* user, int part) = nullptr;
@@ -32,7 +37,7 @@ struct AdistsProf {
 };
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
                  void* ws, float* score, cudaStream_t st, float* map_out = nullptr, const AdistsParts* parts = nullptr,
-                 const AdistsProf* prof = nullptr, unsigned sums_done_mask = 0);
+                 const AdistsProf* prof = nullptr, unsigned sums_done_mask = 0, const AdistsOptions* opt = nullptr);
 // bf16 trunk: level `level`'s NHWC activations [2*pairs][h][w][c] (x images first) -> bf16 planes [2*pairs][c][h*w],
 // with the level's per-channel sums written into the workspace `ws` on the way (one read of the level instead of
 // three).  Pass bit `level` in adists_stage's sums_done_mask afterwards.  Levels 1..5 (c % 64 == 0) with at least 256 pixels.

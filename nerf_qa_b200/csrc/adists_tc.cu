@@ -381,8 +381,8 @@ void window_mma_tiles(int oh, int ow, int* tiles_x, int* tiles_y) {
 }
 
 int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, int w, int window, int csplit, int choff,
-                      const double* chan, const float* wt, const float* taps_f32, float* amap, float* bmap, float* gmap,
-                      cudaStream_t st) {
+                      const double* chan, const float* wt, const float* taps_f32, bool force_two_terms, float* amap, float* bmap,
+                      float* gmap, cudaStream_t st) {
   TcTaps t;
   double sum = 0.0;
   for (int i = 0; i < 32; ++i) {
@@ -398,7 +398,7 @@ int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, i
   // is 1 / (h w) on average, so for maps of >= 400k pixels even a 10x locally concentrated channel errs by ~1e-8, one
   // hundredth of the 1e-6 stabilisers c1 / c2 -- the 1080p levels 1 and 2, 77% of the work.  Smaller maps (deeper
   // levels, small frames) keep the exact two-term products and the hi + lo split between the passes.
-  const bool two = (long long)h * w < 400000 || (getenv("NQA_ADISTS_MMA_TERMS") && atoi(getenv("NQA_ADISTS_MMA_TERMS")) == 2);
+  const bool two = (long long)h * w < 400000 || force_two_terms;
   dim3 grid(tx * ty, csplit, pairs);
   if (two) {
     ensure_dynamic_smem(window_mma_kernel<true>, kSmemBytes);

@@ -14,7 +14,7 @@ bool window_mma_supported(int window, int h, int w, const void* fx, const void* 
 void window_mma_tiles(int oh, int ow, int* tiles_x, int* tiles_y);
 // taps_f32: the `window` fp32 gaussian taps (rounded to bf16 inside; the result is renormalised by their exact sum)
 int launch_window_mma(const __nv_bfloat16* fx, const __nv_bfloat16* fy, int pairs, int c, int h, int w, int window, int csplit,
-                      int choff, const double* chan, const float* wt, const float* taps_f32, float* amap, float* bmap,
-                      float* gmap, cudaStream_t st);
+                      int choff, const double* chan, const float* wt, const float* taps_f32, bool force_two_terms, float* amap,
+                      float* bmap, float* gmap, cudaStream_t st);
 
 }  // namespace nqa

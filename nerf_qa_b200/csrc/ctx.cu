@@ -106,6 +106,7 @@ struct nqa_ctx {
   int micro_images = 16;                 // full-HD-equivalent images per trunk pass (NQA_MICRO_IMAGES)
   bool fuse_pool_stats = true;           // NQA_POOL_STATS_FUSED=0 falls back to separate pooling / statistics kernels
   bool pool_stats_tma = true;            // NQA_POOL_STATS_TMA=0: register-fed pooling + moments kernel for bf16 levels too
+  AdistsOptions adists_opt;              // NQA_ADISTS_MMA / NQA_ADISTS_MMA_TERMS
   bool adists_fused_sums = true;         // NQA_ADISTS_FUSED_SUMS=0: separate planes / sums / entropy kernels (bf16 trunk)
   ConvTcConfig conv_cfg;                 // kernel selection of the tensor-pipe convolutions (environment read at creation)
   // Encoded tensor maps of the convolution launches, keyed on (buffers, shape): the arena hands out the same addresses
@@ -965,6 +966,8 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   ctx->conv_cfg = conv_tc_config_from_env(ctx->sm_count);
   if (const char* e = getenv("NQA_POOL_STATS_TMA")) ctx->pool_stats_tma = atoi(e) != 0;
   if (const char* e = getenv("NQA_ADISTS_FUSED_SUMS")) ctx->adists_fused_sums = atoi(e) != 0;
+  if (const char* e = getenv("NQA_ADISTS_MMA")) ctx->adists_opt.use_mma = atoi(e) != 0;
+  if (const char* e = getenv("NQA_ADISTS_MMA_TERMS")) ctx->adists_opt.mma_terms = atoi(e);
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming));
   if (const char* e = getenv("NQA_STAGE1_FUSED")) ctx->fuse_stage1 = atoi(e) != 0;
   if (const char* e = getenv("NQA_POOL_STATS_FUSED")) ctx->fuse_pool_stats = atoi(e) != 0;
@@ -1378,7 +1381,7 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     const AdistsProf prof = adists_prof_hook(&prof_state);
     adists_stage(fx, fy, planes16, pairs, H, W, window, ws, score_out + b0, st,
                  map_out ? map_out + (size_t)b0 * H * W : nullptr, parts_out ? &parts : nullptr, &prof,
-                 sums_done);   // launches counted by the hook
+                 sums_done, &ctx->adists_opt);   // launches counted by the hook
   }
   return NQA_OK;
 }
@@ -1533,7 +1536,7 @@ int nqa_adists_from_feats(nqa_ctx* ctx, const float* const feats_x[NQA_NUM_LEVEL
     const void* vx[kNumLevels];
     const void* vy[kNumLevels];
     for (int k = 0; k < kNumLevels; ++k) { vx[k] = feats_x[k]; vy[k] = feats_y[k]; }
-    adists_stage(vx, vy, false, B, H, W, window, ws, score_out, st, nullptr, nullptr, &prof);   // launches counted by the hook
+    adists_stage(vx, vy, false, B, H, W, window, ws, score_out, st, nullptr, nullptr, &prof, 0, &ctx->adists_opt);   // launches counted by the hook
   }
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;
@@ -1721,6 +1724,17 @@ int nqa_l2pool(nqa_ctx* ctx, const float* x, int B, int C, int H, int W, float* 
   if (B < 1 || C < 1 || H < 1 || W < 1) return fail(NQA_ERR_SHAPE, "empty tensor %dx%dx%dx%d", B, C, H, W);
   DeviceGuard guard(ctx->device);
   ctx->launches += launch_l2pool_nchw(x, out, B, C, H, W, static_cast<cudaStream_t>(stream));
+  CUDA_TRY(cudaGetLastError());
+  return NQA_OK;
+}
+
+int nqa_resize_bilinear(nqa_ctx* ctx, const float* x, int B, int C, int H, int W, int OH, int OW, int antialias, float* out,
+                        void* stream) {
+  if (!ctx || !x || !out) return fail(NQA_ERR_INVALID, "null argument");
+  if (B < 1 || C < 1 || H < 1 || W < 1 || OH < 1 || OW < 1)
+    return fail(NQA_ERR_SHAPE, "empty tensor %dx%dx%dx%d -> %dx%d", B, C, H, W, OH, OW);
+  DeviceGuard guard(ctx->device);
+  ctx->launches += launch_resize_bilinear(x, out, B * C, H, W, OH, OW, antialias != 0, static_cast<cudaStream_t>(stream));
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;
 }

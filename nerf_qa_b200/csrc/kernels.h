@@ -179,6 +179,10 @@ int launch_conv1_1_bwd(const T* gz, const Conv11BwdWeights& wb, int nx, int n, i
 int launch_pack_w_bwd(const float* w_oihw, int cin, int cout, float* w_f32, bf16* w_hi, cudaStream_t st);
 int launch_pack_w11_bwd(const float* w_oihw, float* out, cudaStream_t st);
 
+// ---- frame resizing (resize.cu): NCHW fp32 planes [planes][h][w] -> [planes][oh][ow], bilinear, align_corners=False
+int launch_resize_bilinear(const float* in, float* out, int planes, int h, int w, int oh, int ow, bool antialias,
+                           cudaStream_t st);
+
 // ---- micro-benchmarks (microbench.cu): measured roofline denominators ------------------------------------------
 // which = 0: packed fp32 FMAs (FFMA2) on the CUDA cores; which = 1: warp-level mma.sync m16n8k16 bf16.  FMA/s.
 int microbench_rate(int which, int sm_count, float* scratch, cudaStream_t st, double* fma_per_s);
