@@ -239,6 +239,11 @@ NQA_API int nqa_workspace_bytes(nqa_ctx* ctx, size_t* bytes);
 /* Number of kernels this library has launched on the context since creation (bench accounting). */
 NQA_API int nqa_launch_count(nqa_ctx* ctx, uint64_t* launches);
 
+/* Small-frame calls (B * H * W <= 2^21, e.g. the reference's 256 x 256 frames at batch 4, nerf_qa/settings.py:1 and
+ * prep.py:163) of nqa_dists_forward (without s1s2_out), nqa_adists_forward and nqa_dists_adists_forward are replayed
+ * from a CUDA graph captured at the second call of a shape (NQA_GRAPHS=0 disables it).  Number of replays so far: */
+NQA_API int nqa_graph_replays(nqa_ctx* ctx, uint64_t* replays);
+
 /* Per-kernel-family device timing with CUDA events recorded on the launching stream around every
  * launch (bench.py's live roofline numbers).  nqa_profile_read synchronises the device, returns the
  * milliseconds and launch counts accumulated since the previous read, and resets them. */

@@ -28,7 +28,7 @@ EXPORTS = (
     "nqa_set_channel_weights", "nqa_adists_map", "nqa_dists_adists_forward", "nqa_dists_forward_saved",
     "nqa_dists_backward_saved", "nqa_tape_release", "nqa_set_alpha_beta_async", "nqa_set_channel_weights_async",
     "nqa_adists_forward_host", "nqa_dists_adists_forward_host", "nqa_adists_parts", "nqa_adists_ps_elems",
-    "nqa_measure_rate", "nqa_resize_bilinear",
+    "nqa_measure_rate", "nqa_resize_bilinear", "nqa_graph_replays",
 )
 KERNEL_FAMILIES = ("conv_tc", "conv1_1", "conv_f32", "l2pool", "stats", "finalize", "layout", "adists", "pool_stats",
                    "stage1", "backward", "adists_window")
@@ -84,6 +84,7 @@ def load_library() -> ctypes.CDLL:
     lib.nqa_conv3x3_relu.argtypes = [vp, fp, fp, fp, ci, ci, ci, ci, ci, ci, fp, vp]
     lib.nqa_workspace_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.nqa_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+    lib.nqa_graph_replays.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
     lib.nqa_profile_enable.argtypes = [vp, ci]
     lib.nqa_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     lib.nqa_resize_bilinear.argtypes = [vp, fp, ci, ci, ci, ci, ci, ci, ci, fp, vp]
@@ -429,6 +430,11 @@ class Context:
     def launch_count(self) -> int:
         n = ctypes.c_uint64()
         _check(self.lib.nqa_launch_count(self.handle, ctypes.byref(n)))
+        return int(n.value)
+
+    def graph_replays(self) -> int:
+        n = ctypes.c_uint64()
+        _check(self.lib.nqa_graph_replays(self.handle, ctypes.byref(n)))
         return int(n.value)
 
     def profile_enable(self, on: bool) -> None:

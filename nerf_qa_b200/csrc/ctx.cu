@@ -127,6 +127,23 @@ struct nqa_ctx {
   cudaEvent_t ev_last = nullptr;
   cudaStream_t last_stream = nullptr;
   bool have_last = false;
+  // CUDA graphs of the device entry points for small frames (the reference's own call pattern is 256 x 256 at batch 4,
+  // nerf_qa/settings.py:1, prep.py:163): ~60 launches of a few microseconds each are launch-bound, so after one plain
+  // call at a shape the sequence is captured once -- on staging buffers, so the graph does not depend on the caller's
+  // addresses -- and replayed.  NQA_GRAPHS=0 switches this off.
+  struct GraphEntry {
+    int kind, B, H, W, prec, window, ab_norm;
+    int state = 0;                 // 0 = seen once (warmed up), 2 = captured, -1 = capture failed (plain path)
+    cudaGraphExec_t exec = nullptr;
+    float *sx = nullptr, *sy = nullptr, *sout = nullptr;
+    int n_out = 1;
+    uint64_t launches = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  bool use_graphs = true;
+  long long graph_max_pixels = 1ll << 21;   // B * H * W up to 32 frames of 256 x 256
+  uint64_t graph_replays = 0;
+  cudaEvent_t ev_graph_in = nullptr, ev_graph_out = nullptr;
   Arena arena;
   uint64_t launches = 0;
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
@@ -186,6 +203,8 @@ struct DeviceGuard {
   }
 };
 
+void drop_graphs(nqa_ctx* ctx);
+
 int ensure_arena(nqa_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->arena.cap) return NQA_OK;
   if (ctx->arena.base) {
@@ -194,6 +213,7 @@ int ensure_arena(nqa_ctx* ctx, size_t bytes) {
     ctx->arena.base = nullptr;
     ctx->arena.cap = 0;
     ctx->plan_cache.clear();   // the cached tensor maps point into the old arena
+    drop_graphs(ctx);          // and so do the captured launch sequences
   }
   const size_t want = bytes + (bytes >> 4) + (1 << 20);
   void* p = nullptr;
@@ -289,6 +309,88 @@ int pick_micro_pairs(const nqa_ctx* ctx, int B, int H, int W) {
   if (pairs > 256) pairs = 256;
   if (pairs > B) pairs = B;
   return (int)pairs;
+}
+
+void drop_graphs(nqa_ctx* ctx) {
+  for (auto& g : ctx->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    cudaFree(g.sx);
+    cudaFree(g.sy);
+    cudaFree(g.sout);
+  }
+  ctx->graphs.clear();
+}
+
+// Runs `body(x, y, outs, stream)` -- the plain launch sequence of an entry point writing n_out vectors of B scores --
+// either directly on `st` or, for small frames from the second call at a shape on, as a replay of its captured graph.
+template <typename F>
+int graphed_call(nqa_ctx* ctx, int kind, const float* x, const float* y, int B, int H, int W, int prec, int window,
+                 float* const* outs, int n_out, cudaStream_t st, F&& body) {
+  const bool eligible = ctx->use_graphs && !ctx->profiling && ctx->lanes == 1 && (long long)B * H * W <= ctx->graph_max_pixels;
+  if (!eligible) return body(x, y, outs, st);
+  nqa_ctx::GraphEntry* e = nullptr;
+  for (auto& g : ctx->graphs)
+    if (g.kind == kind && g.B == B && g.H == H && g.W == W && g.prec == prec && g.window == window &&
+        g.ab_norm == (ctx->ab_normalize ? 1 : 0)) {
+      e = &g;
+      break;
+    }
+  if (!e) {   // first call at this shape: plain (grows the arena, sets kernel attributes, fills the tensor-map cache)
+    const int rc = body(x, y, outs, st);
+    if (rc == NQA_OK) {
+      if (ctx->graphs.size() >= 64) drop_graphs(ctx);
+      nqa_ctx::GraphEntry g;
+      g.kind = kind; g.B = B; g.H = H; g.W = W; g.prec = prec; g.window = window; g.ab_norm = ctx->ab_normalize ? 1 : 0;
+      g.n_out = n_out;
+      ctx->graphs.push_back(g);
+    }
+    return rc;
+  }
+  if (e->state < 0) return body(x, y, outs, st);
+  const size_t frame_bytes = (size_t)B * 3 * H * W * sizeof(float);
+  cudaStream_t gs = ctx->compute_stream;
+  if (e->state == 0) {   // second call: capture on the staging buffers
+    e->state = -1;
+    if (cudaMalloc(&e->sx, frame_bytes) != cudaSuccess || cudaMalloc(&e->sy, frame_bytes) != cudaSuccess ||
+        cudaMalloc(&e->sout, (size_t)n_out * B * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError();
+      return body(x, y, outs, st);
+    }
+    float* souts[2] = {e->sout, e->sout + B};
+    const uint64_t before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    // everything earlier on the internal stream has to be done before it starts capturing
+    CUDA_TRY(cudaStreamSynchronize(gs));
+    if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return body(x, y, outs, st);
+    }
+    const int rc = body(e->sx, e->sy, souts, gs);
+    const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+    e->launches = ctx->launches - before;
+    ctx->launches = before;   // nothing ran yet
+    if (rc != NQA_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&e->exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      e->exec = nullptr;
+      return body(x, y, outs, st);
+    }
+    cudaGraphDestroy(graph);
+    e->state = 2;
+  }
+  // replay: internal stream after the caller's, the caller's after the internal one
+  CUDA_TRY(cudaEventRecord(ctx->ev_graph_in, st));
+  CUDA_TRY(cudaStreamWaitEvent(gs, ctx->ev_graph_in, 0));
+  CUDA_TRY(cudaMemcpyAsync(e->sx, x, frame_bytes, cudaMemcpyDeviceToDevice, gs));
+  CUDA_TRY(cudaMemcpyAsync(e->sy, y, frame_bytes, cudaMemcpyDeviceToDevice, gs));
+  CUDA_TRY(cudaGraphLaunch(e->exec, gs));
+  for (int o = 0; o < n_out; ++o)
+    CUDA_TRY(cudaMemcpyAsync(outs[o], e->sout + (size_t)o * B, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, gs));
+  CUDA_TRY(cudaEventRecord(ctx->ev_graph_out, gs));
+  CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_graph_out, 0));
+  ctx->launches += e->launches;
+  ++ctx->graph_replays;
+  return NQA_OK;
 }
 
 // ---- weight packing kernels ---------------------------------------------------------------------
@@ -969,6 +1071,10 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   if (const char* e = getenv("NQA_ADISTS_MMA")) ctx->adists_opt.use_mma = atoi(e) != 0;
   if (const char* e = getenv("NQA_ADISTS_MMA_TERMS")) ctx->adists_opt.mma_terms = atoi(e);
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_graph_in, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_graph_out, cudaEventDisableTiming));
+  if (const char* e = getenv("NQA_GRAPHS")) ctx->use_graphs = atoi(e) != 0;
+  if (const char* e = getenv("NQA_GRAPH_MAX_PIXELS")) ctx->graph_max_pixels = atoll(e);
   if (const char* e = getenv("NQA_STAGE1_FUSED")) ctx->fuse_stage1 = atoi(e) != 0;
   if (const char* e = getenv("NQA_POOL_STATS_FUSED")) ctx->fuse_pool_stats = atoi(e) != 0;
   if (const char* e = getenv("NQA_STAGE1_PAIR")) ctx->stage1_pair = atoi(e) != 0;
@@ -1043,6 +1149,9 @@ int nqa_ctx_destroy(nqa_ctx* ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
+  if (ctx->ev_graph_in) cudaEventDestroy(ctx->ev_graph_in);
+  if (ctx->ev_graph_out) cudaEventDestroy(ctx->ev_graph_out);
+  drop_graphs(ctx);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
   cudaGetLastError();
@@ -1140,7 +1249,12 @@ int nqa_dists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   StreamOrder so(ctx, st);
   if (so.rc != NQA_OK) return so.rc;
-  return dists_forward_device(ctx, x, y, B, H, W, precision, score_out, s1s2_out, st);
+  if (s1s2_out) return dists_forward_device(ctx, x, y, B, H, W, precision, score_out, s1s2_out, st);
+  float* outs[1] = {score_out};
+  return graphed_call(ctx, 0, x, y, B, H, W, precision, 0, outs, 1, st,
+                      [&](const float* gx, const float* gy, float* const* go, cudaStream_t gs) {
+                        return dists_forward_device(ctx, gx, gy, B, H, W, precision, go[0], nullptr, gs);
+                      });
 }
 
 int nqa_dists_forward_host(nqa_ctx* ctx, const float* x_host, const float* y_host, int B, int H, int W, int precision,
@@ -1413,8 +1527,12 @@ int nqa_adists_map(nqa_ctx* ctx, const float* x, const float* y, int B, int H, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   StreamOrder so(ctx, st);
   if (so.rc != NQA_OK) return so.rc;
-  rc = precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, score_out, map_out, st)
-                                  : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, score_out, map_out, st);
+  auto body = [&](const float* gx, const float* gy, float* const* go, cudaStream_t gs) {
+    return precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, gx, gy, B, H, W, window, precision, go[0], map_out, gs)
+                                      : adists_impl<bf16>(ctx, gx, gy, B, H, W, window, precision, go[0], map_out, gs);
+  };
+  float* outs[1] = {score_out};
+  rc = map_out ? body(x, y, outs, st) : graphed_call(ctx, 1, x, y, B, H, W, precision, window, outs, 1, st, body);
   if (rc != NQA_OK) return rc;
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;
@@ -1466,8 +1584,13 @@ int nqa_dists_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   StreamOrder so(ctx, st);
   if (so.rc != NQA_OK) return so.rc;
-  rc = precision == NQA_PREC_FP32 ? adists_impl<float>(ctx, x, y, B, H, W, window, precision, adists_out, nullptr, st, dists_out)
-                                  : adists_impl<bf16>(ctx, x, y, B, H, W, window, precision, adists_out, nullptr, st, dists_out);
+  float* outs[2] = {adists_out, dists_out};
+  rc = graphed_call(ctx, 2, x, y, B, H, W, precision, window, outs, 2, st,
+                    [&](const float* gx, const float* gy, float* const* go, cudaStream_t gs) {
+                      return precision == NQA_PREC_FP32
+                                 ? adists_impl<float>(ctx, gx, gy, B, H, W, window, precision, go[0], nullptr, gs, go[1])
+                                 : adists_impl<bf16>(ctx, gx, gy, B, H, W, window, precision, go[0], nullptr, gs, go[1]);
+                    });
   if (rc != NQA_OK) return rc;
   CUDA_TRY(cudaGetLastError());
   return NQA_OK;
@@ -1798,6 +1921,12 @@ int nqa_workspace_bytes(nqa_ctx* ctx, size_t* bytes) {
 int nqa_launch_count(nqa_ctx* ctx, uint64_t* launches) {
   if (!ctx || !launches) return fail(NQA_ERR_INVALID, "null argument");
   *launches = ctx->launches;
+  return NQA_OK;
+}
+
+int nqa_graph_replays(nqa_ctx* ctx, uint64_t* replays) {
+  if (!ctx || !replays) return fail(NQA_ERR_INVALID, "null argument");
+  *replays = ctx->graph_replays;
   return NQA_OK;
 }
 

@@ -13,7 +13,9 @@ commits the outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` hol
 those vectors.
 
 Arithmetic follows the reference in fp32 (or fp64 when the inputs are double) with the same ATen ops the
-reference's CPU path dispatches to, so it also serves as the timed host-CPU baseline ("port").
+reference's CPU path dispatches to, so it also serves as the timed host-CPU baseline ("port").  The functions follow
+the device of their inputs (constants are created there), so a test can also run them as eager PyTorch on a GPU -- the
+reference's own GPU mode -- for context timings.
 
 File:line citations are relative to /root/reference/.
 """
@@ -46,7 +48,7 @@ def hanning_filter(dtype=torch.float32) -> torch.Tensor:
 def l2pool(x: torch.Tensor) -> torch.Tensor:
     """sqrt(blur3x3(x^2, stride 2, pad 1) + 1e-12), depthwise (DISTS_pt.py:22-25, ADISTS.py:28-31)."""
     c = x.shape[1]
-    filt = hanning_filter(x.dtype)[None, None].repeat(c, 1, 1, 1)
+    filt = hanning_filter(x.dtype).to(x.device)[None, None].repeat(c, 1, 1, 1)
     out = F.conv2d(x * x, filt, stride=2, padding=1, groups=c)
     return (out + 1e-12).sqrt()
 
@@ -54,8 +56,8 @@ def l2pool(x: torch.Tensor) -> torch.Tensor:
 def trunk(x: torch.Tensor, conv_w: Sequence[torch.Tensor], conv_b: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     """forward_once (DISTS_pt.py:91-103 == ADISTS.py:112-125): returns the six levels
     [raw x, relu1_2, relu2_2, relu3_3, relu4_3, relu5_3]."""
-    mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD, dtype=x.dtype).view(1, 3, 1, 1)
+    mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
     h = (x - mean) / std
     feats = [x]
     li = 0
@@ -149,7 +151,7 @@ def adists_structure_prob(feats_x: Sequence[torch.Tensor], window_size: int = 21
     global-statistics branch (the reference's bare ``except``)."""
     c0 = 1e-12
     x0 = feats_x[0]
-    win = gaussian_window(window_size, x0.dtype)
+    win = gaussian_window(window_size, x0.dtype).to(x0.device)
     prod = torch.ones_like(x0[:, :1])
     out: List[Optional[torch.Tensor]] = [None] * len(feats_x)
     for k in range(len(feats_x) - 1, -1, -1):
@@ -196,7 +198,7 @@ def adists_from_feats(feats_x, feats_y, window_size: int = 21, return_parts: boo
     """ADISTS.forward after the trunk (ADISTS.py:147-197), per-sample scores [B] (as_loss=False)."""
     ps = adists_structure_prob(feats_x, window_size)
     wts = torch.split(adists_channel_weights(feats_x), list(CHNS), dim=1)
-    win = gaussian_window(window_size, feats_x[0].dtype)
+    win = gaussian_window(window_size, feats_x[0].dtype).to(feats_x[0].device)
     d = 0
     per_level = []
     for k in range(len(CHNS) - 1, -1, -1):
