@@ -98,11 +98,23 @@ int launch_stat_grad_planar(const float* x, const float* y, const float* coef, i
 //   gx_j = [x_j > 0] * ( Px + Qx x_j + R y_j  +  x_j * sum_{o covers j} g(o,j) * gpool_o / pooled_o )
 // thread = (input pixel, 16-byte channel vector); POOL = false for the last level.
 // ================================================================================================
-template <typename T, bool POOL>
+// SPLIT (bf16x3 carriers): every tensor is a bf16 hi + lo pair; values are hi + lo, outputs are split again.
+template <typename T, bool SPLIT>
+__device__ inline void load_split(const T* hi, const T* lo, size_t off, float (&v)[Vec<T>::N]) {
+  Vec<T>::load(hi + off, v);
+  if (SPLIT) {
+    float l[Vec<T>::N];
+    Vec<T>::load(lo + off, l);
+#pragma unroll
+    for (int i = 0; i < Vec<T>::N; ++i) v[i] += l[i];
+  }
+}
+
+template <typename T, bool POOL, bool SPLIT>
 __global__ void __launch_bounds__(256)
 level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* __restrict__ qpoolx,
                   const T* __restrict__ qpooly, const float* __restrict__ coef, int level, int h, int w, int c,
-                  int groups_log2, int ho, int wo, T* __restrict__ gx, T* __restrict__ gy) {
+                  int groups_log2, int ho, int wo, T* __restrict__ gx, T* __restrict__ gy, LevelGradLo<T> lo) {
   // grid = (ceil(w * groups / 256), h, pairs): no divisions in the index math, 32-bit offsets inside an image
   constexpr int V = Vec<T>::N;
   const int idx = blockIdx.x * 256 + threadIdx.x;
@@ -111,8 +123,8 @@ level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* _
   const int iy = blockIdx.y, b = blockIdx.z;
   const size_t off = (((size_t)b * h + iy) * w + ix) * c + (size_t)g * V;
   float x[V], y[V], ox[V], oy[V];
-  Vec<T>::load(fx + off, x);
-  Vec<T>::load(fy + off, y);
+  load_split<T, SPLIT>(fx, lo.fx, off, x);
+  load_split<T, SPLIT>(fy, lo.fy, off, y);
   float sx[V], sy[V];
   if (POOL) {
     // Pooled outputs whose 3x3 stride-2 window (rows 2o-1..2o+1) contains this pixel: one if the index is even
@@ -122,18 +134,17 @@ level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* _
     const float my0 = oy0 < ho ? 1.f : 0.f, my1 = ((iy & 1) && oy0 + 1 < ho) ? 1.f : 0.f;
     const float mx0 = ox0 < wo ? 1.f : 0.f, mx1 = ((ix & 1) && ox0 + 1 < wo) ? 1.f : 0.f;
     const int cy0 = min(oy0, ho - 1), cy1 = min(oy0 + 1, ho - 1), cx0 = min(ox0, wo - 1), cx1 = min(ox0 + 1, wo - 1);
-    const T* qx = qpoolx + (size_t)b * ho * wo * c + (size_t)g * V;
-    const T* qy = qpooly + (size_t)b * ho * wo * c + (size_t)g * V;
+    const size_t qbase = (size_t)b * ho * wo * c + (size_t)g * V;
     const int o00 = (cy0 * wo + cx0) * c, o01 = (cy0 * wo + cx1) * c, o10 = (cy1 * wo + cx0) * c, o11 = (cy1 * wo + cx1) * c;
     float a00[V], a01[V], a10[V], a11[V], d00[V], d01[V], d10[V], d11[V];
-    Vec<T>::load(qx + o00, a00);        // = d loss / d pooled  /  pooled  (kEpiDivide epilogue)
-    Vec<T>::load(qx + o01, a01);
-    Vec<T>::load(qx + o10, a10);
-    Vec<T>::load(qx + o11, a11);
-    Vec<T>::load(qy + o00, d00);
-    Vec<T>::load(qy + o01, d01);
-    Vec<T>::load(qy + o10, d10);
-    Vec<T>::load(qy + o11, d11);
+    load_split<T, SPLIT>(qpoolx, lo.qpoolx, qbase + o00, a00);        // = d loss / d pooled  /  pooled  (kEpiDivide epilogue)
+    load_split<T, SPLIT>(qpoolx, lo.qpoolx, qbase + o01, a01);
+    load_split<T, SPLIT>(qpoolx, lo.qpoolx, qbase + o10, a10);
+    load_split<T, SPLIT>(qpoolx, lo.qpoolx, qbase + o11, a11);
+    load_split<T, SPLIT>(qpooly, lo.qpooly, qbase + o00, d00);
+    load_split<T, SPLIT>(qpooly, lo.qpooly, qbase + o01, d01);
+    load_split<T, SPLIT>(qpooly, lo.qpooly, qbase + o10, d10);
+    load_split<T, SPLIT>(qpooly, lo.qpooly, qbase + o11, d11);
     const float m00 = my0 * mx0, m01 = my0 * mx1, m10 = my1 * mx0, m11 = my1 * mx1;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -172,27 +183,47 @@ level_grad_kernel(const T* __restrict__ fx, const T* __restrict__ fy, const T* _
   }
   Vec<T>::store(gx + off, ox);
   Vec<T>::store(gy + off, oy);
+  if (SPLIT) {   // residual carriers: v - round(v)
+    float rx[V], ry[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      rx[i] = ox[i] - to_float(from_float<T>(ox[i]));
+      ry[i] = oy[i] - to_float(from_float<T>(oy[i]));
+    }
+    Vec<T>::store(lo.gx + off, rx);
+    Vec<T>::store(lo.gy + off, ry);
+  }
 }
 
 template <typename T>
 int launch_level_grad(const T* fx, const T* fy, const T* qpoolx, const T* qpooly, const float* coef, int level, int pairs,
-                      int h, int w, int c, T* gx, T* gy, cudaStream_t st) {
+                      int h, int w, int c, T* gx, T* gy, cudaStream_t st, const LevelGradLo<T>* lo) {
   const int groups = c / Vec<T>::N;            // 8 .. 128, a power of two for every VGG level
   int groups_log2 = 0;
   while ((1 << groups_log2) < groups) ++groups_log2;
   if ((1 << groups_log2) != groups || h > 65535 || pairs > 65535) return 0;
   const dim3 grid((unsigned)((w * groups + 255) / 256), (unsigned)h, (unsigned)pairs);
-  if (qpoolx)
-    level_grad_kernel<T, true><<<grid, 256, 0, st>>>(fx, fy, qpoolx, qpooly, coef, level, h, w, c, groups_log2, pooled(h),
-                                                    pooled(w), gx, gy);
-  else
-    level_grad_kernel<T, false><<<grid, 256, 0, st>>>(fx, fy, nullptr, nullptr, coef, level, h, w, c, groups_log2, 0, 0, gx, gy);
+  const LevelGradLo<T> none;
+  if (lo) {
+    if (qpoolx)
+      level_grad_kernel<T, true, true><<<grid, 256, 0, st>>>(fx, fy, qpoolx, qpooly, coef, level, h, w, c, groups_log2,
+                                                            pooled(h), pooled(w), gx, gy, *lo);
+    else
+      level_grad_kernel<T, false, true><<<grid, 256, 0, st>>>(fx, fy, nullptr, nullptr, coef, level, h, w, c, groups_log2, 0,
+                                                             0, gx, gy, *lo);
+  } else if (qpoolx) {
+    level_grad_kernel<T, true, false><<<grid, 256, 0, st>>>(fx, fy, qpoolx, qpooly, coef, level, h, w, c, groups_log2,
+                                                           pooled(h), pooled(w), gx, gy, none);
+  } else {
+    level_grad_kernel<T, false, false><<<grid, 256, 0, st>>>(fx, fy, nullptr, nullptr, coef, level, h, w, c, groups_log2, 0,
+                                                            0, gx, gy, none);
+  }
   return 1;
 }
 template int launch_level_grad<float>(const float*, const float*, const float*, const float*, const float*, int, int, int, int,
-                                      int, float*, float*, cudaStream_t);
+                                      int, float*, float*, cudaStream_t, const LevelGradLo<float>*);
 template int launch_level_grad<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, const float*, int, int, int, int, int,
-                                     bf16*, bf16*, cudaStream_t);
+                                     bf16*, bf16*, cudaStream_t, const LevelGradLo<bf16>*);
 
 // ================================================================================================
 // conv1_1 backward + input normalisation: gz [n,h,w,64] (gradient w.r.t. the pre-ReLU output of conv1_1, already
@@ -205,8 +236,8 @@ template int launch_level_grad<bf16>(const bf16*, const bf16*, const bf16*, cons
 // step time; the kernel is far from the FP32 roofline (0.4 ms) -- a tensor-core N=16 variant is the next step.
 template <typename T>
 __global__ void __launch_bounds__(128)
-conv1_1_bwd_kernel(const T* __restrict__ gz, const __grid_constant__ Conv11BwdWeights wb, int nx, int h, int w,
-                   float* __restrict__ gx, float* __restrict__ gy) {
+conv1_1_bwd_kernel(const T* __restrict__ gz, const T* __restrict__ gz_lo, const __grid_constant__ Conv11BwdWeights wb,
+                   int nx, int h, int w, float* __restrict__ gx, float* __restrict__ gy) {
   constexpr int V = Vec<T>::N;
   const int img = blockIdx.z, y = blockIdx.y, x = blockIdx.x * 128 + threadIdx.x;
   if (x >= w) return;
@@ -219,11 +250,18 @@ conv1_1_bwd_kernel(const T* __restrict__ gz, const __grid_constant__ Conv11BwdWe
     for (int s = 0; s < 3; ++s) {
       const int ox = x + 1 - s;
       if (ox < 0 || ox >= w) continue;
-      const T* src = gz + (((size_t)img * h + oy) * w + ox) * 64;
+      const size_t soff = (((size_t)img * h + oy) * w + ox) * 64;
+      const T* src = gz + soff;
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += V) {
         float v[V];
         Vec<T>::load(src + c0, v);
+        if (gz_lo) {   // bf16x3 carrier
+          float l[V];
+          Vec<T>::load(gz_lo + soff + c0, l);
+#pragma unroll
+          for (int i = 0; i < V; ++i) v[i] += l[i];
+        }
 #pragma unroll
         for (int i = 0; i < V; ++i) {     // weights: compile-time offsets into the constant bank
           acc[0] = fmaf(v[i], wb.w[r * 3 + s][c0 + i][0], acc[0]);
@@ -241,13 +279,15 @@ conv1_1_bwd_kernel(const T* __restrict__ gz, const __grid_constant__ Conv11BwdWe
 
 template <typename T>
 int launch_conv1_1_bwd(const T* gz, const Conv11BwdWeights& wb, int nx, int n, int h, int w, float* gx, float* gy,
-                       cudaStream_t st) {
+                       cudaStream_t st, const T* gz_lo) {
   dim3 grid(ceil_div(w, 128), h, n);
-  conv1_1_bwd_kernel<T><<<grid, 128, 0, st>>>(gz, wb, nx, h, w, gx, gy);
+  conv1_1_bwd_kernel<T><<<grid, 128, 0, st>>>(gz, gz_lo, wb, nx, h, w, gx, gy);
   return 1;
 }
-template int launch_conv1_1_bwd<float>(const float*, const Conv11BwdWeights&, int, int, int, int, float*, float*, cudaStream_t);
-template int launch_conv1_1_bwd<bf16>(const bf16*, const Conv11BwdWeights&, int, int, int, int, float*, float*, cudaStream_t);
+template int launch_conv1_1_bwd<float>(const float*, const Conv11BwdWeights&, int, int, int, int, float*, float*, cudaStream_t,
+                                       const float*);
+template int launch_conv1_1_bwd<bf16>(const bf16*, const Conv11BwdWeights&, int, int, int, int, float*, float*, cudaStream_t,
+                                      const bf16*);
 
 // ================================================================================================
 // weight packing for the data-gradient convolutions
@@ -255,7 +295,7 @@ template int launch_conv1_1_bwd<bf16>(const bf16*, const Conv11BwdWeights&, int,
 // w OIHW [cout][cin][3][3] ->  w_f32 [tap'][cout][cin],  w_hi [cin][tap'][cout] (K-major rows for the tcgen05 B
 // operand), tap' = 8 - tap (180-degree rotation), roles of cin / cout swapped.
 __global__ void pack_w_bwd_kernel(const float* __restrict__ w, int cin, int cout, float* __restrict__ w_f32,
-                                  bf16* __restrict__ w_hi) {
+                                  bf16* __restrict__ w_hi, bf16* __restrict__ w_lo) {
   const size_t total = (size_t)cout * cin * 9;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int tap = (int)(i % 9);
@@ -264,7 +304,9 @@ __global__ void pack_w_bwd_kernel(const float* __restrict__ w, int cin, int cout
     const float v = w[i];
     const int tb = 8 - tap;
     if (w_f32) w_f32[((size_t)tb * cout + co) * cin + ci] = v;
-    w_hi[(size_t)ci * 9 * cout + (size_t)tb * cout + co] = __float2bfloat16_rn(v);
+    const bf16 hi = __float2bfloat16_rn(v);
+    w_hi[(size_t)ci * 9 * cout + (size_t)tb * cout + co] = hi;
+    if (w_lo) w_lo[(size_t)ci * 9 * cout + (size_t)tb * cout + co] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 // conv1_1: w [64][3][3][3] -> [tap][co][ci] (indexed by the FORWARD tap: input pixel p feeds output p - shift(tap))
@@ -275,8 +317,8 @@ __global__ void pack_w11_bwd_kernel(const float* __restrict__ w, float* __restri
   out[(tap * 64 + co) * 3 + ci] = w[i];
 }
 
-int launch_pack_w_bwd(const float* w_oihw, int cin, int cout, float* w_f32, bf16* w_hi, cudaStream_t st) {
-  pack_w_bwd_kernel<<<1024, 256, 0, st>>>(w_oihw, cin, cout, w_f32, w_hi);
+int launch_pack_w_bwd(const float* w_oihw, int cin, int cout, float* w_f32, bf16* w_hi, cudaStream_t st, bf16* w_lo) {
+  pack_w_bwd_kernel<<<1024, 256, 0, st>>>(w_oihw, cin, cout, w_f32, w_hi, w_lo);
   return 1;
 }
 int launch_pack_w11_bwd(const float* w_oihw, float* out, cudaStream_t st) {

@@ -48,6 +48,9 @@ struct Params {
   const float* bias;
   bf16* out;
   bf16* out_lo;
+  int epi;              // ConvEpilogue: bias + ReLU (forward) or the data-gradient epilogues (bf16x3 backward)
+  const bf16* mask;     // kEpiMask / kEpiDivide: saved activation of the output's shape (hi carrier)
+  const bf16* mask_lo;  // kEpiDivide with a bf16x3 carrier: residual of the saved activation
 };
 
 template <int BLOCK_N, bool SPLIT>
@@ -210,8 +213,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + ch * 32, r);
         tmem_ld_wait();
         float v[32];
+        if (p.epi == kEpiBiasRelu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bias_s[n0 + ch * 32 + j], 0.f);
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bias_s[n0 + ch * 32 + j], 0.f);
+        } else {
+          // data-gradient epilogues (kernels.h ConvEpilogue): plain sum, sum masked by the ReLU of the layer below, or
+          // sum / pooled activation; the saved tensor has the output's shape
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.epi != kEpiPlain && valid) {
+            const uint4* mh = reinterpret_cast<const uint4*>(p.mask + obase + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float m[8];
+              Vec<bf16>::unpack(__ldg(mh + q), m);
+              if (p.epi == kEpiDivide && p.mask_lo) {
+                float ml[8];
+                Vec<bf16>::unpack(__ldg(reinterpret_cast<const uint4*>(p.mask_lo + obase + ch * 32) + q), ml);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] += ml[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                v[q * 8 + j] = p.epi == kEpiMask ? (m[j] > 0.f ? v[q * 8 + j] : 0.f) : v[q * 8 + j] / m[j];
+            }
+          }
+        }
         if (valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + obase + ch * 32);
 #pragma unroll
@@ -323,6 +350,7 @@ static int launch_impl(const ConvTcPlan& plan, cudaStream_t st) {
   p.num_n_tiles = plan.cout / BLOCK_N;
   p.num_tiles = plan.n * plan.tiles_h * plan.tiles_w * p.num_n_tiles;
   p.bias = plan.bias; p.out = plan.out; p.out_lo = plan.out_lo;
+  p.epi = plan.epi; p.mask = plan.mask; p.mask_lo = plan.mask_lo;
   const int grid = p.num_tiles < plan.sm_count ? p.num_tiles : plan.sm_count;
   conv3x3_tc_kernel<BLOCK_N, SPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(plan.tmap_a, plan.tmap_a_lo, plan.tmap_b,
                                                                              plan.tmap_b_lo, p);
@@ -368,6 +396,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in,
   // thin layers: halo-reuse kernel (A tile fetched once instead of nine times)
   plan->epi = kEpiBiasRelu;
   plan->mask = nullptr;
+  plan->mask_lo = nullptr;
   plan->fg_x = plan->fg_y = nullptr;
   plan->fg_nx = 0;
   plan->halo = false;
@@ -426,8 +455,8 @@ int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st) {
     fprintf(stderr, "nerfqa_b200: halo conv configuration does not fit (cin %d cout %d)\n", plan.cin, plan.cout);
     return 0;
   }
-  if (plan.epi != kEpiBiasRelu) {
-    fprintf(stderr, "nerfqa_b200: gradient epilogues need the halo / pair convolution kernels\n");
+  if (plan.epi == kEpiFrameGrad) {
+    fprintf(stderr, "nerfqa_b200: the frame-gradient epilogue needs the halo convolution kernel\n");
     return 0;
   }
   if (plan.split) {

@@ -65,6 +65,8 @@ struct TapeBuf {
 struct SavedActs {
   void* act[kNumConvs] = {};
   void* pool[4] = {};
+  void* act_lo[kNumConvs] = {};   // bf16x3: residual carriers of the same tensors
+  void* pool_lo[4] = {};
   float* moments = nullptr;
   int pairs = 0;
 };
@@ -88,6 +90,7 @@ struct nqa_ctx {
   bf16* w_lo[kNumConvs] = {};            // residual of the bf16 rounding (bf16x3)
   float* w_bwd_f32[kNumConvs] = {};      // data-gradient weights [9][cout][cin] (rotated taps)
   bf16* w_bwd_hi[kNumConvs] = {};        // data-gradient weights [cin][9][cout] bf16
+  bf16* w_bwd_lo[kNumConvs] = {};        // their bf16 rounding residual (bf16x3 backward)
   float* w11_bwd = nullptr;              // conv1_1 backward [9][64][3] (device staging of the packed weights)
   Conv11BwdWeights w11_bwd_host;         // the same, passed to the backward kernel as a parameter (constant bank)
   bf16* w11_bwd_hi = nullptr;            // conv1_1 data-gradient weights for the tensor pipe: [64 (3 used)][9][64] bf16
@@ -691,26 +694,30 @@ int dists_forward_device(nqa_ctx* ctx, const float* x, const float* y, int B, in
 // ---- DISTS backward: one micro-batch ------------------------------------------------------------
 // Recomputes the trunk forward with every activation kept (activation recomputation: nothing survives between the
 // forward and the backward C-ABI calls), then walks the layers back.  See backward.cu for the math.
+// gin_lo / gout_lo / mask_lo: bf16x3 carriers (all null for the single-carrier trunks)
 template <typename T>
-int conv_layer_bwd(nqa_ctx* ctx, int li, const T* gin, T* gout, int n, int h, int w, int epi, const T* mask, cudaStream_t st);
+int conv_layer_bwd(nqa_ctx* ctx, int li, const T* gin, T* gout, int n, int h, int w, int epi, const T* mask, cudaStream_t st,
+                   const T* gin_lo = nullptr, T* gout_lo = nullptr, const T* mask_lo = nullptr);
 template <>
 int conv_layer_bwd<float>(nqa_ctx* ctx, int li, const float* gin, float* gout, int n, int h, int w, int epi,
-                          const float* mask, cudaStream_t st) {
+                          const float* mask, cudaStream_t st, const float*, float*, const float*) {
   ProfScope ps(ctx, NQA_K_CONV_F32, st);
   ctx->launches += launch_conv3x3_f32(gin, gout, ctx->w_bwd_f32[li], nullptr, n, h, w, kConvCout[li], kConvCin[li], st, epi, mask);
   return NQA_OK;
 }
 template <>
 int conv_layer_bwd<bf16>(nqa_ctx* ctx, int li, const bf16* gin, bf16* gout, int n, int h, int w, int epi, const bf16* mask,
-                         cudaStream_t st) {
+                         cudaStream_t st, const bf16* gin_lo, bf16* gout_lo, const bf16* mask_lo) {
   ConvTcPlan plan;
   const char* err = "";
+  const bool split = gin_lo != nullptr;   // bf16x3: hi/lo gradients and weights, three MMAs per k-step (per-tap kernel)
   // roles of the channel counts are swapped; the bias pointer is only staged (512 floats), never applied
-  if (cached_plan(ctx, &plan, gin, nullptr, ctx->w_bwd_hi[li], nullptr, ctx->bias[kNumConvs - 1], gout, nullptr, n, h, w,
-                  kConvCout[li], kConvCin[li], false, &err))
+  if (cached_plan(ctx, &plan, gin, gin_lo, ctx->w_bwd_hi[li], split ? ctx->w_bwd_lo[li] : nullptr, ctx->bias[kNumConvs - 1],
+                  gout, gout_lo, n, h, w, kConvCout[li], kConvCin[li], split, &err))
     return fail(NQA_ERR_CUDA, "%s (backward of layer %d, %dx%dx%d)", err, li, n, h, w);
   plan.epi = epi;
   plan.mask = mask;
+  plan.mask_lo = mask_lo;
   ProfScope ps(ctx, NQA_K_CONV_TC, st);
   const int nl = launch_conv3x3_tc(plan, st);
   if (nl <= 0) return fail(NQA_ERR_CUDA, "backward convolution of layer %d could not be launched", li);
@@ -722,18 +729,24 @@ int conv_layer_bwd<bf16>(nqa_ctx* ctx, int li, const bf16* gin, bf16* gout, int 
 // writes the frame gradients (planes).  bf16 trunk: the halo convolution kernel with the three input channels as
 // output rows and the kEpiFrameGrad epilogue (the CUDA-core kernel is ~2.5x slower); fp32 trunk: CUDA cores.
 template <typename T>
-int conv1_1_bwd(nqa_ctx* ctx, const T* gz, T* scratch, int pairs, int n, int H, int W, float* gx, float* gy, cudaStream_t st);
+int conv1_1_bwd(nqa_ctx* ctx, const T* gz, T* scratch, int pairs, int n, int H, int W, float* gx, float* gy, cudaStream_t st,
+                const T* gz_lo = nullptr);
 template <>
 int conv1_1_bwd<float>(nqa_ctx* ctx, const float* gz, float*, int pairs, int n, int H, int W, float* gx, float* gy,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float*) {
   ctx->launches += launch_conv1_1_bwd<float>(gz, ctx->w11_bwd_host, pairs, n, H, W, gx, gy, st);
   return NQA_OK;
 }
 template <>
 int conv1_1_bwd<bf16>(nqa_ctx* ctx, const bf16* gz, bf16* scratch, int pairs, int n, int H, int W, float* gx, float* gy,
-                      cudaStream_t st) {
+                      cudaStream_t st, const bf16* gz_lo) {
   ConvTcPlan plan;
   const char* err = "";
+  if (gz_lo) {   // bf16x3: the CUDA-core kernel sums the two carriers in fp32
+    ProfScope psb(ctx, NQA_K_BACKWARD, st);
+    ctx->launches += launch_conv1_1_bwd<bf16>(gz, ctx->w11_bwd_host, pairs, n, H, W, gx, gy, st, gz_lo);
+    return NQA_OK;
+  }
   if (ctx->conv11_bwd_tc &&
       cached_plan(ctx, &plan, gz, nullptr, ctx->w11_bwd_hi, nullptr, ctx->bias[kNumConvs - 1], scratch, nullptr, n, H, W, 64, 64,
                   false, &err) == 0 &&
@@ -752,7 +765,7 @@ int conv1_1_bwd<bf16>(nqa_ctx* ctx, const bf16* gz, bf16* scratch, int pairs, in
 
 
 template <typename T>
-size_t saved_bytes(int pairs, int H, int W) {
+size_t saved_bytes(int pairs, int H, int W, int prec = NQA_PREC_BF16) {
   int h[kNumLevels], w[kNumLevels];
   level_dims(H, W, h, w);
   const size_t n = 2 * (size_t)pairs;
@@ -763,20 +776,21 @@ size_t saved_bytes(int pairs, int H, int W) {
     for (int j = 0; j < kStageConvs[stage]; ++j, ++li) total += align256(n * hw * kConvCout[li] * sizeof(T));
     if (stage < 4) total += align256(n * (size_t)h[stage + 2] * w[stage + 2] * kConvCout[li - 1] * sizeof(T));
   }
-  return total + align256((size_t)pairs * kTotalChannels * 5 * sizeof(float)) + 4096;
+  return total * carriers(prec) + align256((size_t)pairs * kTotalChannels * 5 * sizeof(float)) + 4096;
 }
 
 // workspace of one micro-batch besides the saved activations: statistics partials, coefficient table, gradient ping-pong
 template <typename T>
 size_t bwd_work_bytes(int pairs, int H, int W, int prec) {
   const size_t n = 2 * (size_t)pairs;
-  return 2 * align256(n * max_act_elems(H, W) * sizeof(T)) + partial_bytes(pairs, H, W, prec, nullptr, false, true) +
+  return 2 * carriers(prec) * align256(n * max_act_elems(H, W) * sizeof(T)) +
+         partial_bytes(pairs, H, W, prec, nullptr, false, prec != NQA_PREC_BF16X3) +
          align256((size_t)pairs * 5 * kCoefStride * sizeof(float)) + align256(pairs * sizeof(float)) + 8192;
 }
 
 template <typename T>
 size_t dists_bwd_bytes(const nqa_ctx*, int pairs, int H, int W, int prec) {
-  return saved_bytes<T>(pairs, H, W) + bwd_work_bytes<T>(pairs, H, W, prec);
+  return saved_bytes<T>(pairs, H, W, prec) + bwd_work_bytes<T>(pairs, H, W, prec);
 }
 
 // Trunk forward of one micro-batch with every activation kept in `store` (not the fused stage-1 kernel: relu1_1 is
@@ -788,8 +802,9 @@ int trunk_forward_keep(nqa_ctx* ctx, Arena& store, const float* x, const float* 
   int lh[kNumLevels], lw[kNumLevels];
   level_dims(H, W, lh, lw);
   const int n = 2 * pairs;
+  const bool split = prec == NQA_PREC_BF16X3;   // bf16 hi + residual lo carriers for every kept tensor
   PartialBufs pb;
-  partial_bytes(pairs, H, W, prec, &pb, false, true);
+  partial_bytes(pairs, H, W, prec, &pb, false, !split);
   partial_alloc(ctx, pairs, &pb);
   sv->pairs = pairs;
   sv->moments = static_cast<float*>(store.take((size_t)pairs * kTotalChannels * 5 * sizeof(float)));
@@ -800,22 +815,46 @@ int trunk_forward_keep(nqa_ctx* ctx, Arena& store, const float* x, const float* 
   if (through_trunk) {
     int li = 0;
     const T* cur = nullptr;
+    const T* cur_lo = nullptr;
     for (int stage = 0; stage < 5; ++stage) {
       const int h = lh[stage + 1], w = lw[stage + 1];
       for (int j = 0; j < kStageConvs[stage]; ++j, ++li) {
-        T* out = static_cast<T*>(store.take((size_t)n * h * w * kConvCout[li] * sizeof(T)));
+        const size_t bytes = (size_t)n * h * w * kConvCout[li] * sizeof(T);
+        T* out = static_cast<T*>(store.take(bytes));
+        T* out_lo = split ? static_cast<T*>(store.take(bytes)) : nullptr;
         sv->act[li] = out;
+        sv->act_lo[li] = out_lo;
         if (li == 0) {
-          conv1_1_layer<T>(ctx, x, y, pairs, n, h, w, out, nullptr, st);
+          conv1_1_layer<T>(ctx, x, y, pairs, n, h, w, out, out_lo, st);
         } else {
-          const int rc = conv_layer<T>(ctx, li, cur, nullptr, out, nullptr, n, h, w, prec, st);
+          const int rc = conv_layer<T>(ctx, li, cur, cur_lo, out, out_lo, n, h, w, prec, st);
           if (rc != NQA_OK) return rc;
         }
         cur = out;
+        cur_lo = out_lo;
       }
       const int k = stage + 1, c = level_channels(k);
       const size_t half = (size_t)pairs * h * w * c;
-      if (stage < 4) {
+      if (split) {
+        // bf16x3: statistics and pooling as separate kernels on the hi + lo carriers
+        {
+          ProfScope ps(ctx, NQA_K_STATS, st);
+          ctx->launches += launch_stats_nhwc<T>(cur, cur + half, cur_lo, cur_lo + half, pairs, h * w, c, pb.chunks[k], pb.p[k], st);
+        }
+        if (stage < 4) {
+          const size_t pbytes = (size_t)n * lh[k + 1] * lw[k + 1] * c * sizeof(T);
+          T* pooled_t = static_cast<T*>(store.take(pbytes));
+          T* pooled_lo = static_cast<T*>(store.take(pbytes));
+          sv->pool[stage] = pooled_t;
+          sv->pool_lo[stage] = pooled_lo;
+          ProfScope ps(ctx, NQA_K_L2POOL, st);
+          const int nl = launch_l2pool_nhwc<T>(cur, cur_lo, pooled_t, pooled_lo, n, h, w, c, st);
+          if (nl <= 0) return fail(NQA_ERR_SHAPE, "L2pooling: %d images of %dx%d exceed the launch grid", n, h, w);
+          ctx->launches += nl;
+          cur = pooled_t;
+          cur_lo = pooled_lo;
+        }
+      } else if (stage < 4) {
         const size_t half_out = (size_t)pairs * lh[k + 1] * lw[k + 1] * c;
         T* pooled_t = static_cast<T*>(store.take(2 * half_out * sizeof(T)));
         sv->pool[stage] = pooled_t;
@@ -847,18 +886,28 @@ int trunk_backward_walk(nqa_ctx* ctx, const float* x, const float* y, int pairs,
   for (int k = 0; k < kNumLevels; ++k) gl.inv_n[k] = 1.0 / ((double)lh[k] * lw[k]);
   const int levels_valid = through_trunk ? kNumLevels : 1;
   int rc = NQA_OK;
-  ProfScope psb(ctx, NQA_K_BACKWARD, st);
-  ctx->launches += launch_stat_coef(sv.moments, ctx->alpha, ctx->beta, ctx->ab_normalize, grad_score, gl, levels_valid, pairs, coef, st);
+  {
+    ProfScope psb(ctx, NQA_K_BACKWARD, st);
+    ctx->launches += launch_stat_coef(sv.moments, ctx->alpha, ctx->beta, ctx->ab_normalize, grad_score, gl, levels_valid, pairs, coef, st);
+  }
 
   if (through_trunk) {
     const size_t gsz = (size_t)n * max_act_elems(H, W) * sizeof(T);
+    T* const* act_lo = reinterpret_cast<T* const*>(sv.act_lo);
+    T* const* pool_lo = reinterpret_cast<T* const*>(sv.pool_lo);
+    const bool split = sv.act_lo[0] != nullptr;   // bf16x3 tape: every tensor travels as hi + lo
     T* g[2] = {static_cast<T*>(ctx->arena.take(gsz)), static_cast<T*>(ctx->arena.take(gsz))};
+    T* gl[2] = {nullptr, nullptr};
+    if (split) { gl[0] = static_cast<T*>(ctx->arena.take(gsz)); gl[1] = static_cast<T*>(ctx->arena.take(gsz)); }
     int cur = 0;
     {  // last level: statistics gradient only
       const int h = lh[5], w = lw[5], c = level_channels(5);
       const size_t half = (size_t)pairs * h * w * c;
+      LevelGradLo<T> lo;
+      if (split) { lo.fx = act_lo[12]; lo.fy = act_lo[12] + half; lo.gx = gl[cur]; lo.gy = gl[cur] + half; }
+      ProfScope psb(ctx, NQA_K_BACKWARD, st);
       const int nl = launch_level_grad<T>(act[12], act[12] + half, nullptr, nullptr, coef, 5, pairs, h, w, c, g[cur],
-                                          g[cur] + half, st);
+                                          g[cur] + half, st, split ? &lo : nullptr);
       if (nl <= 0) return fail(NQA_ERR_INVALID, "level gradient: unsupported shape %dx%dx%d", h, w, c);
       ctx->launches += nl;
     }
@@ -871,7 +920,8 @@ int trunk_backward_walk(nqa_ctx* ctx, const float* x, const float* y, int pairs,
         // is handed on as grad / pooled (the only form the pooling backward needs)
         const bool first = j == 0;
         rc = conv_layer_bwd<T>(ctx, li, g[cur], g[cur ^ 1], n, h, w, first ? kEpiDivide : kEpiMask,
-                               first ? pool[stage - 1] : act[li - 1], st);
+                               first ? pool[stage - 1] : act[li - 1], st, split ? gl[cur] : nullptr,
+                               split ? gl[cur ^ 1] : nullptr, split && first ? pool_lo[stage - 1] : nullptr);
         if (rc != NQA_OK) return rc;
         cur ^= 1;
       }
@@ -881,15 +931,23 @@ int trunk_backward_walk(nqa_ctx* ctx, const float* x, const float* y, int pairs,
       const int k = stage, hp = lh[k], wp = lw[k], c = level_channels(k);
       const size_t half = (size_t)pairs * hp * wp * c, half_pool = (size_t)pairs * h * w * c;
       const T* feat = act[li];                            // li now indexes the last conv of the stage below
+      LevelGradLo<T> lo;
+      if (split) {
+        lo.fx = act_lo[li]; lo.fy = act_lo[li] + half;
+        lo.qpoolx = gl[cur]; lo.qpooly = gl[cur] + half_pool;
+        lo.gx = gl[cur ^ 1]; lo.gy = gl[cur ^ 1] + half;
+      }
+      ProfScope psb(ctx, NQA_K_BACKWARD, st);
       const int nl = launch_level_grad<T>(feat, feat + half, g[cur], g[cur] + half_pool, coef, k, pairs, hp, wp, c, g[cur ^ 1],
-                                          g[cur ^ 1] + half, st);
+                                          g[cur ^ 1] + half, st, split ? &lo : nullptr);
       if (nl <= 0) return fail(NQA_ERR_INVALID, "level gradient: unsupported shape %dx%dx%d", hp, wp, c);
       ctx->launches += nl;
       cur ^= 1;
     }
-    rc = conv1_1_bwd<T>(ctx, g[cur], g[cur ^ 1], pairs, n, H, W, gx, gy, st);
+    rc = conv1_1_bwd<T>(ctx, g[cur], g[cur ^ 1], pairs, n, H, W, gx, gy, st, split ? gl[cur] : nullptr);
     if (rc != NQA_OK) return rc;
   }
+  ProfScope psb(ctx, NQA_K_BACKWARD, st);
   ctx->launches += launch_stat_grad_planar(x, y, coef, 0, pairs, 3, H * W, gx, gy, through_trunk, st);   // level 0
   return NQA_OK;
 }
@@ -1110,6 +1168,7 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
       CUDA_TRY(cudaMalloc(&ctx->w_lo[i], nw * sizeof(bf16)));
       CUDA_TRY(cudaMalloc(&ctx->w_bwd_f32[i], nw * sizeof(float)));
       CUDA_TRY(cudaMalloc(&ctx->w_bwd_hi[i], nw * sizeof(bf16)));
+      CUDA_TRY(cudaMalloc(&ctx->w_bwd_lo[i], nw * sizeof(bf16)));
     }
   }
   *out = ctx;
@@ -1130,6 +1189,7 @@ int nqa_ctx_destroy(nqa_ctx* ctx) {
   for (int i = 0; i < kNumConvs; ++i) {
     cudaFree(ctx->w_bwd_f32[i]);
     cudaFree(ctx->w_bwd_hi[i]);
+    cudaFree(ctx->w_bwd_lo[i]);
     cudaFree(ctx->bias[i]);
     cudaFree(ctx->w_f32[i]);
     cudaFree(ctx->w_hi[i]);
@@ -1183,7 +1243,7 @@ int nqa_set_vgg_weights(nqa_ctx* ctx, const float* const w[NQA_NUM_CONVS], const
       ctx->launches += launch_pack_w_bwd(tmp, 3, 64, nullptr, ctx->w11_bwd_hi, 0);
     } else {
       pack_w_kernel<<<1024, 256>>>(tmp, kConvCin[i], kConvCout[i], ctx->w_f32[i], ctx->w_hi[i], ctx->w_lo[i]);
-      ctx->launches += launch_pack_w_bwd(tmp, kConvCin[i], kConvCout[i], ctx->w_bwd_f32[i], ctx->w_bwd_hi[i], 0);
+      ctx->launches += launch_pack_w_bwd(tmp, kConvCin[i], kConvCout[i], ctx->w_bwd_f32[i], ctx->w_bwd_hi[i], 0, ctx->w_bwd_lo[i]);
     }
     ctx->launches += 1;
     e = cudaDeviceSynchronize();
@@ -1670,14 +1730,13 @@ int nqa_dists_backward(nqa_ctx* ctx, const float* x, const float* y, int B, int 
   int rc = check_ready(ctx, true);
   if (rc != NQA_OK) return rc;
   if (!x || !y || !grad_score || !grad_x || !grad_y) return fail(NQA_ERR_INVALID, "null tensor pointer");
-  if (precision != NQA_PREC_FP32 && precision != NQA_PREC_BF16)
-    return fail(NQA_ERR_INVALID, "the backward pass supports the fp32 and bf16 trunks (got precision %d)", precision);
+  if ((rc = check_prec(precision)) != NQA_OK) return rc;
   if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   StreamOrder so(ctx, st);
   if (so.rc != NQA_OK) return so.rc;
-  int mb = pick_micro_pairs(ctx, B, H, W) / 2;
+  int mb = pick_micro_pairs(ctx, B, H, W) / (precision == NQA_PREC_BF16X3 ? 4 : 2);
   if (mb < 1) mb = 1;
   const size_t need = precision == NQA_PREC_FP32 ? dists_bwd_bytes<float>(ctx, mb, H, W, precision)
                                                  : dists_bwd_bytes<bf16>(ctx, mb, H, W, precision);
@@ -1701,26 +1760,25 @@ int nqa_dists_forward_saved(nqa_ctx* ctx, const float* x, const float* y, int B,
   int rc = check_ready(ctx, true);
   if (rc != NQA_OK) return rc;
   if (!x || !y || !score_out || !tape_out) return fail(NQA_ERR_INVALID, "null tensor pointer");
-  if (precision != NQA_PREC_FP32 && precision != NQA_PREC_BF16)
-    return fail(NQA_ERR_INVALID, "the backward pass supports the fp32 and bf16 trunks (got precision %d)", precision);
+  if ((rc = check_prec(precision)) != NQA_OK) return rc;
   if ((rc = check_shape(B, H, W)) != NQA_OK) return rc;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   StreamOrder so(ctx, st);
   if (so.rc != NQA_OK) return so.rc;
   *tape_out = 0;
-  int mb = pick_micro_pairs(ctx, B, H, W) / 2;
+  int mb = pick_micro_pairs(ctx, B, H, W) / (precision == NQA_PREC_BF16X3 ? 4 : 2);
   if (mb < 1) mb = 1;
   const bool f32 = precision == NQA_PREC_FP32;
   size_t tape_bytes = 0;
   for (int b0 = 0; b0 < B; b0 += mb) {
     const int pairs = B - b0 < mb ? B - b0 : mb;
-    tape_bytes += align256(f32 ? saved_bytes<float>(pairs, H, W) : saved_bytes<bf16>(pairs, H, W));
+    tape_bytes += align256(f32 ? saved_bytes<float>(pairs, H, W, precision) : saved_bytes<bf16>(pairs, H, W, precision));
   }
   const int buf = acquire_tape_buf(ctx, tape_bytes);
   if (buf < 0)   // does not fit: plain forward, the caller differentiates by recomputation (nqa_dists_backward)
     return dists_forward_device(ctx, x, y, B, H, W, precision, score_out, s1s2_out, st);
-  const size_t need = partial_bytes(mb, H, W, precision, nullptr, false, true) + 8192;
+  const size_t need = partial_bytes(mb, H, W, precision, nullptr, false, precision != NQA_PREC_BF16X3) + 8192;
   if ((rc = ensure_arena(ctx, need)) != NQA_OK) {
     ctx->tape_bufs[buf].in_use = false;
     return rc;

@@ -129,6 +129,7 @@ struct ConvTcPlan {
   bf16* out_lo;
   int epi;             // ConvEpilogue (halo / pair kernels; the plain kernel is forward-only)
   const bf16* mask;    // kEpiMask / kEpiDivide: saved activation [n,h,w,cout]
+  const bf16* mask_lo; // bf16x3 carrier of the saved activation (per-tap kernel, kEpiDivide)
   float* fg_x;         // kEpiFrameGrad: frame gradients, NCHW fp32 [nx,3,h,w] / [n-nx,3,h,w]
   float* fg_y;
   int fg_nx;
@@ -167,16 +168,22 @@ int launch_stat_grad_planar(const float* x, const float* y, const float* coef, i
                             float* gx, float* gy, bool accumulate, cudaStream_t st);
 // NHWC level: statistics gradient (+ L2pooling backward when qpoolx != nullptr), masked by the level's ReLU.
 // qpoolx / qpooly: (gradient w.r.t. the pooled tensor) / (pooled tensor), as written by a kEpiDivide convolution.
+// lo (bf16x3 carriers, T = bf16): residual tensors of fx / fy / qpoolx / qpooly and of the two outputs, all or none.
+template <typename T>
+struct LevelGradLo {
+  const T* fx = nullptr; const T* fy = nullptr; const T* qpoolx = nullptr; const T* qpooly = nullptr;
+  T* gx = nullptr; T* gy = nullptr;
+};
 template <typename T>
 int launch_level_grad(const T* fx, const T* fy, const T* qpoolx, const T* qpooly, const float* coef, int level, int pairs,
-                      int h, int w, int c, T* gx, T* gy, cudaStream_t st);
+                      int h, int w, int c, T* gx, T* gy, cudaStream_t st, const LevelGradLo<T>* lo = nullptr);
 // conv1_1 + normalisation backward: gz [n,h,w,64] -> NCHW fp32 frame gradients.  The 9x64x3 weights travel as a kernel
 // parameter (constant bank: every thread reads the same weight at the same time, no shared-memory traffic).
 struct Conv11BwdWeights { float w[9][64][3]; };
 template <typename T>
 int launch_conv1_1_bwd(const T* gz, const Conv11BwdWeights& wb, int nx, int n, int h, int w, float* gx, float* gy,
-                       cudaStream_t st);
-int launch_pack_w_bwd(const float* w_oihw, int cin, int cout, float* w_f32, bf16* w_hi, cudaStream_t st);
+                       cudaStream_t st, const T* gz_lo = nullptr);
+int launch_pack_w_bwd(const float* w_oihw, int cin, int cout, float* w_f32, bf16* w_hi, cudaStream_t st, bf16* w_lo = nullptr);
 int launch_pack_w11_bwd(const float* w_oihw, float* out, cudaStream_t st);
 
 // ---- frame resizing (resize.cu): NCHW fp32 planes [planes][h][w] -> [planes][oh][ow], bilinear, align_corners=False

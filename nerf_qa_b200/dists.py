@@ -174,7 +174,7 @@ class _WeightedScore(torch.autograd.Function):
     def forward(ctx, x, y, a, b, lib_ctx, prec, through_trunk):
         lib_ctx.set_channel_weights(a, b)
         ctx.tape = None
-        if through_trunk and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and prec != _lib.PREC_BF16X3:
+        if through_trunk and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
             # like torch autograd: keep the trunk activations for the backward (the library declines -> tape None ->
             # activation recomputation in nqa_dists_backward)
             score, s1s2, ctx.tape = lib_ctx.dists_forward_saved(x, y, prec)
@@ -291,8 +291,6 @@ class DISTS(_TrunkModule):
         wants_grad = torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or self.alpha.requires_grad
                                                   or self.beta.requires_grad)
         if wants_grad:
-            if (x.requires_grad or y.requires_grad) and self.precision == "bf16x3":
-                raise NotImplementedError("gradients w.r.t. the frames are implemented for precision 'fp32' and 'bf16'")
             # require_grad=False keeps the trunk out of the graph like the reference's torch.no_grad() block; the
             # level-0 statistics of the raw frames stay differentiable (DISTS_pt.py:103, 109-112)
             a, b = self._effective_weights()

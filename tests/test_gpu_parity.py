@@ -270,7 +270,14 @@ def _oracle_frame_grads(x, y, ws, bs, a, b, coeffs, through_trunk):
 
 # bf16 trunk: activations, weights and inter-layer gradients are rounded to 8 mantissa bits over 13 layers forward
 # and 13 backward; measured relative L2 error of the frame gradient vs the fp32 oracle is 6-7% (cosine > 0.997).
+# bf16x3 trunk: the same backward on the tensor pipe with hi + lo carriers for activations, weights and gradients
+# (three MMAs per k-step).  Measured rel L2 2e-3, 30x closer than the bf16 trunk.  That is the floor of a 16-bit carrier,
+# not of the kernels: rounding only the conv WEIGHTS of the fp32 oracle to hi + lo (16 significant bits) moves its
+# autograd frame gradient by the same 2.0e-3 rel L2 (the DISTS gradient is a sum of strongly cancelling per-channel
+# terms); rel L2 <= 1e-3 needs a third weight term, i.e. five MMAs per k-step.
 @pytest.mark.parametrize("prec,shape,tol", [("fp32", (2, 64, 64), 2e-3), ("fp32", (2, 45, 77), 2e-3),
+                                            ("bf16x3", (2, 64, 64), 5e-3), ("bf16x3", (3, 45, 77), 5e-3),
+                                            ("bf16x3", (1, 135, 240), 5e-3),
                                             ("bf16", (2, 64, 64), 0.12), ("bf16", (3, 45, 77), 0.12)])
 def test_frame_gradients_through_trunk_match_oracle(models, vgg_weights, alpha_beta, prec, shape, tol):
     b, h, w = shape
@@ -294,7 +301,7 @@ def test_frame_gradients_through_trunk_match_oracle(models, vgg_weights, alpha_b
               f"frac(|err| > 1e-3 max) = {frac:.2e}, per pair {per_pair}")
         # a ReLU whose pre-activation is within rounding of zero can flip between two fp32 summation orders and moves
         # the gradient of the few pixels in its receptive field: bound the L2 error tightly and the max error loosely
-        assert l2 < tol and err < (10 * tol if prec == "fp32" else 3 * tol)
+        assert l2 < tol and err < (10 * tol if prec != "bf16" else 3 * tol)
 
 
 def _fresh(prec, env):
