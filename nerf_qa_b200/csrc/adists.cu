@@ -127,7 +127,7 @@ Plan make_plan(int pairs, int H, int W, int window) {
     L.csplit_mma = 1;
     if (L.windowed) {
       int tx, ty;
-      window_mma_tiles(L.oh, L.ow, &tx, &ty);
+      window_mma_tiles(L.h, L.w, window, &tx, &ty);
       int cs = ceil_div(2 * kNumSMs, tx * ty);   // one 12-warp block per SM
       if (cs > L.c / 8) cs = L.c / 8;
       if (cs < 1) cs = 1;

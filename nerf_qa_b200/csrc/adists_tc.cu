@@ -32,16 +32,26 @@
 namespace nqa {
 namespace {
 
-constexpr int kWarpsX = 4, kWarpsY = 3, kOB = 3;                 // warp grid, output row blocks (of 8) per warp
-constexpr int kThreads = 32 * kWarpsX * kWarpsY;                  // 384
-constexpr int kTileOW = 16 * kWarpsX, kTileOH = 8 * kOB * kWarpsY;  // 64 x 72 outputs per block
-constexpr int kInW = kTileOW + 32, kInH = kTileOH + 24;           // 96 x 96 inputs (halo of 20 rounded up to blocks)
+constexpr int kWarpsX = 4, kOB = 3;                               // warp columns, output row blocks (of 8) per warp
+constexpr int kTileOW = 16 * kWarpsX;                             // 64 output columns per block
+constexpr int kInW = kTileOW + 32;                                // 96 input columns (halo of 20 rounded up to blocks)
 constexpr int kLD = 104;                                          // padded row stride (208 B): conflict-free ldmatrix
-constexpr int kTileElems = kInH * kLD;
-constexpr int kTileBytes = kTileElems * 2;                        // 19968
 constexpr int kRB = kOB + 3;                                      // input row blocks (of 8) per warp
 constexpr int kChunksPerRow = kInW / 8;                           // 16-byte chunks
-constexpr int kSmemBytes = (4 + 6) * kTileBytes;                  // raw x/y double-buffered + six product tiles
+// kWY warp rows: 3 = one 12-warp block per SM, 64 x 72 outputs, ten (seven for the one-term kernel) 20 KB tiles.
+// Measured alternative for the one-term kernel, kWY = 2 with two 8-warp blocks per SM (seven 15 KB tiles each): the 128
+// registers per thread it leaves spill 0.5 KB per thread and the level-1 launch is 13% slower (68.6 vs 60.5 ms of window
+// time per 32-pair step), so both kernels run with kWY = 3.
+template <int kWY, bool kTwo>
+struct TcCfg {
+  static constexpr int kThreads = 32 * kWarpsX * kWY;
+  static constexpr int kTileOH = 8 * kOB * kWY;
+  static constexpr int kInH = kTileOH + 24;
+  static constexpr int kTileBytes = kInH * kLD * 2;
+  static constexpr int kProdTiles = kTwo ? 6 : 3;
+  static constexpr int kSmemBytes = (4 + kProdTiles) * kTileBytes;   // raw x/y double-buffered + the product tiles
+  static constexpr int kBlocksPerSM = kWY == 2 ? 2 : 1;
+};
 
 struct TcTaps {
   float g[32];      // bf16-representable taps, zero beyond the window
@@ -124,15 +134,18 @@ __device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t la
   }
 }
 
-template <bool kTwo>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kTwo, int kWY>
+__global__ void __launch_bounds__(TcCfg<kWY, kTwo>::kThreads, TcCfg<kWY, kTwo>::kBlocksPerSM)
 window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int c, int h, int w, int oh, int ow, int tiles_x,
                   int csplit, int choff, const double* __restrict__ chan, const float* __restrict__ wt, TcTaps taps,
                   float* __restrict__ amap, float* __restrict__ bmap, float* __restrict__ gmap) {
+  using Cfg = TcCfg<kWY, kTwo>;
+  constexpr int kThreads = Cfg::kThreads, kTileOH = Cfg::kTileOH, kInH = Cfg::kInH, kTileBytes = Cfg::kTileBytes;
+  constexpr int kStep = kTwo ? 1 : 2;   // product tile m of (xx_h, xx_l, yy_h, yy_l, xy_h, xy_l) lives in slot 4 + m / kStep
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
   // tiles: raw[buf][x|y] at (buf*2 + i), products xx_h, xx_l, yy_h, yy_l, xy_h, xy_l at 4..9 (kTwo) or xx, yy, xy
-  // rounded to bf16 at 4, 6, 8
+  // rounded to bf16 at 4, 5, 6
   auto tile = [&](int i) { return smem + (uint32_t)i * kTileBytes; };
 
   const int tile_id = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
@@ -186,7 +199,7 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
   const bool producer = wy != 0;
   // named barrier 1: every thread arrives once per channel, the producers after writing the product tiles, the row-0
   // warps before they read them
-  auto products_ready = [] { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); };
+  auto products_ready = [] { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kThreads) : "memory"); };
 
   float2 acc_a[kOB][2], acc_b[kOB][2], acc_g[kOB][2];   // element i: pixels (row pair) of columns lane/4 + 8 i
 #pragma unroll
@@ -252,7 +265,7 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         }
 #pragma unroll
         for (int m = 0; m < 6; m += (kTwo ? 1 : 2))
-          *reinterpret_cast<uint4*>(smem_raw + (4 + m) * kTileBytes + off[k]) = make_uint4(o[m][0], o[m][1], o[m][2], o[m][3]);
+          *reinterpret_cast<uint4*>(smem_raw + (4 + m / kStep) * kTileBytes + off[k]) = make_uint4(o[m][0], o[m][1], o[m][2], o[m][3]);
       }
     }
     if (producer) products_ready();
@@ -299,7 +312,7 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         const uint32_t t2[2] = {tile(4), tile(5)};
         filtered_map<2, true>(t2, lane_off, ta, tb, d);
       } else {
-        const uint32_t t2[1] = {tile(4)};
+        const uint32_t t2[1] = {tile(4 + 0 / 2)};
         filtered_map<1, false>(t2, lane_off, ta, tb, d);
       }
     }
@@ -318,7 +331,7 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         const uint32_t t3[2] = {tile(6), tile(7)};
         filtered_map<2, true>(t3, lane_off, ta, tb, d);
       } else {
-        const uint32_t t3[1] = {tile(6)};
+        const uint32_t t3[1] = {tile(4 + 2 / 2)};
         filtered_map<1, false>(t3, lane_off, ta, tb, d);
       }
     }
@@ -335,7 +348,7 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         const uint32_t t4[2] = {tile(8), tile(9)};
         filtered_map<2, true>(t4, lane_off, ta, tb, d);
       } else {
-        const uint32_t t4[1] = {tile(8)};
+        const uint32_t t4[1] = {tile(4 + 4 / 2)};
         filtered_map<1, false>(t4, lane_off, ta, tb, d);
       }
     }
@@ -375,9 +388,12 @@ bool window_mma_supported(int window, int h, int w, const void* fx, const void* 
          (reinterpret_cast<uintptr_t>(fx) & 15) == 0 && (reinterpret_cast<uintptr_t>(fy) & 15) == 0;
 }
 
-void window_mma_tiles(int oh, int ow, int* tiles_x, int* tiles_y) {
+static bool two_terms(int h, int w, bool force) { return (long long)h * w < 400000 || force; }
+
+void window_mma_tiles(int h, int w, int window, int* tiles_x, int* tiles_y) {
+  const int oh = h - window + 1, ow = w - window + 1;
   *tiles_x = ceil_div(ow, kTileOW);
-  *tiles_y = ceil_div(oh, kTileOH);
+  *tiles_y = ceil_div(oh, two_terms(h, w, false) ? TcCfg<3, true>::kTileOH : TcCfg<3, false>::kTileOH);
 }
 
 int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, int w, int window, int csplit, int choff,
@@ -391,21 +407,25 @@ int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, i
   }
   t.inv_sum2 = (float)(1.0 / (sum * sum));
   const int oh = h - window + 1, ow = w - window + 1;
-  int tx, ty;
-  window_mma_tiles(oh, ow, &tx, &ty);
   // One bf16 term per operand or two.  The rounding of a one-term operand (2^-9 per element, ~4e-4 after the window
   // average) is an error of that fraction of E[f^2] in a variance; in the L2-normalised units of ADISTS.py:166-167 E[f^2]
   // is 1 / (h w) on average, so for maps of >= 400k pixels even a 10x locally concentrated channel errs by ~1e-8, one
   // hundredth of the 1e-6 stabilisers c1 / c2 -- the 1080p levels 1 and 2, 77% of the work.  Smaller maps (deeper
   // levels, small frames) keep the exact two-term products and the hi + lo split between the passes.
-  const bool two = (long long)h * w < 400000 || force_two_terms;
-  dim3 grid(tx * ty, csplit, pairs);
+  const bool two = two_terms(h, w, force_two_terms);
+  const int tx = ceil_div(ow, kTileOW);
   if (two) {
-    ensure_dynamic_smem(window_mma_kernel<true>, kSmemBytes);
-    window_mma_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap);
+    using Cfg = TcCfg<3, true>;
+    ensure_dynamic_smem(window_mma_kernel<true, 3>, Cfg::kSmemBytes);
+    dim3 grid(tx * ceil_div(oh, Cfg::kTileOH), csplit, pairs);
+    window_mma_kernel<true, 3><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t,
+                                                                       amap, bmap, gmap);
   } else {
-    ensure_dynamic_smem(window_mma_kernel<false>, kSmemBytes);
-    window_mma_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap);
+    using Cfg = TcCfg<3, false>;
+    ensure_dynamic_smem(window_mma_kernel<false, 3>, Cfg::kSmemBytes);
+    dim3 grid(tx * ceil_div(oh, Cfg::kTileOH), csplit, pairs);
+    window_mma_kernel<false, 3><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t,
+                                                                        amap, bmap, gmap);
   }
   return 1;
 }

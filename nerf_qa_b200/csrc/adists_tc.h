@@ -10,8 +10,8 @@ namespace nqa {
 
 // bf16 planes with 16-byte aligned rows (w % 8 == 0) and an odd window <= 21
 bool window_mma_supported(int window, int h, int w, const void* fx, const void* fy);
-// block tiling of the output map (64 x 72 outputs per block)
-void window_mma_tiles(int oh, int ow, int* tiles_x, int* tiles_y);
+// block tiling of the output map of an h x w level (64 x 72 or 64 x 48 outputs per block)
+void window_mma_tiles(int h, int w, int window, int* tiles_x, int* tiles_y);
 // taps_f32: the `window` fp32 gaussian taps (rounded to bf16 inside; the result is renormalised by their exact sum)
 int launch_window_mma(const __nv_bfloat16* fx, const __nv_bfloat16* fy, int pairs, int c, int h, int w, int window, int csplit,
                       int choff, const double* chan, const float* wt, const float* taps_f32, bool force_two_terms, float* amap,
