@@ -1082,11 +1082,15 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
     csplit_used[k] = L.csplit;
-    if (L.windowed && is16(k) && use_mma && window_mma_supported(window, L.h, L.w, fx[k], fy[k])) {
-      // bf16 planes: the two gaussian passes as banded-Toeplitz products on the tensor pipe (adists_tc.cu)
+    int mma_launches = 0;
+    if (L.windowed && is16(k) && use_mma && window_mma_supported(window, L.h, L.w, fx[k], fy[k]))
+      // bf16 planes: the two gaussian passes as banded-Toeplitz products on the tensor pipe (adists_tc.cu); 0 = no
+      // tensor map for these planes, the CUDA-core kernel serves the level
+      mma_launches = launch_window_mma(B16(fx[k]), B16(fy[k]), pairs, L.c, L.h, L.w, window, L.csplit_mma, L.choff, chan, wt,
+                                       taps.g, options.mma_terms == 2, F(L.off_a), F(L.off_b), F(L.off_g), st);
+    if (mma_launches > 0) {
       csplit_used[k] = L.csplit_mma;
-      launches += launch_window_mma(B16(fx[k]), B16(fy[k]), pairs, L.c, L.h, L.w, window, L.csplit_mma, L.choff, chan, wt,
-                                    taps.g, options.mma_terms == 2, F(L.off_a), F(L.off_b), F(L.off_g), st);
+      launches += mma_launches;
     } else if (L.windowed) {
       launches += is16(k) ? level_window<bf16>(window, L, B16(fx[k]), B16(fy[k]), pairs, chan, wt, taps, F(L.off_a), F(L.off_b),
                                                F(L.off_g), st)

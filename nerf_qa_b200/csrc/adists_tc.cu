@@ -15,12 +15,15 @@
 // tolerance of the bf16 path; the fp32 / bf16x3 trunks keep the CUDA-core kernel (adists.cu).
 //
 // Block = 12 warps = 4 (columns) x 3 (rows); warp tile = 16 output columns x 24 output rows; block tile 64 x 72 outputs
-// from a 96 x 96 input tile.  Per channel: the raw x / y tiles arrive by cp.async (double-buffered), all threads write
-// the six product tiles (x^2, y^2, xy as hi / lo) once, then every warp runs, per map q in (x, y, x^2, y^2, xy):
+// from a 96 x 96 input tile.  Per channel: the raw x / y tiles arrive by TMA (three 32-column SWIZZLE_64B boxes per tile,
+// zero-filled outside the image, double-buffered on two mbarriers; one thread issues them), the producer warps write the
+// product tiles (x^2, y^2, xy, rounded or as hi / lo; packed bf16 multiplies) once, then every warp runs, per map q in
+// (x, y, x^2, y^2, xy):
 //   pass 1:  D1[16 out cols][8 rows] += T[16 x 16] * tile[16 cols x 8 rows]      3 k-steps x 6 row blocks x terms
 //   split :  D1 -> bf16 hi / lo A fragments (in registers)
 //   pass 2:  D2[16 out cols][8 out rows] += D1[16 x 16 rows] * T2[16 rows x 8]   2 k-steps x 3 row blocks x 2 terms
 // and folds the five maps into T, S and gamma per pixel, accumulated over the channel loop in registers.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -35,9 +38,12 @@ namespace {
 constexpr int kWarpsX = 4, kOB = 3;                               // warp columns, output row blocks (of 8) per warp
 constexpr int kTileOW = 16 * kWarpsX;                             // 64 output columns per block
 constexpr int kInW = kTileOW + 32;                                // 96 input columns (halo of 20 rounded up to blocks)
-constexpr int kLD = 104;                                          // padded row stride (208 B): conflict-free ldmatrix
+constexpr int kParts = kInW / 32;                                 // a tile = three 32-column parts of kInH rows x 64 bytes,
+                                                                  // each in the SWIZZLE_64B layout TMA writes: the 16-byte
+                                                                  // chunk q of row r sits at chunk q ^ ((r >> 1) & 3), which
+                                                                  // makes the 8-row ldmatrix reads conflict-free
 constexpr int kRB = kOB + 3;                                      // input row blocks (of 8) per warp
-constexpr int kChunksPerRow = kInW / 8;                           // 16-byte chunks
+constexpr int kMaxCPer = 512;                                     // channels per block (per-channel scalars in smem)
 // kWY warp rows: 3 = one 12-warp block per SM, 64 x 72 outputs, ten (seven for the one-term kernel) 20 KB tiles.
 // Measured alternative for the one-term kernel, kWY = 2 with two 8-warp blocks per SM (seven 15 KB tiles each): the 128
 // registers per thread it leaves spill 0.5 KB per thread and the level-1 launch is 13% slower (68.6 vs 60.5 ms of window
@@ -47,9 +53,11 @@ struct TcCfg {
   static constexpr int kThreads = 32 * kWarpsX * kWY;
   static constexpr int kTileOH = 8 * kOB * kWY;
   static constexpr int kInH = kTileOH + 24;
-  static constexpr int kTileBytes = kInH * kLD * 2;
+  static constexpr int kPartBytes = kInH * 64;
+  static constexpr int kTileBytes = kParts * kPartBytes;
   static constexpr int kProdTiles = kTwo ? 6 : 3;
-  static constexpr int kSmemBytes = (4 + kProdTiles) * kTileBytes;   // raw x/y double-buffered + the product tiles
+  static constexpr int kTilesBytes = (4 + kProdTiles) * kTileBytes;  // raw x/y double-buffered + the product tiles
+  static constexpr int kSmemBytes = kTilesBytes + 3 * kMaxCPer * 4 + 64 + 1024;   // + scalars, mbarriers, alignment
   static constexpr int kBlocksPerSM = kWY == 2 ? 2 : 1;
 };
 
@@ -84,29 +92,46 @@ __device__ inline void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
 __device__ inline void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
-__device__ inline void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+__device__ inline void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ inline void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// lean mbarrier wait (no printf: this kernel has no registers to spare); traps instead of hanging the GPU
+__device__ inline void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ inline float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// num / den for denominators in the normal range (all of them carry a 1e-6 or larger stabiliser): MUFU.RCP + FMUL
+// instead of the five instructions of div.approx with its range check
+__device__ inline float2 div2_approx(float2 num, float2 den) {
+  return __fmul2_rn(num, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+}
 
 // One filtered map of the warp tile: pass 1 over the NT term tiles, hi/lo split, pass 2.  out[ob][4] (raw sums, to be
 // scaled by 1/sum(g')^2): thread (lane) holds columns lane/4 (+8), rows 8*ob + 2*(lane%4) + {0,1}.
 // kTwo = false: the first-pass results go into the second pass as ONE bf16 term (levels whose maps are large enough
 // that the 1e-6 stabilisers of T and S dwarf the rounding, see launch_window_mma).
 template <int NT, bool kTwo>
-__device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t lane_off, const uint32_t (&ta)[3][4],
-                                    const uint32_t (&tb)[2][2], float (&out)[kOB][4]) {
+__device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t lane_off, uint32_t lane_off2,
+                                    const uint32_t (&ta)[3][4], const uint32_t (&tb)[2][2], float (&out)[kOB][4]) {
   uint32_t fh[kRB][2], fl[kTwo ? kRB : 1][2];
 #pragma unroll
   for (int rb = 0; rb < kRB; ++rb) {
     float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      const uint32_t base = tile_addr[t] + lane_off + rb * 8 * kLD * 2;
       uint32_t b01[4], b2[2];
-      ldmatrix_x4(b01, base);            // k-blocks 0 and 1 (columns +0, +8, +16, +24)
-      ldmatrix_x2(b2, base + 32 * 2);    // k-block 2 (columns +32, +40)
+      ldmatrix_x4(b01, tile_addr[t] + lane_off + rb * 8 * 64);    // k-blocks 0 and 1 (columns +0, +8, +16, +24)
+      ldmatrix_x2(b2, tile_addr[t] + lane_off2 + rb * 8 * 64);    // k-block 2 (columns +32, +40)
       mma16816(c, ta[0][0], ta[0][1], ta[0][2], ta[0][3], b01[0], b01[1]);
       mma16816(c, ta[1][0], ta[1][1], ta[1][2], ta[1][3], b01[2], b01[3]);
       mma16816(c, ta[2][0], ta[2][1], ta[2][2], ta[2][3], b2[0], b2[1]);
@@ -136,14 +161,23 @@ __device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t la
 
 template <bool kTwo, int kWY>
 __global__ void __launch_bounds__(TcCfg<kWY, kTwo>::kThreads, TcCfg<kWY, kTwo>::kBlocksPerSM)
-window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int c, int h, int w, int oh, int ow, int tiles_x,
-                  int csplit, int choff, const double* __restrict__ chan, const float* __restrict__ wt, TcTaps taps,
+window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, int c, int oh, int ow,
+                  int tiles_x, int csplit, int choff, const double* __restrict__ chan, const float* __restrict__ wt, TcTaps taps,
                   float* __restrict__ amap, float* __restrict__ bmap, float* __restrict__ gmap) {
   using Cfg = TcCfg<kWY, kTwo>;
-  constexpr int kThreads = Cfg::kThreads, kTileOH = Cfg::kTileOH, kInH = Cfg::kInH, kTileBytes = Cfg::kTileBytes;
+  constexpr int kThreads = Cfg::kThreads, kTileOH = Cfg::kTileOH, kTileBytes = Cfg::kTileBytes;
+  constexpr int kPartBytes = Cfg::kPartBytes;
   constexpr int kStep = kTwo ? 1 : 2;   // product tile m of (xx_h, xx_l, yy_h, yy_l, xy_h, xy_l) lives in slot 4 + m / kStep
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ unsigned char smem_dyn[];
+  // the swizzle pattern is a function of the shared-memory ADDRESS: tiles start on a 1024-byte boundary (aligned by
+  // offset from the __shared__ array so that accesses stay LDS / STS)
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_dyn);
+  unsigned char* smem_raw = smem_dyn + ((1024 - (smem_base & 1023)) & 1023);
   const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  float* s_ax = reinterpret_cast<float*>(smem_raw + Cfg::kTilesBytes);   // per-channel scalars of this block's channels
+  float* s_ay = s_ax + kMaxCPer;
+  float* s_wc = s_ay + kMaxCPer;
+  const uint32_t full_bar = smem + Cfg::kTilesBytes + 3 * kMaxCPer * 4;   // two mbarriers: raw[buf] has landed
   // tiles: raw[buf][x|y] at (buf*2 + i), products xx_h, xx_l, yy_h, yy_l, xy_h, xy_l at 4..9 (kTwo) or xx, yy, xy
   // rounded to bf16 at 4, 5, 6
   auto tile = [&](int i) { return smem + (uint32_t)i * kTileBytes; };
@@ -175,26 +209,25 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
     }
   }
 
-  // raw tile loader: 96 rows x 12 chunks per image; out-of-image chunks are zero-filled (w % 8 == 0: a chunk is either
-  // inside or outside)
-  const size_t plane = (size_t)h * w;
+  // raw tile loader (ONE thread): the x and y tiles of channel ch as 2 x 3 TMA boxes of 32 columns x kInH rows; parts of
+  // a box outside the image arrive as zeros
   auto load_raw = [&](int ch, int buf) {
-    const bf16* px = fx + ((size_t)b * c + ch) * plane;
-    const bf16* py = fy + ((size_t)b * c + ch) * plane;
-    for (int i = threadIdx.x; i < kInH * kChunksPerRow; i += kThreads) {
-      const int r = i / kChunksPerRow, q = i - r * kChunksPerRow;
-      const int gy = oy0 + r, gx = ox0 + 8 * q;
-      const bool ok = gy < h && gx < w;
-      const size_t off = ok ? (size_t)gy * w + gx : 0;
-      const uint32_t dst = (uint32_t)(r * kLD + 8 * q) * 2;
-      cp_async16(tile(buf * 2 + 0) + dst, px + off, ok ? 16 : 0);
-      cp_async16(tile(buf * 2 + 1) + dst, py + off, ok ? 16 : 0);
+    const uint32_t bar = full_bar + 8 * buf;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kTileBytes) : "memory");
+#pragma unroll
+    for (int part = 0; part < kParts; ++part) {
+      tma_load_3d(tile(buf * 2 + 0) + part * kPartBytes, &map_x, bar, ox0 + 32 * part, oy0, b * c + ch);
+      tma_load_3d(tile(buf * 2 + 1) + part * kPartBytes, &map_y, bar, ox0 + 32 * part, oy0, b * c + ch);
     }
-    cp_async_commit();
   };
 
-  // per-lane part of the ldmatrix address inside the warp's 48 x 48 input window: row (lane % 8), column 8 * (lane / 8)
-  const uint32_t lane_off = (uint32_t)(((wy * 8 * kOB + (lane & 7)) * kLD) + wx * 16 + 8 * (lane >> 3)) * 2;
+  // per-lane part of the ldmatrix addresses inside the warp's 48 x 48 input window: row (lane % 8) of chunk
+  // 2 wx + lane / 8 (x4: columns +0 .. +24) and of chunk 2 wx + 4 + (lane / 8) % 2 (x2: columns +32, +40); row blocks
+  // start at multiples of 8 rows, so the swizzle term (row >> 1) & 3 is (lane >> 1) & 3 for every block
+  const uint32_t row_off = (uint32_t)((wy * 8 * kOB + (lane & 7)) * 64), sw = (uint32_t)((lane >> 1) & 3);
+  const uint32_t q4 = (uint32_t)(wx * 2 + (lane >> 3)), q2 = (uint32_t)(wx * 2 + 4 + ((lane >> 3) & 1));
+  const uint32_t lane_off = (q4 >> 2) * kPartBytes + row_off + (((q4 & 3) ^ sw) << 4);
+  const uint32_t lane_off2 = (q2 >> 2) * kPartBytes + row_off + (((q2 & 3) ^ sw) << 4);
   const bool warp_live = (oy0 + wy * 8 * kOB) < oh && (ox0 + wx * 16) < ow;
   const bool producer = wy != 0;
   // named barrier 1: every thread arrives once per channel, the producers after writing the product tiles, the row-0
@@ -207,42 +240,48 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
 #pragma unroll
     for (int i = 0; i < 2; ++i) acc_a[ob][i] = acc_b[ob][i] = acc_g[ob][i] = make_float2(0.f, 0.f);
 
+  // per-channel scalars of this block's channels -> shared memory once (1/||x||, 1/||y||, entropy weight)
+  for (int i = threadIdx.x; i < c_end - c_begin; i += kThreads) {
+    const double* cs = chan + ((size_t)b * kTotalChannels + choff + c_begin + i) * 10;
+    s_ax[i] = (float)__ldg(cs);
+    s_ay[i] = (float)__ldg(cs + 1);
+    s_wc[i] = __ldg(wt + (size_t)b * kTotalChannels + choff + c_begin + i);
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_bar) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_bar + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (c_begin < c_end) load_raw(c_begin, 0);
+  }
   int buf = 0;
-  if (c_begin < c_end) load_raw(c_begin, 0);
-  for (int ch = c_begin; ch < c_end; ++ch, buf ^= 1) {
-    cp_async_wait_all();
-    __syncthreads();   // raw[buf] has landed for every thread; every warp is done with the previous channel's tiles
-    if (ch + 1 < c_end) load_raw(ch + 1, buf ^ 1);
-    // per-channel scalars: requested here, first used after a map has been filtered (L2 latency off the critical path)
-    const double* cs = chan + ((size_t)b * kTotalChannels + choff + ch) * 10;
-    const double sc_ax = __ldg(cs), sc_ay = __ldg(cs + 1);
-    const float sc_wc = __ldg(wt + (size_t)b * kTotalChannels + choff + ch);
+  uint32_t phase = 0;   // parity of raw[buf]'s barrier: flips every second channel
+  for (int ch = c_begin; ch < c_end; ++ch, buf ^= 1, phase ^= (uint32_t)(buf == 0)) {
+    __syncthreads();   // every warp is done with the previous channel's tiles (first pass: barriers + scalars visible)
+    if (threadIdx.x == 0 && ch + 1 < c_end) load_raw(ch + 1, buf ^ 1);
+    mbar_wait_parity(full_bar + 8 * buf, phase);   // raw[buf] has landed
 
     // ---- products: x^2, y^2, xy as exact bf16 hi + lo, written once per block by the warps of rows 1 and 2, while the
     // warps of row 0 already filter the two maps that only need the raw tiles.  The three warps of a scheduler (same
     // wx) thereby run out of phase: one issues its MMA bursts while the others do the scalar work between theirs. ----
     if (producer) {
-      // chunk i = tid + 256 k of the 96 x 12 grid; (row, column chunk) advance by (21, 4) per step (256 = 21 * 12 + 4).
-      // All loads of the thread are issued before the arithmetic (the shared-memory latency is paid once).
+      // The products are elementwise, so the producers walk the tile's 16-byte chunks in PHYSICAL order (chunk tid + 256 k)
+      // whatever the swizzle; all loads of the thread are issued before the arithmetic (the shared-memory latency is paid
+      // once).  Packed bf16 arithmetic: hi = x * y rounded to bf16 (one HMUL2 per element pair); lo = fma(x, y, -hi), the
+      // exact residual (it has <= 8 significant bits).
       constexpr int kProducers = kThreads - 32 * kWarpsX;                           // 256
-      constexpr int kIters = (kInH * kChunksPerRow + kProducers - 1) / kProducers;  // 5
+      constexpr int kIters = (kTileBytes / 16 + kProducers - 1) / kProducers;      // 5
       const int tid = threadIdx.x - 32 * kWarpsX;
       uint4 vx[kIters], vy[kIters];
       uint32_t off[kIters];
-      {
-        int r = tid / kChunksPerRow, q = tid - r * kChunksPerRow;
 #pragma unroll
-        for (int k = 0; k < kIters; ++k) {
-          off[k] = (uint32_t)(r * kLD + 8 * q) * 2;
-          if (r < kInH) {
-            vx[k] = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 0) * kTileBytes + off[k]);
-            vy[k] = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 1) * kTileBytes + off[k]);
-          } else {
-            off[k] = 0xffffffffu;
-          }
-          r += kProducers / kChunksPerRow;
-          q += kProducers % kChunksPerRow;
-          if (q >= kChunksPerRow) { q -= kChunksPerRow; ++r; }
+      for (int k = 0; k < kIters; ++k) {
+        off[k] = (uint32_t)(tid + kProducers * k) * 16;
+        if (off[k] < (uint32_t)kTileBytes) {
+          vx[k] = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 0) * kTileBytes + off[k]);
+          vy[k] = *reinterpret_cast<const uint4*>(smem_raw + (buf * 2 + 1) * kTileBytes + off[k]);
+        } else {
+          off[k] = 0xffffffffu;
         }
       }
 #pragma unroll
@@ -252,15 +291,17 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         uint32_t o[6][4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 x = make_float2(bf16_lo(xs[e]), bf16_hi(xs[e])), y = make_float2(bf16_lo(ys[e]), bf16_hi(ys[e]));
+          const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&xs[e]);
+          const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(&ys[e]);
+          const __nv_bfloat162 xx = __hmul2(x, x), yy = __hmul2(y, y), xy = __hmul2(x, y);
+          o[0][e] = *reinterpret_cast<const uint32_t*>(&xx);
+          o[2][e] = *reinterpret_cast<const uint32_t*>(&yy);
+          o[4][e] = *reinterpret_cast<const uint32_t*>(&xy);
           if (kTwo) {
-            split_bf16x2(__fmul2_rn(x, x), o[0][e], o[1][e]);   // products of bf16 values: the residuals are exact
-            split_bf16x2(__fmul2_rn(y, y), o[2][e], o[3][e]);
-            split_bf16x2(__fmul2_rn(x, y), o[4][e], o[5][e]);
-          } else {
-            o[0][e] = pack_bf16x2(__fmul2_rn(x, x));
-            o[2][e] = pack_bf16x2(__fmul2_rn(y, y));
-            o[4][e] = pack_bf16x2(__fmul2_rn(x, y));
+            const __nv_bfloat162 xl = __hfma2(x, x, __hneg2(xx)), yl = __hfma2(y, y, __hneg2(yy)), zl = __hfma2(x, y, __hneg2(xy));
+            o[1][e] = *reinterpret_cast<const uint32_t*>(&xl);
+            o[3][e] = *reinterpret_cast<const uint32_t*>(&yl);
+            o[5][e] = *reinterpret_cast<const uint32_t*>(&zl);
           }
         }
 #pragma unroll
@@ -273,7 +314,7 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
       if (!producer) products_ready();
       continue;
     }
-    const float ax = (float)sc_ax, ay = (float)sc_ay, wc = sc_wc;
+    const float ax = s_ax[ch - c_begin], ay = s_ay[ch - c_begin], wc = s_wc[ch - c_begin];
     // maps arrive as raw sums D; the 1 / sum(g')^2 renormalisation and the per-channel 1/||f|| scales are folded
     const float inv = taps.inv_sum2;
     const float2 kx = make_float2(ax * inv, ax * inv), ky = make_float2(ay * inv, ay * inv);
@@ -288,13 +329,13 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
     float d[kOB][4];
     {
       const uint32_t t0[1] = {tile(buf * 2 + 0)};
-      filtered_map<1, kTwo>(t0, lane_off, ta, tb, d);
+      filtered_map<1, kTwo>(t0, lane_off, lane_off2, ta, tb, d);
 #pragma unroll
       for (int ob = 0; ob < kOB; ++ob)
 #pragma unroll
         for (int i = 0; i < 2; ++i) mx[ob][i] = __fmul2_rn(kx, make_float2(d[ob][2 * i], d[ob][2 * i + 1]));
       const uint32_t t1[1] = {tile(buf * 2 + 1)};
-      filtered_map<1, kTwo>(t1, lane_off, ta, tb, d);
+      filtered_map<1, kTwo>(t1, lane_off, lane_off2, ta, tb, d);
     }
 #pragma unroll
     for (int ob = 0; ob < kOB; ++ob)
@@ -303,17 +344,16 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         my[ob][i] = __fmul2_rn(ky, make_float2(d[ob][2 * i], d[ob][2 * i + 1]));
         const float2 num = __ffma2_rn(two, __fmul2_rn(mx[ob][i], my[ob][i]), c6);
         const float2 den = __ffma2_rn(mx[ob][i], mx[ob][i], __ffma2_rn(my[ob][i], my[ob][i], c6));
-        const float2 t = make_float2(__fdividef(num.x, den.x), __fdividef(num.y, den.y));
-        acc_a[ob][i] = __ffma2_rn(wc2, t, acc_a[ob][i]);
+        acc_a[ob][i] = __ffma2_rn(wc2, div2_approx(num, den), acc_a[ob][i]);
       }
     if (!producer) products_ready();
     {
       if (kTwo) {
         const uint32_t t2[2] = {tile(4), tile(5)};
-        filtered_map<2, true>(t2, lane_off, ta, tb, d);
+        filtered_map<2, true>(t2, lane_off, lane_off2, ta, tb, d);
       } else {
         const uint32_t t2[1] = {tile(4 + 0 / 2)};
-        filtered_map<1, false>(t2, lane_off, ta, tb, d);
+        filtered_map<1, false>(t2, lane_off, lane_off2, ta, tb, d);
       }
     }
 #pragma unroll
@@ -323,16 +363,17 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         const float2 m2 = __fmul2_rn(mx[ob][i], mx[ob][i]);
         const float2 vx = __ffma2_rn(kxx, make_float2(d[ob][2 * i], d[ob][2 * i + 1]), make_float2(-m2.x, -m2.y));
         vs[ob][i] = vx;
-        const float2 gd = __ffma2_rn(gk, mx[ob][i], ge);
-        acc_g[ob][i] = __fadd2_rn(acc_g[ob][i], make_float2(__fdividef(vx.x, gd.x), __fdividef(vx.y, gd.y)));
+        float2 gd = __ffma2_rn(gk, mx[ob][i], ge);                         // >= ax^2 1e-12; kept out of the denormals
+        gd = make_float2(fmaxf(gd.x, 1e-30f), fmaxf(gd.y, 1e-30f));
+        acc_g[ob][i] = __fadd2_rn(acc_g[ob][i], div2_approx(vx, gd));
       }
     {
       if (kTwo) {
         const uint32_t t3[2] = {tile(6), tile(7)};
-        filtered_map<2, true>(t3, lane_off, ta, tb, d);
+        filtered_map<2, true>(t3, lane_off, lane_off2, ta, tb, d);
       } else {
         const uint32_t t3[1] = {tile(4 + 2 / 2)};
-        filtered_map<1, false>(t3, lane_off, ta, tb, d);
+        filtered_map<1, false>(t3, lane_off, lane_off2, ta, tb, d);
       }
     }
 #pragma unroll
@@ -346,10 +387,10 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
     {
       if (kTwo) {
         const uint32_t t4[2] = {tile(8), tile(9)};
-        filtered_map<2, true>(t4, lane_off, ta, tb, d);
+        filtered_map<2, true>(t4, lane_off, lane_off2, ta, tb, d);
       } else {
         const uint32_t t4[1] = {tile(4 + 4 / 2)};
-        filtered_map<1, false>(t4, lane_off, ta, tb, d);
+        filtered_map<1, false>(t4, lane_off, lane_off2, ta, tb, d);
       }
     }
 #pragma unroll
@@ -359,8 +400,7 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
         const float2 mm = __fmul2_rn(mx[ob][i], my[ob][i]);
         const float2 cov = __ffma2_rn(kxy, make_float2(d[ob][2 * i], d[ob][2 * i + 1]), make_float2(-mm.x, -mm.y));
         const float2 num = __ffma2_rn(two, cov, c6);
-        const float2 sv = make_float2(__fdividef(num.x, vs[ob][i].x), __fdividef(num.y, vs[ob][i].y));
-        acc_b[ob][i] = __ffma2_rn(wc2, sv, acc_b[ob][i]);
+        acc_b[ob][i] = __ffma2_rn(wc2, div2_approx(num, vs[ob][i]), acc_b[ob][i]);
       }
   }
 
@@ -384,6 +424,7 @@ window_mma_kernel(const bf16* __restrict__ fx, const bf16* __restrict__ fy, int 
 }  // namespace
 
 bool window_mma_supported(int window, int h, int w, const void* fx, const void* fy) {
+  // (w % 8 == 0 and 16-byte aligned planes: what a tensor map over the planes needs)
   return window >= 3 && window <= 21 && (window & 1) && h >= window && w >= window && (w % 8) == 0 &&
          (reinterpret_cast<uintptr_t>(fx) & 15) == 0 && (reinterpret_cast<uintptr_t>(fy) & 15) == 0;
 }
@@ -414,17 +455,22 @@ int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, i
   // levels, small frames) keep the exact two-term products and the hi + lo split between the passes.
   const bool two = two_terms(h, w, force_two_terms);
   const int tx = ceil_div(ow, kTileOW);
+  if (ceil_div(c, csplit) > kMaxCPer) return 0;
+  CUtensorMap map_x, map_y;
+  if (make_plane_map_sw64(&map_x, fx, pairs * c, h, w, TcCfg<3, true>::kInH) != 0 ||
+      make_plane_map_sw64(&map_y, fy, pairs * c, h, w, TcCfg<3, true>::kInH) != 0)
+    return 0;   // the caller falls back to the CUDA-core window kernel
   if (two) {
     using Cfg = TcCfg<3, true>;
     ensure_dynamic_smem(window_mma_kernel<true, 3>, Cfg::kSmemBytes);
     dim3 grid(tx * ceil_div(oh, Cfg::kTileOH), csplit, pairs);
-    window_mma_kernel<true, 3><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t,
+    window_mma_kernel<true, 3><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_x, map_y, c, oh, ow, tx, csplit, choff, chan, wt, t,
                                                                        amap, bmap, gmap);
   } else {
     using Cfg = TcCfg<3, false>;
     ensure_dynamic_smem(window_mma_kernel<false, 3>, Cfg::kSmemBytes);
     dim3 grid(tx * ceil_div(oh, Cfg::kTileOH), csplit, pairs);
-    window_mma_kernel<false, 3><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(fx, fy, c, h, w, oh, ow, tx, csplit, choff, chan, wt, t,
+    window_mma_kernel<false, 3><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_x, map_y, c, oh, ow, tx, csplit, choff, chan, wt, t,
                                                                         amap, bmap, gmap);
   }
   return 1;

@@ -367,6 +367,18 @@ int conv_tc_make_weight_map(CUtensorMap* map, const bf16* wk, int cout, int k, i
   return tc::encode_w_map(map, wk, cout, k, block_n) ? 0 : 1;
 }
 
+int make_plane_map_sw64(CUtensorMap* map, const bf16* ptr, int planes, int h, int w, int box_h) {
+  tc::EncodeTiledFn fn = tc::get_encode_fn();
+  if (!fn) return 1;
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)w * 2, (cuuint64_t)h * w * 2};
+  const cuuint32_t box[3] = {32, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
+}
+
 // NQA_CONV_HALO: 0 = plain kernel everywhere; 1..4 = halo-reuse kernel with
 // (halo width, base-offset mode) = (10,0) (10,1) (16,0) (16,1).
 ConvTcConfig conv_tc_config_from_env(int sm_count) {

@@ -145,6 +145,9 @@ int launch_conv3x3_tc_pair(const ConvTcPlan& plan, int sm_count, cudaStream_t st
 int conv_tc_make_act_map(CUtensorMap* map, const bf16* ptr, int n, int h, int w, int c, int box_w, int box_h);
 // 2-D SWIZZLE_128B tensor map over K-major weights [cout][k] bf16 with box {64, block_n}; 0 on success.
 int conv_tc_make_weight_map(CUtensorMap* map, const bf16* wk, int cout, int k, int block_n);
+// 3-D SWIZZLE_64B tensor map over bf16 planes [planes][h][w] (w % 8 == 0) with box {32 columns, box_h rows, 1}; out-of-image
+// parts of a box are zero-filled.  0 on success.
+int make_plane_map_sw64(CUtensorMap* map, const bf16* ptr, int planes, int h, int w, int box_h);
 
 // Fused VGG stage 1 (bf16 trunk): normalise + conv1_1 + ReLU + conv1_2 + ReLU, relu1_1 stays on chip
 // (stage1_fused.cu).  w1img from launch_pack_w11_tc, w2map from conv_tc_make_weight_map(.., 64, 576, 64).
