@@ -1,7 +1,10 @@
-"""ctypes binding of the C-ABI library ``libnerfqa_b200.so`` (include/nerfqa_b200.h).
+"""Binding of the C-ABI library ``libnerfqa_b200.so`` (include/nerfqa_b200.h).
 
 PyTorch is plumbing here (device memory, streams); every scoring call goes through the C-ABI with raw
-pointers.  There is no CPU fallback: if the library is missing or no CUDA device exists, calls raise.
+pointers.  The no-grad scoring calls (``dists_forward``, ``adists_forward``, ``dists_adists_forward``, ``features``,
+``l2pool``) go through the thin torch extension ``torch.ops.nerfqa_b200.*`` (torch_ops.py, csrc_torch/) when it is built,
+everything else -- and everything when ``NQA_BINDING=ctypes`` -- through ctypes; both reach the same ``nqa_*`` entry points.
+There is no CPU fallback: if the library is missing or no CUDA device exists, calls raise.
 """
 from __future__ import annotations
 
@@ -157,6 +160,15 @@ class Context:
         self.handle = h
         self.weights_key = None
         self.ab_key = None
+        from . import torch_ops
+        self.ops = torch_ops.load_if_enabled()   # torch.ops.nerfqa_b200 or None (ctypes only)
+
+    def _op(self, fn, *args):
+        """One torch.ops.nerfqa_b200 call on this context; library errors surface as NerfQAError like the ctypes path."""
+        try:
+            return fn(int(self.handle.value), *args)
+        except RuntimeError as e:
+            raise NerfQAError(str(e)) from None
 
     def __del__(self):
         try:
@@ -204,6 +216,9 @@ class Context:
         if x.dim() != 4 or x.shape[1] != 3:
             raise NerfQAError(f"expected [B,3,H,W] frames, got {tuple(x.shape)}")
         x, y = _as_input(x, "x"), _as_input(y, "y")
+        if self.ops is not None:
+            score, s1s2 = self._op(self.ops.dists_forward, x, y, precision, want_s1s2)
+            return score, (s1s2 if want_s1s2 else None)
         b, _, h, w = x.shape
         score = torch.empty(b, device=x.device, dtype=torch.float32)
         s1s2 = torch.empty(b, 2, NUM_CHANNELS, device=x.device, dtype=torch.float32) if want_s1s2 else None
@@ -256,6 +271,8 @@ class Context:
         if x.dim() != 4 or x.shape[1] != 3:
             raise NerfQAError(f"expected [B,3,H,W] frames, got {tuple(x.shape)}")
         x = _as_input(x, "x")
+        if self.ops is not None:
+            return list(self._op(self.ops.dists_features, x, precision))
         b, _, h, w = x.shape
         outs = [torch.empty(s, device=x.device, dtype=torch.float32) for s in level_shapes(b, h, w)[1:]]
         arr = (ctypes.c_void_p * (NUM_LEVELS - 1))(*[o.data_ptr() for o in outs])
@@ -339,6 +356,8 @@ class Context:
         if x.dim() != 4 or x.shape[1] != 3:
             raise NerfQAError(f"expected [B,3,H,W] frames, got {tuple(x.shape)}")
         x, y = _as_input(x, "x"), _as_input(y, "y")
+        if self.ops is not None:
+            return self._op(self.ops.adists_forward, x, y, window, precision)
         b, _, h, w = x.shape
         score = torch.empty(b, device=x.device, dtype=torch.float32)
         _check(self.lib.nqa_adists_forward(self.handle, _ptr(x), _ptr(y), b, h, w, window, precision, _ptr(score),
@@ -373,6 +392,8 @@ class Context:
         if x.shape != y.shape:
             raise NerfQAError(f"shape mismatch: x {tuple(x.shape)} vs y {tuple(y.shape)}")
         x, y = _as_input(x, "x"), _as_input(y, "y")
+        if self.ops is not None:
+            return self._op(self.ops.dists_adists_forward, x, y, window, precision)
         b, _, h, w = x.shape
         d = torch.empty(b, device=x.device, dtype=torch.float32)
         a = torch.empty(b, device=x.device, dtype=torch.float32)
@@ -401,6 +422,8 @@ class Context:
 
     def l2pool(self, x: torch.Tensor) -> torch.Tensor:
         x = _as_input(x, "input")
+        if self.ops is not None and x.dim() == 4:
+            return self._op(self.ops.l2pool, x)
         b, c, h, w = x.shape
         out = torch.empty(b, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, device=x.device, dtype=torch.float32)
         _check(self.lib.nqa_l2pool(self.handle, _ptr(x), b, c, h, w, _ptr(out), _stream(x.device)))
