@@ -3,7 +3,7 @@
 NVCC ?= nvcc
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden
 SRC_DIR := nerf_qa_b200/csrc
-SRCS := $(SRC_DIR)/ctx.cu $(SRC_DIR)/conv_tc.cu $(SRC_DIR)/conv_tc_halo.cu $(SRC_DIR)/conv_tc_pair.cu $(SRC_DIR)/conv_f32.cu $(SRC_DIR)/conv1_1_tc.cu $(SRC_DIR)/stage1_fused.cu $(SRC_DIR)/pool_stats.cu $(SRC_DIR)/pool_stats_tma.cu $(SRC_DIR)/backward.cu $(SRC_DIR)/adists.cu $(SRC_DIR)/microbench.cu $(SRC_DIR)/adists_tc.cu $(SRC_DIR)/resize.cu
+SRCS := $(SRC_DIR)/ctx.cu $(SRC_DIR)/conv_tc.cu $(SRC_DIR)/conv_tc_halo.cu $(SRC_DIR)/conv_tc_pair.cu $(SRC_DIR)/conv_f32.cu $(SRC_DIR)/conv1_1_tc.cu $(SRC_DIR)/stage1_fused.cu $(SRC_DIR)/pool_stats.cu $(SRC_DIR)/pool_stats_tma.cu $(SRC_DIR)/backward.cu $(SRC_DIR)/adists.cu $(SRC_DIR)/microbench.cu $(SRC_DIR)/adists_tc.cu $(SRC_DIR)/adists_strips.cu $(SRC_DIR)/resize.cu
 OBJS := $(SRCS:.cu=.o)
 LIB := nerf_qa_b200/libnerfqa_b200.so
 

@@ -87,6 +87,8 @@ struct LevelPlan {
   int csplit_mma;          // channel split of the tensor-pipe window kernel (64 x 72 tiles: fewer blocks per map)
   int chunks8;             // pixel chunks of the fused NHWC -> planes + channel-sums kernel (levels with c % 64 == 0)
   size_t off_sum8;         // its partials [pairs][chunks8][8][c]
+  int chunks_s;            // chunks of the strip-plane pooling + sums kernel (adists_strips.cu), 0 = level not served
+  size_t off_sum_s;        // its partials [pairs][chunks_s][8][c]
   size_t off_sum, off_ent, off_a, off_b, off_g, off_ps;  // byte offsets into the workspace
 };
 
@@ -144,6 +146,13 @@ Plan make_plan(int pairs, int H, int W, int window) {
       if (ch8 > ntiles) ch8 = ntiles;
       L.chunks8 = ch8 < 1 ? 1 : ch8;
       L.off_sum8 = take((size_t)pairs * L.chunks8 * 8 * L.c * sizeof(float));
+    }
+    L.chunks_s = 0;
+    L.off_sum_s = 0;
+    if (k >= 1 && L.c % 64 == 0 && (w & 7) == 0 && L.windowed) {
+      int spb, n_sg;
+      adists_strips_plan(L.c, h, w, &spb, &n_sg, &L.chunks_s);
+      L.off_sum_s = take((size_t)pairs * L.chunks_s * 8 * L.c * sizeof(float));
     }
     const int cs_max = L.csplit > L.csplit_mma ? L.csplit : L.csplit_mma;
     L.off_sum = take((size_t)pairs * L.chunks * 7 * L.c * sizeof(float));
@@ -228,7 +237,7 @@ sums7_kernel(const TI* __restrict__ x, const TI* __restrict__ y, int c, int hw, 
 // ================================================================================================
 __global__ void __launch_bounds__(256)
 planes_sums_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int pairs, int c, int hw, int chunks8,
-                   float* __restrict__ partials) {
+                   float* __restrict__ partials, int strip_w, int strip_h) {
   extern __shared__ uint32_t ps_smem[];
   uint32_t (*tx)[33] = reinterpret_cast<uint32_t (*)[33]>(ps_smem);                      // [pixel][channel pair]
   uint32_t (*ty)[33] = reinterpret_cast<uint32_t (*)[33]>(ps_smem + kPlaneTile * 33);
@@ -291,7 +300,14 @@ planes_sums_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int pair
         const uint32_t ay = ty[2 * pp][ch >> 1], by = ty[2 * pp + 1][ch >> 1];
         const uint32_t lox = (ch & 1) ? (ax >> 16) : (ax & 0xffffu), hix = (ch & 1) ? (bx >> 16) : (bx & 0xffffu);
         const uint32_t loy = (ch & 1) ? (ay >> 16) : (ay & 0xffffu), hiy = (ch & 1) ? (by >> 16) : (by & 0xffffu);
-        if (even && p + 1 < hw) {
+        if (strip_w > 0) {   // strip layout [w / 8][h][8]: the pixel pair (p, p + 1) stays inside one strip row (w % 8 == 0)
+          if (p < hw) {
+            const int yy = p / strip_w, xx = p - yy * strip_w;
+            const size_t o = ((size_t)(xx >> 3) * strip_h + yy) * 8 + (xx & 7);
+            *reinterpret_cast<uint32_t*>(rowx + o) = lox | (hix << 16);
+            *reinterpret_cast<uint32_t*>(rowy + o) = loy | (hiy << 16);
+          }
+        } else if (even && p + 1 < hw) {
           *reinterpret_cast<uint32_t*>(rowx + p) = lox | (hix << 16);
           *reinterpret_cast<uint32_t*>(rowy + p) = loy | (hiy << 16);
         } else {
@@ -1001,8 +1017,17 @@ bool adists_planes_sums_supported(int level, int H, int W) {
   return level >= 1 && level_channels(level) % 64 == 0 && h * w >= kPlaneTile;
 }
 
+int adists_pool_strips_and_sums(const bf16* planes, bf16* pooled_out, int pairs, int level, int H, int W, int window, void* ws,
+                                cudaStream_t st) {
+  const Plan p = make_plan(pairs, H, W, window);
+  const LevelPlan& L = p.lv[level];
+  if (L.chunks_s <= 0) return 0;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  return launch_pool_strips_sums(planes, pooled_out, pairs, L.c, L.h, L.w, reinterpret_cast<float*>(base + L.off_sum_s), st);
+}
+
 int adists_planes_and_sums(const bf16* nhwc, bf16* planes, int pairs, int level, int H, int W, int window, void* ws,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool strips) {
   const Plan p = make_plan(pairs, H, W, window);
   const LevelPlan& L = p.lv[level];
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
@@ -1010,7 +1035,7 @@ int adists_planes_and_sums(const bf16* nhwc, bf16* planes, int pairs, int level,
   ensure_dynamic_smem(planes_sums_kernel, smem);
   dim3 grid(L.chunks8, L.c / 64, pairs);
   planes_sums_kernel<<<grid, 256, smem, st>>>(nhwc, planes, pairs, L.c, L.hw, L.chunks8,
-                                             reinterpret_cast<float*>(base + L.off_sum8));
+                                             reinterpret_cast<float*>(base + L.off_sum8), strips ? L.w : 0, L.h);
   return 1;
 }
 
@@ -1018,7 +1043,7 @@ size_t adists_ps_elems(int H, int W, int window, int level) { return (size_t)mak
 
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
                  void* ws, float* score, cudaStream_t st, float* map_out, const AdistsParts* parts, const AdistsProf* prof,
-                 unsigned sums_done_mask, const AdistsOptions* opt) {
+                 unsigned sums_done_mask, const AdistsOptions* opt, unsigned strips_mask) {
   const AdistsOptions options = opt ? *opt : AdistsOptions();
   const bool use_mma = options.use_mma;
   int launches = 0;
@@ -1051,11 +1076,15 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
   Part part(prof, 0, &launches);
   for (int k = 0; k < kNumLevels; ++k) {
     const LevelPlan& L = p.lv[k];
-    const bool fused = ((sums_done_mask >> k) & 1) != 0 && L.chunks8 > 0;   // planes_sums_kernel has run for this level
+    // sums already in the workspace: from planes_sums_kernel (bit 0..5 of the mask) or, bit 8 + k, from the strip-plane
+    // pooling kernel (adists_strips.cu); same partial layout, different chunking
+    const bool from_strips = ((sums_done_mask >> (8 + k)) & 1) != 0 && L.chunks_s > 0;
+    const bool fused = from_strips || (((sums_done_mask >> k) & 1) != 0 && L.chunks8 > 0);
     sl.hw[k] = L.hw;
     sl.fused[k] = fused ? 1 : 0;
     if (fused) {
-      sl.partials[k] = F(L.off_sum8); sl.chunks[k] = L.chunks8;
+      sl.partials[k] = from_strips ? F(L.off_sum_s) : F(L.off_sum8);
+      sl.chunks[k] = from_strips ? L.chunks_s : L.chunks8;
       el.partials[k] = nullptr; el.chunks[k] = 0;
       continue;
     }
@@ -1083,11 +1112,14 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
     const LevelPlan& L = p.lv[k];
     csplit_used[k] = L.csplit;
     int mma_launches = 0;
-    if (L.windowed && is16(k) && use_mma && window_mma_supported(window, L.h, L.w, fx[k], fy[k]))
+    const bool strips = ((strips_mask >> k) & 1) != 0;
+    if (strips && !(L.windowed && is16(k) && window_mma_supported(window, L.h, L.w, fx[k], fy[k]))) return -1;
+    if (L.windowed && is16(k) && (use_mma || strips) && window_mma_supported(window, L.h, L.w, fx[k], fy[k]))
       // bf16 planes: the two gaussian passes as banded-Toeplitz products on the tensor pipe (adists_tc.cu); 0 = no
       // tensor map for these planes, the CUDA-core kernel serves the level
       mma_launches = launch_window_mma(B16(fx[k]), B16(fy[k]), pairs, L.c, L.h, L.w, window, L.csplit_mma, L.choff, chan, wt,
-                                       taps.g, options.mma_terms == 2, F(L.off_a), F(L.off_b), F(L.off_g), st);
+                                       taps.g, options.mma_terms == 2, strips, F(L.off_a), F(L.off_b), F(L.off_g), st);
+    if (mma_launches < 0 || (strips && mma_launches == 0)) return -1;
     if (mma_launches > 0) {
       csplit_used[k] = L.csplit_mma;
       launches += mma_launches;

@@ -37,13 +37,25 @@ struct AdistsProf {
 };
 int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf16, int pairs, int H, int W, int window,
                  void* ws, float* score, cudaStream_t st, float* map_out = nullptr, const AdistsParts* parts = nullptr,
-                 const AdistsProf* prof = nullptr, unsigned sums_done_mask = 0, const AdistsOptions* opt = nullptr);
+                 const AdistsProf* prof = nullptr, unsigned sums_done_mask = 0, const AdistsOptions* opt = nullptr,
+                 unsigned strips_mask = 0);   // strips_mask: levels whose bf16 planes are in the strip layout
 // bf16 trunk: level `level`'s NHWC activations [2*pairs][h][w][c] (x images first) -> bf16 planes [2*pairs][c][h*w],
 // with the level's per-channel sums written into the workspace `ws` on the way (one read of the level instead of
 // three).  Pass bit `level` in adists_stage's sums_done_mask afterwards.  Levels 1..5 (c % 64 == 0) with at least 256 pixels.
 bool adists_planes_sums_supported(int level, int H, int W);
 int adists_planes_and_sums(const __nv_bfloat16* nhwc, __nv_bfloat16* planes, int pairs, int level, int H, int W, int window,
-                           void* ws, cudaStream_t st);
+                           void* ws, cudaStream_t st, bool strips = false);   // strips: write the strip layout (validation path)
+// Strip planes (bf16 trunk): level `level`'s features as written by the convolution epilogues, [2*pairs][c][w/8][h][8]
+// (kernels.h make_strip_map).  adists_pool_strips_and_sums reads them once: L2-pooled NHWC input of the next stage
+// (pooled_out, may be null for level 5) + the level's channel sums into the workspace; pass bit `level` in BOTH masks of
+// adists_stage afterwards.  Supported for levels whose width is a multiple of 8 and that are windowed (the tensor-pipe
+// window kernel is the only reader of strip planes).
+bool adists_strips_supported(int level, int H, int W, int window);
+int adists_pool_strips_and_sums(const __nv_bfloat16* planes, __nv_bfloat16* pooled_out, int pairs, int level, int H, int W,
+                                int window, void* ws, cudaStream_t st);
+void adists_strips_plan(int c, int h, int w, int* spb, int* n_sg, int* chunks);
+int launch_pool_strips_sums(const __nv_bfloat16* planes, __nv_bfloat16* pooled_out, int pairs, int c, int h, int w, float* partials,
+                            cudaStream_t st);
 // number of elements of the level-k ps map of one frame (1 for a fallback level)
 size_t adists_ps_elems(int H, int W, int window, int level);
 

@@ -120,7 +120,7 @@ __device__ inline float2 div2_approx(float2 num, float2 den) {
 // scaled by 1/sum(g')^2): thread (lane) holds columns lane/4 (+8), rows 8*ob + 2*(lane%4) + {0,1}.
 // kTwo = false: the first-pass results go into the second pass as ONE bf16 term (levels whose maps are large enough
 // that the 1e-6 stabilisers of T and S dwarf the rounding, see launch_window_mma).
-template <int NT, bool kTwo>
+template <int NT, bool kTwo, int kRbStride>
 __device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t lane_off, uint32_t lane_off2,
                                     const uint32_t (&ta)[3][4], const uint32_t (&tb)[2][2], float (&out)[kOB][4]) {
   uint32_t fh[kRB][2], fl[kTwo ? kRB : 1][2];
@@ -130,8 +130,8 @@ __device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t la
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       uint32_t b01[4], b2[2];
-      ldmatrix_x4(b01, tile_addr[t] + lane_off + rb * 8 * 64);    // k-blocks 0 and 1 (columns +0, +8, +16, +24)
-      ldmatrix_x2(b2, tile_addr[t] + lane_off2 + rb * 8 * 64);    // k-block 2 (columns +32, +40)
+      ldmatrix_x4(b01, tile_addr[t] + lane_off + rb * kRbStride);    // k-blocks 0 and 1 (columns +0, +8, +16, +24)
+      ldmatrix_x2(b2, tile_addr[t] + lane_off2 + rb * kRbStride);    // k-block 2 (columns +32, +40)
       mma16816(c, ta[0][0], ta[0][1], ta[0][2], ta[0][3], b01[0], b01[1]);
       mma16816(c, ta[1][0], ta[1][1], ta[1][2], ta[1][3], b01[2], b01[3]);
       mma16816(c, ta[2][0], ta[2][1], ta[2][2], ta[2][3], b2[0], b2[1]);
@@ -159,7 +159,11 @@ __device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t la
   }
 }
 
-template <bool kTwo, int kWY>
+// kStrips: the planes are in the strip layout the trunk's convolution epilogues write for A-DISTS ([plane][w / 8][h][8]:
+// 8-pixel-wide column strips, rows contiguous inside a strip; see conv_tc_pair.cu / stage1_fused.cu).  A tile then is
+// [row block of 8][strip][8 rows][16 bytes], loaded as one {64 elements, 12 strips} box per row block (each warp issues
+// its own row block), and an 8-row ldmatrix read is 128 contiguous bytes.
+template <bool kTwo, int kWY, bool kStrips>
 __global__ void __launch_bounds__(TcCfg<kWY, kTwo>::kThreads, TcCfg<kWY, kTwo>::kBlocksPerSM)
 window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, int c, int oh, int ow,
                   int tiles_x, int csplit, int choff, const double* __restrict__ chan, const float* __restrict__ wt, TcTaps taps,
@@ -168,6 +172,9 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   constexpr int kThreads = Cfg::kThreads, kTileOH = Cfg::kTileOH, kTileBytes = Cfg::kTileBytes;
   constexpr int kPartBytes = Cfg::kPartBytes;
   constexpr int kStep = kTwo ? 1 : 2;   // product tile m of (xx_h, xx_l, yy_h, yy_l, xy_h, xy_l) lives in slot 4 + m / kStep
+  constexpr int kRowBlocks = Cfg::kInH / 8, kStripRow = (kInW / 8) * 128;   // strip layout: bytes per 8-row block
+  constexpr int kRbStride = kStrips ? kStripRow : 8 * 64;
+  static_assert(!kStrips || kRowBlocks == kThreads / 32, "strip layout: one row block of the tile per warp");
   extern __shared__ unsigned char smem_dyn[];
   // the swizzle pattern is a function of the shared-memory ADDRESS: tiles start on a 1024-byte boundary (aligned by
   // offset from the __shared__ array so that accesses stay LDS / STS)
@@ -211,13 +218,23 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
   // raw tile loader (ONE thread): the x and y tiles of channel ch as 2 x 3 TMA boxes of 32 columns x kInH rows; parts of
   // a box outside the image arrive as zeros
+  // (strip layout: called by every thread after a block barrier; thread 0 announces the bytes, lane 0 of warp j loads
+  // row block j of both tiles)
   auto load_raw = [&](int ch, int buf) {
     const uint32_t bar = full_bar + 8 * buf;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kTileBytes) : "memory");
+    if (threadIdx.x == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kTileBytes) : "memory");
+    if (kStrips) {
+      if (lane == 0) {
+        tma_load_3d(tile(buf * 2 + 0) + warp * kStripRow, &map_x, bar, (oy0 + 8 * warp) * 8, ox0 >> 3, b * c + ch);
+        tma_load_3d(tile(buf * 2 + 1) + warp * kStripRow, &map_y, bar, (oy0 + 8 * warp) * 8, ox0 >> 3, b * c + ch);
+      }
+    } else if (threadIdx.x == 0) {
 #pragma unroll
-    for (int part = 0; part < kParts; ++part) {
-      tma_load_3d(tile(buf * 2 + 0) + part * kPartBytes, &map_x, bar, ox0 + 32 * part, oy0, b * c + ch);
-      tma_load_3d(tile(buf * 2 + 1) + part * kPartBytes, &map_y, bar, ox0 + 32 * part, oy0, b * c + ch);
+      for (int part = 0; part < kParts; ++part) {
+        tma_load_3d(tile(buf * 2 + 0) + part * kPartBytes, &map_x, bar, ox0 + 32 * part, oy0, b * c + ch);
+        tma_load_3d(tile(buf * 2 + 1) + part * kPartBytes, &map_y, bar, ox0 + 32 * part, oy0, b * c + ch);
+      }
     }
   };
 
@@ -226,8 +243,9 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   // start at multiples of 8 rows, so the swizzle term (row >> 1) & 3 is (lane >> 1) & 3 for every block
   const uint32_t row_off = (uint32_t)((wy * 8 * kOB + (lane & 7)) * 64), sw = (uint32_t)((lane >> 1) & 3);
   const uint32_t q4 = (uint32_t)(wx * 2 + (lane >> 3)), q2 = (uint32_t)(wx * 2 + 4 + ((lane >> 3) & 1));
-  const uint32_t lane_off = (q4 >> 2) * kPartBytes + row_off + (((q4 & 3) ^ sw) << 4);
-  const uint32_t lane_off2 = (q2 >> 2) * kPartBytes + row_off + (((q2 & 3) ^ sw) << 4);
+  const uint32_t strip_row = (uint32_t)(wy * kOB * kStripRow + (lane & 7) * 16);
+  const uint32_t lane_off = kStrips ? strip_row + q4 * 128 : (q4 >> 2) * kPartBytes + row_off + (((q4 & 3) ^ sw) << 4);
+  const uint32_t lane_off2 = kStrips ? strip_row + q2 * 128 : (q2 >> 2) * kPartBytes + row_off + (((q2 & 3) ^ sw) << 4);
   const bool warp_live = (oy0 + wy * 8 * kOB) < oh && (ox0 + wx * 16) < ow;
   const bool producer = wy != 0;
   // named barrier 1: every thread arrives once per channel, the producers after writing the product tiles, the row-0
@@ -252,13 +270,14 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_bar + 8) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (c_begin < c_end) load_raw(c_begin, 0);
   }
+  __syncthreads();   // barriers initialised before any warp's TMA signals them
+  if (c_begin < c_end) load_raw(c_begin, 0);
   int buf = 0;
   uint32_t phase = 0;   // parity of raw[buf]'s barrier: flips every second channel
   for (int ch = c_begin; ch < c_end; ++ch, buf ^= 1, phase ^= (uint32_t)(buf == 0)) {
     __syncthreads();   // every warp is done with the previous channel's tiles (first pass: barriers + scalars visible)
-    if (threadIdx.x == 0 && ch + 1 < c_end) load_raw(ch + 1, buf ^ 1);
+    if (ch + 1 < c_end) load_raw(ch + 1, buf ^ 1);
     mbar_wait_parity(full_bar + 8 * buf, phase);   // raw[buf] has landed
 
     // ---- products: x^2, y^2, xy as exact bf16 hi + lo, written once per block by the warps of rows 1 and 2, while the
@@ -329,13 +348,13 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     float d[kOB][4];
     {
       const uint32_t t0[1] = {tile(buf * 2 + 0)};
-      filtered_map<1, kTwo>(t0, lane_off, lane_off2, ta, tb, d);
+      filtered_map<1, kTwo, kRbStride>(t0, lane_off, lane_off2, ta, tb, d);
 #pragma unroll
       for (int ob = 0; ob < kOB; ++ob)
 #pragma unroll
         for (int i = 0; i < 2; ++i) mx[ob][i] = __fmul2_rn(kx, make_float2(d[ob][2 * i], d[ob][2 * i + 1]));
       const uint32_t t1[1] = {tile(buf * 2 + 1)};
-      filtered_map<1, kTwo>(t1, lane_off, lane_off2, ta, tb, d);
+      filtered_map<1, kTwo, kRbStride>(t1, lane_off, lane_off2, ta, tb, d);
     }
 #pragma unroll
     for (int ob = 0; ob < kOB; ++ob)
@@ -350,10 +369,10 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     {
       if (kTwo) {
         const uint32_t t2[2] = {tile(4), tile(5)};
-        filtered_map<2, true>(t2, lane_off, lane_off2, ta, tb, d);
+        filtered_map<2, true, kRbStride>(t2, lane_off, lane_off2, ta, tb, d);
       } else {
         const uint32_t t2[1] = {tile(4 + 0 / 2)};
-        filtered_map<1, false>(t2, lane_off, lane_off2, ta, tb, d);
+        filtered_map<1, false, kRbStride>(t2, lane_off, lane_off2, ta, tb, d);
       }
     }
 #pragma unroll
@@ -370,10 +389,10 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     {
       if (kTwo) {
         const uint32_t t3[2] = {tile(6), tile(7)};
-        filtered_map<2, true>(t3, lane_off, lane_off2, ta, tb, d);
+        filtered_map<2, true, kRbStride>(t3, lane_off, lane_off2, ta, tb, d);
       } else {
         const uint32_t t3[1] = {tile(4 + 2 / 2)};
-        filtered_map<1, false>(t3, lane_off, lane_off2, ta, tb, d);
+        filtered_map<1, false, kRbStride>(t3, lane_off, lane_off2, ta, tb, d);
       }
     }
 #pragma unroll
@@ -387,10 +406,10 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     {
       if (kTwo) {
         const uint32_t t4[2] = {tile(8), tile(9)};
-        filtered_map<2, true>(t4, lane_off, lane_off2, ta, tb, d);
+        filtered_map<2, true, kRbStride>(t4, lane_off, lane_off2, ta, tb, d);
       } else {
         const uint32_t t4[1] = {tile(4 + 4 / 2)};
-        filtered_map<1, false>(t4, lane_off, lane_off2, ta, tb, d);
+        filtered_map<1, false, kRbStride>(t4, lane_off, lane_off2, ta, tb, d);
       }
     }
 #pragma unroll
@@ -437,9 +456,19 @@ void window_mma_tiles(int h, int w, int window, int* tiles_x, int* tiles_y) {
   *tiles_y = ceil_div(oh, two_terms(h, w, false) ? TcCfg<3, true>::kTileOH : TcCfg<3, false>::kTileOH);
 }
 
+template <bool kTwo, bool kStrips>
+static void launch_cfg(const CUtensorMap& mx, const CUtensorMap& my, int pairs, int c, int oh, int ow, int tx, int csplit, int choff,
+                       const double* chan, const float* wt, const TcTaps& t, float* amap, float* bmap, float* gmap, cudaStream_t st) {
+  using Cfg = TcCfg<3, kTwo>;
+  ensure_dynamic_smem(window_mma_kernel<kTwo, 3, kStrips>, Cfg::kSmemBytes);
+  dim3 grid(tx * ceil_div(oh, Cfg::kTileOH), csplit, pairs);
+  window_mma_kernel<kTwo, 3, kStrips><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(mx, my, c, oh, ow, tx, csplit, choff, chan, wt, t,
+                                                                                 amap, bmap, gmap);
+}
+
 int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, int w, int window, int csplit, int choff,
-                      const double* chan, const float* wt, const float* taps_f32, bool force_two_terms, float* amap, float* bmap,
-                      float* gmap, cudaStream_t st) {
+                      const double* chan, const float* wt, const float* taps_f32, bool force_two_terms, bool strips, float* amap,
+                      float* bmap, float* gmap, cudaStream_t st) {
   TcTaps t;
   double sum = 0.0;
   for (int i = 0; i < 32; ++i) {
@@ -457,21 +486,19 @@ int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, i
   const int tx = ceil_div(ow, kTileOW);
   if (ceil_div(c, csplit) > kMaxCPer) return 0;
   CUtensorMap map_x, map_y;
-  if (make_plane_map_sw64(&map_x, fx, pairs * c, h, w, TcCfg<3, true>::kInH) != 0 ||
-      make_plane_map_sw64(&map_y, fy, pairs * c, h, w, TcCfg<3, true>::kInH) != 0)
+  if (strips) {
+    if (make_strip_map(&map_x, fx, pairs * c, h, w, 64, kInW / 8) != 0 || make_strip_map(&map_y, fy, pairs * c, h, w, 64, kInW / 8) != 0)
+      return -1;   // strip planes have no other reader
+  } else if (make_plane_map_sw64(&map_x, fx, pairs * c, h, w, TcCfg<3, true>::kInH) != 0 ||
+             make_plane_map_sw64(&map_y, fy, pairs * c, h, w, TcCfg<3, true>::kInH) != 0) {
     return 0;   // the caller falls back to the CUDA-core window kernel
+  }
   if (two) {
-    using Cfg = TcCfg<3, true>;
-    ensure_dynamic_smem(window_mma_kernel<true, 3>, Cfg::kSmemBytes);
-    dim3 grid(tx * ceil_div(oh, Cfg::kTileOH), csplit, pairs);
-    window_mma_kernel<true, 3><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_x, map_y, c, oh, ow, tx, csplit, choff, chan, wt, t,
-                                                                       amap, bmap, gmap);
+    if (strips) launch_cfg<true, true>(map_x, map_y, pairs, c, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap, st);
+    else launch_cfg<true, false>(map_x, map_y, pairs, c, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap, st);
   } else {
-    using Cfg = TcCfg<3, false>;
-    ensure_dynamic_smem(window_mma_kernel<false, 3>, Cfg::kSmemBytes);
-    dim3 grid(tx * ceil_div(oh, Cfg::kTileOH), csplit, pairs);
-    window_mma_kernel<false, 3><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_x, map_y, c, oh, ow, tx, csplit, choff, chan, wt, t,
-                                                                        amap, bmap, gmap);
+    if (strips) launch_cfg<false, true>(map_x, map_y, pairs, c, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap, st);
+    else launch_cfg<false, false>(map_x, map_y, pairs, c, oh, ow, tx, csplit, choff, chan, wt, t, amap, bmap, gmap, st);
   }
   return 1;
 }

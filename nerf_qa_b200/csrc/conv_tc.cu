@@ -367,6 +367,30 @@ int conv_tc_make_weight_map(CUtensorMap* map, const bf16* wk, int cout, int k, i
   return tc::encode_w_map(map, wk, cout, k, block_n) ? 0 : 1;
 }
 
+int make_strip_map(CUtensorMap* map, const bf16* ptr, int planes, int h, int w, int box_elems, int box_strips) {
+  tc::EncodeTiledFn fn = tc::get_encode_fn();
+  if (!fn || (w & 7) != 0) return 1;
+  const cuuint64_t dims[3] = {(cuuint64_t)8 * h, (cuuint64_t)(w / 8), (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)h * 16, (cuuint64_t)h * w * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)box_elems, (cuuint32_t)box_strips, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
+}
+
+int make_strip_out_map(CUtensorMap* map, const bf16* ptr, int n, int c, int h, int w) {
+  tc::EncodeTiledFn fn = tc::get_encode_fn();
+  if (!fn || (w & 7) != 0) return 1;
+  const cuuint64_t dims[4] = {(cuuint64_t)8 * h, (cuuint64_t)(w / 8), (cuuint64_t)c, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)h * 16, (cuuint64_t)h * w * 2, (cuuint64_t)c * h * w * 2};
+  const cuuint32_t box[4] = {128, 1, 64, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
+}
+
 int make_plane_map_sw64(CUtensorMap* map, const bf16* ptr, int planes, int h, int w, int box_h) {
   tc::EncodeTiledFn fn = tc::get_encode_fn();
   if (!fn) return 1;
@@ -394,9 +418,14 @@ ConvTcConfig conv_tc_config_from_env(int sm_count) {
   return c;
 }
 
+bool conv_tc_uses_pair(const ConvTcConfig& cfg, int cin, int cout, bool split) {
+  return cfg.halo_mode > 0 && !split && cin <= cfg.halo_max_cin && cin % tc::BLOCK_K == 0 && cfg.pair && cout >= 128 &&
+         cin >= cfg.pair_min_cin && (cfg.sm_count & 1) == 0;
+}
+
 int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in, const bf16* in_lo, const bf16* wk,
                       const bf16* wk_lo, const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout,
-                      bool split, const char** err) {
+                      bool split, const char** err, bool strips_out) {
   if (cin % tc::BLOCK_K != 0 || cout % 64 != 0 || cout > 512) { *err = "conv_tc: cin must be a multiple of 64, cout a multiple of 64 and <= 512"; return 1; }
   plan->n = n; plan->h = h; plan->w = w; plan->cin = cin; plan->cout = cout;
   plan->sm_count = cfg.sm_count;
@@ -413,6 +442,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in,
   plan->fg_nx = 0;
   plan->halo = false;
   plan->pair = false;
+  plan->strips_out = false;
   plan->halo_hbw = 10;
   plan->halo_desc_mode = 0;
   const int halo_mode = cfg.halo_mode;
@@ -438,7 +468,13 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in,
   bool ok = (plan->halo ? tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, plan->halo_hbw, th + 2)
                         : tc::encode_act_map(&plan->tmap_a, in, n, h, w, cin, tw, th)) &&
             tc::encode_w_map(&plan->tmap_b, wk, cout, 9 * cin, plan->pair ? plan->block_n / 2 : plan->block_n);
-  if (plan->halo) ok = ok && tc::encode_act_map(&plan->tmap_out, out, n, h, w, cout, tw, th);
+  if (strips_out) {
+    if (!plan->pair) { *err = "conv_tc: strip-plane output needs the CTA-pair kernel"; return 1; }
+    plan->strips_out = true;
+    ok = ok && make_strip_out_map(&plan->tmap_out, out, n, cout, h, w) == 0;
+  } else if (plan->halo) {
+    ok = ok && tc::encode_act_map(&plan->tmap_out, out, n, h, w, cout, tw, th);
+  }
   if (split)
     ok = ok && tc::encode_act_map(&plan->tmap_a_lo, in_lo, n, h, w, cin, tw, th) &&
          tc::encode_w_map(&plan->tmap_b_lo, wk_lo, cout, 9 * cin, plan->block_n);

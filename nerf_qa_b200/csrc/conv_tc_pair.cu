@@ -42,6 +42,7 @@ struct Params {
   const float* bias;
   int epi;             // ConvEpilogue
   const bf16* mask;    // kEpiMask: saved activation of the layer below, [n,h,w,cout]
+  int strips;          // 1: the output goes out as strip planes (kernels.h make_strip_out_map), kEpiBiasRelu only
 };
 
 template <int BLOCK_N, bool RESIDENT>
@@ -287,7 +288,18 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             t.y = Vec<bf16>::pack2(v[2], v[3]);
             t.z = Vec<bf16>::pack2(v[4], v[5]);
             t.w = Vec<bf16>::pack2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(stg + m * 128 + (((half * 4 + q) ^ (m & 7)) << 4)) = t;
+            if (p.strips) {
+              // [channel][pixel]: a warp's 32 pixels of one channel are 64 contiguous bytes (conflict-free 2-byte stores)
+              unsigned short* col = reinterpret_cast<unsigned short*>(stg) + (half * 32 + q * 8) * 128 + m;
+              const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                col[(2 * j) * 128] = (unsigned short)(tw[j] & 0xffffu);
+                col[(2 * j + 1) * 128] = (unsigned short)(tw[j] >> 16);
+              }
+            } else {
+              *reinterpret_cast<uint4*>(stg + m * 128 + (((half * 4 + q) ^ (m & 7)) << 4)) = t;
+            }
           }
         }
         if (c64 == BLOCK_N / 64 - 1) {                // accumulator fully read: hand it back to the leader's MMA warp
@@ -298,7 +310,8 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         fence_proxy_async_smem();
         named_bar_sync(3, 128);
         if (elected) {
-          tma_store_4d(&tmap_out, stg, n0 + c64 * 64, w0, h0, img);
+          if (p.strips) tma_store_4d(&tmap_out, stg, h0 * 8, w0 >> 3, n0 + c64 * 64, img);
+          else tma_store_4d(&tmap_out, stg, n0 + c64 * 64, w0, h0, img);
           tma_store_commit();
         }
       }
@@ -329,6 +342,8 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
   p.hbw = plan.halo_hbw;
   p.a_stage_bytes = (HALO_H * plan.halo_hbw * 128 + 1023) & ~1023;
   p.bias = plan.bias; p.epi = plan.epi; p.mask = plan.mask;
+  p.strips = plan.strips_out ? 1 : 0;
+  if (p.strips && p.epi != kEpiBiasRelu) return -1;
   const int chunks = plan.cin / BLOCK_K;
   const int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - 2048 /*bias*/ - STG_BYTES;
   int a_stages, b_stages = 0;

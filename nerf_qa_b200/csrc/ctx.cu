@@ -111,6 +111,9 @@ struct nqa_ctx {
   bool pool_stats_tma = true;            // NQA_POOL_STATS_TMA=0: register-fed pooling + moments kernel for bf16 levels too
   AdistsOptions adists_opt;              // NQA_ADISTS_MMA / NQA_ADISTS_MMA_TERMS
   bool adists_fused_sums = true;         // NQA_ADISTS_FUSED_SUMS=0: separate planes / sums / entropy kernels (bf16 trunk)
+  int adists_strips = 2;                 // NQA_ADISTS_STRIPS: 2 = the last convolution of a stage writes strip planes and one
+                                         // kernel pools + sums them (A-DISTS-only calls of the bf16 trunk); 1 = strip planes
+                                         // from the NHWC level (validation); 0 = planar planes
   ConvTcConfig conv_cfg;                 // kernel selection of the tensor-pipe convolutions (environment read at creation)
   // Encoded tensor maps of the convolution launches, keyed on (buffers, shape): the arena hands out the same addresses
   // for the same shape, so after the first call at a shape no launch goes through cuTensorMapEncodeTiled again.
@@ -254,8 +257,8 @@ struct StreamOrder {
 // conv_tc_make_plan through the context's cache of encoded tensor maps
 int cached_plan(nqa_ctx* ctx, ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
                 const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout, bool split,
-                const char** err) {
-  const nqa_ctx::PlanKey key{in, in_lo, wk, out, out_lo, n, h, w, cin, cout, split ? 1 : 0};
+                const char** err, bool strips_out = false) {
+  const nqa_ctx::PlanKey key{in, in_lo, wk, out, out_lo, n, h, w, cin, cout, (split ? 1 : 0) | (strips_out ? 2 : 0)};
   for (auto& e : ctx->plan_cache)
     if (e.first == key) {
       *plan = e.second;
@@ -263,7 +266,8 @@ int cached_plan(nqa_ctx* ctx, ConvTcPlan* plan, const bf16* in, const bf16* in_l
       ++ctx->plan_hits;
       return 0;
     }
-  const int rc = conv_tc_make_plan(plan, ctx->conv_cfg, in, in_lo, wk, wk_lo, bias, out, out_lo, n, h, w, cin, cout, split, err);
+  const int rc = conv_tc_make_plan(plan, ctx->conv_cfg, in, in_lo, wk, wk_lo, bias, out, out_lo, n, h, w, cin, cout, split, err,
+                                   strips_out);
   if (rc) return rc;
   ++ctx->plan_misses;
   if (ctx->plan_cache.size() >= 512) ctx->plan_cache.clear();
@@ -442,9 +446,10 @@ void trunk_alloc(nqa_ctx* ctx, TrunkBufs<T>* b, int n, int H, int W, int prec) {
   }
 }
 
+// strips_out (bf16 trunk, CTA-pair layers): `out` is a strip-plane buffer [n][cout][w/8][h][8] instead of NHWC
 template <typename T>
 int conv_layer(nqa_ctx* ctx, int li, const T* in, const T* in_lo, T* out, T* out_lo, int n, int h, int w, int prec,
-               cudaStream_t st);
+               cudaStream_t st, bool strips_out = false);
 
 template <typename T>
 void conv1_1_layer(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int h, int w, T* out, T* out_lo,
@@ -464,19 +469,19 @@ void conv1_1_layer<bf16>(nqa_ctx* ctx, const float* x, const float* y, int nx, i
 
 template <>
 int conv_layer<float>(nqa_ctx* ctx, int li, const float* in, const float*, float* out, float*, int n, int h, int w, int,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool) {
   ProfScope ps(ctx, NQA_K_CONV_F32, st);
   ctx->launches += launch_conv3x3_f32(in, out, ctx->w_f32[li], ctx->bias[li], n, h, w, kConvCin[li], kConvCout[li], st);
   return NQA_OK;
 }
 template <>
 int conv_layer<bf16>(nqa_ctx* ctx, int li, const bf16* in, const bf16* in_lo, bf16* out, bf16* out_lo, int n, int h,
-                     int w, int prec, cudaStream_t st) {
+                     int w, int prec, cudaStream_t st, bool strips_out) {
   ConvTcPlan plan;
   const char* err = "";
   const bool split = prec == NQA_PREC_BF16X3;
   if (cached_plan(ctx, &plan, in, in_lo, ctx->w_hi[li], ctx->w_lo[li], ctx->bias[li], out, out_lo, n, h, w,
-                  kConvCin[li], kConvCout[li], split, &err))
+                  kConvCin[li], kConvCout[li], split, &err, strips_out))
     return fail(NQA_ERR_CUDA, "%s (layer %d, %dx%dx%d)", err, li, n, h, w);
   ProfScope ps(ctx, NQA_K_CONV_TC, st);
   const int nl = launch_conv3x3_tc(plan, st);
@@ -491,22 +496,26 @@ int conv_layer<bf16>(nqa_ctx* ctx, int li, const bf16* in, const bf16* in_lo, bf
 // next stage reads (nullptr after stage 5).  A consumer that already wrote the L2-pooled features there (the fused
 // pool + statistics kernel) returns true; otherwise the trunk enqueues the pooling kernel itself.  The level buffer
 // stays valid until the next stage's first conv is enqueued, i.e. consumers enqueued inside on_level are safe.
+// strips_dst (optional, bf16 trunk): strips_dst[k] != nullptr makes the last convolution of stage k write its output as
+// strip planes into that buffer (trunk_strips_capable says whether it can) instead of the NHWC ping-pong slot; on_level
+// is then called with feat == nullptr and must do the pooling itself (return true) if pooled_dst is set.
 template <typename T, typename F>
 int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H, int W, int prec, TrunkBufs<T>& bufs,
-              cudaStream_t st, F&& on_level) {
+              cudaStream_t st, F&& on_level, bf16* const* strips_dst = nullptr) {
   const bool split = prec == NQA_PREC_BF16X3;
   int h = H, w = W;
   int cur = 0;  // ping-pong slot holding the live activation
   int li = 0;
   for (int stage = 0; stage < 5; ++stage) {
+    bool level_in_strips = false;
     for (int j = 0; j < kStageConvs[stage]; ++j, ++li) {
       if (li == 0 && std::is_same<T, bf16>::value && !split && ctx->fuse_stage1) {
         // normalise + conv1_1 + conv1_2 in one kernel; relu1_1 never reaches HBM
         ProfScope ps(ctx, NQA_K_STAGE1, st);
         const bool pair = ctx->stage1_pair && (ctx->sm_count & 1) == 0;
         const int nl = launch_stage1_fused(x, y, nx, n, h, w, ctx->w11_img, ctx->bias[0], pair ? ctx->w12_map_pair : ctx->w12_map,
-                                           ctx->bias[1], reinterpret_cast<bf16*>(bufs.ping[1]), ctx->sm_count, pair,
-                                           ctx->stage1_a2_linear, st);
+                                           ctx->bias[1], strips_dst && strips_dst[1] ? strips_dst[1] : reinterpret_cast<bf16*>(bufs.ping[1]),
+                                           ctx->sm_count, pair, ctx->stage1_a2_linear, st, strips_dst && strips_dst[1]);
         if (nl <= 0) return fail(NQA_ERR_CUDA, "stage-1 kernel: tensor map or cluster launch failed (%dx%dx%d)", n, h, w);
         ctx->launches += nl;
         cur = 1;
@@ -515,6 +524,13 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
       } else if (li == 0) {
         conv1_1_layer<T>(ctx, x, y, nx, n, h, w, bufs.ping[0], split ? bufs.ping_lo[0] : nullptr, st);
         cur = 0;
+      } else if (strips_dst && strips_dst[stage + 1] && j == kStageConvs[stage] - 1 && li > 1) {
+        // last convolution of the stage -> strip planes; the ping-pong slot it would have written stays free for the
+        // pooled tensor
+        const int rc = conv_layer<T>(ctx, li, bufs.ping[cur], nullptr, reinterpret_cast<T*>(strips_dst[stage + 1]), nullptr, n, h, w,
+                                     prec, st, true);
+        if (rc != NQA_OK) return rc;
+        level_in_strips = true;
       } else {
         const int rc = conv_layer<T>(ctx, li, bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, bufs.ping[cur ^ 1],
                                      split ? bufs.ping_lo[cur ^ 1] : nullptr, n, h, w, prec, st);
@@ -522,8 +538,11 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
         cur ^= 1;
       }
     }
+    if (stage == 0 && strips_dst && strips_dst[1] && std::is_same<T, bf16>::value && !split && ctx->fuse_stage1) level_in_strips = true;
     T* pooled_dst = stage < 4 ? bufs.ping[cur ^ 1] : nullptr;
-    const bool pooled_done = on_level(stage + 1, bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, h, w, pooled_dst);
+    const bool pooled_done = on_level(stage + 1, level_in_strips ? nullptr : bufs.ping[cur], split ? bufs.ping_lo[cur] : nullptr, h, w,
+                                      pooled_dst);
+    if (level_in_strips && stage < 4 && !pooled_done) return fail(NQA_ERR_INVALID, "strip-plane level %d was not pooled", stage + 1);
     if (stage < 4) {
       if (!pooled_done) {
         ProfScope ps(ctx, NQA_K_L2POOL, st);
@@ -538,6 +557,15 @@ int run_trunk(nqa_ctx* ctx, const float* x, const float* y, int nx, int n, int H
     }
   }
   return NQA_OK;
+}
+
+// Whether the kernel that produces level k (1..5) of the bf16 trunk can write strip planes: the fused stage-1 kernel for
+// level 1, a CTA-pair convolution for the others (the default kernel selection; switches that pick other kernels turn
+// the strip path off for that level).
+bool trunk_strips_capable(const nqa_ctx* ctx, int k) {
+  static const int last_conv[kNumLevels] = {-1, 1, 3, 6, 9, 12};
+  if (k == 1) return ctx->fuse_stage1;
+  return k >= 2 && k < kNumLevels && conv_tc_uses_pair(ctx->conv_cfg, kConvCin[last_conv[k]], kConvCout[last_conv[k]], false);
 }
 
 template <typename T>
@@ -1126,6 +1154,7 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   ctx->conv_cfg = conv_tc_config_from_env(ctx->sm_count);
   if (const char* e = getenv("NQA_POOL_STATS_TMA")) ctx->pool_stats_tma = atoi(e) != 0;
   if (const char* e = getenv("NQA_ADISTS_FUSED_SUMS")) ctx->adists_fused_sums = atoi(e) != 0;
+  if (const char* e = getenv("NQA_ADISTS_STRIPS")) ctx->adists_strips = atoi(e);
   if (const char* e = getenv("NQA_ADISTS_MMA")) ctx->adists_opt.use_mma = atoi(e) != 0;
   if (const char* e = getenv("NQA_ADISTS_MMA_TERMS")) ctx->adists_opt.mma_terms = atoi(e);
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming));
@@ -1494,7 +1523,20 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     for (int k = 1; k < kNumLevels; ++k)
       planar[k] = static_cast<char*>(ctx->arena.take((size_t)2 * pairs * level_channels(k) * lh[k] * lw[k] * pelem));
     void* ws = ctx->arena.take(adists_workspace_bytes(pairs, H, W, window));
-    unsigned sums_done = 0;   // levels whose channel sums were produced together with the planes
+    unsigned sums_done = 0;   // levels whose channel sums were produced together with the planes (bit 8 + k: from strips)
+    // Strip planes (adists.h): mode 2 = written by the convolution epilogues and pooled + summed by one kernel (A-DISTS
+    // alone: the DISTS moments still want the NHWC level), mode 1 = transposed from the NHWC level (validation)
+    unsigned strips_mask = 0;
+    bf16* strips_dst[kNumLevels] = {};
+    if (planes16 && ctx->adists_strips > 0 && ctx->adists_fused_sums)
+      for (int k = 1; k < kNumLevels; ++k)
+        if (adists_strips_supported(k, H, W, window) && adists_planes_sums_supported(k, H, W)) {
+          if (ctx->adists_strips >= 2) {
+            if (with_dists || !trunk_strips_capable(ctx, k)) continue;
+            strips_dst[k] = reinterpret_cast<bf16*>(planar[k]);
+          }
+          strips_mask |= 1u << k;
+        }
     const float* xb = x + b0 * frame;
     const float* yb = y + b0 * frame;
     PartialBufs pb;
@@ -1507,11 +1549,19 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     rc = run_trunk<T>(ctx, xb, yb, pairs, 2 * pairs, H, W, prec, bufs, st,
                       [&](int k, const T* f, const T* f_lo, int h, int w, T* pooled_dst) {
                         const int c = level_channels(k);
+                        if (strips_dst[k]) {
+                          // the level arrived as strip planes: pooled input of the next stage + channel sums in one read
+                          ProfScope ps(ctx, NQA_K_L2POOL, st);
+                          ctx->launches += adists_pool_strips_and_sums(strips_dst[k], reinterpret_cast<bf16*>(pooled_dst), pairs, k, H, W,
+                                                                       window, ws, st);
+                          sums_done |= 1u << (8 + k);
+                          return true;
+                        }
                         if (planes16 && ctx->adists_fused_sums && adists_planes_sums_supported(k, H, W)) {
                           // transposition + the level's channel sums in one read (adists.cu planes_sums_kernel)
                           ProfScope ps(ctx, NQA_K_LAYOUT, st);
                           ctx->launches += adists_planes_and_sums(reinterpret_cast<const bf16*>(f), reinterpret_cast<bf16*>(planar[k]),
-                                                                  pairs, k, H, W, window, ws, st);
+                                                                  pairs, k, H, W, window, ws, st, (strips_mask >> k) & 1);
                           sums_done |= 1u << k;
                         } else if (planes16) {
                           ProfScope ps(ctx, NQA_K_LAYOUT, st);
@@ -1533,7 +1583,7 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
                         ctx->launches += launch_stats_nhwc<T>(f, f + half, f_lo, f_lo ? f_lo + half : nullptr, pairs, h * w, c,
                                                              pb.chunks[k], pb.p[k], st);
                         return false;
-                      });
+                      }, strips_dst);
     if (rc != NQA_OK) return rc;
     if (with_dists && (rc = finalize(ctx, pb, pairs, H, W, dists_out + b0, nullptr, st)) != NQA_OK) return rc;
     const void* fx[kNumLevels];
@@ -1553,9 +1603,10 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
     }
     AdistsProfState prof_state{ctx, st, nullptr};
     const AdistsProf prof = adists_prof_hook(&prof_state);
-    adists_stage(fx, fy, planes16, pairs, H, W, window, ws, score_out + b0, st,
-                 map_out ? map_out + (size_t)b0 * H * W : nullptr, parts_out ? &parts : nullptr, &prof,
-                 sums_done, &ctx->adists_opt);   // launches counted by the hook
+    if (adists_stage(fx, fy, planes16, pairs, H, W, window, ws, score_out + b0, st,
+                     map_out ? map_out + (size_t)b0 * H * W : nullptr, parts_out ? &parts : nullptr, &prof,
+                     sums_done, &ctx->adists_opt, strips_mask) < 0)   // launches counted by the hook
+      return fail(NQA_ERR_CUDA, "A-DISTS statistics stage: no tensor map for the strip planes (%dx%d)", H, W);
   }
   return NQA_OK;
 }

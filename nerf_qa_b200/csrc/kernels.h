@@ -127,6 +127,7 @@ struct ConvTcPlan {
   const float* bias;
   bf16* out;
   bf16* out_lo;
+  bool strips_out;     // pair kernel: `out` is a strip-plane buffer [n][cout][w/8][h][8] (tmap_out = make_strip_out_map)
   int epi;             // ConvEpilogue (halo / pair kernels; the plain kernel is forward-only)
   const bf16* mask;    // kEpiMask / kEpiDivide: saved activation [n,h,w,cout]
   const bf16* mask_lo; // bf16x3 carrier of the saved activation (per-tap kernel, kEpiDivide)
@@ -137,7 +138,9 @@ struct ConvTcPlan {
 // Fills the tensor maps; returns 0 on success, nonzero + message on failure.
 int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in, const bf16* in_lo, const bf16* wk,
                       const bf16* wk_lo, const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout,
-                      bool split, const char** err);
+                      bool split, const char** err, bool strips_out = false);
+// whether conv_tc_make_plan picks the CTA-pair kernel for a layer (the kernel that can write strip planes)
+bool conv_tc_uses_pair(const ConvTcConfig& cfg, int cin, int cout, bool split);
 int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st);
 int launch_conv3x3_tc_halo(const ConvTcPlan& plan, int sm_count, cudaStream_t st);
 int launch_conv3x3_tc_pair(const ConvTcPlan& plan, int sm_count, cudaStream_t st);
@@ -148,12 +151,21 @@ int conv_tc_make_weight_map(CUtensorMap* map, const bf16* wk, int cout, int k, i
 // 3-D SWIZZLE_64B tensor map over bf16 planes [planes][h][w] (w % 8 == 0) with box {32 columns, box_h rows, 1}; out-of-image
 // parts of a box are zero-filled.  0 on success.
 int make_plane_map_sw64(CUtensorMap* map, const bf16* ptr, int planes, int h, int w, int box_h);
+// Strip layout of bf16 planes, [plane][w / 8][h][8] (w % 8 == 0): 8-pixel-wide column strips with the rows of a strip
+// contiguous, so that a 16 x 8 pixel tile of one channel is 256 contiguous bytes (what a convolution epilogue holds per
+// channel) and 8 rows of a strip are 128 contiguous bytes (what an ldmatrix of the window kernel reads).  3-D tensor map
+// {8 h, w / 8, planes} with box {box_elems, box_strips, 1}, no swizzle; 0 on success.
+int make_strip_map(CUtensorMap* map, const bf16* ptr, int planes, int h, int w, int box_elems, int box_strips);
+// The same layout seen from a convolution epilogue: 4-D map {8 h, w / 8, c, n} with box {128, 1, 64, 1} -- the 16 x 8
+// pixel tile of 64 channels, staged as [channel][pixel], leaves as 64 runs of 256 contiguous bytes; rows beyond the
+// image are clipped.  0 on success.
+int make_strip_out_map(CUtensorMap* map, const bf16* ptr, int n, int c, int h, int w);
 
 // Fused VGG stage 1 (bf16 trunk): normalise + conv1_1 + ReLU + conv1_2 + ReLU, relu1_1 stays on chip
 // (stage1_fused.cu).  w1img from launch_pack_w11_tc, w2map from conv_tc_make_weight_map(.., 64, 576, 64).
 int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, int w, const bf16* w1img,
                         const float* bias1, const CUtensorMap& w2map, const float* bias2, bf16* out, int sm_count, bool pair,
-                        bool a2_linear, cudaStream_t st);
+                        bool a2_linear, cudaStream_t st, bool strips_out = false);   // strips_out: `out` = strip planes
 
 // ---- backward (backward.cu) -------------------------------------------------------------------------
 struct GradLevels {

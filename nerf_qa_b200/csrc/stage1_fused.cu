@@ -74,6 +74,7 @@ struct Params {
   const float* bias1;
   const float* bias2;
   bf16* out;           // relu1_2, NHWC [n, h, w, 64]
+  int strips;          // 1: relu1_2 leaves as strip planes [n][64][w/8][h][8] (kernels.h make_strip_out_map)
 };
 
 template <bool PAIR, bool A2_LINEAR>
@@ -451,7 +452,18 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
           t.y = Vec<bf16>::pack2(v[2], v[3]);
           t.z = Vec<bf16>::pack2(v[4], v[5]);
           t.w = Vec<bf16>::pack2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(row + (((ch * 4 + j) ^ (m & 7)) << 4)) = t;
+          if (p.strips) {
+            // [channel][pixel]: a warp's 32 pixels of one channel are 64 contiguous bytes (conflict-free 2-byte stores)
+            unsigned short* col = reinterpret_cast<unsigned short*>(stg_s + s * (128 * 128)) + (ch * 32 + j * 8) * 128 + m;
+            const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              col[(2 * e) * 128] = (unsigned short)(tw[e] & 0xffffu);
+              col[(2 * e + 1) * 128] = (unsigned short)(tw[e] >> 16);
+            }
+          } else {
+            *reinterpret_cast<uint4*>(row + (((ch * 4 + j) ^ (m & 7)) << 4)) = t;
+          }
         }
       }
       tc_fence_before();
@@ -460,7 +472,8 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
       fence_proxy_async_smem();
       named_bar_sync(3, 128);
       if (elected) {
-        tma_store_4d(&tmap_out, stg_s + s * (128 * 128), 0, w0, h0, img);
+        if (p.strips) tma_store_4d(&tmap_out, stg_s + s * (128 * 128), h0 * 8, w0 >> 3, 0, img);
+        else tma_store_4d(&tmap_out, stg_s + s * (128 * 128), 0, w0, h0, img);
         tma_store_commit();
       }
     }
@@ -486,9 +499,11 @@ stage1_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_co
 // (0 if the output tensor map cannot be encoded or the launch fails).
 int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, int w, const bf16* w1img,
                         const float* bias1, const CUtensorMap& w2map, const float* bias2, bf16* out, int sm_count, bool pair,
-                        bool a2_linear, cudaStream_t st) {
+                        bool a2_linear, cudaStream_t st, bool strips_out) {
   CUtensorMap outmap;
-  if (conv_tc_make_act_map(&outmap, out, n, h, w, s1::C, s1::TW, s1::TH) != 0) return 0;
+  if (strips_out ? make_strip_out_map(&outmap, out, n, s1::C, h, w) != 0
+                 : conv_tc_make_act_map(&outmap, out, n, h, w, s1::C, s1::TW, s1::TH) != 0)
+    return 0;
   using namespace s1;
   Params p;
   p.x = x; p.y = y; p.nx = nx; p.n = n; p.h = h; p.w = w;
@@ -496,6 +511,7 @@ int launch_stage1_fused(const float* x, const float* y, int nx, int n, int h, in
   p.tiles_h = ceil_div(h, TH);
   p.num_tiles = n * p.tiles_h * p.tiles_w;
   p.w1img = w1img; p.bias1 = bias1; p.bias2 = bias2; p.out = out;
+  p.strips = strips_out ? 1 : 0;
   if (pair) {
     auto kern = a2_linear ? stage1_fused_kernel<true, true> : stage1_fused_kernel<true, false>;
     ensure_dynamic_smem(kern, SMEM_BYTES);
