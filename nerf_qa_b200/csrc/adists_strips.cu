@@ -29,6 +29,9 @@ namespace {
 constexpr int kRowsPerChunk = 31;      // pooled rows per block (lane 0 of a warp is the halo lane)
 constexpr int kPitch = 136;            // bytes per staged pixel row (64 channels + 8 bytes of padding)
 constexpr int kTileBytes = 4 * 32 * kPitch;
+constexpr int kCarryBytes = 8 * 8 * 32 * 8;   // [warp][channel][lane] last pixels of the previous strip's four rows
+
+__device__ uint4 g_zero_rows;          // what a row outside the image reads as
 
 __device__ __forceinline__ float2 lo_hi(uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
 __device__ __forceinline__ float root_approx(float v) {   // rounded to bf16 afterwards (same as pool_stats_kernel)
@@ -36,26 +39,52 @@ __device__ __forceinline__ float root_approx(float v) {   // rounded to bf16 aft
   asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
-
-__device__ __forceinline__ void unpack_row(const uint4& t, float2 (&v)[4]) {
-  v[0] = lo_hi(t.x); v[1] = lo_hi(t.y); v[2] = lo_hi(t.z); v[3] = lo_hi(t.w);
+__device__ __forceinline__ float lg2_approx(float v) {    // v >= 1e-30: no denormal handling needed
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 }
 
-// horizontal [1 2 1] of squares at the four pooled columns of a strip row: left = the pixel in front of the strip
-__device__ __forceinline__ void hsum(const float2 (&v)[4], float left, float (&h)[4]) {
-  float prev = left;
+// horizontal [1 2 1] of squares at the four pooled columns of a strip row from the squares of its pixel pairs;
+// left2 = square of the pixel in front of the strip.  Same values as fma(x0, x0, fma(2, x1 x1, x2 x2)): the squares of
+// bf16 values are exact in fp32.
+__device__ __forceinline__ void hsum(const float2 (&sq)[4], float left2, float (&h)[4]) {
+  float prev = left2;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float xx1 = v[j].x * v[j].x, xx2 = v[j].y * v[j].y;
-    h[j] = fmaf(prev, prev, fmaf(2.f, xx1, xx2));
-    prev = v[j].y;
+    h[j] = fmaf(2.f, sq[j].x, sq[j].y) + prev;
+    prev = sq[j].y;
   }
 }
 
-__global__ void __launch_bounds__(256)
+// Sum of each of eight per-lane values over the warp by recursive halving (9 shuffles instead of 40): afterwards lane l
+// holds the total of value l / 4.  Fixed order.
+__device__ __forceinline__ float reduce8(float (&v)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float a[4], c[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = b3 ? a[i + 2] : a[i], send = b3 ? a[i] : a[i + 2];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const float keep = b2 ? c[1] : c[0], send = b2 ? c[0] : c[1];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+__global__ void __launch_bounds__(256, 4)
 pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pooled_out, int pairs, int c, int h, int w, int ho,
                         int wo, int spb, int n_sg, int chunks, float* __restrict__ partials) {
-  extern __shared__ __align__(16) unsigned char stage[];   // [image 2][pooled column 4][lane 32][kPitch]
+  extern __shared__ __align__(16) unsigned char smem[];   // staging [image 2][pooled column 4][lane 32][kPitch] + carry
+  unsigned char* stage = smem;
+  uint2* carry = reinterpret_cast<uint2*>(smem + 2 * kTileBytes);
   const int chunk = blockIdx.x, slab = blockIdx.y, b = blockIdx.z;
   const int sg = chunk % n_sg, rc = chunk / n_sg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -65,89 +94,103 @@ pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pool
   const bool own = lane > 0 && oy < ho;
   const int r0 = 2 * oy, r1 = 2 * oy + 1;
   const bool ok0 = oy >= 0 && r0 < h, ok1 = oy >= 0 && r1 < h;      // lane 0 of the first chunk stands for row -1: zeros
-  const int cr0 = min(max(r0, 0), h - 1), cr1 = min(max(r1, 0), h - 1);
   const size_t plane = (size_t)h * w;
   const size_t strip_stride = (size_t)h * 8;
-
-  float tot0 = 0.f, tot1 = 0.f;   // entries lane and lane + 32 of the warp's [8 channels][8 sums] table
   const bool do_pool = pooled_out != nullptr;   // level 5 has no pooling behind it: sums only
+  const bf16* zero = reinterpret_cast<const bf16*>(&g_zero_rows);
+
+  float tot0 = 0.f, tot1 = 0.f;   // lane l: totals of sum l / 4 for the channels l % 4 and l % 4 + 4 of the warp
 
   for (int s = s_begin; s < s_end; ++s) {
 #pragma unroll 1
     for (int ci = 0; ci < 8; ++ci) {
       const int ch = slab * 64 + warp * 8 + ci;
-      float sum[8];
+      const bf16* px = planes + ((size_t)b * c + ch) * plane + (size_t)s * strip_stride;
+      const bf16* py = px + (size_t)pairs * c * plane;
+      // rows outside the image read a zero row (no select per loaded word, no load under a branch)
+      const uint4 tx0 = __ldg(reinterpret_cast<const uint4*>(ok0 ? px + (size_t)r0 * 8 : zero));
+      const uint4 tx1 = __ldg(reinterpret_cast<const uint4*>(ok1 ? px + (size_t)r1 * 8 : zero));
+      const uint4 ty0 = __ldg(reinterpret_cast<const uint4*>(ok0 ? py + (size_t)r0 * 8 : zero));
+      const uint4 ty1 = __ldg(reinterpret_cast<const uint4*>(ok1 ? py + (size_t)r1 * 8 : zero));
+      // left taps: the last pixels of the previous strip's rows -- from global memory for the first strip of the block,
+      // from the carry this lane left in shared memory afterwards (pixels x r0, x r1, y r0, y r1 as bf16)
+      uint2 left;
+      if (s == s_begin) {
+        left = make_uint2(0u, 0u);
+        if (s > 0) {
+          const bf16* lx = px - strip_stride + 7;
+          const bf16* ly = py - strip_stride + 7;
+          const uint32_t a0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(lx + (size_t)r0 * 8)) : 0u;
+          const uint32_t a1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(lx + (size_t)r1 * 8)) : 0u;
+          const uint32_t d0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(ly + (size_t)r0 * 8)) : 0u;
+          const uint32_t d1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(ly + (size_t)r1 * 8)) : 0u;
+          left = make_uint2(a0 | (a1 << 16), d0 | (d1 << 16));
+        }
+      } else {
+        left = carry[(warp * 8 + ci) * 32 + lane];
+      }
+      carry[(warp * 8 + ci) * 32 + lane] = make_uint2((tx0.w >> 16) | (tx1.w & 0xffff0000u), (ty0.w >> 16) | (ty1.w & 0xffff0000u));
+
+      const uint32_t wx[2][4] = {{tx0.x, tx0.y, tx0.z, tx0.w}, {tx1.x, tx1.y, tx1.z, tx1.w}};
+      const uint32_t wy[2][4] = {{ty0.x, ty0.y, ty0.z, ty0.w}, {ty1.x, ty1.y, ty1.z, ty1.w}};
+      // sums (packed fp32 pairs; the features are ReLU outputs, so relu x = x and its sums are sums 0 and 2):
+      // x, y, x^2, y^2, xy, x log2 x
+      float2 acc[6];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) sum[q] = 0.f;
-      float2 rows[2][2][4];   // [image][row][pixel pair]
+      for (int q = 0; q < 6; ++q) acc[q] = make_float2(0.f, 0.f);
+      float2 sqx[2][4], sqy[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = lo_hi(wx[r][k]), d = lo_hi(wy[r][k]);
+          sqx[r][k] = __fmul2_rn(a, a);
+          sqy[r][k] = __fmul2_rn(d, d);
+          const float2 lg = make_float2(lg2_approx(fmaxf(a.x, 1e-30f)), lg2_approx(fmaxf(a.y, 1e-30f)));
+          acc[0] = __fadd2_rn(acc[0], a);
+          acc[1] = __fadd2_rn(acc[1], d);
+          acc[2] = __fadd2_rn(acc[2], sqx[r][k]);
+          acc[3] = __fadd2_rn(acc[3], sqy[r][k]);
+          acc[4] = __ffma2_rn(a, d, acc[4]);
+          acc[5] = __ffma2_rn(a, lg, acc[5]);
+        }
+      // pooling: horizontal sums of the two rows, the row above from the lane above, sqrt, bf16
       uint32_t outw[2][2];
 #pragma unroll
       for (int im = 0; im < 2; ++im) {
-        const bf16* p = planes + ((size_t)(im * pairs + b) * c + ch) * plane + (size_t)s * strip_stride;
-        // unconditional loads from clamped rows, zeroed afterwards (loads under branches serialise)
-        uint4 t0 = __ldg(reinterpret_cast<const uint4*>(p + (size_t)cr0 * 8));
-        uint4 t1 = __ldg(reinterpret_cast<const uint4*>(p + (size_t)cr1 * 8));
-        // left tap: last pixel of the previous strip's rows (the image border is zero)
-        const bf16* pl = p - strip_stride + 7;
-        const unsigned short l0 = s > 0 ? __ldg(reinterpret_cast<const unsigned short*>(pl + (size_t)cr0 * 8)) : (unsigned short)0;
-        const unsigned short l1 = s > 0 ? __ldg(reinterpret_cast<const unsigned short*>(pl + (size_t)cr1 * 8)) : (unsigned short)0;
-        if (!ok0) t0 = make_uint4(0u, 0u, 0u, 0u);
-        if (!ok1) t1 = make_uint4(0u, 0u, 0u, 0u);
-        const float left0 = ok0 ? __uint_as_float((uint32_t)l0 << 16) : 0.f;
-        const float left1 = ok1 ? __uint_as_float((uint32_t)l1 << 16) : 0.f;
-        unpack_row(t0, rows[im][0]);
-        unpack_row(t1, rows[im][1]);
-        float ha[4], hb[4], hp[4];
-        hsum(rows[im][0], left0, ha);
-        hsum(rows[im][1], left1, hb);
-        float o[4];
+        const uint32_t lw = im ? left.y : left.x;
+        const float l0 = __uint_as_float(lw << 16), l1 = __uint_as_float(lw & 0xffff0000u);
+        float ha[4], hb[4], o[4];
+        hsum(im ? sqy[0] : sqx[0], l0 * l0, ha);
+        hsum(im ? sqy[1] : sqx[1], l1 * l1, hb);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          hp[j] = __shfl_up_sync(0xffffffffu, hb[j], 1);   // row 2oy - 1 = the odd row of the lane above
-          o[j] = root_approx(fmaf(fmaf(2.f, ha[j], hp[j]) + hb[j], 1.f / 16.f, 1e-12f));
+          const float hp = __shfl_up_sync(0xffffffffu, hb[j], 1);   // row 2oy - 1 = the odd row of the lane above
+          o[j] = root_approx(fmaf(fmaf(2.f, ha[j], hp) + hb[j], 1.f / 16.f, 1e-12f));
         }
         outw[im][0] = Vec<bf16>::pack2(o[0], o[1]);
         outw[im][1] = Vec<bf16>::pack2(o[2], o[3]);
       }
-      // the eight sums over the pixels this lane owns (rows 2oy, 2oy + 1 inside the image; zeros add nothing)
-      if (own) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 a = rows[0][r][k], d = rows[1][r][k];
-            const float2 rl = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
-            const float2 lg = make_float2(__log2f(fmaxf(a.x, 1e-30f)), __log2f(fmaxf(a.y, 1e-30f)));
-            sum[0] += a.x + a.y; sum[1] += d.x + d.y;
-            sum[2] = fmaf(a.x, a.x, fmaf(a.y, a.y, sum[2]));
-            sum[3] = fmaf(d.x, d.x, fmaf(d.y, d.y, sum[3]));
-            sum[4] = fmaf(a.x, d.x, fmaf(a.y, d.y, sum[4]));
-            sum[5] += rl.x + rl.y;
-            sum[6] = fmaf(rl.x, rl.x, fmaf(rl.y, rl.y, sum[6]));
-            sum[7] = fmaf(rl.x, lg.x, fmaf(rl.y, lg.y, sum[7]));
-          }
+      if (own && do_pool) {
         // stage the four pooled pixels of both images: 2-byte stores, pixel index = column * 32 + lane
         const int chl = warp * 8 + ci;
-        if (do_pool) {
 #pragma unroll
-          for (int im = 0; im < 2; ++im)
+        for (int im = 0; im < 2; ++im)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t wv = outw[im][j >> 1];
-              *reinterpret_cast<unsigned short*>(stage + im * kTileBytes + (j * 32 + lane) * kPitch + chl * 2) =
-                  (unsigned short)((j & 1) ? (wv >> 16) : (wv & 0xffffu));
-            }
-        }
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t wv = outw[im][j >> 1];
+            *reinterpret_cast<unsigned short*>(stage + im * kTileBytes + (j * 32 + lane) * kPitch + chl * 2) =
+                (unsigned short)((j & 1) ? (wv >> 16) : (wv & 0xffffu));
+          }
       }
-      // butterfly: every lane gets the warp total of each sum (lanes that own nothing contribute zeros)
+      // per-lane sums (lanes that own nothing contribute zeros) -> warp totals; lane l keeps sum l / 4 of channel l % 4 (+ 4)
+      float v[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float v = sum[q];
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-        const float add = ((lane >> 3) == (ci & 3) && (lane & 7) == q) ? v : 0.f;
-        if (ci < 4) tot0 += add; else tot1 += add;
-      }
+      for (int q = 0; q < 6; ++q) v[q] = own ? acc[q].x + acc[q].y : 0.f;
+      v[6] = v[7] = 0.f;
+      const float t = reduce8(v, lane);
+      const float add = ((lane & 3) == (ci & 3)) ? t : 0.f;
+      if (ci < 4) tot0 += add; else tot1 += add;
     }
     if (!do_pool) continue;
     __syncthreads();
@@ -156,17 +199,26 @@ pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pool
       const int piece = i & 15, j = (i >> 4) & 3, ln = (i >> 6) & 31, im = i >> 11;
       const int oyy = rc * kRowsPerChunk + ln - 1;
       if (ln == 0 || oyy >= ho) continue;
-      const uint2 v = *reinterpret_cast<const uint2*>(stage + im * kTileBytes + (j * 32 + ln) * kPitch + piece * 8);
+      const uint2 val = *reinterpret_cast<const uint2*>(stage + im * kTileBytes + (j * 32 + ln) * kPitch + piece * 8);
       bf16* dst = pooled_out + (((size_t)(im * pairs + b) * ho + oyy) * wo + (size_t)s * 4 + j) * c + slab * 64 + piece * 4;
-      *reinterpret_cast<uint2*>(dst) = v;
+      *reinterpret_cast<uint2*>(dst) = val;
     }
     __syncthreads();
   }
-  // lane l of warp wq holds entries (ci = l / 8 + 4 t, q = l % 8), t = 0, 1, of the warp's table
+  // lane l: sum q = l / 4 (0..5: x, y, x^2, y^2, xy, x log2 x) of channels l % 4 and l % 4 + 4; the partial layout of
+  // planes_sums_kernel has eight sums per channel: 5 = relu x = sum 0, 6 = relu(x)^2 = sum 2, 7 = the entropy sum
+  const int q = lane >> 2;
+  if (q < 6) {
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int ci = (lane >> 3) + 4 * t, q = lane & 7;
-    partials[(((size_t)b * chunks + chunk) * 8 + q) * c + slab * 64 + warp * 8 + ci] = t ? tot1 : tot0;
+    for (int t = 0; t < 2; ++t) {
+      const int ch = slab * 64 + warp * 8 + (lane & 3) + 4 * t;
+      const float val = t ? tot1 : tot0;
+      float* dst = partials + ((size_t)b * chunks + chunk) * 8 * c + ch;
+      if (q < 5) dst[(size_t)q * c] = val;
+      if (q == 0) dst[(size_t)5 * c] = val;
+      if (q == 2) dst[(size_t)6 * c] = val;
+      if (q == 5) dst[(size_t)7 * c] = val;
+    }
   }
 }
 
@@ -194,7 +246,7 @@ void adists_strips_plan(int c, int h, int w, int* spb, int* n_sg, int* chunks) {
 int launch_pool_strips_sums(const bf16* planes, bf16* pooled_out, int pairs, int c, int h, int w, float* partials, cudaStream_t st) {
   int spb, n_sg, chunks;
   adists_strips_plan(c, h, w, &spb, &n_sg, &chunks);
-  const int smem = 2 * kTileBytes;
+  const int smem = 2 * kTileBytes + kCarryBytes;
   ensure_dynamic_smem(pool_strips_sums_kernel, smem);
   dim3 grid(chunks, c / 64, pairs);
   pool_strips_sums_kernel<<<grid, 256, smem, st>>>(planes, pooled_out, pairs, c, h, w, pooled(h), pooled(w), spb, n_sg, chunks,
