@@ -104,16 +104,23 @@ def family_models(workload, h, w, precision, train_recompute=False):
     pooled_in = 2 * level_elems(h, w, range(1, 5)) * eb
     d = level_dims(h, w)
     pooled_out = 2 * sum(CHNS[k] * d[k + 1][0] * d[k + 1][1] for k in range(1, 5)) * eb   # C_k channels at level k+1's size
+    # A-DISTS on the bf16 trunk: the levels reach the statistics as strip planes written by the convolution epilogues; one
+    # kernel (the "l2pool" family then) reads levels 1-5 of both images once and writes the pooled tensors; there is no
+    # layout pass.  The "adists" family is what remains around the window kernels: level-0 sums (x, y read, x read again
+    # for the entropy) and the compute_prob chain, ~6 passes over the fp32 window maps (gamma statistics, min / max,
+    # products).  fp32 / bf16x3 trunks: separate pooling, transposition and channel-sum kernels.
+    strips = precision == "bf16" and workload in ("adists", "both", "video")
+    wmaps = sum(4 * (d[k][0] - WINDOW + 1) * (d[k][1] - WINDOW + 1) for k in range(6) if min(d[k]) >= WINDOW)
     m = {
         # fused stage 1 + the 11 other convolutions (+ the 13 data-gradient convolutions of a training step; + a second
         # forward when the backward recomputes activations instead of using the tape)
         "conv": ("tensor", fl * ((3.0 if train_recompute else 2.0) if workload == "train" else 1.0), "flop"),
         "pool_stats": ("hbm", pooled_in + pooled_out, "bytes"),          # levels 1-4 read once, pooled tensors written
-        "l2pool": ("hbm", pooled_in + pooled_out, "bytes"),
+        "l2pool": ("hbm", (2 * level_elems(h, w) * eb if strips else pooled_in) + pooled_out, "bytes"),
         "stats": ("hbm", 2 * 3 * hw * 4 + 2 * CHNS[5] * level_dims(h, w)[5][0] * level_dims(h, w)[5][1] * eb, "bytes"),
         "layout": ("hbm", 2 * 2 * level_elems(h, w) * eb, "bytes"),       # NHWC -> planes: read + write of levels 1-5
         # channel sums read x and y, the entropy pass reads x again (levels 1-5 at eb bytes, level 0 fp32)
-        "adists": ("hbm", 3 * level_elems(h, w) * eb + 3 * 3 * hw * 4, "bytes"),
+        "adists": ("hbm", (0 if strips else 3 * level_elems(h, w) * eb) + 3 * 3 * hw * 4 + 6 * wmaps, "bytes"),
         "adists_window": ("fma", window_fma_per_pair(h, w), "fma"),
     }
     return m
@@ -437,9 +444,13 @@ def rooflines(env, ctx, name, prof, steps, pairs, h, w, precision):
                                   else "forward + data gradients of the 13 convolutions (2x forward); no weight gradients (frozen trunk)")
         elif bound == "hbm":
             e.update(kernel={"pool_stats": "pool_stats_tma_kernel: L2pooling + DISTS moments of levels 1-4 in one read",
-                             "l2pool": "l2pool_nhwc_kernel", "stats": "stats_planar / stats_nhwc (levels 0 and 5)",
-                             "layout": "nhwc_to_planes_bf16_kernel (A-DISTS feature planes)",
-                             "adists": "A-DISTS channel sums + entropy weights + ps chain"}.get(fam, fam),
+                             "l2pool": ("pool_strips_sums_kernel: L2pooling + channel sums (+ DISTS moments) from the strip planes "
+                                        "the convolution epilogues wrote, levels 1-5 in one read"
+                                        if precision == "bf16" and name in ("adists", "both", "video") else "l2pool_nhwc_kernel"),
+                             "stats": "stats_planar / stats_nhwc (levels 0 and 5)",
+                             "layout": "planes_sums_kernel / nhwc_to_planes (A-DISTS feature planes)",
+                             "adists": "A-DISTS level-0 sums, entropy weights and the compute_prob chain over the window maps "
+                                       "(small dependent launches: latency-bound)"}.get(fam, fam),
                      achieved=per_s / 1e9, peak=hbm, unit="GB/s", frac=per_s / 1e9 / hbm,
                      peak_source=f"MEASURED_PEAKS.json hbm_gbs ({env.peaks['source']})",
                      algorithmic_bytes_per_launch=work * pairs * steps / n)

@@ -155,10 +155,11 @@ NQA_API int nqa_adists_parts(nqa_ctx* ctx, const float* x, const float* y, int B
 NQA_API int nqa_adists_ps_elems(int H, int W, int window, int level, size_t* elems);
 
 /* DISTS and A-DISTS scores of the same batch from ONE trunk evaluation: what prep.py:186-190 /
- * test2_prep.py:151-155 compute with two model calls (four trunk forwards per pair in the reference).  The DISTS
- * scores are bit-identical to nqa_dists_forward; the A-DISTS scores equal nqa_adists_forward up to the rounding of the
- * pooled activations (the fused pool + moments kernel replaces the stand-alone pooling kernel).  Needs VGG weights and
- * alpha/beta. */
+ * test2_prep.py:151-155 compute with two model calls (four trunk forwards per pair in the reference).  Same trunk
+ * activations as the single-metric calls; the DISTS scores equal nqa_dists_forward up to the summation order of the
+ * fp32 moment partials (1e-6 relative: levels that travel as strip planes are summed by the strip-plane kernel; identical
+ * for the fp32 / bf16x3 trunks), the A-DISTS scores equal nqa_adists_forward up to the rounding of the pooled
+ * activations.  Both stay independent of the batch a frame travels in.  Needs VGG weights and alpha/beta. */
 NQA_API int nqa_dists_adists_forward(nqa_ctx* ctx, const float* x, const float* y, int B, int H, int W, int window,
                                      int precision, float* dists_out, float* adists_out, void* stream);
 

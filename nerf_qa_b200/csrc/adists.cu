@@ -1018,12 +1018,13 @@ bool adists_planes_sums_supported(int level, int H, int W) {
 }
 
 int adists_pool_strips_and_sums(const bf16* planes, bf16* pooled_out, int pairs, int level, int H, int W, int window, void* ws,
-                                cudaStream_t st) {
+                                cudaStream_t st, float* dists_partials) {
   const Plan p = make_plan(pairs, H, W, window);
   const LevelPlan& L = p.lv[level];
   if (L.chunks_s <= 0) return 0;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  return launch_pool_strips_sums(planes, pooled_out, pairs, L.c, L.h, L.w, reinterpret_cast<float*>(base + L.off_sum_s), st);
+  return launch_pool_strips_sums(planes, pooled_out, pairs, L.c, L.h, L.w, reinterpret_cast<float*>(base + L.off_sum_s),
+                                 dists_partials, st);
 }
 
 int adists_planes_and_sums(const bf16* nhwc, bf16* planes, int pairs, int level, int H, int W, int window, void* ws,

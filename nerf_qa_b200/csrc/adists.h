@@ -51,11 +51,14 @@ int adists_planes_and_sums(const __nv_bfloat16* nhwc, __nv_bfloat16* planes, int
 // adists_stage afterwards.  Supported for levels whose width is a multiple of 8 and that are windowed (the tensor-pipe
 // window kernel is the only reader of strip planes).
 bool adists_strips_supported(int level, int H, int W, int window);
+// dists_partials (optional): the level's pivot-shifted DISTS moments as well, [pairs][adists_strips_chunks][5][c] floats +
+// [pairs][2][c] pivots (the layout dists_finalize reads), for calls that score both metrics from one trunk pass.
 int adists_pool_strips_and_sums(const __nv_bfloat16* planes, __nv_bfloat16* pooled_out, int pairs, int level, int H, int W,
-                                int window, void* ws, cudaStream_t st);
+                                int window, void* ws, cudaStream_t st, float* dists_partials = nullptr);
+int adists_strips_chunks(int c, int h, int w);
 void adists_strips_plan(int c, int h, int w, int* spb, int* n_sg, int* chunks);
 int launch_pool_strips_sums(const __nv_bfloat16* planes, __nv_bfloat16* pooled_out, int pairs, int c, int h, int w, float* partials,
-                            cudaStream_t st);
+                            float* dists_partials, cudaStream_t st);
 // number of elements of the level-k ps map of one frame (1 for a fallback level)
 size_t adists_ps_elems(int H, int W, int window, int level);
 

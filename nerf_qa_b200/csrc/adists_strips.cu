@@ -79,9 +79,13 @@ __device__ __forceinline__ float reduce8(float (&v)[8], int lane) {
   return r;
 }
 
-__global__ void __launch_bounds__(256, 4)
+// kDists: also the five pivot-shifted DISTS moments of the level (x - x0, y - y0, their squares and product; pivot = the
+// channel's first pixel; DISTS_pt.py:110-125, layout of pool_stats_kernel: dpartials[((b * chunks + chunk) * 5 + q) * c + ch],
+// pivots behind them), for calls that want both metrics from one trunk pass.
+template <bool kDists>
+__global__ void __launch_bounds__(256, kDists ? 3 : 4)
 pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pooled_out, int pairs, int c, int h, int w, int ho,
-                        int wo, int spb, int n_sg, int chunks, float* __restrict__ partials) {
+                        int wo, int spb, int n_sg, int chunks, float* __restrict__ partials, float* __restrict__ dpartials) {
   extern __shared__ __align__(16) unsigned char smem[];   // staging [image 2][pooled column 4][lane 32][kPitch] + carry
   unsigned char* stage = smem;
   uint2* carry = reinterpret_cast<uint2*>(smem + 2 * kTileBytes);
@@ -100,18 +104,20 @@ pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pool
   const bf16* zero = reinterpret_cast<const bf16*>(&g_zero_rows);
 
   float tot0 = 0.f, tot1 = 0.f;   // lane l: totals of sum l / 4 for the channels l % 4 and l % 4 + 4 of the warp
+  float dtot0 = 0.f, dtot1 = 0.f;  // the same for the DISTS moments
 
+  const uint32_t off0 = (uint32_t)max(r0, 0) * 8u, off1 = (uint32_t)max(r1, 0) * 8u;   // element offsets inside a strip
+  const size_t xy = (size_t)pairs * c * plane;
   for (int s = s_begin; s < s_end; ++s) {
+    const bf16* px = planes + ((size_t)b * c + slab * 64 + warp * 8) * plane + (size_t)s * strip_stride;
 #pragma unroll 1
-    for (int ci = 0; ci < 8; ++ci) {
-      const int ch = slab * 64 + warp * 8 + ci;
-      const bf16* px = planes + ((size_t)b * c + ch) * plane + (size_t)s * strip_stride;
-      const bf16* py = px + (size_t)pairs * c * plane;
+    for (int ci = 0; ci < 8; ++ci, px += plane) {
+      const bf16* py = px + xy;
       // rows outside the image read a zero row (no select per loaded word, no load under a branch)
-      const uint4 tx0 = __ldg(reinterpret_cast<const uint4*>(ok0 ? px + (size_t)r0 * 8 : zero));
-      const uint4 tx1 = __ldg(reinterpret_cast<const uint4*>(ok1 ? px + (size_t)r1 * 8 : zero));
-      const uint4 ty0 = __ldg(reinterpret_cast<const uint4*>(ok0 ? py + (size_t)r0 * 8 : zero));
-      const uint4 ty1 = __ldg(reinterpret_cast<const uint4*>(ok1 ? py + (size_t)r1 * 8 : zero));
+      const uint4 tx0 = __ldg(reinterpret_cast<const uint4*>(ok0 ? px + off0 : zero));
+      const uint4 tx1 = __ldg(reinterpret_cast<const uint4*>(ok1 ? px + off1 : zero));
+      const uint4 ty0 = __ldg(reinterpret_cast<const uint4*>(ok0 ? py + off0 : zero));
+      const uint4 ty1 = __ldg(reinterpret_cast<const uint4*>(ok1 ? py + off1 : zero));
       // left taps: the last pixels of the previous strip's rows -- from global memory for the first strip of the block,
       // from the carry this lane left in shared memory afterwards (pixels x r0, x r1, y r0, y r1 as bf16)
       uint2 left;
@@ -120,10 +126,10 @@ pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pool
         if (s > 0) {
           const bf16* lx = px - strip_stride + 7;
           const bf16* ly = py - strip_stride + 7;
-          const uint32_t a0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(lx + (size_t)r0 * 8)) : 0u;
-          const uint32_t a1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(lx + (size_t)r1 * 8)) : 0u;
-          const uint32_t d0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(ly + (size_t)r0 * 8)) : 0u;
-          const uint32_t d1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(ly + (size_t)r1 * 8)) : 0u;
+          const uint32_t a0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(lx + off0)) : 0u;
+          const uint32_t a1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(lx + off1)) : 0u;
+          const uint32_t d0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(ly + off0)) : 0u;
+          const uint32_t d1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(ly + off1)) : 0u;
           left = make_uint2(a0 | (a1 << 16), d0 | (d1 << 16));
         }
       } else {
@@ -139,11 +145,38 @@ pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pool
 #pragma unroll
       for (int q = 0; q < 6; ++q) acc[q] = make_float2(0.f, 0.f);
       float2 sqx[2][4], sqy[2][4];
+      // DISTS moments: pivots negated; a row outside the image (zeros) is shifted by zero so that it adds nothing
+      float2 dacc[5];
+      float2 npx[2], npy[2];
+      if (kDists) {
+        const bf16* cx = px - (size_t)s * strip_stride;
+        const float x0 = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(cx)) << 16);
+        const float y0 = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(cx + xy)) << 16);
+        if (chunk == 0 && s == s_begin && lane == 0) {
+          float* piv = dpartials + (size_t)gridDim.z * chunks * 5 * c + (size_t)b * 2 * c + slab * 64 + warp * 8 + ci;
+          piv[0] = x0;
+          piv[c] = y0;
+        }
+        npx[0] = ok0 ? make_float2(-x0, -x0) : make_float2(0.f, 0.f);
+        npx[1] = ok1 ? make_float2(-x0, -x0) : make_float2(0.f, 0.f);
+        npy[0] = ok0 ? make_float2(-y0, -y0) : make_float2(0.f, 0.f);
+        npy[1] = ok1 ? make_float2(-y0, -y0) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) dacc[q] = make_float2(0.f, 0.f);
+      }
 #pragma unroll
       for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 a = lo_hi(wx[r][k]), d = lo_hi(wy[r][k]);
+          if (kDists) {
+            const float2 dx = __fadd2_rn(a, npx[r]), dy = __fadd2_rn(d, npy[r]);
+            dacc[0] = __fadd2_rn(dacc[0], dx);
+            dacc[1] = __fadd2_rn(dacc[1], dy);
+            dacc[2] = __ffma2_rn(dx, dx, dacc[2]);
+            dacc[3] = __ffma2_rn(dy, dy, dacc[3]);
+            dacc[4] = __ffma2_rn(dx, dy, dacc[4]);
+          }
           sqx[r][k] = __fmul2_rn(a, a);
           sqy[r][k] = __fmul2_rn(d, d);
           const float2 lg = make_float2(lg2_approx(fmaxf(a.x, 1e-30f)), lg2_approx(fmaxf(a.y, 1e-30f)));
@@ -191,6 +224,14 @@ pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pool
       const float t = reduce8(v, lane);
       const float add = ((lane & 3) == (ci & 3)) ? t : 0.f;
       if (ci < 4) tot0 += add; else tot1 += add;
+      if (kDists) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) v[q] = own ? dacc[q].x + dacc[q].y : 0.f;
+        v[5] = v[6] = v[7] = 0.f;
+        const float dt = reduce8(v, lane);
+        const float dadd = ((lane & 3) == (ci & 3)) ? dt : 0.f;
+        if (ci < 4) dtot0 += dadd; else dtot1 += dadd;
+      }
     }
     if (!do_pool) continue;
     __syncthreads();
@@ -218,6 +259,7 @@ pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pool
       if (q == 0) dst[(size_t)5 * c] = val;
       if (q == 2) dst[(size_t)6 * c] = val;
       if (q == 5) dst[(size_t)7 * c] = val;
+      if (kDists && q < 5) dpartials[(((size_t)b * chunks + chunk) * 5 + q) * c + ch] = t ? dtot1 : dtot0;
     }
   }
 }
@@ -234,8 +276,10 @@ bool adists_strips_supported(int level, int H, int W, int window) {
 
 void adists_strips_plan(int c, int h, int w, int* spb, int* n_sg, int* chunks) {
   const int strips = w >> 3, rcs = ceil_div(pooled(h), kRowsPerChunk);
-  // ~512 chunks per (pair, 64-channel slab) at most: the partition depends on the level shape only
-  int per = 1;
+  // ~16 strip groups per row chunk (the first strip of a group fetches its left taps from global memory: the longer
+  // the group, the fewer of those sector-sized 2-byte loads) and at most 512 chunks per (pair, 64-channel slab); the
+  // partition depends on the level shape only
+  int per = ceil_div(strips, 16);
   while (ceil_div(strips, per) * rcs > 512) ++per;
   *spb = per;
   *n_sg = ceil_div(strips, per);
@@ -243,15 +287,28 @@ void adists_strips_plan(int c, int h, int w, int* spb, int* n_sg, int* chunks) {
 }
 
 // pooled_out may be null (level 5: no pooling after stage 5, sums only)
-int launch_pool_strips_sums(const bf16* planes, bf16* pooled_out, int pairs, int c, int h, int w, float* partials, cudaStream_t st) {
+int launch_pool_strips_sums(const bf16* planes, bf16* pooled_out, int pairs, int c, int h, int w, float* partials,
+                            float* dists_partials, cudaStream_t st) {
   int spb, n_sg, chunks;
   adists_strips_plan(c, h, w, &spb, &n_sg, &chunks);
   const int smem = 2 * kTileBytes + kCarryBytes;
-  ensure_dynamic_smem(pool_strips_sums_kernel, smem);
   dim3 grid(chunks, c / 64, pairs);
-  pool_strips_sums_kernel<<<grid, 256, smem, st>>>(planes, pooled_out, pairs, c, h, w, pooled(h), pooled(w), spb, n_sg, chunks,
-                                                  partials);
+  if (dists_partials) {
+    ensure_dynamic_smem(pool_strips_sums_kernel<true>, smem);
+    pool_strips_sums_kernel<true><<<grid, 256, smem, st>>>(planes, pooled_out, pairs, c, h, w, pooled(h), pooled(w), spb, n_sg, chunks,
+                                                          partials, dists_partials);
+  } else {
+    ensure_dynamic_smem(pool_strips_sums_kernel<false>, smem);
+    pool_strips_sums_kernel<false><<<grid, 256, smem, st>>>(planes, pooled_out, pairs, c, h, w, pooled(h), pooled(w), spb, n_sg, chunks,
+                                                           partials, nullptr);
+  }
   return 1;
+}
+
+int adists_strips_chunks(int c, int h, int w) {
+  int spb, n_sg, chunks;
+  adists_strips_plan(c, h, w, &spb, &n_sg, &chunks);
+  return chunks;
 }
 
 }  // namespace nqa

@@ -593,14 +593,16 @@ struct PartialBufs {
   double* terms;
 };
 
+// strips_mask: levels whose moments come from the strip-plane kernel (adists_strips.cu) and follow its chunking
 size_t partial_bytes(int pairs, int H, int W, int prec, PartialBufs* pb /* may be null */, bool planar_all,
-                     bool fused_pool = false) {
+                     bool fused_pool = false, unsigned strips_mask = 0) {
   int h[kNumLevels], w[kNumLevels];
   level_dims(H, W, h, w);
   size_t total = 0;
   for (int k = 0; k < kNumLevels; ++k) {
     const int c = level_channels(k);
-    const int chunks = (k == 0 || planar_all) ? stats_chunks_planar(h[k] * w[k], c, pairs)
+    const int chunks = ((strips_mask >> k) & 1) ? adists_strips_chunks(c, h[k], w[k])
+                       : (k == 0 || planar_all) ? stats_chunks_planar(h[k] * w[k], c, pairs)
                        : (fused_pool && k < kNumLevels - 1) ? pool_stats_chunks(h[k], w[k], c, elem_bytes(prec))
                                                             : stats_chunks_nhwc(h[k] * w[k], c, elem_bytes(prec), pairs);
     if (pb) pb->chunks[k] = chunks;
@@ -1489,12 +1491,33 @@ static int adists_micro_pairs(const nqa_ctx* ctx, int B, int H, int W, int prec)
   return mb < 1 ? 1 : mb;
 }
 
+// Strip planes (adists.h), bf16 trunk only.  Mode 2 (default): the levels whose producing kernel can write strips get
+// them from the convolution epilogue and one kernel pools + sums them (*from_conv); mode 1: strip planes transposed from
+// the NHWC level (validation of the readers).  Returns the mask of levels in the strip layout.
+static unsigned adists_strip_levels(const nqa_ctx* ctx, int H, int W, int window, bool planes16, unsigned* from_conv) {
+  unsigned mask = 0;
+  *from_conv = 0;
+  if (!planes16 || ctx->adists_strips <= 0 || !ctx->adists_fused_sums) return 0;
+  for (int k = 1; k < kNumLevels; ++k) {
+    if (!adists_strips_supported(k, H, W, window) || !adists_planes_sums_supported(k, H, W)) continue;
+    if (ctx->adists_strips >= 2) {
+      if (!trunk_strips_capable(ctx, k)) continue;
+      *from_conv |= 1u << k;
+    }
+    mask |= 1u << k;
+  }
+  return mask;
+}
+
 template <typename T>
 static size_t adists_need_bytes(const nqa_ctx* ctx, int mb, int H, int W, int window, int prec, bool with_dists) {
   const bool planes16 = std::is_same<T, bf16>::value && prec == NQA_PREC_BF16;
   const bool fused_pool = with_dists && prec != NQA_PREC_BF16X3;
+  unsigned from_conv = 0;
+  adists_strip_levels(ctx, H, W, window, planes16, &from_conv);
   return trunk_bytes<T>(2 * mb, H, W, prec) + adists_feat_bytes(mb, H, W, planes16 ? sizeof(bf16) : sizeof(float)) +
-         adists_workspace_bytes(mb, H, W, window) + (with_dists ? partial_bytes(mb, H, W, prec, nullptr, false, fused_pool) : 0);
+         adists_workspace_bytes(mb, H, W, window) +
+         (with_dists ? partial_bytes(mb, H, W, prec, nullptr, false, fused_pool, from_conv) : 0);
 }
 
 // dists_out != nullptr: the same trunk pass also feeds the DISTS statistics (fused pool + moments kernel), so a
@@ -1524,24 +1547,18 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
       planar[k] = static_cast<char*>(ctx->arena.take((size_t)2 * pairs * level_channels(k) * lh[k] * lw[k] * pelem));
     void* ws = ctx->arena.take(adists_workspace_bytes(pairs, H, W, window));
     unsigned sums_done = 0;   // levels whose channel sums were produced together with the planes (bit 8 + k: from strips)
-    // Strip planes (adists.h): mode 2 = written by the convolution epilogues and pooled + summed by one kernel (A-DISTS
-    // alone: the DISTS moments still want the NHWC level), mode 1 = transposed from the NHWC level (validation)
-    unsigned strips_mask = 0;
+    // Strip planes (adists.h): written by the convolution epilogues, pooled + summed (+ the DISTS moments when both
+    // metrics are wanted) by one kernel; see adists_strip_levels
+    unsigned from_conv = 0;
+    const unsigned strips_mask = adists_strip_levels(ctx, H, W, window, planes16, &from_conv);
     bf16* strips_dst[kNumLevels] = {};
-    if (planes16 && ctx->adists_strips > 0 && ctx->adists_fused_sums)
-      for (int k = 1; k < kNumLevels; ++k)
-        if (adists_strips_supported(k, H, W, window) && adists_planes_sums_supported(k, H, W)) {
-          if (ctx->adists_strips >= 2) {
-            if (with_dists || !trunk_strips_capable(ctx, k)) continue;
-            strips_dst[k] = reinterpret_cast<bf16*>(planar[k]);
-          }
-          strips_mask |= 1u << k;
-        }
+    for (int k = 1; k < kNumLevels; ++k)
+      if ((from_conv >> k) & 1) strips_dst[k] = reinterpret_cast<bf16*>(planar[k]);
     const float* xb = x + b0 * frame;
     const float* yb = y + b0 * frame;
     PartialBufs pb;
     if (with_dists) {
-      partial_bytes(pairs, H, W, prec, &pb, false, fused_pool);
+      partial_bytes(pairs, H, W, prec, &pb, false, fused_pool, from_conv);
       partial_alloc(ctx, pairs, &pb);
       ProfScope ps(ctx, NQA_K_STATS, st);
       ctx->launches += launch_stats_planar(xb, yb, pairs, 3, H * W, pb.chunks[0], pb.p[0], st);
@@ -1553,7 +1570,7 @@ static int adists_impl(nqa_ctx* ctx, const float* x, const float* y, int B, int 
                           // the level arrived as strip planes: pooled input of the next stage + channel sums in one read
                           ProfScope ps(ctx, NQA_K_L2POOL, st);
                           ctx->launches += adists_pool_strips_and_sums(strips_dst[k], reinterpret_cast<bf16*>(pooled_dst), pairs, k, H, W,
-                                                                       window, ws, st);
+                                                                       window, ws, st, with_dists ? pb.p[k] : nullptr);
                           sums_done |= 1u << (8 + k);
                           return true;
                         }

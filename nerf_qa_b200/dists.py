@@ -329,8 +329,8 @@ class DISTS(_TrunkModule):
     def score_with_adists(self, x: torch.Tensor, y: torch.Tensor, window_size: int = 21):
         """(DISTS [B], A-DISTS [B]) of the batch from ONE trunk evaluation -- the pair of calls prep.py:186-190 /
         test2_prep.py:151-155 make per batch (``adists_model(ref, render, as_loss=False)``, ``dists_model(ref,
-        render)``), whose trunks are the same VGG16.  DISTS is bit-identical to ``forward``; A-DISTS equals ``ADISTS.forward``
-        up to the rounding of the pooled activations."""
+        render)``), whose trunks are the same VGG16.  DISTS equals ``forward`` up to the summation order of the fp32 moment
+        partials (1e-6 relative), A-DISTS equals ``ADISTS.forward`` up to the rounding of the pooled activations."""
         ctx = self._context(x.device)
         self._sync_weights_nograd(ctx)
         return ctx.dists_adists_forward(x, y, window_size, self._prec())

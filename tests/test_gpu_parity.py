@@ -612,7 +612,12 @@ def test_shared_trunk_scores_match_separate_calls(models, amodels, prec):
     x, y = synth.make_frame_pairs(3, 176, 208, seed=61)
     xs, ys = x.cuda(), y.cuda()
     d, a = models[prec].score_with_adists(xs, ys)
-    assert torch.equal(d, models[prec](xs, ys))
+    if prec == "bf16":
+        # levels that travel as strip planes (widths 208 and 104 here) get their DISTS moments from the strip-plane kernel:
+        # same pivot-shifted fp32 sums in another (fixed) order
+        assert torch.allclose(d, models[prec](xs, ys), rtol=1e-5, atol=1e-7)
+    else:
+        assert torch.equal(d, models[prec](xs, ys))
     want_a = amodels[prec](xs, ys, as_loss=False)
     report(f"shared-trunk A-DISTS vs separate ({prec})", a.cpu().numpy(), want_a.cpu().numpy())
     # the fused pool + moments kernel (separable sums, MUFU sqrt before the bf16 rounding) replaces the stand-alone pooling
