@@ -85,12 +85,19 @@ __device__ inline void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// m16n8k8: the last k-block of the first pass only reaches 4 columns into its 16 (window 21: 36 input columns per 16
+// outputs), so its upper half is all zero taps
+__device__ inline void mma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ inline void ldmatrix_x1(uint32_t& r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r) : "r"(addr));
+}
 __device__ inline void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ inline void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
 __device__ inline void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -129,12 +136,12 @@ __device__ inline void filtered_map(const uint32_t (&tile_addr)[NT], uint32_t la
     float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      uint32_t b01[4], b2[2];
+      uint32_t b01[4], b2;
       ldmatrix_x4(b01, tile_addr[t] + lane_off + rb * kRbStride);    // k-blocks 0 and 1 (columns +0, +8, +16, +24)
-      ldmatrix_x2(b2, tile_addr[t] + lane_off2 + rb * kRbStride);    // k-block 2 (columns +32, +40)
+      ldmatrix_x1(b2, tile_addr[t] + lane_off2 + rb * kRbStride);    // first half of k-block 2 (columns +32 .. +39)
       mma16816(c, ta[0][0], ta[0][1], ta[0][2], ta[0][3], b01[0], b01[1]);
       mma16816(c, ta[1][0], ta[1][1], ta[1][2], ta[1][3], b01[2], b01[3]);
-      mma16816(c, ta[2][0], ta[2][1], ta[2][2], ta[2][3], b2[0], b2[1]);
+      mma1688(c, ta[2][0], ta[2][1], b2);
     }
     // fp32 -> bf16 hi + lo (round to nearest both; hi + lo carries 16 significant bits)
     if (kTwo) {
