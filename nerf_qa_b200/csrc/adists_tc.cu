@@ -112,6 +112,11 @@ __device__ inline void mbar_wait_parity(uint32_t bar, uint32_t parity) {
     if (spins > (1u << 26)) __trap();
   }
 }
+__device__ inline bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ inline float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -201,6 +206,7 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const int c_per = ceil_div(c, csplit);
   const int c_begin = split * c_per, c_end = min(c, c_begin + c_per);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // the same value, known to be warp-uniform
   const int wx = warp % kWarpsX, wy = warp / kWarpsX;
 
   // Toeplitz fragments (constant over the kernel).  Pass 1, A operand (16 output columns x 16 input columns of k-block
@@ -232,15 +238,23 @@ window_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (threadIdx.x == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kTileBytes) : "memory");
     if (kStrips) {
-      if (lane == 0) {
-        tma_load_3d(tile(buf * 2 + 0) + warp * kStripRow, &map_x, bar, (oy0 + 8 * warp) * 8, ox0 >> 3, b * c + ch);
-        tma_load_3d(tile(buf * 2 + 1) + warp * kStripRow, &map_y, bar, (oy0 + 8 * warp) * 8, ox0 >> 3, b * c + ch);
+      // executed by the whole warp with warp-uniform operands, only the instruction predicated on the elected lane
+      // (inside an `if (lane == 0)` region every UTMALDG is wrapped in an R2UR + ELECT + BRA.U.ANY loop)
+      const uint32_t dst = tile(buf * 2) + warp_u * kStripRow;
+      const int row0 = (oy0 + 8 * warp_u) * 8, strip0 = ox0 >> 3, pl = b * c + ch;
+      if (elect_one_sync()) {
+        tma_load_3d(dst, &map_x, bar, row0, strip0, pl);
+        tma_load_3d(dst + kTileBytes, &map_y, bar, row0, strip0, pl);
       }
-    } else if (threadIdx.x == 0) {
+    } else if (warp_u == 0) {
+      const uint32_t dst = tile(buf * 2);
+      const int pl = b * c + ch;
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int part = 0; part < kParts; ++part) {
-        tma_load_3d(tile(buf * 2 + 0) + part * kPartBytes, &map_x, bar, ox0 + 32 * part, oy0, b * c + ch);
-        tma_load_3d(tile(buf * 2 + 1) + part * kPartBytes, &map_y, bar, ox0 + 32 * part, oy0, b * c + ch);
+        for (int part = 0; part < kParts; ++part) {
+          tma_load_3d(dst + part * kPartBytes, &map_x, bar, ox0 + 32 * part, oy0, pl);
+          tma_load_3d(dst + kTileBytes + part * kPartBytes, &map_y, bar, ox0 + 32 * part, oy0, pl);
+        }
       }
     }
   };
