@@ -39,6 +39,7 @@ __device__ __forceinline__ float root_approx(float v) {   // rounded to bf16 aft
   asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float lg2_approx(float v) {    // v >= 1e-30: no denormal handling needed
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -101,35 +102,47 @@ pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pool
   const size_t plane = (size_t)h * w;
   const size_t strip_stride = (size_t)h * 8;
   const bool do_pool = pooled_out != nullptr;   // level 5 has no pooling behind it: sums only
-  const bf16* zero = reinterpret_cast<const bf16*>(&g_zero_rows);
 
   float tot0 = 0.f, tot1 = 0.f;   // lane l: totals of sum l / 4 for the channels l % 4 and l % 4 + 4 of the warp
   float dtot0 = 0.f, dtot1 = 0.f;  // the same for the DISTS moments
 
-  const uint32_t off0 = (uint32_t)max(r0, 0) * 8u, off1 = (uint32_t)max(r1, 0) * 8u;   // element offsets inside a strip
-  const size_t xy = (size_t)pairs * c * plane;
+  // Byte pointers to this lane's two rows of x and y, advanced by one plane per channel (32-bit increment: H W <= 2^28).
+  // Rows outside the image point at a zero row and do not advance: no select per loaded word, no load under a branch,
+  // and ~10 integer instructions of address arithmetic per channel instead of ~100 for indices rebuilt from scratch.
+  const uint32_t plane_b = (uint32_t)(plane * 2);
+  const uint32_t inc0 = ok0 ? plane_b : 0u, inc1 = ok1 ? plane_b : 0u;
+  const size_t xy_b = (size_t)pairs * c * plane * 2;
+  const char* zero = reinterpret_cast<const char*>(&g_zero_rows);
   for (int s = s_begin; s < s_end; ++s) {
-    const bf16* px = planes + ((size_t)b * c + slab * 64 + warp * 8) * plane + (size_t)s * strip_stride;
+    const char* base = reinterpret_cast<const char*>(planes) +
+                       (((size_t)b * c + slab * 64 + warp * 8) * plane + (size_t)s * strip_stride) * 2;
+    const char* ax0 = ok0 ? base + (size_t)r0 * 16 : zero;
+    const char* ax1 = ok1 ? base + (size_t)r1 * 16 : zero;
+    const char* ay0 = ok0 ? ax0 + xy_b : zero;
+    const char* ay1 = ok1 ? ax1 + xy_b : zero;
 #pragma unroll 1
-    for (int ci = 0; ci < 8; ++ci, px += plane) {
-      const bf16* py = px + xy;
-      // rows outside the image read a zero row (no select per loaded word, no load under a branch)
-      const uint4 tx0 = __ldg(reinterpret_cast<const uint4*>(ok0 ? px + off0 : zero));
-      const uint4 tx1 = __ldg(reinterpret_cast<const uint4*>(ok1 ? px + off1 : zero));
-      const uint4 ty0 = __ldg(reinterpret_cast<const uint4*>(ok0 ? py + off0 : zero));
-      const uint4 ty1 = __ldg(reinterpret_cast<const uint4*>(ok1 ? py + off1 : zero));
+    for (int ci = 0; ci < 8; ++ci, ax0 += inc0, ax1 += inc1, ay0 += inc0, ay1 += inc1) {
+      // the next channel's rows on their way into L2 while this one is processed (every other lane: one request per 64
+      // bytes; costs no registers, unlike a software pipeline of the loads)
+      if ((lane & 1) == 0 && ci < 7) {   // (stays inside the slab: never past the end of the planes)
+        prefetch_l2(ax0 + inc0);
+        prefetch_l2(ay0 + inc0);
+      }
+      const uint4 tx0 = __ldg(reinterpret_cast<const uint4*>(ax0));
+      const uint4 tx1 = __ldg(reinterpret_cast<const uint4*>(ax1));
+      const uint4 ty0 = __ldg(reinterpret_cast<const uint4*>(ay0));
+      const uint4 ty1 = __ldg(reinterpret_cast<const uint4*>(ay1));
       // left taps: the last pixels of the previous strip's rows -- from global memory for the first strip of the block,
       // from the carry this lane left in shared memory afterwards (pixels x r0, x r1, y r0, y r1 as bf16)
       uint2 left;
       if (s == s_begin) {
         left = make_uint2(0u, 0u);
-        if (s > 0) {
-          const bf16* lx = px - strip_stride + 7;
-          const bf16* ly = py - strip_stride + 7;
-          const uint32_t a0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(lx + off0)) : 0u;
-          const uint32_t a1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(lx + off1)) : 0u;
-          const uint32_t d0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(ly + off0)) : 0u;
-          const uint32_t d1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(ly + off1)) : 0u;
+        if (s > 0) {   // (a zero row stays a zero row 16 h - 14 bytes earlier only by luck: select)
+          const ptrdiff_t back = 14 - (ptrdiff_t)strip_stride * 2;
+          const uint32_t a0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(ax0 + back)) : 0u;
+          const uint32_t a1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(ax1 + back)) : 0u;
+          const uint32_t d0 = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(ay0 + back)) : 0u;
+          const uint32_t d1 = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(ay1 + back)) : 0u;
           left = make_uint2(a0 | (a1 << 16), d0 | (d1 << 16));
         }
       } else {
@@ -149,9 +162,9 @@ pool_strips_sums_kernel(const bf16* __restrict__ planes, bf16* __restrict__ pool
       float2 dacc[5];
       float2 npx[2], npy[2];
       if (kDists) {
-        const bf16* cx = px - (size_t)s * strip_stride;
+        const char* cx = reinterpret_cast<const char*>(planes) + ((size_t)b * c + slab * 64 + warp * 8 + ci) * plane * 2;
         const float x0 = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(cx)) << 16);
-        const float y0 = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(cx + xy)) << 16);
+        const float y0 = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(cx + xy_b)) << 16);
         if (chunk == 0 && s == s_begin && lane == 0) {
           float* piv = dpartials + (size_t)gridDim.z * chunks * 5 * c + (size_t)b * 2 * c + slab * 64 + warp * 8 + ci;
           piv[0] = x0;

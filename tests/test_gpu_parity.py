@@ -528,20 +528,28 @@ def test_dists_edge_shapes_against_oracle(models, vgg_weights, alpha_beta, shape
 @pytest.mark.parametrize("shape", [(1, 21, 21), (2, 24, 40), (1, 8, 8), (2, 3, 5), (1, 40, 21), (1, 22, 22)])
 def test_adists_edge_shapes_against_oracle(amodels, vgg_weights, shape):
     """Fallback-only pyramids, 1x1 levels (zero entropy weights in the reference) and the 21x21 frame whose single
-    window position makes the reference itself return NaN (unbiased std of one element): same here.  Known limit
-    (DESIGN.md): fallback levels with 2..~16 pixels per map (frames of 12..31 px) use one-pass global moments of the
-    normalised features and land 1e-3..1e-1 relative (<= 3e-4 absolute) from the reference's two-pass variance."""
+    window position makes the reference itself return NaN (unbiased std of one element): same here.  Frames of a few
+    pixels are ill-conditioned in the reference itself: with 2..~16 pixels per map the variances of the L2-normalised
+    features are of the size of the 1e-6 stabilisers, and the reference's fp32 result sits 3e-4 (8x8) to 1.5e-3 (3x5)
+    absolute -- 11% to 23% -- from its own fp64 result.  There the check is against the fp64 evaluation: this
+    implementation (fp32 sums, fp64 moments) must be at least as close to it as the reference's fp32 arithmetic is."""
     b, h, w = shape
     x, y = _edge_frames(b, h, w, 43)
     ws, bs = vgg_weights
     with torch.no_grad():
         want = O.adists_score(x, y, ws, bs).numpy()
+        want64 = O.adists_score(x.double(), y.double(), [t.double() for t in ws], [t.double() for t in bs]).numpy()
     got = amodels["fp32"](x.cuda(), y.cuda(), as_loss=False).cpu().numpy()
     report(f"A-DISTS {shape} fp32", got, want)
     if np.isnan(want).any():
         assert np.array_equal(np.isnan(got), np.isnan(want))
         return
-    assert rel_err(got, want) < 1e-4 or np.max(np.abs(got - want)) < 2e-6
+    ref_spread = float(np.max(np.abs(want - want64)))
+    print(f"[parity] A-DISTS {shape}: reference fp32 vs its fp64 {ref_spread:.3e}, this implementation vs fp64 "
+          f"{np.max(np.abs(got - want64)):.3e}")
+    assert (rel_err(got, want) < 1e-4 or np.max(np.abs(got - want)) < 2e-6
+            or np.max(np.abs(got - want64)) <= 1.05 * ref_spread + 1e-7)
+    assert np.max(np.abs(got - want64)) <= max(1.05 * ref_spread, 1e-4 * float(np.max(np.abs(want64)))) + 2e-6
     got16 = amodels["bf16"](x.cuda(), y.cuda(), as_loss=False).cpu().numpy()
     assert np.max(np.abs(got16 - want)) < 2e-3
 
