@@ -1119,7 +1119,7 @@ int adists_stage(const void* const fx[6], const void* const fy[6], bool feats_bf
       // bf16 planes: the two gaussian passes as banded-Toeplitz products on the tensor pipe (adists_tc.cu); 0 = no
       // tensor map for these planes, the CUDA-core kernel serves the level
       mma_launches = launch_window_mma(B16(fx[k]), B16(fy[k]), pairs, L.c, L.h, L.w, window, L.csplit_mma, L.choff, chan, wt,
-                                       taps.g, options.mma_terms == 2, strips, F(L.off_a), F(L.off_b), F(L.off_g), st);
+                                       taps.g, options.mma_terms == 2 ? -1 : options.one_term_min_pixels, strips, F(L.off_a), F(L.off_b), F(L.off_g), st);
     if (mma_launches < 0 || (strips && mma_launches == 0)) return -1;
     if (mma_launches > 0) {
       csplit_used[k] = L.csplit_mma;

@@ -28,7 +28,8 @@ struct AdistsParts {
 // Kernel selection of the stage, owned by the context (read from the environment once, at nqa_ctx_create).
 struct AdistsOptions {
   bool use_mma = true;   // NQA_ADISTS_MMA=0: CUDA-core window kernel for bf16 planes too
-  int mma_terms = 0;     // NQA_ADISTS_MMA_TERMS: 0 = one bf16 term per operand for maps >= 400k pixels, else two; 2 = always two
+  int mma_terms = 0;     // NQA_ADISTS_MMA_TERMS: 0 = one bf16 term per operand for maps >= one_term_min_pixels, else two; 2 = always two
+  long long one_term_min_pixels = 100000;   // NQA_ADISTS_ONE_TERM_MIN_PIXELS (see adists_tc.cu launch_window_mma)
 };
 struct AdistsProf {
   void* user = nullptr;

@@ -469,12 +469,15 @@ bool window_mma_supported(int window, int h, int w, const void* fx, const void* 
          (reinterpret_cast<uintptr_t>(fx) & 15) == 0 && (reinterpret_cast<uintptr_t>(fy) & 15) == 0;
 }
 
-static bool two_terms(int h, int w, bool force) { return (long long)h * w < 400000 || force; }
+static bool two_terms(int h, int w, long long one_term_min_pixels) {
+  return one_term_min_pixels < 0 || (long long)h * w < one_term_min_pixels;
+}
 
 void window_mma_tiles(int h, int w, int window, int* tiles_x, int* tiles_y) {
   const int oh = h - window + 1, ow = w - window + 1;
   *tiles_x = ceil_div(ow, kTileOW);
-  *tiles_y = ceil_div(oh, two_terms(h, w, false) ? TcCfg<3, true>::kTileOH : TcCfg<3, false>::kTileOH);
+  *tiles_y = ceil_div(oh, TcCfg<3, true>::kTileOH);   // (the same for the one-term kernel)
+  static_assert(TcCfg<3, true>::kTileOH == TcCfg<3, false>::kTileOH, "tile height does not depend on the term count");
 }
 
 template <bool kTwo, bool kStrips>
@@ -488,7 +491,7 @@ static void launch_cfg(const CUtensorMap& mx, const CUtensorMap& my, int pairs, 
 }
 
 int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, int w, int window, int csplit, int choff,
-                      const double* chan, const float* wt, const float* taps_f32, bool force_two_terms, bool strips, float* amap,
+                      const double* chan, const float* wt, const float* taps_f32, long long one_term_min_pixels, bool strips, float* amap,
                       float* bmap, float* gmap, cudaStream_t st) {
   TcTaps t;
   double sum = 0.0;
@@ -500,10 +503,13 @@ int launch_window_mma(const bf16* fx, const bf16* fy, int pairs, int c, int h, i
   const int oh = h - window + 1, ow = w - window + 1;
   // One bf16 term per operand or two.  The rounding of a one-term operand (2^-9 per element, ~4e-4 after the window
   // average) is an error of that fraction of E[f^2] in a variance; in the L2-normalised units of ADISTS.py:166-167 E[f^2]
-  // is 1 / (h w) on average, so for maps of >= 400k pixels even a 10x locally concentrated channel errs by ~1e-8, one
-  // hundredth of the 1e-6 stabilisers c1 / c2 -- the 1080p levels 1 and 2, 77% of the work.  Smaller maps (deeper
-  // levels, small frames) keep the exact two-term products and the hi + lo split between the passes.
-  const bool two = two_terms(h, w, force_two_terms);
+  // is 1 / (h w) on average, so the error shrinks against the 1e-6 stabilisers c1 / c2 as the maps grow.  Measured on the
+  // 1080p golden pair (profiles/r3o_window_one_term_sweep.log; distance of the score to the all-two-terms score, i.e.
+  // the window arithmetic alone; the bf16 trunk itself sits 1.1e-5 from the fp32 reference): threshold 400k pixels
+  // (levels 1-2 one-term) 3.6e-7, 100k (levels 1-3) 3.6e-6, 30k (levels 1-4) 5.0e-5, everything one-term 3.6e-4.  The
+  // default, 100k, keeps the window rounding a factor 3 below the trunk's; smaller maps (deeper levels, small frames) keep
+  // the exact two-term products and the hi + lo split between the passes.
+  const bool two = two_terms(h, w, one_term_min_pixels);
   const int tx = ceil_div(ow, kTileOW);
   if (ceil_div(c, csplit) > kMaxCPer) return 0;
   CUtensorMap map_x, map_y;

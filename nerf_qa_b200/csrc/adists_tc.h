@@ -16,7 +16,7 @@ void window_mma_tiles(int h, int w, int window, int* tiles_x, int* tiles_y);
 // strips: the planes are in the strip layout [plane][w / 8][h][8] (kernels.h make_strip_map).  Returns 1, 0 when no tensor
 // map could be made for planar planes (the caller uses the CUDA-core kernel), -1 on failure with strip planes.
 int launch_window_mma(const __nv_bfloat16* fx, const __nv_bfloat16* fy, int pairs, int c, int h, int w, int window, int csplit,
-                      int choff, const double* chan, const float* wt, const float* taps_f32, bool force_two_terms, bool strips,
-                      float* amap, float* bmap, float* gmap, cudaStream_t st);
+                      int choff, const double* chan, const float* wt, const float* taps_f32, long long one_term_min_pixels, bool strips,
+                      float* amap, float* bmap, float* gmap, cudaStream_t st);   // one_term_min_pixels < 0: always two terms
 
 }  // namespace nqa

@@ -1159,6 +1159,7 @@ int nqa_ctx_create(int device, nqa_ctx** out) {
   if (const char* e = getenv("NQA_ADISTS_STRIPS")) ctx->adists_strips = atoi(e);
   if (const char* e = getenv("NQA_ADISTS_MMA")) ctx->adists_opt.use_mma = atoi(e) != 0;
   if (const char* e = getenv("NQA_ADISTS_MMA_TERMS")) ctx->adists_opt.mma_terms = atoi(e);
+  if (const char* e = getenv("NQA_ADISTS_ONE_TERM_MIN_PIXELS")) ctx->adists_opt.one_term_min_pixels = atoll(e);
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_graph_in, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_graph_out, cudaEventDisableTiming));
