@@ -4,7 +4,7 @@
 cd /root/repo
 mkdir -p gpurun_out
 TAG=${1:-r3e}; RX=${2:-pool_strips}; N=${3:-2}
-CMD="python scripts/adists_once.py"
+CMD=${4:-"python scripts/adists_once.py"}
 timeout 300 $CMD > gpurun_out/${TAG}_once.log 2>&1 || { tail -3 gpurun_out/${TAG}_once.log; exit 1; }
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$RX" -c $N -f -o gpurun_out/${TAG}_k $CMD > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"
 ncu -i gpurun_out/${TAG}_k.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
