@@ -117,7 +117,8 @@ def family_models(workload, h, w, precision, train_recompute=False):
         "conv": ("tensor", fl * ((3.0 if train_recompute else 2.0) if workload == "train" else 1.0), "flop"),
         "pool_stats": ("hbm", pooled_in + pooled_out, "bytes"),          # levels 1-4 read once, pooled tensors written
         "l2pool": ("hbm", (2 * level_elems(h, w) * eb if strips else pooled_in) + pooled_out, "bytes"),
-        "stats": ("hbm", 2 * 3 * hw * 4 + 2 * CHNS[5] * level_dims(h, w)[5][0] * level_dims(h, w)[5][1] * eb, "bytes"),
+        # levels 0 and 5 (level 5's moments come from the strip-plane kernel when both metrics share a bf16 trunk pass)
+        "stats": ("hbm", 2 * 3 * hw * 4 + (0 if strips else 2 * CHNS[5] * level_dims(h, w)[5][0] * level_dims(h, w)[5][1] * eb), "bytes"),
         "layout": ("hbm", 2 * 2 * level_elems(h, w) * eb, "bytes"),       # NHWC -> planes: read + write of levels 1-5
         # channel sums read x and y, the entropy pass reads x again (levels 1-5 at eb bytes, level 0 fp32)
         "adists": ("hbm", (0 if strips else 3 * level_elems(h, w) * eb) + 3 * 3 * hw * 4 + 6 * wmaps, "bytes"),
@@ -463,16 +464,28 @@ def rooflines(env, ctx, name, prof, steps, pairs, h, w, precision):
                      algorithmic_bytes_per_launch=work * pairs * steps / n)
         else:   # the A-DISTS window kernels: CUDA-core FMAs (fp32 planes) or warp-level MMAs (bf16 planes)
             fma_peak = env.rate(ctx, "fp32_fma")
+            mma_peak = env.rate(ctx, "mma_sync_bf16")
             gbs = window_bytes_per_pair(h, w, precision) * pairs * steps / (ms / 1e3) / 1e9
-            e.update(kernel="A-DISTS local-window statistics (adists.cu window_kernel / adists_tc.cu window_mma_kernel): "
+            on_mma = precision == "bf16"   # levels 1-5 of the bf16 trunk run on mma.sync (level 0, 3 channels, on CUDA cores)
+            peak = mma_peak if on_mma else fma_peak
+            e.update(kernel="A-DISTS local-window statistics (adists_tc.cu window_mma_kernel: the two 21-tap passes as "
+                            "banded-Toeplitz bf16 MMAs; adists.cu window_kernel for fp32 planes and the 3-channel frame level): "
                             "five 21x21 gaussian-filtered maps per channel + T/S/gamma, reduced over channels on the fly",
-                     achieved=per_s / 1e12, peak=fma_peak / 1e12, unit="TFMA/s", frac=per_s / fma_peak,
-                     peak_source="nqa_measure_rate(NQA_RATE_FP32_FMA): packed fp32 FMAs measured on this GPU in this run; "
-                                 "a value above 1 means the filters run on the tensor pipe (see mma_sync_peak)",
+                     bound="tensor" if on_mma else "fma", pipe="mma.sync (HMMA m16n8k16 bf16)" if on_mma else "fp32 FMA",
+                     achieved=per_s / 1e12, peak=peak / 1e12, unit="TFMA/s", frac=per_s / peak,
+                     peak_source=("nqa_measure_rate(NQA_RATE_MMA_SYNC_BF16): dense m16n8k16 bf16 MMAs measured on this GPU in this "
+                                  "run.  `achieved` counts the ALGORITHMIC FMAs of the separable filter (5 maps x 2 passes x 21 "
+                                  "taps per output); the banded-Toeplitz operands are 44% (first pass) / 66% (second pass) "
+                                  "non-zero and the first pass also covers the 20-row halo, so ~5x as many FMAs are issued: "
+                                  "ncu reads 48-50% HMMA-pipe activity (profiles/r3z_adists_ncu_full_summary.json)" if on_mma else
+                                  "nqa_measure_rate(NQA_RATE_FP32_FMA): packed fp32 FMAs measured on this GPU in this run"),
                      algorithmic_fma_per_launch=work * pairs * steps / n,
+                     fp32_fma_equivalent={"peak": fma_peak / 1e12, "unit": "TFMA/s", "frac": per_s / fma_peak,
+                                          "note": "the same algorithmic rate against the measured CUDA-core FMA peak: what a "
+                                                  "perfectly issued separable CUDA-core kernel could reach at most"},
                      hbm={"achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                           "algorithmic_bytes_per_launch": window_bytes_per_pair(h, w, precision) * pairs * steps / n},
-                     mma_sync_peak={"value": env.rate(ctx, "mma_sync_bf16") / 1e12, "unit": "TFMA/s",
+                     mma_sync_peak={"value": mma_peak / 1e12, "unit": "TFMA/s",
                                     "source": "nqa_measure_rate(NQA_RATE_MMA_SYNC_BF16), this run"})
         e["traffic"] = None
         fams[fam] = e
