@@ -203,3 +203,27 @@ def test_paths_without_a_backward_refuse_gradients(amodels, dmodels):
         with pytest.raises(NotImplementedError):
             dmodels["fp32"].stage2._modules["4"](torch.rand(1, 64, 8, 8, device="cuda", requires_grad=True))
     assert amodels["fp32"](xs.detach(), y.cuda()).dim() == 0
+
+
+@pytest.mark.parametrize("shape", [(2, 352, 368), (3, 176, 208), (1, 540, 960)])
+def test_strip_plane_path_against_the_planar_path(monkeypatch, shape):
+    """bf16 trunk: by default the last convolution of a stage writes its output as strip planes from the epilogue and one
+    kernel pools + sums them (NQA_ADISTS_STRIPS=2).  Against it: strip planes transposed from the NHWC level (1: validates
+    the strip readers alone) and plain planar planes (0: the round-1 kernels).  Same trunk arithmetic; the pooling kernels
+    round the pooled activations differently in rare last bits (MUFU sqrt of separable sums vs sqrtf of nine fmas), hence a
+    tolerance far inside the bf16 budget instead of equality.  Widths 208 -> 104 -> 52: levels that cannot be strips
+    (w % 8 != 0) fall back per level.  DISTS from the shared-trunk call must agree too."""
+    b, h, w = shape
+    x, y = synth.make_frame_pairs(b, h, w, seed=83)
+    xs, ys = x.cuda(), y.cuda()
+    res = {}
+    for mode in ("2", "1", "0"):
+        monkeypatch.setenv("NQA_ADISTS_STRIPS", mode)
+        a, d = make_adists("bf16"), make_dists("bf16")
+        res[mode] = (a(xs, ys, as_loss=False).cpu().numpy(), *[t.cpu().numpy() for t in d.score_with_adists(xs, ys)])
+    for mode in ("1", "0"):
+        for got, want, name in zip(res["2"], res[mode], ("A-DISTS", "DISTS (shared trunk)", "A-DISTS (shared trunk)")):
+            report(f"strips=2 vs strips={mode} {name} {shape}", got, want)
+            assert np.max(np.abs(got - want)) < 1e-4
+    # the strip readers alone (same pooled activations as the planar path: only the layout of the planes differs)
+    assert np.array_equal(res["1"][0], res["0"][0])
