@@ -415,6 +415,7 @@ ConvTcConfig conv_tc_config_from_env(int sm_count) {
   if (const char* e = getenv("NQA_CONV_N64")) c.n64 = atoi(e) != 0;
   if (const char* e = getenv("NQA_CONV_PAIR")) c.pair = atoi(e) != 0;
   if (const char* e = getenv("NQA_PAIR_MINCIN")) c.pair_min_cin = atoi(e);
+  if (const char* e = getenv("NQA_PAIR_SPLIT")) c.split_pair = atoi(e) != 0;
   return c;
 }
 
@@ -425,7 +426,7 @@ bool conv_tc_uses_pair(const ConvTcConfig& cfg, int cin, int cout, bool split) {
 
 int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in, const bf16* in_lo, const bf16* wk,
                       const bf16* wk_lo, const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout,
-                      bool split, const char** err, bool strips_out) {
+                      bool split, const char** err, bool strips_out, bool split_on_pairs) {
   if (cin % tc::BLOCK_K != 0 || cout % 64 != 0 || cout > 512) { *err = "conv_tc: cin must be a multiple of 64, cout a multiple of 64 and <= 512"; return 1; }
   plan->n = n; plan->h = h; plan->w = w; plan->cin = cin; plan->cout = cout;
   plan->sm_count = cfg.sm_count;
@@ -446,7 +447,12 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in,
   plan->halo_hbw = 10;
   plan->halo_desc_mode = 0;
   const int halo_mode = cfg.halo_mode;
-  if (halo_mode > 0 && !split && cin <= cfg.halo_max_cin) {
+  // (bf16x3: conv2_1, 64 -> 128 channels, goes to the pair kernel too -- the alternative is the per-tap kernel, not the
+  // single-CTA halo kernel that serves it on the bf16 path)
+  const int pair_min_cin = split ? 64 : cfg.pair_min_cin;
+  const bool split_pair = split && split_on_pairs && cfg.pair && cfg.split_pair && halo_mode > 0 && cin <= cfg.halo_max_cin &&
+                          cout >= 128 && cin >= pair_min_cin && (cfg.sm_count & 1) == 0;
+  if (halo_mode > 0 && (!split || split_pair) && cin <= cfg.halo_max_cin) {
     plan->halo = true;
     plan->halo_desc_mode = 0;   // base-offset field 0: validated on hardware (swizzle follows absolute address bits)
     plan->halo_hbw = ((halo_mode - 1) & 2) ? 16 : 10;
@@ -457,7 +463,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in,
     // 128-channel tile whose weights stream from L2 for every pixel tile (NQA_CONV_N64=0 restores the latter)
     if (cfg.n64 && cin == 128 && cout == 128) plan->block_n = 64;
     // CTA pairs (tcgen05 cta_group::2): 256 pixels x block_n channels per instruction, each CTA holds half the weights
-    if (cfg.pair && cout >= 128 && cin >= cfg.pair_min_cin && (cfg.sm_count & 1) == 0) {
+    if (cfg.pair && cout >= 128 && cin >= pair_min_cin && (cfg.sm_count & 1) == 0) {
       plan->pair = true;
       plan->block_n = cout >= 256 ? 256 : 128;
     }
@@ -475,7 +481,11 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in,
   } else if (plan->halo) {
     ok = ok && tc::encode_act_map(&plan->tmap_out, out, n, h, w, cout, tw, th);
   }
-  if (split)
+  if (split && plan->pair)
+    ok = ok && tc::encode_act_map(&plan->tmap_a_lo, in_lo, n, h, w, cin, plan->halo_hbw, th + 2) &&
+         tc::encode_w_map(&plan->tmap_b_lo, wk_lo, cout, 9 * cin, plan->block_n / 2) &&
+         tc::encode_act_map(&plan->tmap_out_lo, out_lo, n, h, w, cout, tw, th);
+  else if (split)
     ok = ok && tc::encode_act_map(&plan->tmap_a_lo, in_lo, n, h, w, cin, tw, th) &&
          tc::encode_w_map(&plan->tmap_b_lo, wk_lo, cout, 9 * cin, plan->block_n);
   else {

@@ -20,6 +20,13 @@
 //     memory and TMA-store their own tile; the follower's warps hand the accumulator back with a remote
 //     mbarrier.arrive on the leader's tmem_empty barrier.
 //
+//
+// SPLIT (bf16x3 trunk, forward only): activations and weights arrive as bf16 hi + lo pairs; a stage holds the hi and the
+// lo halo tile, a weight slot the hi and the lo half-tile, every k-step issues hi*hi + hi*lo + lo*hi into the same fp32
+// accumulator, and the epilogue writes the result as hi = bf16(v), lo = bf16(v - hi) through two staging tiles and two
+// TMA stores.  Same halo reuse and CTA pairing as the bf16 path: the per-tap kernel of conv_tc.cu re-fetches the A tile
+// nine times per chunk and is bound by L2 bandwidth at three MMAs per k-step.
+//
 // Reference semantics: torchvision vgg16.features convs (DISTS_pt.py:36-49, ADISTS.py:44-57).
 #include "common.cuh"
 #include "kernels.h"
@@ -45,11 +52,15 @@ struct Params {
   int strips;          // 1: the output goes out as strip planes (kernels.h make_strip_out_map), kEpiBiasRelu only
 };
 
-template <int BLOCK_N, bool RESIDENT>
+template <int BLOCK_N, bool RESIDENT, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       const __grid_constant__ CUtensorMap tmap_out, const Params p, int a_stages, int b_stages) {
+                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_a_lo,
+                       const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_out_lo, const Params p,
+                       int a_stages, int b_stages) {
+  static_assert(!(SPLIT && RESIDENT), "hi + lo weights are streamed");
   constexpr int HALF_N = BLOCK_N / 2;
+  constexpr int NSPLIT = SPLIT ? 2 : 1;                            // hi (+ lo) tiles per stage / slot
   constexpr int ACC = 512 / BLOCK_N;                              // accumulator ring in TMEM: 2 x 256 or 4 x 128 columns
   constexpr int ACC_LOG2 = ACC == 4 ? 2 : 1;
   constexpr int B_TILE = HALF_N * BLOCK_K * 2;                   // this CTA's half of one tap's weight tile
@@ -60,9 +71,11 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const int chunks = p.cin / BLOCK_K;
   uint8_t* stg_smem = smem;
   uint8_t* a_smem = smem + STG_BYTES;
-  uint8_t* b_smem = a_smem + a_stages * p.a_stage_bytes;
+  const int a_stride = NSPLIT * p.a_stage_bytes;                  // bytes per A stage (hi halo tile, then lo)
+  constexpr int B_SLOT = NSPLIT * B_TILE;                          // bytes per weight slot (hi half-tile, then lo)
+  uint8_t* b_smem = a_smem + a_stages * a_stride;
   const int b_slots = RESIDENT ? chunks * 9 : b_stages;
-  uint8_t* tail = b_smem + (size_t)b_slots * B_TILE;
+  uint8_t* tail = b_smem + (size_t)b_slots * B_SLOT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* a_full = bars;                 // [4]  leader's copy collects the bytes of both CTAs
   uint64_t* a_empty = bars + 4;            // [4]  local, multicast commit
@@ -85,6 +98,11 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_out);
+    if (SPLIT) {
+      prefetch_tmap(&tmap_a_lo);
+      prefetch_tmap(&tmap_b_lo);
+      prefetch_tmap(&tmap_out_lo);
+    }
     for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int a = 0; a < 4; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
@@ -137,9 +155,12 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       for (int cb = 0; cb < chunks; ++cb) {
         mbar_wait(&a_empty[as], aph ^ 1);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(&a_full[as], 2 * a_bytes);
-          tma_load_4d_pair(a_smem + (size_t)as * p.a_stage_bytes, &tmap_a, map_to_rank(&a_full[as], 0), cb * BLOCK_K, w0 - 1,
+          if (leader) mbar_expect_tx(&a_full[as], 2 * NSPLIT * a_bytes);
+          tma_load_4d_pair(a_smem + (size_t)as * a_stride, &tmap_a, map_to_rank(&a_full[as], 0), cb * BLOCK_K, w0 - 1,
                            h0 - 1, img);
+          if (SPLIT)
+            tma_load_4d_pair(a_smem + (size_t)as * a_stride + p.a_stage_bytes, &tmap_a_lo, map_to_rank(&a_full[as], 0),
+                             cb * BLOCK_K, w0 - 1, h0 - 1, img);
         }
         __syncwarp();
         if (++as == a_stages) { as = 0; aph ^= 1; }
@@ -147,9 +168,12 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[bs], bph ^ 1);
             if (elect_one()) {
-              if (leader) mbar_expect_tx(&b_full[bs], 2 * B_TILE);
-              tma_load_2d_pair(b_smem + (size_t)bs * B_TILE, &tmap_b, map_to_rank(&b_full[bs], 0), tap * p.cin + cb * BLOCK_K,
+              if (leader) mbar_expect_tx(&b_full[bs], 2 * B_SLOT);
+              tma_load_2d_pair(b_smem + (size_t)bs * B_SLOT, &tmap_b, map_to_rank(&b_full[bs], 0), tap * p.cin + cb * BLOCK_K,
                                n0 + (int)rank * HALF_N);
+              if (SPLIT)
+                tma_load_2d_pair(b_smem + (size_t)bs * B_SLOT + B_TILE, &tmap_b_lo, map_to_rank(&b_full[bs], 0),
+                                 tap * p.cin + cb * BLOCK_K, n0 + (int)rank * HALF_N);
             }
             __syncwarp();
             if (++bs == b_stages) { bs = 0; bph ^= 1; }
@@ -178,7 +202,8 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         for (int cb = 0; cb < chunks; ++cb) {
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
-          const uint64_t da0 = make_desc_sw128(smem_u32(a_smem + (size_t)as * p.a_stage_bytes), a_sbo, 0);
+          const uint64_t da0 = make_desc_sw128(smem_u32(a_smem + (size_t)as * a_stride), a_sbo, 0);
+          const uint64_t da0_lo = SPLIT ? make_desc_sw128(smem_u32(a_smem + (size_t)as * a_stride + p.a_stage_bytes), a_sbo, 0) : da0;
           if (RESIDENT) {
             if (elect_one()) {
 #pragma unroll
@@ -202,11 +227,18 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
               if (elect_one()) {
                 const int r = tap / 3, s = tap - r * 3;
                 const uint64_t da_tap = da0 + (uint64_t)((r * p.hbw + s) * 8);
-                const uint64_t db_tap = make_desc_sw128(smem_u32(b_smem + (size_t)bs * B_TILE), 1024, 0);
+                const uint64_t db_tap = make_desc_sw128(smem_u32(b_smem + (size_t)bs * B_SLOT), 1024, 0);
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                   umma_bf16_pair(d_tmem, da_tap + (uint64_t)(k * 2), db_tap + (uint64_t)(k * 2), idesc,
                                  (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  if (SPLIT) {   // + hi * lo + lo * hi (lo * lo is below fp32 resolution)
+                    const uint64_t da_lo = da0_lo + (uint64_t)((r * p.hbw + s) * 8);
+                    const uint64_t db_lo = make_desc_sw128(smem_u32(b_smem + (size_t)bs * B_SLOT + B_TILE), 1024, 0);
+                    umma_bf16_pair(d_tmem, da_tap + (uint64_t)(k * 2), db_lo + (uint64_t)(k * 2), idesc, 1u);
+                    umma_bf16_pair(d_tmem, da_lo + (uint64_t)(k * 2), db_tap + (uint64_t)(k * 2), idesc, 1u);
+                  }
+                }
                 umma_commit_pair(&b_empty[bs]);
                 if (tap == 8) {
                   umma_commit_pair(&a_empty[as]);
@@ -239,8 +271,12 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       tc_fence_after();
 #pragma unroll 1
       for (int c64 = 0; c64 < BLOCK_N / 64; ++c64, ++sub) {
-        uint8_t* stg = stg_smem + (sub & 1) * (128 * 128);
-        if (elected) tma_store_wait_read<1>();
+        // bf16: two staging tiles used alternately; SPLIT: tile 0 = hi, tile 1 = lo of the same sub-tile
+        uint8_t* stg = stg_smem + (SPLIT ? 0 : (sub & 1)) * (128 * 128);
+        if (elected) {
+          if (SPLIT) tma_store_wait_read<0>();
+          else tma_store_wait_read<1>();
+        }
         named_bar_sync(2, 128);
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -288,7 +324,22 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             t.y = Vec<bf16>::pack2(v[2], v[3]);
             t.z = Vec<bf16>::pack2(v[4], v[5]);
             t.w = Vec<bf16>::pack2(v[6], v[7]);
-            if (p.strips) {
+            if (SPLIT) {
+              *reinterpret_cast<uint4*>(stg + m * 128 + (((half * 4 + q) ^ (m & 7)) << 4)) = t;
+              float l[8];
+              const uint32_t hw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                l[2 * j] = v[2 * j] - __uint_as_float(hw[j] << 16);
+                l[2 * j + 1] = v[2 * j + 1] - __uint_as_float(hw[j] & 0xffff0000u);
+              }
+              uint4 tl;
+              tl.x = Vec<bf16>::pack2(l[0], l[1]);
+              tl.y = Vec<bf16>::pack2(l[2], l[3]);
+              tl.z = Vec<bf16>::pack2(l[4], l[5]);
+              tl.w = Vec<bf16>::pack2(l[6], l[7]);
+              *reinterpret_cast<uint4*>(stg + 128 * 128 + m * 128 + (((half * 4 + q) ^ (m & 7)) << 4)) = tl;
+            } else if (p.strips) {
               // [channel][pixel]: a warp's 32 pixels of one channel are 64 contiguous bytes (conflict-free 2-byte stores)
               unsigned short* col = reinterpret_cast<unsigned short*>(stg) + (half * 32 + q * 8) * 128 + m;
               const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
@@ -312,6 +363,7 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         if (elected) {
           if (p.strips) tma_store_4d(&tmap_out, stg, h0 * 8, w0 >> 3, n0 + c64 * 64, img);
           else tma_store_4d(&tmap_out, stg, n0 + c64 * 64, w0, h0, img);
+          if (SPLIT) tma_store_4d(&tmap_out_lo, stg + 128 * 128, n0 + c64 * 64, w0, h0, img);
           tma_store_commit();
         }
       }
@@ -329,8 +381,9 @@ conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
-template <int BLOCK_N, bool RESIDENT>
+template <int BLOCK_N, bool RESIDENT, bool SPLIT>
 static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
+  constexpr int NSPLIT = SPLIT ? 2 : 1;
   constexpr int B_TILE = (BLOCK_N / 2) * BLOCK_K * 2;
   Params p;
   p.n = plan.n; p.h = plan.h; p.w = plan.w; p.cin = plan.cin; p.cout = plan.cout;
@@ -344,6 +397,7 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
   p.bias = plan.bias; p.epi = plan.epi; p.mask = plan.mask;
   p.strips = plan.strips_out ? 1 : 0;
   if (p.strips && p.epi != kEpiBiasRelu) return -1;
+  if (SPLIT && (p.epi != kEpiBiasRelu || p.strips)) return -1;   // bf16x3: forward convolutions only
   const int chunks = plan.cin / BLOCK_K;
   const int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - 2048 /*bias*/ - STG_BYTES;
   int a_stages, b_stages = 0;
@@ -354,17 +408,18 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
     if (a_stages < 2) return -1;
   } else {
     a_stages = 2;
-    b_stages = (budget - a_stages * p.a_stage_bytes) / B_TILE;
+    b_stages = (budget - a_stages * NSPLIT * p.a_stage_bytes) / (NSPLIT * B_TILE);
     if (b_stages > 8) b_stages = 8;
     if (b_stages < 3) return -1;
   }
-  const int smem = STG_BYTES + a_stages * p.a_stage_bytes + (RESIDENT ? chunks * 9 : b_stages) * B_TILE + 1024 + 512 + 2048;
-  ensure_dynamic_smem(conv3x3_tc_pair_kernel<BLOCK_N, RESIDENT>, smem);
+  const int smem = STG_BYTES + a_stages * NSPLIT * p.a_stage_bytes + (RESIDENT ? chunks * 9 : b_stages) * NSPLIT * B_TILE + 1024 +
+                   512 + 2048;
+  ensure_dynamic_smem(conv3x3_tc_pair_kernel<BLOCK_N, RESIDENT, SPLIT>, smem);
   int clusters = sm_count / 2;
   if (p.num_items < clusters) clusters = p.num_items;
   if (RESIDENT && clusters > p.num_n_tiles) clusters -= clusters % p.num_n_tiles;
-  conv3x3_tc_pair_kernel<BLOCK_N, RESIDENT><<<2 * clusters, NUM_THREADS, smem, st>>>(plan.tmap_a, plan.tmap_b, plan.tmap_out, p,
-                                                                                   a_stages, b_stages);
+  conv3x3_tc_pair_kernel<BLOCK_N, RESIDENT, SPLIT><<<2 * clusters, NUM_THREADS, smem, st>>>(
+      plan.tmap_a, plan.tmap_b, plan.tmap_out, plan.tmap_a_lo, plan.tmap_b_lo, plan.tmap_out_lo, p, a_stages, b_stages);
   return 1;
 }
 
@@ -373,9 +428,16 @@ static int launch_impl(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
 // Returns launches (1) or -1 if the configuration does not fit.  plan.tmap_b must have been encoded with a box of
 // block_n / 2 rows (conv_tc_make_plan does that when plan.pair is set).
 int launch_conv3x3_tc_pair(const ConvTcPlan& plan, int sm_count, cudaStream_t st) {
+  if (plan.split) {
+    if (plan.block_n == 128) return tcp::launch_impl<128, false, true>(plan, sm_count, st);
+    if (plan.block_n == 256) return tcp::launch_impl<256, false, true>(plan, sm_count, st);
+    return -1;
+  }
   const bool resident = (size_t)9 * plan.cin * (plan.block_n / 2) * 2 <= 150 * 1024;
-  if (plan.block_n == 128) return resident ? tcp::launch_impl<128, true>(plan, sm_count, st) : tcp::launch_impl<128, false>(plan, sm_count, st);
-  if (plan.block_n == 256) return resident ? tcp::launch_impl<256, true>(plan, sm_count, st) : tcp::launch_impl<256, false>(plan, sm_count, st);
+  if (plan.block_n == 128)
+    return resident ? tcp::launch_impl<128, true, false>(plan, sm_count, st) : tcp::launch_impl<128, false, false>(plan, sm_count, st);
+  if (plan.block_n == 256)
+    return resident ? tcp::launch_impl<256, true, false>(plan, sm_count, st) : tcp::launch_impl<256, false, false>(plan, sm_count, st);
   return -1;
 }
 

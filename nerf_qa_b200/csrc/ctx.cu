@@ -257,8 +257,9 @@ struct StreamOrder {
 // conv_tc_make_plan through the context's cache of encoded tensor maps
 int cached_plan(nqa_ctx* ctx, ConvTcPlan* plan, const bf16* in, const bf16* in_lo, const bf16* wk, const bf16* wk_lo,
                 const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout, bool split,
-                const char** err, bool strips_out = false) {
-  const nqa_ctx::PlanKey key{in, in_lo, wk, out, out_lo, n, h, w, cin, cout, (split ? 1 : 0) | (strips_out ? 2 : 0)};
+                const char** err, bool strips_out = false, bool split_on_pairs = false) {
+  const nqa_ctx::PlanKey key{in, in_lo, wk, out, out_lo, n, h, w, cin, cout,
+                             (split ? 1 : 0) | (strips_out ? 2 : 0) | (split_on_pairs ? 4 : 0)};
   for (auto& e : ctx->plan_cache)
     if (e.first == key) {
       *plan = e.second;
@@ -267,7 +268,7 @@ int cached_plan(nqa_ctx* ctx, ConvTcPlan* plan, const bf16* in, const bf16* in_l
       return 0;
     }
   const int rc = conv_tc_make_plan(plan, ctx->conv_cfg, in, in_lo, wk, wk_lo, bias, out, out_lo, n, h, w, cin, cout, split, err,
-                                   strips_out);
+                                   strips_out, split_on_pairs);
   if (rc) return rc;
   ++ctx->plan_misses;
   if (ctx->plan_cache.size() >= 512) ctx->plan_cache.clear();
@@ -481,7 +482,7 @@ int conv_layer<bf16>(nqa_ctx* ctx, int li, const bf16* in, const bf16* in_lo, bf
   const char* err = "";
   const bool split = prec == NQA_PREC_BF16X3;
   if (cached_plan(ctx, &plan, in, in_lo, ctx->w_hi[li], ctx->w_lo[li], ctx->bias[li], out, out_lo, n, h, w,
-                  kConvCin[li], kConvCout[li], split, &err, strips_out))
+                  kConvCin[li], kConvCout[li], split, &err, strips_out, /*split_on_pairs=*/split))
     return fail(NQA_ERR_CUDA, "%s (layer %d, %dx%dx%d)", err, li, n, h, w);
   ProfScope ps(ctx, NQA_K_CONV_TC, st);
   const int nl = launch_conv3x3_tc(plan, st);
@@ -637,6 +638,8 @@ int finalize(nqa_ctx* ctx, const PartialBufs& pb, int pairs, int H, int W, float
 }
 
 // levels 1..4 of the non-split trunks: L2pooling and the level's statistics in one pass (pool_stats_kernel)
+// (bf16x3 keeps the separate pooling and moment kernels: a hi + lo version of the register-fed fused kernel was measured
+// slower, 60.4 vs 34.2 + 21.4 ms per 64 pairs)
 bool use_fused_pool(const nqa_ctx* ctx, int prec) { return ctx->fuse_pool_stats && prec != NQA_PREC_BF16X3; }
 
 template <typename T>
@@ -2025,7 +2028,8 @@ int nqa_conv3x3_relu(nqa_ctx* ctx, const float* x, const float* w, const float* 
     ctx->launches += launch_nchw_to_nhwc<bf16>(x, in_hi, split ? in_lo : nullptr, B, Cin, H, W, st);
     ConvTcPlan plan;
     const char* err = "";
-    if (conv_tc_make_plan(&plan, ctx->conv_cfg, in_hi, in_lo, w_hi, w_lo, bias, out_hi, out_lo, B, H, W, Cin, Cout, split, &err))
+    if (conv_tc_make_plan(&plan, ctx->conv_cfg, in_hi, in_lo, w_hi, w_lo, bias, out_hi, out_lo, B, H, W, Cin, Cout, split, &err,
+                          false, /*split_on_pairs=*/split))
       return fail(NQA_ERR_CUDA, "%s", err);
     const int nl = launch_conv3x3_tc(plan, st);
     if (nl <= 0) return fail(NQA_ERR_CUDA, "convolution could not be launched (%dx%dx%d, %d -> %d channels)", B, H, W, Cin, Cout);

@@ -108,12 +108,14 @@ struct ConvTcConfig {
   bool n64 = true;          // NQA_CONV_N64: 128 -> 128 channels as two resident 64-channel tiles (halo kernel)
   bool pair = true;         // NQA_CONV_PAIR: CTA pairs (tcgen05 cta_group::2) for the wide layers
   int pair_min_cin = 128;   // NQA_PAIR_MINCIN
+  bool split_pair = true;   // NQA_PAIR_SPLIT: bf16x3 forward convolutions on the CTA-pair kernel (hi + lo operands)
 };
 ConvTcConfig conv_tc_config_from_env(int sm_count);
 
 struct ConvTcPlan {
   CUtensorMap tmap_a, tmap_a_lo, tmap_b, tmap_b_lo;
   CUtensorMap tmap_out;   // halo kernel: output [n,h,w,cout] with box {64, 8, 16, 1} for the TMA-store epilogue
+  CUtensorMap tmap_out_lo;  // bf16x3 on the CTA-pair kernel: the residual tensor
   int n, h, w, cin, cout;
   int sm_count;        // persistent-grid size (the context's device)
   int tw_log2;
@@ -138,7 +140,9 @@ struct ConvTcPlan {
 // Fills the tensor maps; returns 0 on success, nonzero + message on failure.
 int conv_tc_make_plan(ConvTcPlan* plan, const ConvTcConfig& cfg, const bf16* in, const bf16* in_lo, const bf16* wk,
                       const bf16* wk_lo, const float* bias, bf16* out, bf16* out_lo, int n, int h, int w, int cin, int cout,
-                      bool split, const char** err, bool strips_out = false);
+                      bool split, const char** err, bool strips_out = false, bool split_on_pairs = false);
+// split_on_pairs: a bf16x3 FORWARD convolution may use the CTA-pair kernel (its data-gradient epilogues exist on the per-tap
+// kernel only)
 // whether conv_tc_make_plan picks the CTA-pair kernel for a layer (the kernel that can write strip planes)
 bool conv_tc_uses_pair(const ConvTcConfig& cfg, int cin, int cout, bool split);
 int launch_conv3x3_tc(const ConvTcPlan& plan, cudaStream_t st);
