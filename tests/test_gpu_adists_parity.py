@@ -227,3 +227,22 @@ def test_strip_plane_path_against_the_planar_path(monkeypatch, shape):
             assert np.max(np.abs(got - want)) < 1e-4
     # the strip readers alone (same pooled activations as the planar path: only the layout of the planes differs)
     assert np.array_equal(res["1"][0], res["0"][0])
+
+
+@pytest.mark.parametrize("shape", [(1, 2160, 3840), (2, 1088, 1928)])
+def test_large_and_unaligned_frames_on_the_strip_path(monkeypatch, shape):
+    """4K frames (32-bit plane strides, 17280-element tensor-map rows) and a width whose deeper levels stop being multiples
+    of 8 (1928 -> 964 -> 482 ...: strip planes for level 1 only, planar below): the strip-plane path against the planar one."""
+    b, h, w = shape
+    x, y = synth.make_frame_pairs(b, h, w, seed=5)
+    xs, ys = x.cuda(), y.cuda()
+    out = {}
+    for mode in ("2", "0"):
+        monkeypatch.setenv("NQA_ADISTS_STRIPS", mode)
+        a, d = make_adists("bf16"), make_dists("bf16")
+        out[mode] = (a(xs, ys, as_loss=False).cpu().numpy(), *[t.cpu().numpy() for t in d.score_with_adists(xs, ys)])
+        assert np.all(np.isfinite(out[mode][0])) and np.all(out[mode][0] > 0)
+        del a, d
+        torch.cuda.empty_cache()
+    for got, want in zip(out["2"], out["0"]):
+        assert np.max(np.abs(got - want)) < 1e-4
