@@ -246,3 +246,23 @@ def test_large_and_unaligned_frames_on_the_strip_path(monkeypatch, shape):
         torch.cuda.empty_cache()
     for got, want in zip(out["2"], out["0"]):
         assert np.max(np.abs(got - want)) < 1e-4
+
+
+def test_adists_full_size_properties(amodels, dmodels):
+    """Size-independent properties at the benchmark's frame size (1080p), across a micro-batch boundary (9 pairs = 8 + 1):
+    a frame's A-DISTS score does not depend on the batch it travels in (bit for bit, alone or through the shared-trunk
+    call's A-DISTS half), identical frames score 0 (T = S = 1 and the entropy weights sum to one), and the host path
+    returns the device path's scores."""
+    x, y = synth.make_frame_pairs(9, 1080, 1920, seed=101)
+    xs, ys = x.cuda(), y.cuda()
+    a, d = amodels["bf16"], dmodels["bf16"]
+    s = a(xs, ys, as_loss=False)
+    assert torch.equal(a(xs[:1], ys[:1], as_loss=False), s[:1])
+    assert torch.equal(a(xs[8:], ys[8:], as_loss=False), s[8:])
+    assert torch.equal(a(xs[3:6], ys[3:6], as_loss=False), s[3:6])
+    both = d.score_with_adists(xs, ys)[1]
+    assert torch.equal(d.score_with_adists(xs[8:], ys[8:])[1], both[8:])
+    assert torch.allclose(both, s, rtol=1e-4, atol=1e-5)
+    same = a(xs[:2], xs[:2], as_loss=False)
+    assert float(same.abs().max()) < 1e-5
+    assert torch.equal(a.score_host(x.pin_memory(), y.pin_memory()), s.cpu())
